@@ -1,0 +1,170 @@
+/* mimrl_b200 — C ABI of the B200-native MI / CMI hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream
+ * (passed as void*, i.e. a cudaStream_t).  No ownership is transferred: all
+ * buffers are allocated by the caller (PyTorch on the Python side).  Return
+ * value: 0 = ok, non-zero = error, text via mimrl_last_error().
+ *
+ * The reference (kiva12138/MIMRL) has no FFI of its own — its boundary is a
+ * set of Python symbols.  Each group below names the
+ * reference code it replaces; mimrl_b200/*.py binds these with ctypes and
+ * re-exposes the reference's Python signatures on top.
+ *
+ * Row-block convention (single- and multi-GPU alike): a rank OWNS n_own rows
+ * with global indices [own_offset, own_offset + n_own) and sweeps them against
+ * ALL n_all rows of the other operand.  On one GPU n_own == n_all, offset 0.
+ */
+#ifndef MIMRL_B200_H
+#define MIMRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMRL_ABI_VERSION 1
+
+/* --bound_type values, Model.py:121-146 / Parameters.py:41-51 */
+enum mimrl_bound {
+  MIMRL_BOUND_DV = 0,
+  MIMRL_BOUND_MINE = 1,
+  MIMRL_BOUND_TUBA = 2,
+  MIMRL_BOUND_NWJ = 3,
+  MIMRL_BOUND_INFONCE = 4,
+  MIMRL_BOUND_JS_FGAN = 5,
+  MIMRL_BOUND_JS = 6,
+  MIMRL_BOUND_SMILE = 7,
+  MIMRL_BOUND_INTERPOLATE = 8
+};
+
+/* statistics requested from the score sweep */
+#define MIMRL_STAT_CLAMP 1    /* exp-sum runs on clamp(S,-1,1)  (smile, VMI.py:186-191) */
+#define MIMRL_STAT_SOFTPLUS 2 /* also accumulate sum softplus(S) (js_fgan/js/smile, VMI.py:169-174) */
+
+/* per-pair weight families of the backward sweep */
+#define MIMRL_WEIGHT_EXP 0     /* w_ij = exp(S_ij - shift) */
+#define MIMRL_WEIGHT_SIGMOID 1 /* w_ij = sigmoid(S_ij)     */
+
+/* kernel implementation selector (both are CUDA kernels of this library) */
+#define MIMRL_IMPL_AUTO 0
+#define MIMRL_IMPL_FFMA 1    /* fp32 CUDA-core tiles, any embed width <= 256 */
+#define MIMRL_IMPL_TCGEN05 2 /* tcgen05 + TMA + TMEM, fp16x3 split (fp32-class accuracy), embed <= 128 */
+
+int mimrl_version(void);
+const char *mimrl_last_error(void);
+/* number of kernels this library has launched so far in this process */
+uint64_t mimrl_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Separable critic: fused score + bound.  Replaces VMI.py:57
+ * (scores = y_ @ x_.T) together with the bound functions VMI.py:136-198 as
+ * they are called from VMIEstimator.forward (Model.py:115-148); the B x B
+ * matrix is never written to memory.
+ * ---------------------------------------------------------------------- */
+
+size_t mimrl_sep_workspace_bytes(int n_own, int n_all, int embed);
+/* which implementation a request resolves to: MIMRL_IMPL_FFMA or MIMRL_IMPL_TCGEN05 */
+int mimrl_sep_selected_impl(int n_own, int n_all, int embed, int impl);
+
+/* Forward sweep.  S_ij = own_i . all_j for the owned rows; for every owned row
+ * i, over the columns j != own_offset + i:
+ *   row_max[i] = max_j t(S_ij),  row_sum[i] = sum_j exp(t(S_ij) - row_max[i]),
+ *   row_sp[i]  = sum_j softplus(S_ij)        (only with MIMRL_STAT_SOFTPLUS)
+ * and diag[i] = S_{i, own_offset+i}.  t = clamp(.,-1,1) with MIMRL_STAT_CLAMP. */
+int mimrl_sep_row_stats(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                        int own_offset, int flags, int impl, float *row_max, float *row_sum, float *row_sp,
+                        float *diag, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward sweep.  out_i = coef[0] * sum_{j} w_ij * all_j + dcoef[i] * all_{own_offset+i}
+ * with w_ij from the weight family; the diagonal pair j == own_offset+i is left
+ * out of the sum unless include_diag.  shift is indexed by the owned row
+ * (shift[i], i < n_own) or, with shift_by_swept, by the swept row (shift[j],
+ * j < n_all).  Called twice per backward: rows = h(y) to get d/dh(y), then with
+ * the operands swapped to get d/dg(x). */
+int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                           int own_offset, int weight_family, int include_diag, const float *shift,
+                           int shift_by_swept, const float *coef, const float *dcoef, int impl, float *out,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* Bound value from the per-row statistics of ALL n rows (VMI.py:136-198 and
+ * the MINE branch Model.py:121-124).  log_baseline may be NULL (constant
+ * baseline).  result[0] = mi, result[1] = mi_loss, result[2..15] = scalars kept
+ * for the backward pass. */
+int mimrl_bound_finalize(int bound, const float *row_max, const float *row_sum, const float *row_sp,
+                         const float *diag, const float *log_baseline, int n, float *result, void *stream);
+
+/* Coefficients of the backward sweep from the saved scalars and the incoming
+ * gradients grad[0] = d/d mi, grad[1] = d/d mi_loss:
+ *   coef[0], shift[n], dcoef[n] as consumed by mimrl_sep_weighted_sum and
+ *   dbaseline[n] = d/d log_baseline (written only if log_baseline != NULL).
+ * weight_family / include_diag for the bound are returned by
+ * mimrl_bound_weight_family(). */
+int mimrl_bound_backward_coef(int bound, const float *result, const float *grad, const float *row_max,
+                              const float *row_sum, const float *diag, const float *log_baseline, int n,
+                              float *coef, float *shift, float *dcoef, float *dbaseline, void *stream);
+int mimrl_bound_weight_family(int bound, int *weight_family, int *include_diag, int *stat_flags);
+
+/* ------------------------------------------------------------------------
+ * Materialised-score entry points: the free bound functions of VMI.py:136-250
+ * applied to a score matrix that already exists in memory (API parity for
+ * CriticModel.forward -> bound(scores); also the concat-critic path).
+ * scores is [n_rows, n_cols] row-major, the owned row block of the global
+ * n_cols x n_cols matrix.
+ * ---------------------------------------------------------------------- */
+int mimrl_scores_row_stats(const float *scores, int n_rows, int n_cols, int own_offset, int flags,
+                           float *row_max, float *row_sum, float *row_sp, float *diag, void *stream);
+/* grad_scores[i][j] = coef[0] * w_ij (off-diagonal, or all with include_diag) + dcoef[i] on the diagonal */
+int mimrl_scores_grad(const float *scores, int n_rows, int n_cols, int own_offset, int weight_family,
+                      int include_diag, const float *shift, const float *coef, const float *dcoef,
+                      float *grad_scores, void *stream);
+
+/* ------------------------------------------------------------------------
+ * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of
+ * prod_knn_sample (Model.py:75-106), i.e. sklearn NearestNeighbors.kneighbors.
+ * ---------------------------------------------------------------------- */
+
+size_t mimrl_knn_workspace_bytes(int n_keys, int n_queries, int width, int k);
+
+/* keys [n_keys, width] (the Z pool, fp32), query_ids [n_queries] (int64 row ids
+ * into keys, drawn on the host from numpy's global RNG).  Keys listed in
+ * query_ids are excluded from the search (Model.py:83-84).  exact_form: 1 =
+ * float64 GEMM form ||q||^2 - 2q.z + ||z||^2 (sklearn 'brute' route), 0 =
+ * float64 direct differences ('kd_tree' route).  Output neighbours [n_queries,k]
+ * int64, nearest first, exact ties -> lowest index:
+ *   nbr_orig  = indices into keys,
+ *   nbr_comp  = indices into the pool with the query rows removed (what
+ *               sklearn returns in the reference).
+ * key_index_offset is added to nbr_orig (multi-GPU key shards). radius is
+ * accepted and ignored, like the reference. */
+int mimrl_knn_search(const float *keys, int n_keys, int width, const int64_t *query_ids, int n_queries, int k,
+                     float radius, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist,
+                     void *workspace, size_t workspace_bytes, void *stream);
+/* Same search with explicit query rows (multi-GPU: queries live on another rank).
+ * excluded_sorted: ascending global ids to skip, may be NULL. */
+int mimrl_knn_search_rows(const float *keys, int n_keys, int width, int64_t key_index_offset,
+                          const float *queries, int n_queries, const int64_t *excluded_sorted, int n_excluded,
+                          int k, int exact_form, int64_t *nbr_orig, double *nbr_dist, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* out[r, c] = src[idx[r / repeat], c % width] for c < out_width: row gather +
+ * neighbour repeat + column tiling (Model.py:97-104) in one pass. */
+int mimrl_gather_rows(const float *src, int n_src, int width, const int64_t *idx, int n_idx, int repeat,
+                      int out_width, float *out, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Conditional-MI classifier head.  Replaces Model.py:69-70 (clamp + final
+ * activation), Model.py:198 (BCE) and estimate_cmi Model.py:203-219.
+ * logits [2n, 2]; rows [0,n) joint, [n,2n) product.  act: 0 hardtanh, 1 sigmoid.
+ * result[0] = cmi, result[1] = loss.
+ * ---------------------------------------------------------------------- */
+int mimrl_vcmi_head_fwd(const float *logits, int n, int act, float *result, void *stream);
+/* grad[0] = d/d cmi, grad[1] = d/d loss -> grad_logits [2n, 2] */
+int mimrl_vcmi_head_bwd(const float *logits, int n, int act, const float *grad, float *grad_logits,
+                        void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMRL_B200_H */

@@ -1,0 +1,82 @@
+// Shared helpers for the mimrl_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/mimrl_b200.h"
+
+namespace mimrl {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char *what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+#define MIMRL_REQUIRE(cond, ...)     \
+  do {                               \
+    if (!(cond)) {                   \
+      mimrl::set_error(__VA_ARGS__); \
+      return 2;                      \
+    }                                \
+  } while (0)
+
+// ---- small device math ----------------------------------------------------
+__device__ __forceinline__ float softplusf(float z) {
+  // log(1 + exp(z)), stable on both tails
+  return fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)));
+}
+__device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// merge two (max, sum-of-exp) pairs; (-inf, 0) is the identity
+__device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2) {
+  float mn = fmaxf(m, m2);
+  if (mn == -INFINITY) {
+    m = mn;
+    s = 0.f;
+    return;
+  }
+  s = s * __expf(m - mn) + s2 * __expf(m2 - mn);
+  m = mn;
+}
+__device__ __forceinline__ void lse_merge_d(double &m, double &s, double m2, double s2) {
+  double mn = fmax(m, m2);
+  if (mn == -INFINITY) {
+    m = mn;
+    s = 0.0;
+    return;
+  }
+  s = s * exp(m - mn) + s2 * exp(m2 - mn);
+  m = mn;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Partial-statistics layout shared by every score sweep (FFMA and tcgen05):
+// part[(split * n_own + row) * 3 + {0,1,2}] = {max, sum, softplus-sum}
+int combine_row_stats(const float *part, int n_splits, int n_own, float *row_max, float *row_sum, float *row_sp,
+                      cudaStream_t st);
+
+// implemented in sep_tc.cu; returns 0 and sets *handled = 1 when it ran
+int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
+                     int flags, float *row_max, float *row_sum, float *row_sp, void *ws, size_t ws_bytes,
+                     cudaStream_t st);
+int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
+                        int family, int include_diag, const float *shift, int shift_by_swept, const float *coef,
+                        const float *dcoef, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t sep_tc_workspace_bytes(int n_own, int n_all, int embed);
+bool sep_tc_supported(int n_own, int n_all, int embed);
+
+}  // namespace mimrl

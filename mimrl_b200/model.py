@@ -1,0 +1,276 @@
+"""MI / CMI estimator modules and the k-NN sampler: drop-in for the hot-path
+part of the reference's ``Model.py`` (lines 47-225 and the two stage functions
+305-386).  Same class names, constructor arguments, ``forward`` signatures and
+parameter paths (``critic_model.MLP_g.0.weight``, ``classifier.mlp.0.weight``,
+...), so reference ``state_dict``s load and ``Solver.get_optimizer``'s
+substring grouping (Solver.py:124-133) keeps working.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import rowblock as RB
+from .vmi import (BaselineModel, CriticModel, _scores_bound, get_activation, interp_lower_bound, separable_bound)
+
+
+# --------------------------------------------------------------------------
+# k-NN sampler (Model.py:75-106)
+# --------------------------------------------------------------------------
+
+
+def sklearn_route(width, k, n_fit):
+    """Which algorithm scikit-learn's 'auto' picks (sklearn/neighbors/_base.py:615-648):
+    decides the float64 distance form the re-rank must reproduce."""
+    return "brute" if (width > 15 or k >= n_fit // 2) else "kd_tree"
+
+
+def knn_search(Z, ids, k, radius=1.0, return_distance=False):
+    """Neighbours of ``Z[ids]`` among the rows of ``Z`` not in ``ids``.
+    Returns (nbr_orig, nbr_comp[, dist]) int64 [m, k] CUDA tensors."""
+    Z = L.f32(Z)
+    N, width = Z.shape
+    m = int(ids.numel())
+    ids = ids.to(device=Z.device, dtype=torch.int64).contiguous()
+    ws_bytes = L.lib.mimrl_knn_workspace_bytes(N, m, width, k)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=Z.device)
+    nbr_orig = torch.empty(m, k, dtype=torch.int64, device=Z.device)
+    nbr_comp = torch.empty(m, k, dtype=torch.int64, device=Z.device)
+    dist = torch.empty(m, k, dtype=torch.float64, device=Z.device) if return_distance else None
+    exact = 1 if sklearn_route(width, k, N - m) == "brute" else 0
+    rc = L.lib.mimrl_knn_search(L.ptr(Z), N, width, L.ptr(ids), m, k, float(radius), exact, L.ptr(nbr_orig),
+                                L.ptr(nbr_comp), L.ptr(dist), L.ptr(ws), ws.numel(), L.stream())
+    if rc == 2 and b"n_neighbors" in L.lib.mimrl_last_error():
+        raise ValueError(L.lib.mimrl_last_error().decode())       # sklearn raises ValueError here
+    L.check(rc)
+    return (nbr_orig, nbr_comp, dist) if return_distance else (nbr_orig, nbr_comp)
+
+
+def _gather(src, idx, repeat, out_width):
+    src = L.f32(src)
+    out = torch.empty(idx.numel() * repeat, out_width, dtype=torch.float32, device=src.device)
+    L.check(L.lib.mimrl_gather_rows(L.ptr(src), src.shape[0], src.shape[1], L.ptr(idx), idx.numel(), repeat,
+                                    out_width, L.ptr(out), L.stream()))
+    return out
+
+
+def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
+    """Model.py:75-106.  Draws m = batch_size // k query rows with numpy's GLOBAL
+    RNG (same draw and same RNG state afterwards as the reference's
+    ``np.random.choice(range(N), m, replace=False)``), finds the k nearest
+    neighbours of Z[ids] among the remaining rows, and returns
+    ``(X[neighbours], Y[ids] repeated k, Z[ids] repeated k)`` tiled to the widest
+    of the three, as new CUDA tensors that require grad and carry no history to
+    the pools.  The pools stay on the GPU; only the m ids travel host -> device."""
+    X, Y, Z = X.detach(), Y.detach(), Z.detach()
+    N = X.shape[0]
+    m = batch_size // k_neighbor
+    if m > N:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    ids_host = np.random.permutation(N)[:m]
+    ids = torch.from_numpy(ids_host.astype(np.int64)).to(Z.device, non_blocking=True)
+    nbr_orig, _ = knn_search(Z, ids, k_neighbor, radius)
+    wmax = max(X.shape[1], Y.shape[1], Z.shape[1])
+    batch_x = _gather(X, nbr_orig.reshape(-1), 1, wmax)
+    batch_y = _gather(Y, ids, k_neighbor, wmax)
+    batch_z = _gather(Z, ids, k_neighbor, wmax)
+    return batch_x.requires_grad_(True), batch_y.requires_grad_(True), batch_z.requires_grad_(True)
+
+
+# --------------------------------------------------------------------------
+# variational MI estimator (Model.py:108-148)
+# --------------------------------------------------------------------------
+
+
+class VMIEstimator(nn.Module):
+    def __init__(self, critic_type, baseline_type, bound_type, d_common, hidden_dim, embed_dim, layers, activation,
+                 mu, rho):
+        super().__init__()
+        self.critic_type, self.baseline_type, self.bound_type = critic_type, baseline_type, bound_type
+        self.critic_model = CriticModel(critic_type, d_common, d_common, hidden_dim=hidden_dim, embed_dim=embed_dim,
+                                        layers=layers, activation=activation)
+        self.baseline_model = BaselineModel(baseline_type, d_common, hidden_dim=hidden_dim, layers=layers,
+                                            activation=activation, mu=mu, rho=rho)
+        self.rowblock = None            # set to a rowblock.RowBlock to shard the global batch over ranks
+        self.impl = L.IMPL_AUTO
+
+    def forward(self, features_x, features_y):
+        alpha_logit = 0.01
+        bound = self.bound_type
+        if bound not in L.BOUND_IDS:
+            raise NotImplementedError
+        needs_base = bound in ("tuba", "interpolate")
+        if self.critic_type == 'separate' and bound != 'interpolate':
+            # fused path: the B x B score matrix never exists
+            x_, y_ = self.critic_model.embed(features_x, features_y)
+            base = self.baseline_model(features_y) if needs_base else None
+            return separable_bound(x_, y_, bound, base, self.rowblock, self.impl)
+        scores = self.critic_model(features_x, features_y)
+        if bound == 'interpolate':
+            mi = interp_lower_bound(scores, self.baseline_model(features_y), alpha_logit)
+            return mi, -mi
+        base = self.baseline_model(features_y) if needs_base else None
+        return _scores_bound(scores, bound, base)
+
+
+# --------------------------------------------------------------------------
+# classifier-based conditional MI (Model.py:47-72, 150-225)
+# --------------------------------------------------------------------------
+
+
+class _VCMIHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, act_id):
+        logits = L.f32(logits)
+        n = logits.shape[0] // 2
+        result = torch.empty(2, dtype=torch.float32, device=logits.device)
+        L.check(L.lib.mimrl_vcmi_head_fwd(L.ptr(logits), n, act_id, L.ptr(result), L.stream()))
+        ctx.save_for_backward(logits)
+        ctx.act_id = act_id
+        return result[0].clone(), result[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_cmi, g_loss):
+        (logits,) = ctx.saved_tensors
+        n = logits.shape[0] // 2
+        z = logits.new_zeros(())
+        grad = torch.stack([g_cmi if g_cmi is not None else z, g_loss if g_loss is not None else z]).contiguous()
+        gl = torch.empty_like(logits)
+        L.check(L.lib.mimrl_vcmi_head_bwd(L.ptr(logits), n, ctx.act_id, L.ptr(grad), L.ptr(gl), L.stream()))
+        return gl, None
+
+
+class MLP_For_CMI(nn.Module):
+    """Model.py:47-72.  ``layers`` is accepted and ignored, as in the reference."""
+
+    def __init__(self, dim, hidden_dim, output_dim, layers, activation, last_acticate):
+        super().__init__()
+        act = get_activation(activation)
+        self.mlp = nn.Sequential(
+            nn.Linear(dim, hidden_dim), act(),
+            nn.Linear(hidden_dim, hidden_dim), act(),
+            nn.Linear(hidden_dim, hidden_dim), act(),
+            nn.Linear(hidden_dim, output_dim))
+        if last_acticate == 'hardtanh':
+            self.final_activate = nn.Hardtanh(1e-4, 1 - 1e-4)
+        elif last_acticate == 'sigmoid':
+            self.final_activate = nn.Sigmoid()
+        else:
+            raise NotImplementedError
+        self.act_id = 0 if last_acticate == 'hardtanh' else 1
+
+    def logits(self, features):
+        return self.mlp(features)
+
+    def forward(self, features):
+        return self.final_activate(torch.clamp(self.mlp(features), -10, 10))
+
+
+class VCMIEstimator(nn.Module):
+    def __init__(self, embed_dim, hidden_dim, layers, activation, k_neighbor, radius, last_acticate='hardtanh'):
+        super().__init__()
+        self.classifier = MLP_For_CMI(embed_dim * 3, hidden_dim, output_dim=2, layers=layers, activation=activation,
+                                      last_acticate=last_acticate)
+        self.k_neighbor, self.radius = k_neighbor, radius
+        self.embed_dim = embed_dim
+
+    def forward(self, features_x, features_y, features_z, random_knn_x, random_knn_y, random_knn_z):
+        """I(x;y|z): returns (cmi, loss).  The reference runs the classifier a second
+        time inside estimate_cmi on the same batch (Model.py:189,206); both passes
+        give identical values, so one pass feeds both heads and the gradients add."""
+        e = self.embed_dim
+
+        def widen(f):                                       # Model.py:161-166 (N5)
+            return f.repeat(1, e // f.shape[1]) if f.shape[1] != e else f
+        joint = torch.cat([widen(features_x), widen(features_y), widen(features_z)], dim=1)
+        prod = torch.cat([random_knn_x, random_knn_y, random_knn_z], dim=1)
+        if joint.shape[0] != prod.shape[0]:                 # Model.py:180-182 (N4)
+            joint = joint[:prod.shape[0]]
+        batch = torch.cat([joint, prod], dim=0)
+        return _VCMIHead.apply(self.classifier.logits(batch), self.classifier.act_id)
+
+    def estimate_cmi(self, batch, cmi_type='nwj'):
+        if cmi_type != 'nwj':
+            raise NotImplementedError
+        return _VCMIHead.apply(self.classifier.logits(batch), self.classifier.act_id)[0]
+
+
+# --------------------------------------------------------------------------
+# stage functions (Model.py:305-386) as a mixin over any module that owns the
+# eleven estimators under the reference's attribute names
+# --------------------------------------------------------------------------
+
+_CMI_PLAN = (  # (estimator, X, Y, Z) with C = labels; Z is the searched pool  
+    ("ac_t", "A", "C", "T"), ("ta_c", "T", "A", "C"), ("vc_t", "V", "C", "T"),
+    ("tv_c", "T", "V", "C"), ("tc_a", "T", "C", "A"), ("tc_v", "T", "C", "V"))
+
+
+class MIStageMixin:
+    """compute_vmi_loss_stage1 / stage2 with the reference's call order (and
+    therefore its numpy RNG consumption order)."""
+
+    def _mi_terms(self, F_F, T_F, A_F, V_F):
+        out = {}
+        for name, (a, b) in (("f_t", (F_F, T_F)), ("f_a", (F_F, A_F)), ("f_v", (F_F, V_F)),
+                             ("t_a", (T_F, A_F)), ("t_v", (T_F, V_F))):
+            out[name] = getattr(self, "vmi_estimator_" + name)(a, b)
+        return out
+
+    def _cmi_terms(self, labels, T_F, A_F, V_F, C_F_all, T_F_all, A_F_all, V_F_all):
+        feats = {"T": T_F, "A": A_F, "V": V_F, "C": labels}
+        pools = {"T": T_F_all, "A": A_F_all, "V": V_F_all, "C": C_F_all}
+        bs = labels.shape[0]
+        out = {}
+        for name, x, y, z in _CMI_PLAN:
+            kx, ky, kz = prod_knn_sample(pools[x], pools[y], pools[z], bs, self.k_neighbor, self.radius)
+            out[name] = getattr(self, "vcmi_estimator_" + name)(feats[x], feats[y], feats[z], kx, ky, kz)
+        return out
+
+    def compute_vmi_loss_stage1(self, predictions, labels, F_F, T_F, A_F, V_F, C_F_all, F_F_all, T_F_all, A_F_all,
+                                V_F_all):
+        labels = labels.reshape(-1, 1).repeat((1, self.d_common))
+        mi = self._mi_terms(F_F, T_F, A_F, V_F)
+        cmi = self._cmi_terms(labels, T_F, A_F, V_F, C_F_all, T_F_all, A_F_all, V_F_all)
+        order_mi = ["f_t", "f_a", "f_v", "t_a", "t_v"]
+        order_cmi = ["ac_t", "ta_c", "vc_t", "tv_c", "tc_a", "tc_v"]
+        return ([mi[k][0] for k in order_mi] + [cmi[k][0] for k in order_cmi],
+                [mi[k][1] for k in order_mi] + [cmi[k][1] for k in order_cmi])
+
+    def compute_vmi_loss_stage2(self, predictions, labels, F_F, T_F, A_F, V_F, C_F_all, F_F_all, T_F_all, A_F_all,
+                                V_F_all):
+        labels = labels.reshape(-1, 1).repeat((1, self.d_common))
+        mi = self._mi_terms(F_F, T_F, A_F, V_F)
+        mi_inv = mi["t_a"][0] + mi["t_v"][0]
+        c = {k: v[0] for k, v in self._cmi_terms(labels, T_F, A_F, V_F, C_F_all, T_F_all, A_F_all, V_F_all).items()}
+        mi_spec_t = c["tc_a"] + c["tc_v"] - c["ta_c"] - c["tv_c"]
+        mi_spec_a = c["ac_t"] - c["ta_c"]
+        mi_spec_v = c["vc_t"] - c["tv_c"]
+        mi_comp = c["ta_c"] + c["tv_c"]
+        return ([mi["f_t"][0], mi["f_a"][0], mi["f_v"][0], mi_inv, mi_spec_t, mi_spec_a, mi_spec_v, mi_comp],
+                [mi["f_t"][1], mi["f_a"][1], mi["f_v"][1], -mi_inv, -mi_spec_t, -mi_spec_a, -mi_spec_v, -mi_comp])
+
+
+class MIHeads(nn.Module, MIStageMixin):
+    """The MI/CMI part of reference ``Model.__init__`` (Model.py:283-303): five
+    VMIEstimators and six VCMIEstimators under the reference's attribute names,
+    plus the two stage functions.  A full ``Model`` can inherit ``MIStageMixin``
+    instead and keep its own encoders."""
+
+    def __init__(self, opt, d_common=None):
+        super().__init__()
+        self.d_common = d_common if d_common is not None else opt.d_common
+        hidden_dim, embed_dim, layers, activation = 256, 128, 2, 'relu'      # Model.py:285 (hard-coded there)
+        hidden_dim = getattr(opt, "mi_hidden_dim", hidden_dim)
+        embed_dim = getattr(opt, "mi_embed_dim", embed_dim)
+        mu, rho = 0, 1
+        self.k_neighbor, self.radius = opt.k_neighbor, opt.radius
+        for n in ("f_t", "f_a", "f_v", "t_a", "t_v"):
+            setattr(self, "vmi_estimator_" + n,
+                    VMIEstimator(opt.critic_type, opt.baseline_type, opt.bound_type, self.d_common, hidden_dim,
+                                 embed_dim, layers, activation, mu, rho))
+        for n in ("ac_t", "ta_c", "vc_t", "tv_c", "tc_a", "tc_v"):
+            setattr(self, "vcmi_estimator_" + n,
+                    VCMIEstimator(embed_dim, hidden_dim, layers, activation, opt.k_neighbor, opt.radius,
+                                  opt.cmi_last_acticate))

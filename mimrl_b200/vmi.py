@@ -1,0 +1,340 @@
+"""Variational MI estimators: drop-in for the reference's ``VMI.py``.
+
+Same names, constructor arguments, parameter paths and error behaviour as
+VMI.py:13-250, so ``Model.py:10`` (``from VMI import CriticModel, BaselineModel,
+dv_lower_bound, ...``) can import from here unchanged.  The arithmetic runs in
+the sm_100a kernels of ``libmimrl_b200.so``:
+
+* ``separable_bound`` is the fused fast path used by ``VMIEstimator``
+  (mimrl_b200/model.py): score sweep + bound reductions + both gradient sweeps
+  without the B x B matrix ever reaching HBM, sharded by row blocks over ranks.
+* the free ``*_lower_bound(scores)`` functions keep the reference's
+  materialised-matrix signatures (VMI.py:136-250) and run the row-statistics
+  and gradient kernels over the given matrix.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import rowblock as RB
+
+_ACTIVATIONS = {  # Utils.py:70-82 get_activation
+    "elu": nn.ELU, "gelu": nn.GELU, "hardshrink": nn.Hardshrink, "hardtanh": nn.Hardtanh,
+    "leakyrelu": nn.LeakyReLU, "prelu": nn.PReLU, "relu": nn.ReLU, "rrelu": nn.RReLU, "tanh": nn.Tanh,
+}
+
+
+def get_activation(activation):
+    return _ACTIVATIONS[activation]
+
+
+def mlps(dim, hidden_dim, output_dim, layers, activation):
+    """VMI.py:13-22: Linear+act, `layers` x (Linear+act), Linear."""
+    act = get_activation(activation)
+    seq = [nn.Linear(dim, hidden_dim), act()]
+    for _ in range(layers):
+        seq += [nn.Linear(hidden_dim, hidden_dim), act()]
+    seq += [nn.Linear(hidden_dim, output_dim)]
+    return nn.Sequential(*seq)
+
+
+def _zero_biases(stack):
+    """VMI.py:47-51 init_mlp_params: weights keep torch's default init, biases are zeroed."""
+    for layer in stack:
+        if isinstance(layer, nn.Linear):
+            nn.init.constant_(layer.bias, 0)
+
+
+# --------------------------------------------------------------------------
+# kernels behind autograd
+# --------------------------------------------------------------------------
+
+
+def _family(bound_id):
+    fam, inc, fl = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L.check(L.lib.mimrl_bound_weight_family(bound_id, ctypes.byref(fam), ctypes.byref(inc), ctypes.byref(fl)))
+    return fam.value, inc.value, fl.value
+
+
+def _grad_pair(g_mi, g_loss, like):
+    z = like.new_zeros(())
+    return torch.stack([g_mi if g_mi is not None else z, g_loss if g_loss is not None else z]).float().contiguous()
+
+
+class _SeparableBound(torch.autograd.Function):
+    """(x_emb [n,E] = g(x), y_emb [n,E] = h(y), log_baseline [n,1] | None) -> (mi, mi_loss).
+
+    Rows of the score matrix index y (VMI.py:57: ``y_ @ x_.T``).  Under a
+    sharded RowBlock each rank passes its own rows and receives gradients for
+    its own rows; embeddings and per-row statistics are all-gathered inside."""
+
+    @staticmethod
+    def forward(ctx, x_emb, y_emb, log_baseline, bound_id, impl, rb):
+        x_emb, y_emb = L.f32(x_emb), L.f32(y_emb)
+        n_own, embed = y_emb.shape
+        if rb is None:
+            rb = RB.single(n_own)
+        fam, inc, flags = _family(bound_id)
+        all_x = RB.all_gather_rows(x_emb, rb)
+        n_all = all_x.shape[0]
+        st = L.stream()
+        ws_bytes = L.lib.mimrl_sep_workspace_bytes(n_own, n_all, embed)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=y_emb.device)
+        stats = torch.empty(4, n_own, dtype=torch.float32, device=y_emb.device)  # max, sum, softplus, diag
+        L.check(L.lib.mimrl_sep_row_stats(L.ptr(y_emb), L.ptr(all_x), n_own, n_all, embed, rb.offset, flags, impl,
+                                          L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(stats[2]), L.ptr(stats[3]),
+                                          L.ptr(ws), ws.numel(), st))
+        base = None
+        if log_baseline is not None:
+            base = RB.all_gather_rows(L.f32(log_baseline).reshape(-1), rb)
+        all_stats = RB.all_gather_rows(stats.t().contiguous(), rb).t().contiguous() if rb.sharded else stats
+        result = torch.zeros(16, dtype=torch.float32, device=y_emb.device)
+        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(all_stats[0]), L.ptr(all_stats[1]), L.ptr(all_stats[2]),
+                                           L.ptr(all_stats[3]), L.ptr(base), n_all, L.ptr(result), st))
+        ctx.save_for_backward(x_emb, y_emb, all_x, all_stats, result, base if base is not None else result.new_empty(0))
+        ctx.cfg = (bound_id, impl, rb, fam, inc, log_baseline is not None, ws)
+        return result[0].clone(), result[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_mi, g_loss):
+        x_emb, y_emb, all_x, all_stats, result, base = ctx.saved_tensors
+        bound_id, impl, rb, fam, inc, has_base, ws = ctx.cfg
+        base = base if has_base else None
+        n_own, embed = y_emb.shape
+        n_all = all_x.shape[0]
+        dev = y_emb.device
+        st = L.stream()
+        grad = _grad_pair(g_mi, g_loss, result)
+        coef = torch.empty(1, dtype=torch.float32, device=dev)
+        vec = torch.empty(3, n_all, dtype=torch.float32, device=dev)            # shift, dcoef, dbaseline
+        L.check(L.lib.mimrl_bound_backward_coef(bound_id, L.ptr(result), L.ptr(grad), L.ptr(all_stats[0]),
+                                                L.ptr(all_stats[1]), L.ptr(all_stats[3]), L.ptr(base), n_all,
+                                                L.ptr(coef), L.ptr(vec[0]), L.ptr(vec[1]),
+                                                L.ptr(vec[2]) if has_base else None, st))
+        own = slice(rb.offset, rb.offset + n_own)
+        shift_own, dcoef_own = vec[0, own].contiguous(), vec[1, own].contiguous()
+        # d/d h(y): rows are owned, x is swept, shift indexed by the owned row
+        dy = torch.empty_like(y_emb)
+        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(y_emb), L.ptr(all_x), n_own, n_all, embed, rb.offset, fam, inc,
+                                             L.ptr(shift_own), 0, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dy),
+                                             L.ptr(ws), ws.numel(), st))
+        # d/d g(x): columns are owned, y is swept, shift indexed by the swept row
+        all_y = RB.all_gather_rows(y_emb, rb)
+        dx = torch.empty_like(x_emb)
+        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(x_emb), L.ptr(all_y), n_own, n_all, embed, rb.offset, fam, inc,
+                                             L.ptr(vec[0]), 1, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dx),
+                                             L.ptr(ws), ws.numel(), st))
+        dbase = vec[2, own].reshape(n_own, 1).clone() if has_base else None
+        return dx, dy, dbase, None, None, None
+
+
+def separable_bound(x_emb, y_emb, bound_type, log_baseline=None, rowblock=None, impl=L.IMPL_AUTO):
+    """Fused ``bound(h(y) @ g(x).T)`` for every bound with a single-sweep form
+    (all of VMI.py:136-198 plus the MINE branch of Model.py:121-124).
+    Returns ``(mi, mi_loss)`` exactly as ``VMIEstimator.forward`` does."""
+    if bound_type not in L.BOUND_IDS:
+        raise NotImplementedError
+    return _SeparableBound.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
+
+
+class _ScoresBound(torch.autograd.Function):
+    """Bound over a materialised score matrix [n, n] (API parity with VMI.py:136-198)."""
+
+    @staticmethod
+    def forward(ctx, scores, log_baseline, bound_id):
+        scores = L.f32(scores)
+        n = scores.shape[0]
+        if scores.dim() != 2 or scores.shape[1] != n:
+            raise ValueError("scores must be a square [batch, batch] matrix")
+        fam, inc, flags = _family(bound_id)
+        st = L.stream()
+        stats = torch.empty(4, n, dtype=torch.float32, device=scores.device)
+        L.check(L.lib.mimrl_scores_row_stats(L.ptr(scores), n, n, 0, flags, L.ptr(stats[0]), L.ptr(stats[1]),
+                                             L.ptr(stats[2]), L.ptr(stats[3]), st))
+        base = L.f32(log_baseline).reshape(-1) if log_baseline is not None else None
+        result = torch.zeros(16, dtype=torch.float32, device=scores.device)
+        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(stats[2]), L.ptr(stats[3]),
+                                           L.ptr(base), n, L.ptr(result), st))
+        ctx.save_for_backward(scores, stats, result, base if base is not None else result.new_empty(0))
+        ctx.cfg = (bound_id, fam, inc, base is not None)
+        return result[0].clone(), result[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_mi, g_loss):
+        scores, stats, result, base = ctx.saved_tensors
+        bound_id, fam, inc, has_base = ctx.cfg
+        base = base if has_base else None
+        n = scores.shape[0]
+        st = L.stream()
+        grad = _grad_pair(g_mi, g_loss, result)
+        coef = torch.empty(1, dtype=torch.float32, device=scores.device)
+        vec = torch.empty(3, n, dtype=torch.float32, device=scores.device)
+        L.check(L.lib.mimrl_bound_backward_coef(bound_id, L.ptr(result), L.ptr(grad), L.ptr(stats[0]), L.ptr(stats[1]),
+                                                L.ptr(stats[3]), L.ptr(base), n, L.ptr(coef), L.ptr(vec[0]),
+                                                L.ptr(vec[1]), L.ptr(vec[2]) if has_base else None, st))
+        g = torch.empty_like(scores)
+        L.check(L.lib.mimrl_scores_grad(L.ptr(scores), n, n, 0, fam, inc, L.ptr(vec[0]), L.ptr(coef), L.ptr(vec[1]),
+                                        L.ptr(g), st))
+        return g, (vec[2].reshape(n, 1).clone() if has_base else None), None
+
+
+def _scores_bound(scores, bound_type, log_baseline=None):
+    return _ScoresBound.apply(scores, log_baseline, L.BOUND_IDS[bound_type])
+
+
+# --------------------------------------------------------------------------
+# reference-named free functions (VMI.py:136-250)
+# --------------------------------------------------------------------------
+
+
+def dv_lower_bound(scores):
+    return _scores_bound(scores, "dv")[0]
+
+
+def mine_lower_bound_test(scores):
+    """VMI.py:142-145: (dv bound, diag(scores), exp of the off-diagonal entries)."""
+    mi = _scores_bound(scores, "dv")[0]
+    n = scores.size(0)
+    et = torch.exp(scores).masked_fill(torch.eye(n, dtype=torch.bool, device=scores.device), 0.0)
+    return mi, scores.diag(), et
+
+
+def tuba_lower_bound(scores, log_baseline=None):
+    if log_baseline is not None and not torch.is_tensor(log_baseline):
+        scores = scores - log_baseline          # VMI.py:151 accepts a python scalar too
+        log_baseline = None
+    return _scores_bound(scores, "tuba", log_baseline)[0]
+
+
+def nwj_lower_bound(scores):
+    return _scores_bound(scores, "nwj")[0]
+
+
+def infonce_lower_bound(scores):
+    return _scores_bound(scores, "infonce")[0]
+
+
+def js_fgan_lower_bound(scores):
+    return _scores_bound(scores, "js_fgan")[0]
+
+
+def js_lower_bound(scores):
+    return _scores_bound(scores, "js")[0]
+
+
+def smile_lower_bound(scores, clip=None):
+    return _scores_bound(scores, "smile")[0]     # VMI.py:186 pins clip to 1 whatever is passed
+
+
+def log_interpolate(log_a, log_b, alpha_logit: float):
+    """VMI.py:201-210: log(alpha*a + (1-alpha)*b), alpha = sigmoid(alpha_logit)."""
+    alpha_logit = float(alpha_logit)
+    log_alpha = -math.log1p(math.exp(-alpha_logit))
+    log_1m_alpha = -math.log1p(math.exp(alpha_logit))
+    return torch.logaddexp(log_alpha + log_a, log_1m_alpha + log_b)
+
+
+def compute_log_loomean(scores):
+    """VMI.py:213-226: log of the leave-one-out mean of exp(scores) along dim 1."""
+    lse = torch.logsumexp(scores, dim=1, keepdim=True)
+    d = lse - scores
+    safe = torch.where(d == 0, torch.ones_like(d), d)
+    return scores + safe + torch.log(-torch.expm1(-safe)) - math.log(scores.size(1) - 1.0)
+
+
+def interp_lower_bound(scores, baseline, alpha_logit):
+    """VMI.py:229-250 (two dependent sweeps; runs on the materialised matrix)."""
+    n = scores.size(0)
+    n_off = n * (n - 1.0)
+    ib = log_interpolate(compute_log_loomean(scores), baseline.reshape(n, 1).expand(n, n), alpha_logit)
+    off = ~torch.eye(n, dtype=torch.bool, device=scores.device)
+    marg = torch.exp(torch.logsumexp((scores - ib.diag()[None, :])[off], dim=0) - math.log(n_off))
+    joint = ((scores.diag()[None, :] - ib) * off).sum() / n_off
+    return 1 + joint - marg
+
+
+# --------------------------------------------------------------------------
+# modules (VMI.py:25-110)
+# --------------------------------------------------------------------------
+
+
+class CriticModel(nn.Module):
+    """VMI.py:25-69.  ``forward`` returns the materialised [B,B] matrix like
+    the reference; ``embed`` exposes (g(x), h(y)) for the fused path."""
+
+    def __init__(self, critic_type, dim_x, dim_y, hidden_dim=256, embed_dim=128, layers=2, activation='relu'):
+        super().__init__()
+        self.critic_type = critic_type
+        if critic_type == 'separate':
+            self.MLP_g = mlps(dim_x, hidden_dim, embed_dim, layers, activation)
+            self.MLP_h = mlps(dim_y, hidden_dim, embed_dim, layers, activation)
+            _zero_biases(self.MLP_g)
+            _zero_biases(self.MLP_h)
+        elif critic_type == 'concat':
+            self.MLP_f = mlps(dim_x + dim_y, hidden_dim, 1, layers, activation)
+            _zero_biases(self.MLP_f)
+        else:
+            raise NotImplementedError
+        self.pair_chunk = 1 << 16          # pairs scored per step of the concat critic
+
+    def embed(self, x, y):
+        return self.MLP_g(x), self.MLP_h(y)
+
+    def _concat_rows(self, x_rows, y):
+        """scores[i, :] = f([x_i, y_j]) for a block of rows, first layer factorised
+        (W1 [x;y] = W1x x + W1y y) so the B^2 x (dx+dy) pair matrix is never built."""
+        first = self.MLP_f[0]
+        dx = x_rows.shape[1]
+        u = F.linear(x_rows, first.weight[:, :dx], first.bias)
+        v = F.linear(y, first.weight[:, dx:])
+        h = (u[:, None, :] + v[None, :, :]).reshape(-1, u.shape[1])
+        h = self.MLP_f[1:](h)
+        return h.reshape(x_rows.shape[0], y.shape[0])
+
+    def forward(self, x, y):
+        if self.critic_type == 'separate':
+            x_, y_ = self.embed(x, y)
+            return torch.matmul(y_, x_.t())
+        if self.critic_type == 'concat':
+            from torch.utils.checkpoint import checkpoint
+            n = x.shape[0]
+            rows = max(1, self.pair_chunk // max(n, 1))
+            if rows >= n:
+                return self._concat_rows(x, y)
+            blocks = [checkpoint(self._concat_rows, x[r:r + rows], y, use_reentrant=False)
+                      for r in range(0, n, rows)]
+            return torch.cat(blocks, dim=0)
+        raise NotImplementedError
+
+
+class BaselineModel(nn.Module):
+    """VMI.py:72-110 (``gaussain`` spelled as in the reference)."""
+
+    def __init__(self, baseline_type, dim_y, hidden_dim=256, layers=2, activation='relu', mu=0, rho=1):
+        super().__init__()
+        self.baseline_type = baseline_type
+        if baseline_type == 'unnormalized':
+            self.MLP = mlps(dim_y, hidden_dim, 1, layers, activation)
+            _zero_biases(self.MLP)
+        elif baseline_type == 'constant':
+            pass
+        elif baseline_type == 'gaussain':
+            self.gaussain_dist = torch.distributions.Normal(mu, rho)
+        else:
+            raise NotImplementedError
+
+    def forward(self, y):
+        n = y.shape[0]
+        if self.baseline_type == 'unnormalized':
+            return self.MLP(y).reshape(n, 1)
+        if self.baseline_type == 'constant':
+            return torch.zeros(n, 1, device=y.device, dtype=y.dtype)
+        if self.baseline_type == 'gaussain':
+            return torch.sum(self.gaussain_dist.log_prob(y), -1).reshape(n, 1)
+        raise NotImplementedError

@@ -1,0 +1,185 @@
+"""GPU parity of the conditional-MI path: k-NN sampler (bit-exact indices
+against scikit-learn via the golden vectors and the float64 oracle), the
+classifier estimator, and the two stage functions."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cfg_of, load_golden, rel_err
+from oracle import knn_oracle as K
+from oracle import params as P
+from oracle import vcmi_oracle as VO
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KNN = load_golden("knn")
+VCMI = load_golden("vcmi")
+STAGE = load_golden("stage")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    import __graft_entry__ as g
+    g.build()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a, **kw):
+    return torch.tensor(a, device=dev(), **kw)
+
+
+@pytest.mark.parametrize("case", sorted(KNN))
+def test_sampler_matches_reference_golden(case):
+    from mimrl_b200.model import knn_search, prod_knn_sample
+    rec = KNN[case]
+    c = cfg_of(rec)
+    seed = int(rec["seed"])
+    X = P.features(seed, c["N"], c["wx"])
+    Y = P.features(seed + 1, c["N"], c["wy"])
+    Z = P.features(seed + 2, c["N"], c["wz"])
+    if c["dup"]:
+        Z[c["N"] - c["dup"]:] = Z[: c["dup"]]
+    np.random.seed(seed)
+    bx, by, bz = prod_knn_sample(T(X), T(Y), T(Z), c["bs"], c["k"], 1.0)
+    state = np.random.get_state()
+    np.random.seed(seed)
+    np.random.choice(range(c["N"]), size=c["bs"] // c["k"], replace=False)
+    assert np.array_equal(state[1], np.random.get_state()[1])       # same RNG consumption as the reference
+    _, nbr = knn_search(T(Z), T(rec["ids"]), c["k"])
+    nbr = nbr.cpu().numpy()
+    if c["dup"] == 0:
+        assert np.array_equal(nbr, rec["nbr"])                       # bit-exact, order included
+        assert np.array_equal(bx.detach().cpu().numpy(), rec["bx"])
+    else:
+        assert np.array_equal(np.sort(nbr, 1), np.sort(rec["nbr"], 1))
+    assert np.array_equal(by.detach().cpu().numpy(), rec["by"])
+    assert np.array_equal(bz.detach().cpu().numpy(), rec["bz"])
+    assert bx.requires_grad and by.requires_grad and bz.requires_grad and bx.is_cuda
+
+
+@pytest.mark.parametrize("N,width,m,k", [(20000, 128, 300, 2), (20000, 128, 70, 16), (50000, 1, 257, 4),
+                                         (3000, 8, 64, 3), (5000, 16, 100, 32), (130, 128, 64, 2)])
+def test_knn_indices_vs_float64_oracle(N, width, m, k):
+    from mimrl_b200.model import knn_search, sklearn_route
+    Z = P.features(N + width, N, width)
+    rng = np.random.default_rng(N)
+    ids = rng.permutation(N)[:m]
+    exc = np.zeros(N, np.uint8)
+    exc[ids] = 1
+    want, wdist = K.knn(Z, Z[ids], k, exc, sklearn_route(width, k, N - m))
+    got, comp, dist = knn_search(T(Z), T(ids), k, return_distance=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(comp.cpu().numpy(), want - np.searchsorted(np.sort(ids), want))
+    assert np.allclose(dist.cpu().numpy(), wdist, rtol=1e-12, atol=1e-12)
+
+
+def test_knn_duplicate_keys_lowest_index_wins():
+    from mimrl_b200.model import knn_search
+    Z = P.features(5, 600, 128)
+    Z[300:] = Z[:300]                        # every key has an exact duplicate
+    ids = np.arange(0, 40, dtype=np.int64)   # queries 0..39; their twins 300..339 stay in the pool at distance 0
+    got, _ = knn_search(T(Z), T(ids), 3)
+    got = got.cpu().numpy()
+    exc = np.zeros(600, np.uint8)
+    exc[ids] = 1
+    want, _ = K.knn(Z, Z[ids], 3, exc, "brute")
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[:, 0], ids + 300)
+
+
+def test_knn_errors():
+    from mimrl_b200.model import prod_knn_sample
+    X = T(P.features(1, 10, 16))
+    with pytest.raises(ValueError):
+        prod_knn_sample(X, X, X, 100, 2, 1.0)        # m > N          (numpy's error in the reference)
+    with pytest.raises(ValueError):
+        prod_knn_sample(X, X, X, 10, 10, 1.0)        # k > N - m      (sklearn's error in the reference)
+
+
+def vcmi_inputs(rec):
+    c = cfg_of(rec)
+    seed = int(rec["seed"])
+    stack = P.vcmi_params(seed, c["embed"], c["hidden"])
+    if c["act"] == "hardtanh":
+        stack[-1] = (stack[-1][0] * 0.5, stack[-1][1] + 0.5)
+    ins = [P.features(seed + 1, c["bs"], c["embed"], c["scale"]), P.features(seed + 2, c["bs"], c["wy"], c["scale"]),
+           P.features(seed + 3, c["bs"], c["embed"], c["scale"]), P.features(seed + 4, c["nprod"], c["embed"], c["scale"]),
+           P.features(seed + 5, c["nprod"], c["embed"], c["scale"]), P.features(seed + 6, c["nprod"], c["embed"], c["scale"])]
+    return c, stack, ins
+
+
+@pytest.mark.parametrize("case", sorted(VCMI))
+def test_vcmi_matches_reference_golden(case):
+    from mimrl_b200.model import VCMIEstimator
+    rec = VCMI[case]
+    c, stack, ins = vcmi_inputs(rec)
+    est = VCMIEstimator(c["embed"], c["hidden"], 2, "relu", 2, 1.0, c["act"]).to(dev())
+    est.load_state_dict({k: torch.tensor(v) for k, v in P.vcmi_state_dict(stack).items()}, strict=True)
+    for tag, pick in (("gl", 1), ("gc", 0)):
+        ts = [T(a, requires_grad=True) for a in ins]
+        out = est(*ts)
+        assert abs(float(out[0]) - float(rec["cmi"])) <= TOL * max(1.0, abs(float(rec["cmi"])))
+        assert abs(float(out[1]) - float(rec["loss"])) <= TOL * max(1.0, abs(float(rec["loss"])))
+        params = list(est.parameters())
+        gs = torch.autograd.grad(out[pick], ts + params, allow_unused=True)
+        for i, nm in enumerate(["fx", "fy", "fz", "kx", "ky", "kz"]):
+            ref = rec[f"{tag}_{nm}"]
+            assert np.abs(gs[i].cpu().numpy() - ref).max() <= TOL * np.abs(ref).max() + 1e-8, (tag, nm)
+        names = [n for n, _ in est.named_parameters()]
+        for i, nm in enumerate(names):
+            g = gs[6 + i].cpu().numpy()
+            if f"{tag}p__{nm}" in rec:
+                v = rec[f"{tag}p__{nm}"]
+                assert np.abs(g - v).max() <= TOL * np.abs(v).max() + 2e-7, nm
+            else:
+                v = rec[f"{tag}s__{nm}"]
+                gd = g.ravel().astype(np.float64)
+                assert np.allclose([np.abs(gd).sum(), np.sqrt((gd ** 2).sum())], v[1:], rtol=2e-4, atol=2e-6), nm
+
+
+@pytest.mark.parametrize("case", sorted(STAGE))
+def test_stage_functions_match_reference_golden(case):
+    """compute_vmi_loss_stage1/2 (Model.py:305-386): eleven estimators + six
+    sampler draws in the reference's order, values and feature gradients."""
+    from types import SimpleNamespace
+    from mimrl_b200.model import MIHeads
+    rec = STAGE[case]
+    c = cfg_of(rec)
+    seed = int(rec["seed"])
+    d, hidden = c["d"], c["hidden"]
+    opt = SimpleNamespace(critic_type=c["critic"], baseline_type=c["baseline"], bound_type=c["bound"], k_neighbor=c["k"],
+                          radius=1.0, cmi_last_acticate=c["act"], d_common=d, mi_hidden_dim=hidden, mi_embed_dim=d)
+    heads = MIHeads(opt).to(dev())
+    for i, n in enumerate(["f_t", "f_a", "f_v", "t_a", "t_v"]):
+        sd = P.vmi_state_dict(P.vmi_params(seed + 10 + i, c["critic"], c["baseline"], d, hidden, d, 2))
+        getattr(heads, "vmi_estimator_" + n).load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    for i, n in enumerate(["ac_t", "ta_c", "vc_t", "tv_c", "tc_a", "tc_v"]):
+        stack = P.vcmi_params(seed + 30 + i, d, hidden)
+        if c["act"] == "hardtanh":
+            stack[-1] = (stack[-1][0] * 0.5, stack[-1][1] + 0.5)
+        getattr(heads, "vcmi_estimator_" + n).load_state_dict(
+            {k: torch.tensor(v) for k, v in P.vcmi_state_dict(stack).items()})
+    feats = {n: P.features(seed + 50 + i, c["bs"], d) for i, n in enumerate(["F", "T", "A", "V"])}
+    labels = P.features(seed + 60, c["bs"], 1)[:, 0]
+    pools = {n: T(P.features(seed + 70 + i, c["N"], d)) for i, n in enumerate(["F", "T", "A", "V"])}
+    pool_c = T(P.features(seed + 80, c["N"], 1))
+    for stage in (1, 2):
+        fn = heads.compute_vmi_loss_stage1 if stage == 1 else heads.compute_vmi_loss_stage2
+        ft = {n: T(v, requires_grad=True) for n, v in feats.items()}
+        np.random.seed(seed + stage)
+        mis, losses = fn(None, T(labels), ft["F"], ft["T"], ft["A"], ft["V"], pool_c, pools["F"], pools["T"],
+                         pools["A"], pools["V"])
+        got_mis = np.array([float(m) for m in mis])
+        got_losses = np.array([float(m) for m in losses])
+        assert np.allclose(got_mis, rec[f"s{stage}_mis"], rtol=TOL, atol=TOL), (got_mis, rec[f"s{stage}_mis"])
+        assert np.allclose(got_losses, rec[f"s{stage}_losses"], rtol=TOL, atol=TOL)
+        total = sum(l * (0.1 * (i + 1)) for i, l in enumerate(losses))
+        gs = torch.autograd.grad(total, [ft[n] for n in "FTAV"])
+        for n, g in zip("FTAV", gs):
+            ref = rec[f"s{stage}_g{n}"]
+            assert np.abs(g.cpu().numpy() - ref).max() <= 2 * TOL * np.abs(ref).max() + 1e-7, (stage, n)

@@ -1,0 +1,180 @@
+"""GPU parity of the variational-MI path (through the C ABI) against
+(1) the golden vectors produced by the reference and (2) the numpy oracle on
+seeded inputs, including ragged sizes.  Tolerance: 1e-4 relative on bound
+values and gradients (BASELINE.json north_star), fp32, TF32 disabled."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cfg_of, load_golden, rel_err
+from oracle import params as P
+from oracle import vmi_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+VMI = load_golden("vmi")
+BOUNDS = load_golden("bounds")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    import __graft_entry__ as g
+    g.build()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def make_estimator(c, prm, impl=0):
+    from mimrl_b200.model import VMIEstimator
+    est = VMIEstimator(c["critic"], c["baseline"], c["bound"], c["d"], c["hidden"], c["embed"], c["layers"], "relu", 0, 1)
+    est.load_state_dict({k: torch.tensor(v) for k, v in P.vmi_state_dict(prm).items()}, strict=True)
+    est.impl = impl
+    return est.to(dev())
+
+
+def run(est, x, y):
+    xt = torch.tensor(x, device=dev(), requires_grad=True)
+    yt = torch.tensor(y, device=dev(), requires_grad=True)
+    mi, loss = est(xt, yt)
+    loss.backward()
+    pg = {n: p.grad.detach().cpu().numpy() for n, p in est.named_parameters() if p.grad is not None}
+    return float(mi), float(loss), xt.grad.cpu().numpy(), yt.grad.cpu().numpy(), pg
+
+
+def close_scalar(a, b, tol=TOL):
+    return abs(a - b) <= tol * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("case", sorted(VMI))
+def test_estimator_matches_reference_golden(case):
+    rec = VMI[case]
+    c = cfg_of(rec)
+    seed = int(rec["seed"])
+    prm = P.vmi_params(seed, c["critic"], c["baseline"], c["d"], c["hidden"], c["embed"], c["layers"])
+    x, y = P.features(seed + 7, c["B"], c["d"], scale=c["scale"], corr=0.6)
+    mi, loss, gx, gy, pg = run(make_estimator(c, prm), x, y)
+    assert close_scalar(mi, float(rec["mi"])), (mi, float(rec["mi"]))
+    assert close_scalar(loss, float(rec["loss"]))
+    assert rel_err(gx, rec["gx"]) < TOL and rel_err(gy, rec["gy"]) < TOL
+    for k, v in rec.items():
+        if k.startswith("pg__"):
+            assert np.abs(pg[k[4:]] - v).max() <= TOL * np.abs(v).max() + 2e-7, k
+        elif k.startswith("pgs__"):
+            g = pg[k[5:]].ravel().astype(np.float64)
+            got = np.array([np.abs(g).sum(), np.sqrt((g ** 2).sum())])
+            assert np.allclose(got, v[1:], rtol=2e-4, atol=2e-6), k
+
+
+@pytest.mark.parametrize("bound", ["infonce", "dv", "mine", "tuba", "nwj", "js_fgan", "js", "smile"])
+@pytest.mark.parametrize("B,d,impl", [(1000, 128, 0), (129, 128, 0), (257, 48, 1), (64, 128, 1), (3, 16, 1)])
+def test_separable_bounds_vs_oracle(bound, B, d, impl):
+    """Seeded inputs, ragged batch sizes, both kernel implementations."""
+    baseline = "unnormalized" if bound == "tuba" else "constant"
+    hidden = 64
+    prm = P.vmi_params(7 + B, "separate", baseline, d, hidden, d, 2)
+    x, y = P.features(8 + B, B, d, scale=1.5, corr=0.7)
+    c = dict(critic="separate", baseline=baseline, bound=bound, d=d, hidden=hidden, embed=d, layers=2)
+    mi, loss, gx, gy, pg = run(make_estimator(c, prm, impl), x, y)
+    r = O.vmi_estimator(prm, "separate", baseline, bound, x, y)
+    assert close_scalar(mi, r["mi"]), (mi, r["mi"])
+    assert close_scalar(loss, r["loss"]), (loss, r["loss"])
+    assert rel_err(gx, r["gx"]) < TOL, rel_err(gx, r["gx"])
+    assert rel_err(gy, r["gy"]) < TOL, rel_err(gy, r["gy"])
+    for k, v in r["pg"].items():
+        if k.endswith("weight"):
+            assert rel_err(pg[k], v) < 2 * TOL, k
+
+
+@pytest.mark.parametrize("case", sorted(BOUNDS))
+def test_free_bound_functions_match_reference(case):
+    import mimrl_b200.vmi as V
+    rec = BOUNDS[case]
+    a = torch.tensor(rec["a"], device=dev())
+    fns = dict(dv=V.dv_lower_bound, tuba=lambda s: V.tuba_lower_bound(s, a), tuba_nobase=V.tuba_lower_bound,
+               nwj=V.nwj_lower_bound, infonce=V.infonce_lower_bound, js_fgan=V.js_fgan_lower_bound,
+               js=V.js_lower_bound, smile=V.smile_lower_bound,
+               interpolate=lambda s: V.interp_lower_bound(s, a, 0.01))
+    for name, fn in fns.items():
+        s = torch.tensor(rec["S"], device=dev(), requires_grad=True)
+        v = fn(s)
+        v.backward()
+        assert close_scalar(float(v), float(rec["val_" + name])), name
+        assert rel_err(s.grad.cpu().numpy(), rec["grad_" + name]) < TOL, name
+
+
+def test_mine_mi_gradient_is_dv():
+    """The MINE branch returns (dv value, its own loss); both outputs carry gradients."""
+    import mimrl_b200.vmi as V
+    x, y = P.features(3, 50, 32, corr=0.5)
+    xe = torch.tensor(x, device=dev(), requires_grad=True)
+    ye = torch.tensor(y, device=dev(), requires_grad=True)
+    mi, _ = V.separable_bound(xe, ye, "mine")
+    mi.backward()
+    S = y.astype(np.float64) @ x.astype(np.float64).T
+    _, G, _ = O.bound_dv(S)
+    assert rel_err(ye.grad.cpu().numpy(), G @ x) < TOL
+    assert rel_err(xe.grad.cpu().numpy(), G.T @ y) < TOL
+
+
+@pytest.mark.parametrize("B", [4096, 20000])
+def test_large_batch_against_streamed_oracle(B):
+    """Sizes where B x B does not fit comfortably on the host in float64: the
+    oracle streams row blocks; the fused kernels never build the matrix."""
+    import mimrl_b200.vmi as V
+    prm = P.vmi_params(99, "separate", "constant", 128, 256, 128, 2)
+    x, y = P.features(100, B, 128, corr=0.6)
+    st = O.separable_infonce_streamed(prm, x, y, dtype=np.float64, block=2048)
+    c = dict(critic="separate", baseline="constant", bound="infonce", d=128, hidden=256, embed=128, layers=2)
+    mi, loss, gx, gy, _ = run(make_estimator(c, prm), x, y)
+    assert close_scalar(mi, st["mi"]), (mi, st["mi"])
+    assert rel_err(gx, st["gx"]) < TOL and rel_err(gy, st["gy"]) < TOL
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at its largest size (B = 65536): size-independent
+    properties instead of an oracle run.  (1) InfoNCE <= log B; (2) duplicating
+    nothing but permuting rows of x and y together leaves mi unchanged;
+    (3) row-sums of the InfoNCE gradient vanish: sum_j G_ij = 0 implies
+    sum_i dL/dy_emb_i . 1 relation  ->  d mi / d (a constant shift of all scores) = 0,
+    checked as <grad_y_emb, y_emb> + <grad_x_emb, x_emb> = 2 * sum_ij G_ij S_ij
+    against the same quantity from the two implementations (FFMA vs auto)."""
+    import mimrl_b200.vmi as V
+    from mimrl_b200 import _lib as L
+    B, E = 65536, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xe = torch.randn(B, E, device=dev(), generator=g) * 0.3
+    ye = 0.7 * xe + 0.3 * torch.randn(B, E, device=dev(), generator=g) * 0.3
+    outs = []
+    for impl in (L.IMPL_AUTO,):
+        a = xe.clone().requires_grad_(True)
+        b = ye.clone().requires_grad_(True)
+        mi, loss = V.separable_bound(a, b, "infonce", impl=impl)
+        loss.backward()
+        outs.append((float(mi), a.grad, b.grad))
+    mi0, gx0, gy0 = outs[0]
+    assert mi0 <= np.log(B) + 1e-4
+    perm = torch.randperm(B, device=dev(), generator=g)
+    mi_p, _ = V.separable_bound(xe[perm].contiguous(), ye[perm].contiguous(), "infonce")
+    assert abs(float(mi_p) - mi0) <= 1e-4 * max(1.0, abs(mi0))
+    # gradient of a permuted problem is the permuted gradient
+    a = xe[perm].clone().requires_grad_(True)
+    b = ye[perm].clone().requires_grad_(True)
+    V.separable_bound(a, b, "infonce")[1].backward()
+    assert rel_err(a.grad[:4096].cpu().numpy(), gx0[perm][:4096].cpu().numpy()) < TOL
+    # Euler identity for scores homogeneous of degree 1 in each operand
+    lhs = float((gx0.double() * xe.double()).sum())
+    rhs = float((gy0.double() * ye.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1e-6)
+    # a 2048-row slab of the gradient against a direct float64 evaluation on the GPU
+    rows = slice(1000, 1000 + 2048)
+    S = ye[rows].double() @ xe.double().t()
+    Pm = torch.softmax(S, dim=1)
+    Gs = Pm / B
+    idx = torch.arange(1000, 1000 + 2048, device=dev())
+    Gs[torch.arange(2048, device=dev()), idx] -= 1.0 / B
+    want = (Gs @ xe.double()).cpu().numpy()            # d loss / d y_emb rows
+    assert rel_err(gy0[rows].cpu().numpy(), want) < TOL
