@@ -1,17 +1,872 @@
-// tcgen05 path of the separable-critic sweeps (placeholder until the kernels land).
+// Separable-critic score sweeps on the 5th-generation tensor cores (sm_100a).
+//
+//   S = own . all^T            tcgen05.mma kind::f16, operands staged by TMA
+//                              (128B swizzle), accumulators in TMEM
+//   fp32-class accuracy:       every fp32 operand is pre-scaled by a power of two
+//                              and split v = hi + lo (two fp16 values); each
+//                              contraction runs hi.hi + hi.lo + lo.hi with fp32
+//                              accumulation (dropped lo.lo term ~2^-22 relative).
+//                              fp16 runs at twice the tf32 rate, so this costs
+//                              the same tensor time as 1.5 tf32 passes while
+//                              meeting the 1e-4 parity bound.
+//   row_stats kernel:          warp 0 = TMA producer, warp 1 = MMA issuer,
+//                              warps 2-5 = epilogue (thread = score row): online
+//                              (max, sum exp) straight out of TMEM, double-buffered
+//                              accumulators so the epilogue hides under the MMAs.
+//   weighted_sum kernel:       per 128x64 score tile the epilogue turns S into the
+//                              weight tile W (exp / sigmoid family), writes W as an
+//                              fp16 hi/lo pair into swizzled shared memory, and a
+//                              second MMA accumulates O += W . all into a resident
+//                              128x128 TMEM accumulator (flash-attention shaped).
+// The B x B matrix only ever exists as 128x128 / 128x64 tiles in TMEM.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mimrl {
-bool sep_tc_supported(int, int, int) { return false; }
-size_t sep_tc_workspace_bytes(int, int, int) { return 0; }
-int sep_row_stats_tc(const float *, const float *, int, int, int, int, int, float *, float *, float *, void *, size_t,
-                     cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return 9;
+namespace {
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int sep_weighted_sum_tc(const float *, const float *, int, int, int, int, int, int, const float *, int, const float *,
-                        const float *, float *, void *, size_t, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return 9;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// K-major operand tile, rows of 128 bytes, 128B swizzle, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SWIZZLE_128B=2 <<61)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kWExp = 14;  // weights in [0,1] are scaled by 2^14 before the fp16 split
+
+__device__ __forceinline__ float scale_from_absmax(unsigned bits) {
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)
+  int sh = 14 - e;               // m * 2^sh in [2^13, 2^14): safely inside fp16 range
+  sh = sh < -60 ? -60 : (sh > 60 ? 60 : sh);
+  return ldexpf(1.f, sh);
+}
+
+// --------------------------------------------------------------- prepass ----
+// absmax[which] = max |v| over the tensor (float bits compare as unsigned for v >= 0)
+__global__ void absmax2_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
+                               unsigned *__restrict__ out) {
+  const float *src = blockIdx.y == 0 ? a : b;
+  const size_t n = blockIdx.y == 0 ? na : nb;
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out + blockIdx.y, __float_as_uint(m));
+}
+
+// [n, embed] fp32 -> hi, lo [n, 128] fp16 (K padded with zeros), scaled by 2^k
+__global__ void split_rows_kernel(const float *__restrict__ a, int na, const float *__restrict__ b, int nb, int embed,
+                                  const unsigned *__restrict__ absmax, __half *__restrict__ a_hi,
+                                  __half *__restrict__ a_lo, __half *__restrict__ b_hi, __half *__restrict__ b_lo) {
+  const int which = blockIdx.y;
+  const float *src = which == 0 ? a : b;
+  const int n = which == 0 ? na : nb;
+  __half *hi = which == 0 ? a_hi : b_hi, *lo = which == 0 ? a_lo : b_lo;
+  const float sc = scale_from_absmax(absmax[which]);
+  const size_t total = (size_t)n * 64;  // two elements per thread
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx >> 6;
+    const int e = (int)(idx & 63) * 2;
+    const float v0 = e < embed ? src[r * embed + e] * sc : 0.f;
+    const float v1 = e + 1 < embed ? src[r * embed + e + 1] * sc : 0.f;
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<__half2 *>(hi + r * 128 + e) = h;
+    *reinterpret_cast<__half2 *>(lo + r * 128 + e) = l;
+  }
+}
+
+// [n, embed] fp32 -> hiT, loT [128, ldt] fp16 (transposed: swept index contiguous)
+__global__ void __launch_bounds__(256)
+split_transposed_kernel(const float *__restrict__ b, int nb, int embed, const unsigned *__restrict__ absmax, int ldt,
+                        __half *__restrict__ hiT, __half *__restrict__ loT) {
+  __shared__ float tile[64][129];
+  const float sc = scale_from_absmax(absmax[1]);
+  const int r0 = blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 64 * 128; idx += 256) {
+    const int r = idx >> 7, e = idx & 127;
+    tile[r][e] = (r0 + r < nb && e < embed) ? b[(size_t)(r0 + r) * embed + e] * sc : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
+    const int e = idx >> 5, rp = (idx & 31) * 2;
+    const float v0 = tile[rp][e], v1 = tile[rp + 1][e];
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    const size_t o = (size_t)e * ldt + r0 + rp;
+    *reinterpret_cast<__half2 *>(hiT + o) = h;
+    *reinterpret_cast<__half2 *>(loT + o) = l;
+  }
+}
+
+// -------------------------------------------------------------- row stats ----
+constexpr int kTcThreads = 192;
+constexpr uint32_t kTileA = 128 * 128;  // 128 rows x 128 B
+constexpr uint32_t kStatsSmem = 4 * kTileA + 2 * 4 * kTileA + 256 + 1024;
+
+struct StatsParams {
+  int n_own, n_all, own_offset, tiles_per_split;
+  const unsigned *absmax;
+  float *part;
+};
+
+template <int FLAGS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_constant__ CUtensorMap map_own_lo,
+                    const __grid_constant__ CUtensorMap map_all_hi, const __grid_constant__ CUtensorMap map_all_lo,
+                    const StatsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  // operand tiles
+  const uint32_t sA = base;                  // [hi kb0, hi kb1, lo kb0, lo kb1] x 16 KB
+  const uint32_t sB = base + 4 * kTileA;     // 2 stages x [hi kb0, hi kb1, lo kb0, lo kb1]
+  const uint32_t bars = base + 12 * kTileA;
+  const uint32_t bFull = bars, bEmpty = bars + 16, bTFull = bars + 32, bTEmpty = bars + 48, bAFull = bars + 64;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + 12 * kTileA + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128;
+  const int split = blockIdx.y;
+  const int n_tiles = (p.n_all + 127) / 128;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(n_tiles, t0 + p.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bFull + 8 * i, 1);
+      mbar_init(bEmpty + 8 * i, 1);
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 128);
+    }
+    mbar_init(bAFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + 12 * kTileA + 128), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&map_own_hi);
+      prefetch_tmap(&map_own_lo);
+      prefetch_tmap(&map_all_hi);
+      prefetch_tmap(&map_all_lo);
+      mbar_expect_tx(bAFull, 4 * kTileA);
+      tma_load_2d(sA + 0 * kTileA, &map_own_hi, bAFull, 0, row0);
+      tma_load_2d(sA + 1 * kTileA, &map_own_hi, bAFull, 64, row0);
+      tma_load_2d(sA + 2 * kTileA, &map_own_lo, bAFull, 0, row0);
+      tma_load_2d(sA + 3 * kTileA, &map_own_lo, bAFull, 64, row0);
+      for (int t = t0, i = 0; t < t1; ++t, ++i) {
+        const int stage = i & 1;
+        mbar_wait(bEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(bFull + 8 * stage, 4 * kTileA);
+        const uint32_t dst = sB + stage * 4 * kTileA;
+        tma_load_2d(dst + 0 * kTileA, &map_all_hi, bFull + 8 * stage, 0, t * 128);
+        tma_load_2d(dst + 1 * kTileA, &map_all_hi, bFull + 8 * stage, 64, t * 128);
+        tma_load_2d(dst + 2 * kTileA, &map_all_lo, bFull + 8 * stage, 0, t * 128);
+        tma_load_2d(dst + 3 * kTileA, &map_all_lo, bFull + 8 * stage, 64, t * 128);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc_f16(128, 128);
+    mbar_wait(bAFull, 0);
+    for (int t = t0, i = 0; t < t1; ++t, ++i) {
+      const int stage = i & 1, buf = i & 1;
+      mbar_wait(bTEmpty + 8 * buf, ((i >> 1) & 1) ^ 1);
+      mbar_wait(bFull + 8 * stage, (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d = tmem_base + buf * 128;
+        const uint32_t b0 = sB + stage * 4 * kTileA;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t a_sel = prod == 2 ? 2 : 0;   // hi, hi, lo
+          const uint32_t b_sel = prod == 1 ? 2 : 0;   // hi, lo, hi
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
+                       smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32), idesc, acc);
+              acc = 1;
+            }
+        }
+        umma_commit(bEmpty + 8 * stage);
+        umma_commit(bTFull + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int gr = p.own_offset + row0 + r;
+    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
+    const float c2 = inv * kLog2e;
+    // running max kept in RAW accumulator units for the clean path (acc - max is exact-ish, then scaled), in
+    // log2 units for the masked/clamped path; FLAGS == 0 uses raw units throughout
+    float m2 = -INFINITY, s = 0.f, sp = 0.f;
+    const int grmin = p.own_offset + row0, grmax = grmin + 127;
+    for (int t = t0, i = 0; t < t1; ++t, ++i) {
+      const int buf = i & 1;
+      const int col0 = t * 128;
+      const bool clean = FLAGS == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
+      mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, v);
+        tmem_ld_wait();
+        if (clean) {
+          float cmax = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+          if (cmax > m2) {
+            s *= ex2((m2 - cmax) * c2);
+            m2 = cmax;
+          }
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            a0 += ex2((__uint_as_float(v[j]) - m2) * c2);
+            a1 += ex2((__uint_as_float(v[j + 1]) - m2) * c2);
+          }
+          s += a0 + a1;
+        } else {
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = col0 + ch * 32 + j;
+            const bool ok = gc < p.n_all && gc != gr;
+            const float z = __uint_as_float(v[j]) * inv;
+            const float tz = (FLAGS & MIMRL_STAT_CLAMP) ? fminf(fmaxf(z, -1.f), 1.f) : z;
+            if ((FLAGS & MIMRL_STAT_SOFTPLUS) && ok)
+              sp += fmaxf(z, 0.f) + kLn2 * lg2(1.f + ex2(-fabsf(z) * kLog2e));
+            // masked path works on t(S) in natural units, stored back in raw units (t(S) / inv) so that both
+            // paths share one running max
+            const float val = ok ? ((FLAGS & MIMRL_STAT_CLAMP) ? tz * (1.f / inv) : __uint_as_float(v[j])) : -INFINITY;
+            v[j] = __float_as_uint(val);
+            cmax = fmaxf(cmax, val);
+          }
+          if (cmax > -INFINITY) {
+            if (cmax > m2) {
+              s *= ex2((m2 - cmax) * c2);
+              m2 = cmax;
+            }
+            float a0 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a0 += ex2((__uint_as_float(v[j]) - m2) * c2);
+            s += a0;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bTEmpty + 8 * buf);
+    }
+    if (row0 + r < p.n_own) {
+      float *o = p.part + ((size_t)split * p.n_own + row0 + r) * 3;
+      o[0] = m2 * inv;          // inv is a power of two: exact
+      o[1] = s;
+      o[2] = sp;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ----------------------------------------------------------- weighted sum ----
+constexpr uint32_t kXTile = 64 * 128;                     // 64 rows x 128 B = 8 KB
+constexpr uint32_t kStage = 4 * kXTile + 2 * kTileA;      // X hi/lo (2 kb each) + XT hi/lo = 64 KB
+constexpr uint32_t kWsumSmem = 4 * kTileA + 2 * kStage + 2 * kTileA + 256 + 1024;
+
+struct WsumParams {
+  int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept;
+  const unsigned *absmax;
+  const float *shift;
+  float *part;  // [split][n_own][128]
+};
+
+template <int FAMILY>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_constant__ CUtensorMap map_own_lo,
+                   const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                   const __grid_constant__ CUtensorMap map_xt_hi, const __grid_constant__ CUtensorMap map_xt_lo,
+                   const WsumParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  const uint32_t sA = base;                               // own: hi kb0, hi kb1, lo kb0, lo kb1
+  const uint32_t sStage = base + 4 * kTileA;              // 2 stages
+  const uint32_t sW = sStage + 2 * kStage;                // W hi, W lo (128 rows x 128 B each)
+  const uint32_t bars = sW + 2 * kTileA;
+  // X ring (operand of the score MMAs) and XT ring (operand of the W.X MMAs) are released separately: X(i) is
+  // free as soon as the scores of tile i are done, one and a half tiles before XT(i)
+  const uint32_t bXFull = bars, bXEmpty = bars + 16, bTFull = bars + 32, bTEmpty = bars + 48, bSFull = bars + 64,
+                 bSEmpty = bars + 80, bWFull = bars + 96, bWEmpty = bars + 104, bOFull = bars + 112, bAFull = bars + 120;
+  const uint32_t slot_off = 4 * kTileA + 2 * kStage + 2 * kTileA + 192;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + slot_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128;
+  const int split = blockIdx.y;
+  const int n_tiles = (p.n_all + 63) / 64;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(n_tiles, t0 + p.tiles_per_split);
+  const int T = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bXFull + 8 * i, 1);
+      mbar_init(bXEmpty + 8 * i, 1);
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 1);
+      mbar_init(bSFull + 8 * i, 1);
+      mbar_init(bSEmpty + 8 * i, 128);
+    }
+    mbar_init(bWFull, 128);
+    mbar_init(bWEmpty, 1);
+    mbar_init(bOFull, 1);
+    mbar_init(bAFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + slot_off), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&map_own_hi);
+      prefetch_tmap(&map_x_hi);
+      prefetch_tmap(&map_xt_hi);
+      mbar_expect_tx(bAFull, 4 * kTileA);
+      tma_load_2d(sA + 0 * kTileA, &map_own_hi, bAFull, 0, row0);
+      tma_load_2d(sA + 1 * kTileA, &map_own_hi, bAFull, 64, row0);
+      tma_load_2d(sA + 2 * kTileA, &map_own_lo, bAFull, 0, row0);
+      tma_load_2d(sA + 3 * kTileA, &map_own_lo, bAFull, 64, row0);
+      auto load_x = [&](int i) {
+        const int t = t0 + i, stage = i & 1;
+        mbar_wait(bXEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
+        const uint32_t fb = bXFull + 8 * stage;
+        mbar_expect_tx(fb, 4 * kXTile);
+        const uint32_t dst = sStage + stage * kStage;
+        tma_load_2d(dst + 0 * kXTile, &map_x_hi, fb, 0, t * 64);
+        tma_load_2d(dst + 1 * kXTile, &map_x_hi, fb, 64, t * 64);
+        tma_load_2d(dst + 2 * kXTile, &map_x_lo, fb, 0, t * 64);
+        tma_load_2d(dst + 3 * kXTile, &map_x_lo, fb, 64, t * 64);
+      };
+      if (T > 0) load_x(0);
+      for (int i = 0; i < T; ++i) {
+        if (i + 1 < T) load_x(i + 1);
+        const int t = t0 + i, stage = i & 1;
+        mbar_wait(bTEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
+        const uint32_t fb = bTFull + 8 * stage;
+        mbar_expect_tx(fb, 2 * kTileA);
+        const uint32_t dst = sStage + stage * kStage + 4 * kXTile;
+        tma_load_2d(dst, &map_xt_hi, fb, t * 64, 0);
+        tma_load_2d(dst + kTileA, &map_xt_lo, fb, t * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc1 = instr_desc_f16(128, 64);
+    constexpr uint32_t idesc2 = instr_desc_f16(128, 128);
+    auto issue_scores = [&](int i) {
+      const int stage = i & 1;
+      mbar_wait(bSEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
+      mbar_wait(bXFull + 8 * stage, (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d = tmem_base + stage * 64;
+        const uint32_t x0 = sStage + stage * kStage;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t a_sel = prod == 2 ? 2 : 0;
+          const uint32_t b_sel = prod == 1 ? 2 : 0;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
+                       smem_desc_sw128(x0 + (b_sel + kb) * kXTile + k * 32), idesc1, acc);
+              acc = 1;
+            }
+        }
+        umma_commit(bXEmpty + 8 * stage);
+        umma_commit(bSFull + 8 * stage);
+      }
+      __syncwarp();
+    };
+    if (T > 0) {
+      mbar_wait(bAFull, 0);
+      issue_scores(0);
+      for (int i = 0; i < T; ++i) {
+        if (i + 1 < T) issue_scores(i + 1);
+        const int stage = i & 1;
+        mbar_wait(bTFull + 8 * stage, (i >> 1) & 1);
+        mbar_wait(bWFull, i & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t xt = sStage + stage * kStage + 4 * kXTile;
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t w_sel = prod == 2 ? 1 : 0;    // W hi, hi, lo
+            const uint32_t x_sel = prod == 1 ? 1 : 0;    // XT hi, lo, hi
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
+                       smem_desc_sw128(xt + x_sel * kTileA + k * 32), idesc2, (i > 0 || prod > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bTEmpty + 8 * stage);
+          umma_commit(bWEmpty);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(bOFull);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int gr = p.own_offset + row0 + r;
+    const bool row_ok = row0 + r < p.n_own;
+    const float s_all = scale_from_absmax(p.absmax[1]);
+    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * s_all);
+    const float c2 = inv * kLog2e;
+    // exp family: w * 2^14 = ex2((acc*inv - shift) * log2e + 14); acc*inv is exact (power of two), the
+    // subtraction happens at score magnitude so the dominant weights keep full fp32 accuracy
+    float shift_row = 0.f;
+    if (FAMILY == MIMRL_WEIGHT_EXP && !p.shift_by_swept) shift_row = row_ok ? p.shift[row0 + r] : 0.f;
+    const int grmin = p.own_offset + row0, grmax = grmin + 127;
+    const uint32_t wrow_hi = sW + r * 128, wrow_lo = sW + kTileA + r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    for (int i = 0; i < T; ++i) {
+      const int buf = i & 1;
+      const int col0 = (t0 + i) * 64;
+      const bool clean = col0 + 64 <= p.n_all && (p.include_diag || col0 + 64 <= grmin || col0 > grmax);
+      mbar_wait(bSFull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + half * 32, v);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(bSEmpty + 8 * buf);
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float w[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int gc = col0 + half * 32 + j + u;
+            const float a = __uint_as_float(v[j + u]);
+            float wv;
+            if (FAMILY == MIMRL_WEIGHT_EXP) {
+              float sh = shift_row;
+              if (p.shift_by_swept) sh = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
+              wv = ex2(fmaf(fmaf(a, inv, -sh), kLog2e, (float)kWExp));
+            } else {
+              wv = __fdividef(16384.f, 1.f + ex2(-a * c2));
+            }
+            if (!clean && !(gc < p.n_all && (p.include_diag || gc != gr))) wv = 0.f;
+            w[u] = wv;
+          }
+          const __half2 h = __floats2half2_rn(w[0], w[1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(w[0] - hf.x, w[1] - hf.y);
+          hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+          lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l);
+        }
+        if (half == 0) mbar_wait(bWEmpty, (i & 1) ^ 1);   // previous tile's W.X MMAs are done with the buffer
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(half * 4 + c);
+          const uint32_t off = ((chunk ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_hi + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
+                       "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_lo + off), "r"(lo[4 * c]), "r"(lo[4 * c + 1]),
+                       "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(bWFull);
+    }
+    if (T > 0) {
+      mbar_wait(bOFull, 0);
+      tc_fence_after();
+      const float oscale = 1.f / (16384.f * s_all);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + ch * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]) * oscale, __uint_as_float(v[4 * j + 1]) * oscale,
+                               __uint_as_float(v[4 * j + 2]) * oscale, __uint_as_float(v[4 * j + 3]) * oscale);
+        }
+      }
+    } else if (row_ok) {
+      float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128);
+      for (int j = 0; j < 32; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// out[r][e] = coef * sum_splits part[s][r][e] + dcoef[r] * all[own_offset + r][e]     (part rows are 128 wide)
+__global__ void wsum_reduce_tc_kernel(const float *__restrict__ part, int n_splits, int n_own, int embed,
+                                      const float *__restrict__ all, int own_offset, const float *__restrict__ coef,
+                                      const float *__restrict__ dcoef, float *__restrict__ out) {
+  const size_t total = (size_t)n_own * embed;
+  const float c = coef[0];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / embed), e = (int)(idx - (size_t)r * embed);
+    float a = 0.f;
+    for (int s = 0; s < n_splits; ++s) a += part[((size_t)s * n_own + r) * 128 + e];
+    const float d = dcoef ? dcoef[r] * all[(size_t)(own_offset + r) * embed + e] : 0.f;
+    out[idx] = fmaf(c, a, d);
+  }
+}
+
+// ------------------------------------------------------------------ host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 tensor [rows, inner] with row pitch `ld` elements; box = [box_rows, 64] (128 B inner), 128B swizzle
+int make_map(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return 1;
+  }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu ld=%llu)", (int)r, (unsigned long long)inner,
+              (unsigned long long)rows, (unsigned long long)ld);
+    return 1;
+  }
+  return 0;
+}
+
+struct TcLayout {
+  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_all_hiT, off_all_loT, off_part, total;
+  int ldt;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int tc_max_splits() { return 16; }
+
+TcLayout tc_layout(int n_own, int n_all) {
+  TcLayout L;
+  L.ldt = (n_all + 63) & ~63;
+  size_t o = 0;
+  L.off_absmax = o;
+  o += 256;
+  L.off_own_hi = o;
+  o += align256((size_t)n_own * 128 * 2);
+  L.off_own_lo = o;
+  o += align256((size_t)n_own * 128 * 2);
+  L.off_all_hi = o;
+  o += align256((size_t)n_all * 128 * 2);
+  L.off_all_lo = o;
+  o += align256((size_t)n_all * 128 * 2);
+  L.off_all_hiT = o;
+  o += align256((size_t)128 * L.ldt * 2);
+  L.off_all_loT = o;
+  o += align256((size_t)128 * L.ldt * 2);
+  L.off_part = o;
+  o += align256((size_t)tc_max_splits() * n_own * 128 * sizeof(float));
+  L.total = o;
+  return L;
+}
+
+// number of column splits: fill the 148 SMs (one CTA each) with as few idle waves as possible
+int tc_pick_splits(int row_tiles, int col_tiles) {
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= tc_max_splits() && s <= col_tiles; ++s) {
+    const int per = ceil_div(col_tiles, s);
+    const int eff = ceil_div(col_tiles, per);
+    const double waves = (double)ceil_div(row_tiles * eff, 148);
+    const double cost = waves * (per + 2.0);   // +2: per-CTA prologue/epilogue in tile units
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = eff;
+    }
+  }
+  return best;
+}
+
+int tc_prepass(const float *own, const float *all, int n_own, int n_all, int embed, bool transposed,
+               const TcLayout &L, unsigned char *ws, cudaStream_t st) {
+  unsigned *absmax = reinterpret_cast<unsigned *>(ws + L.off_absmax);
+  cudaMemsetAsync(absmax, 0, 8, st);
+  const size_t na = (size_t)n_own * embed, nb = (size_t)n_all * embed;
+  int blocks = (int)(((na > nb ? na : nb) + 1023) / 1024);
+  blocks = blocks > 296 ? 296 : (blocks < 1 ? 1 : blocks);
+  absmax2_kernel<<<dim3(blocks, 2), 256, 0, st>>>(own, na, all, nb, absmax);
+  if (check_launch("tc absmax")) return 1;
+  const size_t pairs = (size_t)(n_own > n_all ? n_own : n_all) * 64;
+  blocks = (int)((pairs + 255) / 256);
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  split_rows_kernel<<<dim3(blocks, 2), 256, 0, st>>>(
+      own, n_own, all, n_all, embed, absmax, reinterpret_cast<__half *>(ws + L.off_own_hi),
+      reinterpret_cast<__half *>(ws + L.off_own_lo), reinterpret_cast<__half *>(ws + L.off_all_hi),
+      reinterpret_cast<__half *>(ws + L.off_all_lo));
+  if (check_launch("tc split_rows")) return 1;
+  if (transposed) {
+    split_transposed_kernel<<<ceil_div(n_all, 64), 256, 0, st>>>(all, n_all, embed, absmax, L.ldt,
+                                                                reinterpret_cast<__half *>(ws + L.off_all_hiT),
+                                                                reinterpret_cast<__half *>(ws + L.off_all_loT));
+    if (check_launch("tc split_transposed")) return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+bool sep_tc_supported(int n_own, int n_all, int embed) { return embed <= 128 && n_own > 0 && n_all > 0; }
+
+size_t sep_tc_workspace_bytes(int n_own, int n_all, int embed) {
+  if (!sep_tc_supported(n_own, n_all, embed)) return 0;
+  return tc_layout(n_own, n_all).total + 256;
+}
+
+int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset, int flags,
+                     float *row_max, float *row_sum, float *row_sp, void *workspace, size_t ws_bytes,
+                     cudaStream_t st) {
+  const TcLayout L = tc_layout(n_own, n_all);
+  MIMRL_REQUIRE(ws_bytes >= L.total, "sep_row_stats(tcgen05): workspace too small");
+  unsigned char *ws = (unsigned char *)workspace;
+  if (tc_prepass(own, all, n_own, n_all, embed, false, L, ws, st)) return 1;
+  CUtensorMap m_own_hi, m_own_lo, m_all_hi, m_all_lo;
+  if (make_map(&m_own_hi, ws + L.off_own_hi, 128, n_own, 128, 128)) return 1;
+  if (make_map(&m_own_lo, ws + L.off_own_lo, 128, n_own, 128, 128)) return 1;
+  if (make_map(&m_all_hi, ws + L.off_all_hi, 128, n_all, 128, 128)) return 1;
+  if (make_map(&m_all_lo, ws + L.off_all_lo, 128, n_all, 128, 128)) return 1;
+  const int row_tiles = ceil_div(n_own, 128), col_tiles = ceil_div(n_all, 128);
+  const int splits = tc_pick_splits(row_tiles, col_tiles);
+  StatsParams p;
+  p.n_own = n_own;
+  p.n_all = n_all;
+  p.own_offset = own_offset;
+  p.tiles_per_split = ceil_div(col_tiles, splits);
+  p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
+  p.part = reinterpret_cast<float *>(ws + L.off_part);
+  dim3 grid(row_tiles, splits);
+#define LAUNCH_STATS(F)                                                                                          \
+  do {                                                                                                           \
+    cudaFuncSetAttribute(sep_stats_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem);   \
+    sep_stats_tc_kernel<F><<<grid, kTcThreads, kStatsSmem, st>>>(m_own_hi, m_own_lo, m_all_hi, m_all_lo, p);      \
+  } while (0)
+  switch (flags & 3) {
+    case 0: LAUNCH_STATS(0); break;
+    case 1: LAUNCH_STATS(1); break;
+    case 2: LAUNCH_STATS(2); break;
+    default: LAUNCH_STATS(3); break;
+  }
+#undef LAUNCH_STATS
+  if (check_launch("sep_stats_tc")) return 1;
+  return combine_row_stats(p.part, splits, n_own, row_max, row_sum, row_sp, st);
+}
+
+int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
+                        int family, int include_diag, const float *shift, int shift_by_swept, const float *coef,
+                        const float *dcoef, float *out, void *workspace, size_t ws_bytes, cudaStream_t st) {
+  const TcLayout L = tc_layout(n_own, n_all);
+  MIMRL_REQUIRE(ws_bytes >= L.total, "sep_weighted_sum(tcgen05): workspace too small");
+  unsigned char *ws = (unsigned char *)workspace;
+  if (tc_prepass(own, all, n_own, n_all, embed, true, L, ws, st)) return 1;
+  CUtensorMap m_own_hi, m_own_lo, m_x_hi, m_x_lo, m_xt_hi, m_xt_lo;
+  if (make_map(&m_own_hi, ws + L.off_own_hi, 128, n_own, 128, 128)) return 1;
+  if (make_map(&m_own_lo, ws + L.off_own_lo, 128, n_own, 128, 128)) return 1;
+  if (make_map(&m_x_hi, ws + L.off_all_hi, 128, n_all, 128, 64)) return 1;
+  if (make_map(&m_x_lo, ws + L.off_all_lo, 128, n_all, 128, 64)) return 1;
+  if (make_map(&m_xt_hi, ws + L.off_all_hiT, n_all, 128, L.ldt, 128)) return 1;
+  if (make_map(&m_xt_lo, ws + L.off_all_loT, n_all, 128, L.ldt, 128)) return 1;
+  const int row_tiles = ceil_div(n_own, 128), col_tiles = ceil_div(n_all, 64);
+  const int splits = tc_pick_splits(row_tiles, col_tiles);
+  WsumParams p;
+  p.n_own = n_own;
+  p.n_all = n_all;
+  p.own_offset = own_offset;
+  p.tiles_per_split = ceil_div(col_tiles, splits);
+  p.include_diag = include_diag;
+  p.shift_by_swept = shift_by_swept;
+  p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
+  p.shift = shift;
+  p.part = reinterpret_cast<float *>(ws + L.off_part);
+  dim3 grid(row_tiles, splits);
+  if (family == MIMRL_WEIGHT_EXP) {
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsumSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP><<<grid, kTcThreads, kWsumSmem, st>>>(m_own_hi, m_own_lo, m_x_hi, m_x_lo, m_xt_hi,
+                                                                             m_xt_lo, p);
+  } else {
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kWsumSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID><<<grid, kTcThreads, kWsumSmem, st>>>(m_own_hi, m_own_lo, m_x_hi, m_x_lo,
+                                                                                 m_xt_hi, m_xt_lo, p);
+  }
+  if (check_launch("sep_wsum_tc")) return 1;
+  const size_t total = (size_t)n_own * embed;
+  int blocks = (int)((total + 255) / 256);
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  wsum_reduce_tc_kernel<<<blocks, 256, 0, st>>>(p.part, splits, n_own, embed, all, own_offset, coef, dcoef, out);
+  return check_launch("wsum_reduce_tc");
+}
+
 }  // namespace mimrl

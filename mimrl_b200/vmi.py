@@ -120,8 +120,16 @@ class _SeparableBound(torch.autograd.Function):
         own = slice(rb.offset, rb.offset + n_own)
         shift_own, dcoef_own = vec[0, own].contiguous(), vec[1, own].contiguous()
         # d/d h(y): rows are owned, x is swept, shift indexed by the owned row
+        swept = all_x
+        if bound_id == L.BOUND_IDS["infonce"]:
+            # InfoNCE rows: sum_j P_ij x_j - x_i with sum_j P_ij = 1 cancels the common mean of the x embeddings.
+            # Sweep the CENTRED embeddings instead (S_ij = y_i.(x_j - mu) + y_i.mu, the row constant moves into the
+            # shift): algebraically identical, but the cancellation no longer happens in floating point.
+            mu = all_x.mean(dim=0)
+            swept = (all_x - mu).contiguous()
+            shift_own = (shift_own - y_emb @ mu).contiguous()
         dy = torch.empty_like(y_emb)
-        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(y_emb), L.ptr(all_x), n_own, n_all, embed, rb.offset, fam, inc,
+        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, fam, inc,
                                              L.ptr(shift_own), 0, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dy),
                                              L.ptr(ws), ws.numel(), st))
         # d/d g(x): columns are owned, y is swept, shift indexed by the swept row
