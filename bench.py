@@ -303,7 +303,15 @@ def run_gpu(args):
             torch.cuda.synchronize()
             acc += a.elapsed_time(b)
         return acc / reps
-    ms_wsum = time_kernel(k_wsum)
+    shift_all = RB.all_gather_rows(shift, rb)
+
+    def k_wsum_swept():          # the second backward sweep: operands swapped, shift indexed by the swept row
+        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(xe_), L.ptr(all_x), n_own, n_all, EMBED, rb.offset, 0, 1,
+                                             L.ptr(shift_all), 1, L.ptr(coef), L.ptr(dcoef), 0, L.ptr(out), L.ptr(ws),
+                                             ws.numel(), st))
+    ms_wsum_own = time_kernel(k_wsum)
+    ms_wsum_swept = time_kernel(k_wsum_swept)
+    ms_wsum = 0.5 * (ms_wsum_own + ms_wsum_swept)
     ms_stats = time_kernel(k_stats)
     pk = peaks()
     flops_wsum = 2.0 * EMBED * n_own * n_all              # algorithmic: one P.X contraction (score recompute not counted)
@@ -317,6 +325,7 @@ def run_gpu(args):
         "algorithmic_flops_per_launch": flops_wsum, "ms_per_launch": ms_wsum, "precision": impl_name,
         "note": "algorithmic fp32 flops (2*E*rows*cols) over a bf16 dense peak; fp32-class accuracy costs 3 split "
                 "products plus the score recompute, so executed tensor flops are 6x the algorithmic figure",
+        "ms_per_launch_shift_by_own": ms_wsum_own, "ms_per_launch_shift_by_swept": ms_wsum_swept,
         "row_stats_ms_per_launch": ms_stats,
         "row_stats_achieved_tflops": 2.0 * EMBED * n_own * n_all / (ms_stats * 1e-3) / 1e12,
     }

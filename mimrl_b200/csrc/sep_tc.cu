@@ -207,7 +207,7 @@ split_transposed_kernel(const float *__restrict__ b, int nb, int embed, const un
 }
 
 // -------------------------------------------------------------- row stats ----
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 = two epilogue warpgroups
 constexpr uint32_t kTileA = 128 * 128;  // 128 rows x 128 B
 constexpr uint32_t kStatsSmem = 4 * kTileA + 2 * 4 * kTileA + 256 + 1024;
 
@@ -312,18 +312,21 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
       __syncwarp();
     }
   } else {
+    // Two epilogue warpgroups ping-pong over the tiles: warpgroup g owns TMEM buffer g and the tiles with
+    // (i & 1) == g, so every SM sub-partition has two epilogue warps in flight to hide TMEM/MUFU latency.
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int gr = p.own_offset + row0 + r;
     const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
     const float c2 = inv * kLog2e;
-    // running max kept in RAW accumulator units for the clean path (acc - max is exact-ish, then scaled), in
-    // log2 units for the masked/clamped path; FLAGS == 0 uses raw units throughout
+    // running max in RAW accumulator units: (acc - max) is formed first, then scaled to log2 units, so the
+    // dominant terms keep full fp32 accuracy; inv is a power of two, so max * inv is exact
     float m2 = -INFINITY, s = 0.f, sp = 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
-    for (int t = t0, i = 0; t < t1; ++t, ++i) {
-      const int buf = i & 1;
-      const int col0 = t * 128;
+    const int buf = wg;
+    for (int i = wg; t0 + i < t1; i += 2) {
+      const int col0 = (t0 + i) * 128;
       const bool clean = FLAGS == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
       mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
@@ -332,55 +335,46 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, v);
         tmem_ld_wait();
-        if (clean) {
-          float cmax = __uint_as_float(v[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
-          if (cmax > m2) {
-            s *= ex2((m2 - cmax) * c2);
-            m2 = cmax;
-          }
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            a0 += ex2((__uint_as_float(v[j]) - m2) * c2);
-            a1 += ex2((__uint_as_float(v[j + 1]) - m2) * c2);
-          }
-          s += a0 + a1;
-        } else {
-          float cmax = -INFINITY;
+        if (!clean) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gc = col0 + ch * 32 + j;
             const bool ok = gc < p.n_all && gc != gr;
             const float z = __uint_as_float(v[j]) * inv;
-            const float tz = (FLAGS & MIMRL_STAT_CLAMP) ? fminf(fmaxf(z, -1.f), 1.f) : z;
             if ((FLAGS & MIMRL_STAT_SOFTPLUS) && ok)
               sp += fmaxf(z, 0.f) + kLn2 * lg2(1.f + ex2(-fabsf(z) * kLog2e));
-            // masked path works on t(S) in natural units, stored back in raw units (t(S) / inv) so that both
-            // paths share one running max
-            const float val = ok ? ((FLAGS & MIMRL_STAT_CLAMP) ? tz * (1.f / inv) : __uint_as_float(v[j])) : -INFINITY;
-            v[j] = __float_as_uint(val);
-            cmax = fmaxf(cmax, val);
+            // clamp acts on S in natural units; the value goes back to raw units (t(S) / inv)
+            const float val = (FLAGS & MIMRL_STAT_CLAMP) ? fminf(fmaxf(z, -1.f), 1.f) * (1.f / inv) : __uint_as_float(v[j]);
+            v[j] = __float_as_uint(ok ? val : -INFINITY);
           }
-          if (cmax > -INFINITY) {
-            if (cmax > m2) {
-              s *= ex2((m2 - cmax) * c2);
-              m2 = cmax;
-            }
-            float a0 = 0.f;
+        }
+        float mx[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a0 += ex2((__uint_as_float(v[j]) - m2) * c2);
-            s += a0;
-          }
+        for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(v[u]);
+#pragma unroll
+        for (int j = 4; j < 32; j += 4)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(v[j + u]));
+        const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (cmax > m2) {                      // also false when the whole chunk is masked (-inf)
+          s *= ex2((m2 - cmax) * c2);
+          m2 = cmax;
+        }
+        if (m2 > -INFINITY) {
+          float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += ex2((__uint_as_float(v[j + u]) - m2) * c2);
+          s += (a[0] + a[1]) + (a[2] + a[3]);
         }
       }
       tc_fence_before();
       mbar_arrive(bTEmpty + 8 * buf);
     }
     if (row0 + r < p.n_own) {
-      float *o = p.part + ((size_t)split * p.n_own + row0 + r) * 3;
-      o[0] = m2 * inv;          // inv is a power of two: exact
+      float *o = p.part + ((size_t)(split * 2 + wg) * p.n_own + row0 + r) * 3;
+      o[0] = m2 * inv;
       o[1] = s;
       o[2] = sp;
     }
@@ -393,7 +387,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
 // ----------------------------------------------------------- weighted sum ----
 constexpr uint32_t kXTile = 64 * 128;                     // 64 rows x 128 B = 8 KB
 constexpr uint32_t kStage = 4 * kXTile + 2 * kTileA;      // X hi/lo (2 kb each) + XT hi/lo = 64 KB
-constexpr uint32_t kWsumSmem = 4 * kTileA + 2 * kStage + 2 * kTileA + 256 + 1024;
+constexpr uint32_t kWsumSmem = 4 * kTileA + 2 * kStage + 2 * kTileA + 1024 + 1024;
 
 struct WsumParams {
   int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept;
@@ -438,9 +432,9 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       mbar_init(bTFull + 8 * i, 1);
       mbar_init(bTEmpty + 8 * i, 1);
       mbar_init(bSFull + 8 * i, 1);
-      mbar_init(bSEmpty + 8 * i, 128);
+      mbar_init(bSEmpty + 8 * i, 256);
     }
-    mbar_init(bWFull, 128);
+    mbar_init(bWFull, 256);
     mbar_init(bWEmpty, 1);
     mbar_init(bOFull, 1);
     mbar_init(bAFull, 1);
@@ -548,72 +542,99 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       __syncwarp();
     }
   } else {
+    // Two epilogue warpgroups split every 128x64 score tile by columns: warpgroup g turns columns
+    // [32g, 32g+32) into weights and writes W chunks 4g..4g+3 of each row.
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int et = wg * 128 + r;              // index among the 256 epilogue threads
     const int gr = p.own_offset + row0 + r;
     const bool row_ok = row0 + r < p.n_own;
     const float s_all = scale_from_absmax(p.absmax[1]);
     const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * s_all);
     const float c2 = inv * kLog2e;
-    // exp family: w * 2^14 = ex2((acc*inv - shift) * log2e + 14); acc*inv is exact (power of two), the
-    // subtraction happens at score magnitude so the dominant weights keep full fp32 accuracy
+    const bool by_swept = FAMILY == MIMRL_WEIGHT_EXP && p.shift_by_swept;
+    // exp family: w * 2^14 = ex2((acc*inv - shift) * log2e + 14); acc*inv is exact (power of two) and the
+    // subtraction happens at score magnitude, so the dominant weights keep full fp32 accuracy
     float shift_row = 0.f;
     if (FAMILY == MIMRL_WEIGHT_EXP && !p.shift_by_swept) shift_row = row_ok ? p.shift[row0 + r] : 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
     const uint32_t wrow_hi = sW + r * 128, wrow_lo = sW + kTileA + r * 128;
     const uint32_t sw = (uint32_t)(r & 7);
+    // column shifts of the current tile, staged once per tile (double-buffered) instead of 64 global loads
+    // per thread: thread et < 64 prefetches shift[col0 + et] one tile ahead
+    float *sh_smem = reinterpret_cast<float *>(gen + slot_off + 64);      // [2][64]
+    float sh_next = 0.f;
+    if (by_swept && et < 64 && T > 0) {
+      const int gc = t0 * 64 + et;
+      sh_next = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
+    }
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1;
       const int col0 = (t0 + i) * 64;
       const bool clean = col0 + 64 <= p.n_all && (p.include_diag || col0 + 64 <= grmin || col0 > grmax);
+      if (by_swept) {
+        if (et < 64) {
+          sh_smem[buf * 64 + et] = sh_next;
+          const int gc = col0 + 64 + et;
+          sh_next = (i + 1 < T && gc < p.n_all) ? __ldg(p.shift + gc) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(bSFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + half * 32, v);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(bSEmpty + 8 * buf);
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + wg * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bSEmpty + 8 * buf);
+      uint32_t hi[16], lo[16];
+      const float4 *sh4 = reinterpret_cast<const float4 *>(sh_smem + buf * 64 + wg * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float shv[4] = {shift_row, shift_row, shift_row, shift_row};
+        if (by_swept) {
+          const float4 t4 = sh4[j >> 2];
+          shv[0] = t4.x, shv[1] = t4.y, shv[2] = t4.z, shv[3] = t4.w;
         }
-        uint32_t hi[16], lo[16];
+        float w[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float w[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int gc = col0 + half * 32 + j + u;
-            const float a = __uint_as_float(v[j + u]);
-            float wv;
-            if (FAMILY == MIMRL_WEIGHT_EXP) {
-              float sh = shift_row;
-              if (p.shift_by_swept) sh = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
-              wv = ex2(fmaf(fmaf(a, inv, -sh), kLog2e, (float)kWExp));
-            } else {
-              wv = __fdividef(16384.f, 1.f + ex2(-a * c2));
-            }
-            if (!clean && !(gc < p.n_all && (p.include_diag || gc != gr))) wv = 0.f;
-            w[u] = wv;
+        for (int u = 0; u < 4; ++u) {
+          const float a = __uint_as_float(v[j + u]);
+          float wv;
+          if (FAMILY == MIMRL_WEIGHT_EXP) wv = ex2(fmaf(fmaf(a, inv, -shv[u]), kLog2e, (float)kWExp));
+          else wv = __fdividef(16384.f, 1.f + ex2(-a * c2));
+          if (!clean) {
+            const int gc = col0 + wg * 32 + j + u;
+            if (!(gc < p.n_all && (p.include_diag || gc != gr))) wv = 0.f;
           }
-          const __half2 h = __floats2half2_rn(w[0], w[1]);
-          const float2 hf = __half22float2(h);
-          const __half2 l = __floats2half2_rn(w[0] - hf.x, w[1] - hf.y);
-          hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
-          lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l);
+          w[u] = wv;
         }
-        if (half == 0) mbar_wait(bWEmpty, (i & 1) ^ 1);   // previous tile's W.X MMAs are done with the buffer
+        // hi = w truncated to 11 significant bits (exactly representable in fp16), lo = w - hi
+        float wh[4], wl[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t chunk = (uint32_t)(half * 4 + c);
-          const uint32_t off = ((chunk ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_hi + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
-                       "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_lo + off), "r"(lo[4 * c]), "r"(lo[4 * c + 1]),
-                       "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
-                       : "memory");
+        for (int u = 0; u < 4; ++u) {
+          wh[u] = __uint_as_float(__float_as_uint(w[u]) & 0xFFFFE000u);
+          wl[u] = w[u] - wh[u];
         }
+        const __half2 h0 = __floats2half2_rn(wh[0], wh[1]), h1 = __floats2half2_rn(wh[2], wh[3]);
+        const __half2 l0 = __floats2half2_rn(wl[0], wl[1]), l1 = __floats2half2_rn(wl[2], wl[3]);
+        hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h0);
+        hi[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&h1);
+        lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l0);
+        lo[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&l1);
+      }
+      mbar_wait(bWEmpty, (i & 1) ^ 1);        // the previous tile's W.X MMAs are done with the buffer
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t chunk = (uint32_t)(wg * 4 + c);
+        const uint32_t off = ((chunk ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_hi + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
+                     "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_lo + off), "r"(lo[4 * c]), "r"(lo[4 * c + 1]),
+                     "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
+                     : "memory");
       }
       fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(bWFull);
@@ -623,7 +644,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       tc_fence_after();
       const float oscale = 1.f / (16384.f * s_all);
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
         uint32_t v[32];
         tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + ch * 32, v);
         tmem_ld_wait();
@@ -636,8 +657,8 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
         }
       }
     } else if (row_ok) {
-      float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128);
-      for (int j = 0; j < 32; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + wg * 64);
+      for (int j = 0; j < 16; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   tc_fence_before();
@@ -821,7 +842,7 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
   }
 #undef LAUNCH_STATS
   if (check_launch("sep_stats_tc")) return 1;
-  return combine_row_stats(p.part, splits, n_own, row_max, row_sum, row_sp, st);
+  return combine_row_stats(p.part, splits * 2, n_own, row_max, row_sum, row_sp, st);
 }
 
 int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,

@@ -123,15 +123,32 @@ def test_mine_mi_gradient_is_dv():
 @pytest.mark.parametrize("B", [4096, 20000])
 def test_large_batch_against_streamed_oracle(B):
     """Sizes where B x B does not fit comfortably on the host in float64: the
-    oracle streams row blocks; the fused kernels never build the matrix."""
-    import mimrl_b200.vmi as V
+    oracle streams row blocks; the fused kernels never build the matrix.
+
+    Rows whose float64 pre-activations sit within 1e-5 of a ReLU kink are left
+    out of the input-gradient comparison: there the fp32 reference itself
+    (torch, checked on the B200) flips the ReLU mask against float64 and
+    differs by ~5e-3, which says nothing about the kernels under test."""
     prm = P.vmi_params(99, "separate", "constant", 128, 256, 128, 2)
     x, y = P.features(100, B, 128, corr=0.6)
     st = O.separable_infonce_streamed(prm, x, y, dtype=np.float64, block=2048)
     c = dict(critic="separate", baseline="constant", bound="infonce", d=128, hidden=256, embed=128, layers=2)
     mi, loss, gx, gy, _ = run(make_estimator(c, prm), x, y)
     assert close_scalar(mi, st["mi"]), (mi, st["mi"])
-    assert rel_err(gx, st["gx"]) < TOL and rel_err(gy, st["gy"]) < TOL
+
+    def safe_rows(stack, inp):
+        _, acts = O.mlp_forward(O.cast_stack(stack, np.float64), inp.astype(np.float64))
+        pre_min = np.min([np.abs(a).min(axis=1) if i < len(acts) - 1 else np.full(len(inp), 1.0)
+                          for i, a in enumerate(acts[1:], 1)], axis=0)
+        # post-ReLU activations: exact zeros are inactive units (fine); tiny positives are kink-adjacent
+        tiny = np.zeros(len(inp), bool)
+        for a in acts[1:-1]:
+            tiny |= ((a > 0) & (a < 1e-5)).any(axis=1)
+        return ~tiny
+    okx, oky = safe_rows(prm["g"], x), safe_rows(prm["h"], y)
+    assert okx.mean() > 0.98 and oky.mean() > 0.98
+    assert rel_err(gx[okx], st["gx"][okx]) < TOL, rel_err(gx[okx], st["gx"][okx])
+    assert rel_err(gy[oky], st["gy"][oky]) < TOL, rel_err(gy[oky], st["gy"][oky])
 
 
 def test_full_size_properties():
