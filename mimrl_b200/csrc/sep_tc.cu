@@ -21,6 +21,7 @@
 // The B x B matrix only ever exists as 128x128 / 128x64 tiles in TMEM.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -129,6 +130,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// same, B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t instr_desc_f16_bmn(int m, int n) { return instr_desc_f16(m, n) | (1u << 16); }
+// MN-major operand, 128B swizzle (cute canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): a
+// 128-byte row holds 64 consecutive MN elements of one K index, 8 K rows form a 1024-byte swizzle atom, the
+// next 8 K rows are SBO bytes further, the next 64 MN elements LBO bytes further.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -245,7 +255,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
       mbar_init(bFull + 8 * i, 1);
       mbar_init(bEmpty + 8 * i, 1);
       mbar_init(bTFull + 8 * i, 1);
-      mbar_init(bTEmpty + 8 * i, 128);
+      mbar_init(bTEmpty + 8 * i, 4);        // one elected arrive per epilogue warp of the owning warpgroup
     }
     mbar_init(bAFull, 1);
     fence_barrier_init();
@@ -370,7 +380,8 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(bTEmpty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
     }
     if (row0 + r < p.n_own) {
       float *o = p.part + ((size_t)(split * 2 + wg) * p.n_own + row0 + r) * 3;
@@ -390,7 +401,7 @@ constexpr uint32_t kStage = 4 * kXTile + 2 * kTileA;      // X hi/lo (2 kb each)
 constexpr uint32_t kWsumSmem = 4 * kTileA + 2 * kStage + 2 * kTileA + 1024 + 1024;
 
 struct WsumParams {
-  int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept;
+  int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept, b_mn;
   const unsigned *absmax;
   const float *shift;
   float *part;  // [split][n_own][128]
@@ -432,9 +443,9 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       mbar_init(bTFull + 8 * i, 1);
       mbar_init(bTEmpty + 8 * i, 1);
       mbar_init(bSFull + 8 * i, 1);
-      mbar_init(bSEmpty + 8 * i, 256);
+      mbar_init(bSEmpty + 8 * i, 8);        // one elected arrive per epilogue warp
     }
-    mbar_init(bWFull, 256);
+    mbar_init(bWFull, 8);
     mbar_init(bWEmpty, 1);
     mbar_init(bOFull, 1);
     mbar_init(bAFull, 1);
@@ -524,14 +535,22 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
         tc_fence_after();
         if (lane == 0) {
           const uint32_t xt = sStage + stage * kStage + 4 * kXTile;
+          const uint32_t xs = sStage + stage * kStage;
 #pragma unroll
           for (int prod = 0; prod < 3; ++prod) {
             const uint32_t w_sel = prod == 2 ? 1 : 0;    // W hi, hi, lo
             const uint32_t x_sel = prod == 1 ? 1 : 0;    // XT hi, lo, hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
-                       smem_desc_sw128(xt + x_sel * kTileA + k * 32), idesc2, (i > 0 || prod > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accf = (i > 0 || prod > 0 || k > 0) ? 1u : 0u;
+              if (p.b_mn)   // B = the K-major X tile read as an MN-major operand: 16 swept rows (2 atoms) per k-step
+                umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
+                         smem_desc_sw128_mn(xs + x_sel * 2 * kXTile + k * 2048, kXTile, 1024), instr_desc_f16_bmn(128, 128),
+                         accf);
+              else
+                umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
+                         smem_desc_sw128(xt + x_sel * kTileA + k * 32), idesc2, accf);
+            }
           }
           umma_commit(bTEmpty + 8 * stage);
           umma_commit(bWEmpty);
@@ -587,7 +606,8 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + wg * 32, v);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bSEmpty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bSEmpty + 8 * buf);
       uint32_t hi[16], lo[16];
       const float4 *sh4 = reinterpret_cast<const float4 *>(sh_smem + buf * 64 + wg * 32);
 #pragma unroll
@@ -637,7 +657,8 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
                      : "memory");
       }
       fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(bWFull);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bWFull);
     }
     if (T > 0) {
       mbar_wait(bOFull, 0);
@@ -868,6 +889,7 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   p.tiles_per_split = ceil_div(col_tiles, splits);
   p.include_diag = include_diag;
   p.shift_by_swept = shift_by_swept;
+  p.b_mn = getenv("MIMRL_TC_BMN") ? atoi(getenv("MIMRL_TC_BMN")) : 0;
   p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
   p.shift = shift;
   p.part = reinterpret_cast<float *>(ws + L.off_part);

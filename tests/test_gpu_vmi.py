@@ -62,7 +62,8 @@ def test_estimator_matches_reference_golden(case):
     assert rel_err(gx, rec["gx"]) < TOL and rel_err(gy, rec["gy"]) < TOL
     for k, v in rec.items():
         if k.startswith("pg__"):
-            assert np.abs(pg[k[4:]] - v).max() <= TOL * np.abs(v).max() + 2e-7, k
+            # analytically-zero sums (e.g. InfoNCE last-layer bias: rows of G sum to 0) are pure fp32 noise
+            assert np.abs(pg[k[4:]] - v).max() <= TOL * np.abs(v).max() + 5e-7, k
         elif k.startswith("pgs__"):
             g = pg[k[5:]].ravel().astype(np.float64)
             got = np.array([np.abs(g).sum(), np.sqrt((g ** 2).sum())])
@@ -137,14 +138,13 @@ def test_large_batch_against_streamed_oracle(B):
     assert close_scalar(mi, st["mi"]), (mi, st["mi"])
 
     def safe_rows(stack, inp):
-        _, acts = O.mlp_forward(O.cast_stack(stack, np.float64), inp.astype(np.float64))
-        pre_min = np.min([np.abs(a).min(axis=1) if i < len(acts) - 1 else np.full(len(inp), 1.0)
-                          for i, a in enumerate(acts[1:], 1)], axis=0)
-        # post-ReLU activations: exact zeros are inactive units (fine); tiny positives are kink-adjacent
-        tiny = np.zeros(len(inp), bool)
-        for a in acts[1:-1]:
-            tiny |= ((a > 0) & (a < 1e-5)).any(axis=1)
-        return ~tiny
+        h = inp.astype(np.float64)
+        ok = np.ones(len(inp), bool)
+        for w, b in stack[:-1]:
+            z = h @ w.T.astype(np.float64) + b.astype(np.float64)      # pre-activation of a hidden layer
+            ok &= (np.abs(z) > 1e-5).all(axis=1)
+            h = np.maximum(z, 0)
+        return ok
     okx, oky = safe_rows(prm["g"], x), safe_rows(prm["h"], y)
     assert okx.mean() > 0.98 and oky.mean() > 0.98
     assert rel_err(gx[okx], st["gx"][okx]) < TOL, rel_err(gx[okx], st["gx"][okx])
