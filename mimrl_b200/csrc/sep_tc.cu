@@ -110,6 +110,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (predicate), without making the surrounding code divergent
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred;
+}
+// warp index as a value the compiler knows to be warp-uniform (keeps descriptors in uniform registers)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -243,7 +256,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
   const uint32_t bFull = bars, bEmpty = bars + 16, bTFull = bars + 32, bTEmpty = bars + 48, bAFull = bars + 64;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + 12 * kTileA + 128);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
   const int split = blockIdx.y;
   const int n_tiles = (p.n_all + 127) / 128;
@@ -267,10 +280,11 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    const uint32_t leader = elect_one();
+    if (leader) {
       prefetch_tmap(&map_own_hi);
       prefetch_tmap(&map_own_lo);
       prefetch_tmap(&map_all_hi);
@@ -292,6 +306,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
       }
     }
   } else if (warp == 1) {
+    const uint32_t leader = elect_one();
     constexpr uint32_t idesc = instr_desc_f16(128, 128);
     mbar_wait(bAFull, 0);
     for (int t = t0, i = 0; t < t1; ++t, ++i) {
@@ -299,7 +314,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
       mbar_wait(bTEmpty + 8 * buf, ((i >> 1) & 1) ^ 1);
       mbar_wait(bFull + 8 * stage, (i >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (leader) {
         const uint32_t d = tmem_base + buf * 128;
         const uint32_t b0 = sB + stage * 4 * kTileA;
         uint32_t acc = 0;
@@ -428,7 +443,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
   const uint32_t slot_off = 4 * kTileA + 2 * kStage + 2 * kTileA + 192;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + slot_off);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
   const int split = blockIdx.y;
   const int n_tiles = (p.n_all + 63) / 64;
@@ -458,11 +473,12 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const uint32_t leader = elect_one();
+    if (leader) {
       prefetch_tmap(&map_own_hi);
       prefetch_tmap(&map_x_hi);
       prefetch_tmap(&map_xt_hi);
@@ -495,6 +511,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       }
     }
   } else if (warp == 1) {
+    const uint32_t leader = elect_one();
     constexpr uint32_t idesc1 = instr_desc_f16(128, 64);
     constexpr uint32_t idesc2 = instr_desc_f16(128, 128);
     auto issue_scores = [&](int i) {
@@ -502,7 +519,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       mbar_wait(bSEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
       mbar_wait(bXFull + 8 * stage, (i >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (leader) {
         const uint32_t d = tmem_base + stage * 64;
         const uint32_t x0 = sStage + stage * kStage;
         uint32_t acc = 0;
@@ -533,7 +550,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
         mbar_wait(bTFull + 8 * stage, (i >> 1) & 1);
         mbar_wait(bWFull, i & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (leader) {
           const uint32_t xt = sStage + stage * kStage + 4 * kXTile;
           const uint32_t xs = sStage + stage * kStage;
 #pragma unroll
@@ -557,7 +574,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(bOFull);
+      if (leader) umma_commit(bOFull);
       __syncwarp();
     }
   } else {
