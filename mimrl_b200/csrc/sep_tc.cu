@@ -93,6 +93,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from TMEM (lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -235,7 +258,8 @@ constexpr uint32_t kTileA = 128 * 128;  // 128 rows x 128 B
 constexpr uint32_t kStatsSmem = 4 * kTileA + 2 * 4 * kTileA + 256 + 1024;
 
 struct StatsParams {
-  int n_own, n_all, own_offset, tiles_per_split;
+  int n_own, n_all, own_offset, tiles_per_split, a_tmem;
+  const __half *own_hi, *own_lo;
   const unsigned *absmax;
   float *part;
 };
@@ -274,13 +298,37 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(gen + 12 * kTileA + 128), 256);
+    tmem_alloc(smem_u32(gen + 12 * kTileA + 128), 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t tmem_a = tmem_base + 256;          // own operand: hi in columns [256,320), lo in [320,384)
+  if (p.a_tmem) {
+    // the owned row block is reused by every MMA of the sweep: park it in TMEM (lane = row, column = K pair) so
+    // that only the streamed operand is read from shared memory
+    if (warp >= 2 && warp < 6) {
+      const int r = (warp & 3) * 32 + lane;
+      const bool ok = row0 + r < p.n_own;
+#pragma unroll 1
+      for (int part = 0; part < 4; ++part) {          // hi[0:64), hi[64:128), lo[0:64), lo[64:128) in K
+        const __half *src = (part < 2 ? p.own_hi : p.own_lo) + (size_t)(row0 + r) * 128 + (part & 1) * 64;
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 t = ok ? __ldg(reinterpret_cast<const uint4 *>(src) + j) : make_uint4(0, 0, 0, 0);
+          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+        }
+        tmem_st32(tmem_a + ((uint32_t)((warp & 3) * 32) << 16) + part * 32, v);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 0) {
     const uint32_t leader = elect_one();
@@ -326,8 +374,12 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
-                       smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32), idesc, acc);
+              if (p.a_tmem)
+                umma_f16_ts(d, tmem_a + (a_sel + kb) * 32 + k * 8, smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32),
+                            idesc, acc);
+              else
+                umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
+                         smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32), idesc, acc);
               acc = 1;
             }
         }
@@ -407,7 +459,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ----------------------------------------------------------- weighted sum ----
@@ -866,6 +918,9 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
   p.tiles_per_split = ceil_div(col_tiles, splits);
   p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
   p.part = reinterpret_cast<float *>(ws + L.off_part);
+  p.a_tmem = getenv("MIMRL_TC_ATMEM") ? atoi(getenv("MIMRL_TC_ATMEM")) : 0;
+  p.own_hi = reinterpret_cast<const __half *>(ws + L.off_own_hi);
+  p.own_lo = reinterpret_cast<const __half *>(ws + L.off_own_lo);
   dim3 grid(row_tiles, splits);
 #define LAUNCH_STATS(F)                                                                                          \
   do {                                                                                                           \
