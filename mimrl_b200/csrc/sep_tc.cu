@@ -9,15 +9,22 @@
 //                              fp16 runs at twice the tf32 rate, so this costs
 //                              the same tensor time as 1.5 tf32 passes while
 //                              meeting the 1e-4 parity bound.
-//   row_stats kernel:          warp 0 = TMA producer, warp 1 = MMA issuer,
-//                              warps 2-5 = epilogue (thread = score row): online
-//                              (max, sum exp) straight out of TMEM, double-buffered
-//                              accumulators so the epilogue hides under the MMAs.
+//   operand residency:         the owned 128-row block is parked in TMEM once per CTA
+//                              (A operand of every score MMA); only the swept
+//                              operand streams through a 6-deep ring of 32 KB
+//                              shared-memory units, so shared-memory bandwidth is
+//                              spent on one operand and TMA runs tiles ahead.
+//   row_stats kernel:          warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 =
+//                              two epilogue warpgroups (thread = score row) that
+//                              ping-pong over double-buffered TMEM accumulators:
+//                              online (max, sum exp) straight out of TMEM.
 //   weighted_sum kernel:       per 128x64 score tile the epilogue turns S into the
-//                              weight tile W (exp / sigmoid family), writes W as an
-//                              fp16 hi/lo pair into swizzled shared memory, and a
-//                              second MMA accumulates O += W . all into a resident
-//                              128x128 TMEM accumulator (flash-attention shaped).
+//                              weight tile W (exp / sigmoid family) and writes W as
+//                              an fp16 hi/lo pair back INTO the TMEM columns S came
+//                              from; a second MMA (A = W from TMEM, B = the same
+//                              shared-memory tile read MN-major) accumulates
+//                              O += W . all into a resident 128x128 TMEM accumulator
+//                              (flash-attention shaped, operands loaded once).
 // The B x B matrix only ever exists as 128x128 / 128x64 tiles in TMEM.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -112,6 +119,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
       "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -228,57 +243,59 @@ __global__ void split_rows_kernel(const float *__restrict__ a, int na, const flo
   }
 }
 
-// [n, embed] fp32 -> hiT, loT [128, ldt] fp16 (transposed: swept index contiguous)
-__global__ void __launch_bounds__(256)
-split_transposed_kernel(const float *__restrict__ b, int nb, int embed, const unsigned *__restrict__ absmax, int ldt,
-                        __half *__restrict__ hiT, __half *__restrict__ loT) {
-  __shared__ float tile[64][129];
-  const float sc = scale_from_absmax(absmax[1]);
-  const int r0 = blockIdx.x * 64;
-  for (int idx = threadIdx.x; idx < 64 * 128; idx += 256) {
-    const int r = idx >> 7, e = idx & 127;
-    tile[r][e] = (r0 + r < nb && e < embed) ? b[(size_t)(r0 + r) * embed + e] * sc : 0.f;
+
+// ------------------------------------------------------------ common bits ----
+constexpr int kTcThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2-9 = two epilogue warpgroups
+constexpr int kStages = 6;               // ring depth
+constexpr uint32_t kUnit = 32768;        // ring unit: 32 KB of the swept operand
+constexpr uint32_t kTile16 = 128 * 128;  // 128 rows x 128 B
+constexpr uint32_t kXTile = 64 * 128;    // 64 rows x 128 B
+constexpr uint32_t kAux = 1024;          // barriers, tmem slot, staged shifts
+constexpr uint32_t kRingSmem = kStages * kUnit + kAux + 1024;
+// TMEM columns: [0,128) owned block (hi kb0, hi kb1, lo kb0, lo kb1: 32 columns each, one column = two K values)
+constexpr uint32_t kTmemA = 0;
+
+// Park the owned 128-row block (fp16 hi/lo, K = 128) in TMEM: lane = row, column c of a 32-column part holds
+// K elements (2c, 2c+1).  Executed by epilogue warpgroup 0 (warps 2-5).
+__device__ __forceinline__ void park_own_block(uint32_t tmem_a, const __half *own_hi, const __half *own_lo, int row0,
+                                               int n_own, int warp, int lane) {
+  const int r = (warp & 3) * 32 + lane;
+  const bool ok = row0 + r < n_own;
+#pragma unroll 1
+  for (int part = 0; part < 4; ++part) {
+    const __half *src = (part < 2 ? own_hi : own_lo) + (size_t)(row0 + r) * 128 + (part & 1) * 64;
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 t = ok ? __ldg(reinterpret_cast<const uint4 *>(src) + j) : make_uint4(0, 0, 0, 0);
+      v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+    }
+    tmem_st32(tmem_a + ((uint32_t)((warp & 3) * 32) << 16) + part * 32, v);
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
-    const int e = idx >> 5, rp = (idx & 31) * 2;
-    const float v0 = tile[rp][e], v1 = tile[rp + 1][e];
-    const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-    const size_t o = (size_t)e * ldt + r0 + rp;
-    *reinterpret_cast<__half2 *>(hiT + o) = h;
-    *reinterpret_cast<__half2 *>(loT + o) = l;
-  }
+  tmem_st_wait();
 }
 
 // -------------------------------------------------------------- row stats ----
-constexpr int kTcThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 = two epilogue warpgroups
-constexpr uint32_t kTileA = 128 * 128;  // 128 rows x 128 B
-constexpr uint32_t kStatsSmem = 4 * kTileA + 2 * 4 * kTileA + 256 + 1024;
-
+// TMEM: [0,128) owned block, [128,256) accumulator 0, [256,384) accumulator 1.
+// Ring unit u = 2*tile + h: the hi (h=0) or lo (h=1) half of a 128-column tile, [kb0 | kb1] x (128 rows x 128 B).
 struct StatsParams {
-  int n_own, n_all, own_offset, tiles_per_split, a_tmem;
-  const __half *own_hi, *own_lo;
+  int n_own, n_all, own_offset, tiles_per_split;
   const unsigned *absmax;
+  const __half *own_hi, *own_lo;
   float *part;
 };
 
 template <int FLAGS>
 __global__ void __launch_bounds__(kTcThreads, 1)
-sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_constant__ CUtensorMap map_own_lo,
-                    const __grid_constant__ CUtensorMap map_all_hi, const __grid_constant__ CUtensorMap map_all_lo,
+sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid_constant__ CUtensorMap map_all_lo,
                     const StatsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - raw);
-  // operand tiles
-  const uint32_t sA = base;                  // [hi kb0, hi kb1, lo kb0, lo kb1] x 16 KB
-  const uint32_t sB = base + 4 * kTileA;     // 2 stages x [hi kb0, hi kb1, lo kb0, lo kb1]
-  const uint32_t bars = base + 12 * kTileA;
-  const uint32_t bFull = bars, bEmpty = bars + 16, bTFull = bars + 32, bTEmpty = bars + 48, bAFull = bars + 64;
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + 12 * kTileA + 128);
+  const uint32_t bars = base + kStages * kUnit;
+  const uint32_t bFull = bars, bEmpty = bars + 64, bTFull = bars + 128, bTEmpty = bars + 144;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kStages * kUnit + 256);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
@@ -286,110 +303,90 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
   const int n_tiles = (p.n_all + 127) / 128;
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(n_tiles, t0 + p.tiles_per_split);
+  const int T = t1 - t0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(bFull + 8 * i, 1);
       mbar_init(bEmpty + 8 * i, 1);
-      mbar_init(bTFull + 8 * i, 1);
-      mbar_init(bTEmpty + 8 * i, 4);        // one elected arrive per epilogue warp of the owning warpgroup
     }
-    mbar_init(bAFull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 4);          // one elected arrive per warp of the owning epilogue warpgroup
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(gen + 12 * kTileA + 128), 512);
+    tmem_alloc(smem_u32(gen + kStages * kUnit + 256), 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t tmem_a = tmem_base + 256;          // own operand: hi in columns [256,320), lo in [320,384)
-  if (p.a_tmem) {
-    // the owned row block is reused by every MMA of the sweep: park it in TMEM (lane = row, column = K pair) so
-    // that only the streamed operand is read from shared memory
-    if (warp >= 2 && warp < 6) {
-      const int r = (warp & 3) * 32 + lane;
-      const bool ok = row0 + r < p.n_own;
-#pragma unroll 1
-      for (int part = 0; part < 4; ++part) {          // hi[0:64), hi[64:128), lo[0:64), lo[64:128) in K
-        const __half *src = (part < 2 ? p.own_hi : p.own_lo) + (size_t)(row0 + r) * 128 + (part & 1) * 64;
-        uint32_t v[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 t = ok ? __ldg(reinterpret_cast<const uint4 *>(src) + j) : make_uint4(0, 0, 0, 0);
-          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
-        }
-        tmem_st32(tmem_a + ((uint32_t)((warp & 3) * 32) << 16) + part * 32, v);
-      }
-      tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
+  const uint32_t tmem_a = tmem_base + kTmemA;
+  if (warp >= 2 && warp < 6) park_own_block(tmem_a, p.own_hi, p.own_lo, row0, p.n_own, warp, lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     const uint32_t leader = elect_one();
     if (leader) {
-      prefetch_tmap(&map_own_hi);
-      prefetch_tmap(&map_own_lo);
       prefetch_tmap(&map_all_hi);
       prefetch_tmap(&map_all_lo);
-      mbar_expect_tx(bAFull, 4 * kTileA);
-      tma_load_2d(sA + 0 * kTileA, &map_own_hi, bAFull, 0, row0);
-      tma_load_2d(sA + 1 * kTileA, &map_own_hi, bAFull, 64, row0);
-      tma_load_2d(sA + 2 * kTileA, &map_own_lo, bAFull, 0, row0);
-      tma_load_2d(sA + 3 * kTileA, &map_own_lo, bAFull, 64, row0);
-      for (int t = t0, i = 0; t < t1; ++t, ++i) {
-        const int stage = i & 1;
-        mbar_wait(bEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(bFull + 8 * stage, 4 * kTileA);
-        const uint32_t dst = sB + stage * 4 * kTileA;
-        tma_load_2d(dst + 0 * kTileA, &map_all_hi, bFull + 8 * stage, 0, t * 128);
-        tma_load_2d(dst + 1 * kTileA, &map_all_hi, bFull + 8 * stage, 64, t * 128);
-        tma_load_2d(dst + 2 * kTileA, &map_all_lo, bFull + 8 * stage, 0, t * 128);
-        tma_load_2d(dst + 3 * kTileA, &map_all_lo, bFull + 8 * stage, 64, t * 128);
+      for (int u = 0; u < 2 * T; ++u) {
+        const int stage = u % kStages;
+        const int col = (t0 + (u >> 1)) * 128;
+        mbar_wait(bEmpty + 8 * stage, ((u / kStages) & 1) ^ 1);
+        mbar_expect_tx(bFull + 8 * stage, kUnit);
+        const CUtensorMap *m = (u & 1) ? &map_all_lo : &map_all_hi;
+        tma_load_2d(base + stage * kUnit, m, bFull + 8 * stage, 0, col);
+        tma_load_2d(base + stage * kUnit + kTile16, m, bFull + 8 * stage, 64, col);
       }
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc = instr_desc_f16(128, 128);
-    mbar_wait(bAFull, 0);
-    for (int t = t0, i = 0; t < t1; ++t, ++i) {
-      const int stage = i & 1, buf = i & 1;
+    for (int i = 0; i < T; ++i) {
+      const int buf = i & 1;
+      const uint32_t d = tmem_base + 128 + buf * 128;
       mbar_wait(bTEmpty + 8 * buf, ((i >> 1) & 1) ^ 1);
-      mbar_wait(bFull + 8 * stage, (i >> 1) & 1);
+      // hi half of the swept tile: own_hi . x_hi and own_lo . x_hi
+      int u = 2 * i, stage = u % kStages;
+      mbar_wait(bFull + 8 * stage, (u / kStages) & 1);
       tc_fence_after();
       if (leader) {
-        const uint32_t d = tmem_base + buf * 128;
-        const uint32_t b0 = sB + stage * 4 * kTileA;
-        uint32_t acc = 0;
+        const uint32_t b0 = base + stage * kUnit;
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t a_sel = prod == 2 ? 2 : 0;   // hi, hi, lo
-          const uint32_t b_sel = prod == 1 ? 2 : 0;   // hi, lo, hi
+        for (int a_sel = 0; a_sel < 4; a_sel += 2)          // own hi (parts 0,1) then own lo (parts 2,3)
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (p.a_tmem)
-                umma_f16_ts(d, tmem_a + (a_sel + kb) * 32 + k * 8, smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32),
-                            idesc, acc);
-              else
-                umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
-                         smem_desc_sw128(b0 + (b_sel + kb) * kTileA + k * 32), idesc, acc);
-              acc = 1;
-            }
-        }
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(d, tmem_a + (a_sel + kb) * 32 + k * 8, smem_desc_sw128(b0 + kb * kTile16 + k * 32), idesc,
+                          (a_sel | kb | k) ? 1u : 0u);
+        umma_commit(bEmpty + 8 * stage);
+      }
+      __syncwarp();
+      // lo half: own_hi . x_lo
+      u = 2 * i + 1, stage = u % kStages;
+      mbar_wait(bFull + 8 * stage, (u / kStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t b0 = base + stage * kUnit;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(d, tmem_a + kb * 32 + k * 8, smem_desc_sw128(b0 + kb * kTile16 + k * 32), idesc, 1u);
         umma_commit(bEmpty + 8 * stage);
         umma_commit(bTFull + 8 * buf);
       }
       __syncwarp();
     }
   } else {
-    // Two epilogue warpgroups ping-pong over the tiles: warpgroup g owns TMEM buffer g and the tiles with
+    // Two epilogue warpgroups ping-pong over the tiles: warpgroup g owns accumulator g and the tiles with
     // (i & 1) == g, so every SM sub-partition has two epilogue warps in flight to hide TMEM/MUFU latency.
     const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
@@ -402,7 +399,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
     float m2 = -INFINITY, s = 0.f, sp = 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
     const int buf = wg;
-    for (int i = wg; t0 + i < t1; i += 2) {
+    for (int i = wg; i < T; i += 2) {
       const int col0 = (t0 + i) * 128;
       const bool clean = FLAGS == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
       mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
@@ -410,7 +407,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + buf * 128 + ch * 32, v);
         tmem_ld_wait();
         if (!clean) {
 #pragma unroll
@@ -463,37 +460,29 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid
 }
 
 // ----------------------------------------------------------- weighted sum ----
-constexpr uint32_t kXTile = 64 * 128;                     // 64 rows x 128 B = 8 KB
-constexpr uint32_t kStage = 4 * kXTile + 2 * kTileA;      // X hi/lo (2 kb each) + XT hi/lo = 64 KB
-constexpr uint32_t kWsumSmem = 4 * kTileA + 2 * kStage + 2 * kTileA + 1024 + 1024;
-
+// TMEM: [0,128) owned block, [128,192) S/W buffer 0, [192,256) S/W buffer 1, [256,384) output accumulator.
+// Ring unit = one 64-row tile of the swept operand: [hi kb0 | hi kb1 | lo kb0 | lo kb1] x (64 rows x 128 B).
+// It is read K-major by the score MMAs (rows = N) and MN-major by the W.X MMAs (rows = K).
 struct WsumParams {
-  int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept, b_mn;
+  int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept;
   const unsigned *absmax;
+  const __half *own_hi, *own_lo;
   const float *shift;
   float *part;  // [split][n_own][128]
 };
 
 template <int FAMILY>
 __global__ void __launch_bounds__(kTcThreads, 1)
-sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_constant__ CUtensorMap map_own_lo,
-                   const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-                   const __grid_constant__ CUtensorMap map_xt_hi, const __grid_constant__ CUtensorMap map_xt_lo,
+sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                    const WsumParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - raw);
-  const uint32_t sA = base;                               // own: hi kb0, hi kb1, lo kb0, lo kb1
-  const uint32_t sStage = base + 4 * kTileA;              // 2 stages
-  const uint32_t sW = sStage + 2 * kStage;                // W hi, W lo (128 rows x 128 B each)
-  const uint32_t bars = sW + 2 * kTileA;
-  // X ring (operand of the score MMAs) and XT ring (operand of the W.X MMAs) are released separately: X(i) is
-  // free as soon as the scores of tile i are done, one and a half tiles before XT(i)
-  const uint32_t bXFull = bars, bXEmpty = bars + 16, bTFull = bars + 32, bTEmpty = bars + 48, bSFull = bars + 64,
-                 bSEmpty = bars + 80, bWFull = bars + 96, bWEmpty = bars + 104, bOFull = bars + 112, bAFull = bars + 120;
-  const uint32_t slot_off = 4 * kTileA + 2 * kStage + 2 * kTileA + 192;
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + slot_off);
+  const uint32_t bars = base + kStages * kUnit;
+  const uint32_t bXFull = bars, bXEmpty = bars + 64, bSFull = bars + 128, bWFull = bars + 144, bOFull = bars + 160;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kStages * kUnit + 256);
+  float *sh_smem = reinterpret_cast<float *>(gen + kStages * kUnit + 512);      // [2][64] staged column shifts
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
@@ -504,134 +493,112 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
   const int T = t1 - t0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(bXFull + 8 * i, 1);
       mbar_init(bXEmpty + 8 * i, 1);
-      mbar_init(bTFull + 8 * i, 1);
-      mbar_init(bTEmpty + 8 * i, 1);
-      mbar_init(bSFull + 8 * i, 1);
-      mbar_init(bSEmpty + 8 * i, 8);        // one elected arrive per epilogue warp
     }
-    mbar_init(bWFull, 8);
-    mbar_init(bWEmpty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bSFull + 8 * i, 1);
+      mbar_init(bWFull + 8 * i, 8);           // one elected arrive per epilogue warp
+    }
     mbar_init(bOFull, 1);
-    mbar_init(bAFull, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(gen + slot_off), 256);
+    tmem_alloc(smem_u32(gen + kStages * kUnit + 256), 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_a = tmem_base + kTmemA;
+  const uint32_t tmem_s = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + 256;
+  if (warp >= 2 && warp < 6) park_own_block(tmem_a, p.own_hi, p.own_lo, row0, p.n_own, warp, lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     const uint32_t leader = elect_one();
     if (leader) {
-      prefetch_tmap(&map_own_hi);
       prefetch_tmap(&map_x_hi);
-      prefetch_tmap(&map_xt_hi);
-      mbar_expect_tx(bAFull, 4 * kTileA);
-      tma_load_2d(sA + 0 * kTileA, &map_own_hi, bAFull, 0, row0);
-      tma_load_2d(sA + 1 * kTileA, &map_own_hi, bAFull, 64, row0);
-      tma_load_2d(sA + 2 * kTileA, &map_own_lo, bAFull, 0, row0);
-      tma_load_2d(sA + 3 * kTileA, &map_own_lo, bAFull, 64, row0);
-      auto load_x = [&](int i) {
-        const int t = t0 + i, stage = i & 1;
-        mbar_wait(bXEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
-        const uint32_t fb = bXFull + 8 * stage;
-        mbar_expect_tx(fb, 4 * kXTile);
-        const uint32_t dst = sStage + stage * kStage;
-        tma_load_2d(dst + 0 * kXTile, &map_x_hi, fb, 0, t * 64);
-        tma_load_2d(dst + 1 * kXTile, &map_x_hi, fb, 64, t * 64);
-        tma_load_2d(dst + 2 * kXTile, &map_x_lo, fb, 0, t * 64);
-        tma_load_2d(dst + 3 * kXTile, &map_x_lo, fb, 64, t * 64);
-      };
-      if (T > 0) load_x(0);
+      prefetch_tmap(&map_x_lo);
       for (int i = 0; i < T; ++i) {
-        if (i + 1 < T) load_x(i + 1);
-        const int t = t0 + i, stage = i & 1;
-        mbar_wait(bTEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
-        const uint32_t fb = bTFull + 8 * stage;
-        mbar_expect_tx(fb, 2 * kTileA);
-        const uint32_t dst = sStage + stage * kStage + 4 * kXTile;
-        tma_load_2d(dst, &map_xt_hi, fb, t * 64, 0);
-        tma_load_2d(dst + kTileA, &map_xt_lo, fb, t * 64, 0);
+        const int stage = i % kStages;
+        const int col = (t0 + i) * 64;
+        mbar_wait(bXEmpty + 8 * stage, ((i / kStages) & 1) ^ 1);
+        const uint32_t fb = bXFull + 8 * stage;
+        mbar_expect_tx(fb, kUnit);
+        const uint32_t dst = base + stage * kUnit;
+        tma_load_2d(dst + 0 * kXTile, &map_x_hi, fb, 0, col);
+        tma_load_2d(dst + 1 * kXTile, &map_x_hi, fb, 64, col);
+        tma_load_2d(dst + 2 * kXTile, &map_x_lo, fb, 0, col);
+        tma_load_2d(dst + 3 * kXTile, &map_x_lo, fb, 64, col);
       }
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc1 = instr_desc_f16(128, 64);
-    constexpr uint32_t idesc2 = instr_desc_f16(128, 128);
+    constexpr uint32_t idesc2 = instr_desc_f16_bmn(128, 128);
+    // S(i) = own . x_i^T : own from TMEM, x tile K-major
     auto issue_scores = [&](int i) {
-      const int stage = i & 1;
-      mbar_wait(bSEmpty + 8 * stage, ((i >> 1) & 1) ^ 1);
-      mbar_wait(bXFull + 8 * stage, (i >> 1) & 1);
+      const int stage = i % kStages, buf = i & 1;
+      mbar_wait(bXFull + 8 * stage, (i / kStages) & 1);
       tc_fence_after();
       if (leader) {
-        const uint32_t d = tmem_base + stage * 64;
-        const uint32_t x0 = sStage + stage * kStage;
-        uint32_t acc = 0;
+        const uint32_t d = tmem_s + buf * 64;
+        const uint32_t x0 = base + stage * kUnit;
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t a_sel = prod == 2 ? 2 : 0;
-          const uint32_t b_sel = prod == 1 ? 2 : 0;
+          const uint32_t a_sel = prod == 2 ? 2 : 0;   // own hi, hi, lo
+          const uint32_t b_sel = prod == 1 ? 2 : 0;   // x   hi, lo, hi
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(d, smem_desc_sw128(sA + (a_sel + kb) * kTileA + k * 32),
-                       smem_desc_sw128(x0 + (b_sel + kb) * kXTile + k * 32), idesc1, acc);
-              acc = 1;
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(d, tmem_a + (a_sel + kb) * 32 + k * 8, smem_desc_sw128(x0 + (b_sel + kb) * kXTile + k * 32),
+                          idesc1, (prod | kb | k) ? 1u : 0u);
         }
-        umma_commit(bXEmpty + 8 * stage);
-        umma_commit(bSFull + 8 * stage);
+        umma_commit(bSFull + 8 * buf);
       }
       __syncwarp();
     };
     if (T > 0) {
-      mbar_wait(bAFull, 0);
       issue_scores(0);
+      if (T > 1) issue_scores(1);
       for (int i = 0; i < T; ++i) {
-        if (i + 1 < T) issue_scores(i + 1);
-        const int stage = i & 1;
-        mbar_wait(bTFull + 8 * stage, (i >> 1) & 1);
-        mbar_wait(bWFull, i & 1);
+        const int stage = i % kStages, buf = i & 1;
+        mbar_wait(bWFull + 8 * buf, (i >> 1) & 1);
         tc_fence_after();
         if (leader) {
-          const uint32_t xt = sStage + stage * kStage + 4 * kXTile;
-          const uint32_t xs = sStage + stage * kStage;
+          // O += W(i) . x_i : W from the TMEM columns the scores came from (hi | lo per warpgroup half), the x
+          // tile read MN-major (row = K index, 64 contiguous N per 128-byte row, next 64 N one kb block further)
+          const uint32_t x0 = base + stage * kUnit;
+          const uint32_t w0 = tmem_s + buf * 64;
 #pragma unroll
           for (int prod = 0; prod < 3; ++prod) {
-            const uint32_t w_sel = prod == 2 ? 1 : 0;    // W hi, hi, lo
-            const uint32_t x_sel = prod == 1 ? 1 : 0;    // XT hi, lo, hi
+            const uint32_t w_lo = prod == 2 ? 16 : 0;    // W hi, hi, lo
+            const uint32_t x_sel = prod == 1 ? 2 : 0;    // x hi, lo, hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t accf = (i > 0 || prod > 0 || k > 0) ? 1u : 0u;
-              if (p.b_mn)   // B = the K-major X tile read as an MN-major operand: 16 swept rows (2 atoms) per k-step
-                umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
-                         smem_desc_sw128_mn(xs + x_sel * 2 * kXTile + k * 2048, kXTile, 1024), instr_desc_f16_bmn(128, 128),
-                         accf);
-              else
-                umma_f16(tmem_o, smem_desc_sw128(sW + w_sel * kTileA + k * 32),
-                         smem_desc_sw128(xt + x_sel * kTileA + k * 32), idesc2, accf);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(tmem_o, w0 + 32 * (k >> 1) + 8 * (k & 1) + w_lo,
+                          smem_desc_sw128_mn(x0 + x_sel * kXTile + k * 2048, kXTile, 1024), idesc2,
+                          (i > 0 || prod > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(bTEmpty + 8 * stage);
-          umma_commit(bWEmpty);
+          umma_commit(bXEmpty + 8 * stage);
         }
         __syncwarp();
+        if (i + 2 < T) issue_scores(i + 2);      // overwrites S/W buffer (i & 1): ordered after the MMAs above
       }
       if (leader) umma_commit(bOFull);
       __syncwarp();
     }
   } else {
     // Two epilogue warpgroups split every 128x64 score tile by columns: warpgroup g turns columns
-    // [32g, 32g+32) into weights and writes W chunks 4g..4g+3 of each row.
+    // [32g, 32g+32) into weights and writes them back over those same TMEM columns: hi in the first 16,
+    // lo in the last 16 (one 32-bit column = two consecutive K values).
     const int wg = (warp - 2) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -647,11 +614,9 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
     float shift_row = 0.f;
     if (FAMILY == MIMRL_WEIGHT_EXP && !p.shift_by_swept) shift_row = row_ok ? p.shift[row0 + r] : 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
-    const uint32_t wrow_hi = sW + r * 128, wrow_lo = sW + kTileA + r * 128;
-    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     // column shifts of the current tile, staged once per tile (double-buffered) instead of 64 global loads
     // per thread: thread et < 64 prefetches shift[col0 + et] one tile ahead
-    float *sh_smem = reinterpret_cast<float *>(gen + slot_off + 64);      // [2][64]
     float sh_next = 0.f;
     if (by_swept && et < 64 && T > 0) {
       const int gc = t0 * 64 + et;
@@ -671,12 +636,10 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
       }
       mbar_wait(bSFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
+      const uint32_t tcol = tmem_s + lane_off + buf * 64 + wg * 32;
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + wg * 32, v);
+      tmem_ld32(tcol, v);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bSEmpty + 8 * buf);
       uint32_t hi[16], lo[16];
       const float4 *sh4 = reinterpret_cast<const float4 *>(sh_smem + buf * 64 + wg * 32);
 #pragma unroll
@@ -713,21 +676,12 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
         lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l0);
         lo[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&l1);
       }
-      mbar_wait(bWEmpty, (i & 1) ^ 1);        // the previous tile's W.X MMAs are done with the buffer
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t chunk = (uint32_t)(wg * 4 + c);
-        const uint32_t off = ((chunk ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_hi + off), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
-                     "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
-                     : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow_lo + off), "r"(lo[4 * c]), "r"(lo[4 * c + 1]),
-                     "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
-                     : "memory");
-      }
-      fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tmem_st16(tcol, hi);
+      tmem_st16(tcol + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bWFull);
+      if (lane == 0) mbar_arrive(bWFull + 8 * buf);
     }
     if (T > 0) {
       mbar_wait(bOFull, 0);
@@ -736,7 +690,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
 #pragma unroll 1
       for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + ch * 32, v);
+        tmem_ld32(tmem_o + lane_off + ch * 32, v);
         tmem_ld_wait();
         if (row_ok) {
           float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + ch * 32);
@@ -753,7 +707,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_own_hi, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // out[r][e] = coef * sum_splits part[s][r][e] + dcoef[r] * all[own_offset + r][e]     (part rows are 128 wide)
@@ -813,8 +767,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uin
 }
 
 struct TcLayout {
-  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_all_hiT, off_all_loT, off_part, total;
-  int ldt;
+  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_part, total;
 };
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -823,7 +776,6 @@ int tc_max_splits() { return 16; }
 
 TcLayout tc_layout(int n_own, int n_all) {
   TcLayout L;
-  L.ldt = (n_all + 63) & ~63;
   size_t o = 0;
   L.off_absmax = o;
   o += 256;
@@ -835,10 +787,6 @@ TcLayout tc_layout(int n_own, int n_all) {
   o += align256((size_t)n_all * 128 * 2);
   L.off_all_lo = o;
   o += align256((size_t)n_all * 128 * 2);
-  L.off_all_hiT = o;
-  o += align256((size_t)128 * L.ldt * 2);
-  L.off_all_loT = o;
-  o += align256((size_t)128 * L.ldt * 2);
   L.off_part = o;
   o += align256((size_t)tc_max_splits() * n_own * 128 * sizeof(float));
   L.total = o;
@@ -862,8 +810,8 @@ int tc_pick_splits(int row_tiles, int col_tiles) {
   return best;
 }
 
-int tc_prepass(const float *own, const float *all, int n_own, int n_all, int embed, bool transposed,
-               const TcLayout &L, unsigned char *ws, cudaStream_t st) {
+int tc_prepass(const float *own, const float *all, int n_own, int n_all, int embed, const TcLayout &L,
+               unsigned char *ws, cudaStream_t st) {
   unsigned *absmax = reinterpret_cast<unsigned *>(ws + L.off_absmax);
   cudaMemsetAsync(absmax, 0, 8, st);
   const size_t na = (size_t)n_own * embed, nb = (size_t)n_all * embed;
@@ -878,14 +826,7 @@ int tc_prepass(const float *own, const float *all, int n_own, int n_all, int emb
       own, n_own, all, n_all, embed, absmax, reinterpret_cast<__half *>(ws + L.off_own_hi),
       reinterpret_cast<__half *>(ws + L.off_own_lo), reinterpret_cast<__half *>(ws + L.off_all_hi),
       reinterpret_cast<__half *>(ws + L.off_all_lo));
-  if (check_launch("tc split_rows")) return 1;
-  if (transposed) {
-    split_transposed_kernel<<<ceil_div(n_all, 64), 256, 0, st>>>(all, n_all, embed, absmax, L.ldt,
-                                                                reinterpret_cast<__half *>(ws + L.off_all_hiT),
-                                                                reinterpret_cast<__half *>(ws + L.off_all_loT));
-    if (check_launch("tc split_transposed")) return 1;
-  }
-  return 0;
+  return check_launch("tc split_rows");
 }
 
 }  // namespace
@@ -903,10 +844,8 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
   const TcLayout L = tc_layout(n_own, n_all);
   MIMRL_REQUIRE(ws_bytes >= L.total, "sep_row_stats(tcgen05): workspace too small");
   unsigned char *ws = (unsigned char *)workspace;
-  if (tc_prepass(own, all, n_own, n_all, embed, false, L, ws, st)) return 1;
-  CUtensorMap m_own_hi, m_own_lo, m_all_hi, m_all_lo;
-  if (make_map(&m_own_hi, ws + L.off_own_hi, 128, n_own, 128, 128)) return 1;
-  if (make_map(&m_own_lo, ws + L.off_own_lo, 128, n_own, 128, 128)) return 1;
+  if (tc_prepass(own, all, n_own, n_all, embed, L, ws, st)) return 1;
+  CUtensorMap m_all_hi, m_all_lo;
   if (make_map(&m_all_hi, ws + L.off_all_hi, 128, n_all, 128, 128)) return 1;
   if (make_map(&m_all_lo, ws + L.off_all_lo, 128, n_all, 128, 128)) return 1;
   const int row_tiles = ceil_div(n_own, 128), col_tiles = ceil_div(n_all, 128);
@@ -918,14 +857,13 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
   p.tiles_per_split = ceil_div(col_tiles, splits);
   p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
   p.part = reinterpret_cast<float *>(ws + L.off_part);
-  p.a_tmem = getenv("MIMRL_TC_ATMEM") ? atoi(getenv("MIMRL_TC_ATMEM")) : 0;
   p.own_hi = reinterpret_cast<const __half *>(ws + L.off_own_hi);
   p.own_lo = reinterpret_cast<const __half *>(ws + L.off_own_lo);
   dim3 grid(row_tiles, splits);
 #define LAUNCH_STATS(F)                                                                                          \
   do {                                                                                                           \
-    cudaFuncSetAttribute(sep_stats_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem);   \
-    sep_stats_tc_kernel<F><<<grid, kTcThreads, kStatsSmem, st>>>(m_own_hi, m_own_lo, m_all_hi, m_all_lo, p);      \
+    cudaFuncSetAttribute(sep_stats_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);    \
+    sep_stats_tc_kernel<F><<<grid, kTcThreads, kRingSmem, st>>>(m_all_hi, m_all_lo, p);                           \
   } while (0)
   switch (flags & 3) {
     case 0: LAUNCH_STATS(0); break;
@@ -944,14 +882,10 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   const TcLayout L = tc_layout(n_own, n_all);
   MIMRL_REQUIRE(ws_bytes >= L.total, "sep_weighted_sum(tcgen05): workspace too small");
   unsigned char *ws = (unsigned char *)workspace;
-  if (tc_prepass(own, all, n_own, n_all, embed, true, L, ws, st)) return 1;
-  CUtensorMap m_own_hi, m_own_lo, m_x_hi, m_x_lo, m_xt_hi, m_xt_lo;
-  if (make_map(&m_own_hi, ws + L.off_own_hi, 128, n_own, 128, 128)) return 1;
-  if (make_map(&m_own_lo, ws + L.off_own_lo, 128, n_own, 128, 128)) return 1;
+  if (tc_prepass(own, all, n_own, n_all, embed, L, ws, st)) return 1;
+  CUtensorMap m_x_hi, m_x_lo;
   if (make_map(&m_x_hi, ws + L.off_all_hi, 128, n_all, 128, 64)) return 1;
   if (make_map(&m_x_lo, ws + L.off_all_lo, 128, n_all, 128, 64)) return 1;
-  if (make_map(&m_xt_hi, ws + L.off_all_hiT, n_all, 128, L.ldt, 128)) return 1;
-  if (make_map(&m_xt_lo, ws + L.off_all_loT, n_all, 128, L.ldt, 128)) return 1;
   const int row_tiles = ceil_div(n_own, 128), col_tiles = ceil_div(n_all, 64);
   const int splits = tc_pick_splits(row_tiles, col_tiles);
   WsumParams p;
@@ -961,20 +895,19 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   p.tiles_per_split = ceil_div(col_tiles, splits);
   p.include_diag = include_diag;
   p.shift_by_swept = shift_by_swept;
-  p.b_mn = getenv("MIMRL_TC_BMN") ? atoi(getenv("MIMRL_TC_BMN")) : 0;
+  p.own_hi = reinterpret_cast<const __half *>(ws + L.off_own_hi);
+  p.own_lo = reinterpret_cast<const __half *>(ws + L.off_own_lo);
   p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
   p.shift = shift;
   p.part = reinterpret_cast<float *>(ws + L.off_part);
   dim3 grid(row_tiles, splits);
   if (family == MIMRL_WEIGHT_EXP) {
-    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsumSmem);
-    sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP><<<grid, kTcThreads, kWsumSmem, st>>>(m_own_hi, m_own_lo, m_x_hi, m_x_lo, m_xt_hi,
-                                                                             m_xt_lo, p);
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP><<<grid, kTcThreads, kRingSmem, st>>>(m_x_hi, m_x_lo, p);
   } else {
     cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kWsumSmem);
-    sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID><<<grid, kTcThreads, kWsumSmem, st>>>(m_own_hi, m_own_lo, m_x_hi, m_x_lo,
-                                                                                 m_xt_hi, m_xt_lo, p);
+                         (int)kRingSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID><<<grid, kTcThreads, kRingSmem, st>>>(m_x_hi, m_x_lo, p);
   }
   if (check_launch("sep_wsum_tc")) return 1;
   const size_t total = (size_t)n_own * embed;
