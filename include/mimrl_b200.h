@@ -164,6 +164,32 @@ int mimrl_vcmi_head_fwd(const float *logits, int n, int act, float *result, void
 int mimrl_vcmi_head_bwd(const float *logits, int n, int act, const float *grad, float *grad_logits,
                         void *stream);
 
+/* ------------------------------------------------------------------------
+ * CubeMLP axis mix.  Replaces one third of MLPsBlock.forward_ln_last /
+ * forward_ln_first (MLPProcess.py:64-122): for x [outer, A, inner] (A = the
+ * mixed axis, inner = product of the faster axes)
+ *   y = LN_{A'}( W2 act(W1 x + b1) + b2 + (Wres x | x) )            ln_first = 0
+ *   y = W2 act(W1 LN_A(x) + b1) + b2 + (Wres x | x)                 ln_first = 1
+ * without any permute copy.  act: 0 gelu(erf), 1 relu, 2 tanh.  Biases and wres
+ * may be NULL.  `saved` receives the LayerNorm (mean, rstd) per fibre
+ * (mimrl_cubemlp_saved_floats).  The backward recomputes the forward per tile,
+ * writes gx, ACCUMULATES gln_w / gln_b (caller zero-fills) and leaves
+ * s_gz [outer,a_out,inner], s_h = act(W1 u + b1) and s_gpre [outer,a_hid,inner]
+ * (and s_u = LN(x) [outer,a_in,inner] when ln_first) for the weight gradients:
+ *   gW2 = sum s_gz s_h^T, gb2 = sum s_gz, gW1 = sum s_gpre u^T, gb1 = sum s_gpre,
+ *   gWres = sum s_gz x^T.
+ * ---------------------------------------------------------------------- */
+size_t mimrl_cubemlp_saved_floats(int outer, int a_in, int a_hid, int a_out, int inner);
+int mimrl_cubemlp_mix_fwd(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
+                          int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
+                          const float *ln_w, const float *ln_b, int ln_first, int act, float *y, float *saved,
+                          void *stream);
+int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                          const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
+                          const float *wres, const float *ln_w, const float *ln_b, int ln_first, int act,
+                          const float *saved, float *gx, float *s_gz, float *s_h, float *s_gpre, float *s_u,
+                          float *gln_w, float *gln_b, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

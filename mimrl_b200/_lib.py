@@ -50,6 +50,11 @@ _SIGS = {
     "mimrl_gather_rows": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P]),
     "mimrl_vcmi_head_fwd": (c_int, [_P, c_int, c_int, _P, _P]),
     "mimrl_vcmi_head_bwd": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "mimrl_cubemlp_saved_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mimrl_cubemlp_mix_fwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, c_int,
+                                      _P, _P, _P]),
+    "mimrl_cubemlp_mix_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int,
+                                      c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

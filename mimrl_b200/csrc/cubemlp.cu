@@ -1,0 +1,495 @@
+// CubeMLP axis mix (reference MLPProcess.py:9-122), permute-free and fused.
+//
+// x is viewed as [outer, A, inner] with A the mixed axis (L-mix: outer = bs,
+// inner = K*D; K-mix: outer = bs*L, inner = D; D-mix: outer = bs*L*K, inner = 1).
+// A "column" is one (outer, inner) position, i.e. one fibre of length A.  One
+// CTA owns a tile of 32 columns: the fibre tile is staged in shared memory once
+// (coalesced along `inner`, or as one contiguous chunk when inner == 1), both
+// Linear layers, the residual projection and the LayerNorm over the new axis
+// run on it in place, and the result tile is written once.  The reference does
+// the same with 4 permute copies + 3 GEMMs + residual + LN passes per mix.
+//
+//   ln_first = 0 (MLPProcess.py:94-122):  y = LN_{A'}( W2 act(W1 x + b1) + b2 + R x )
+//   ln_first = 1 (MLPProcess.py:64-92):   y = W2 act(W1 LN_A(x) + b1) + b2 + R x
+// with R = Wres (res_project) or the identity.  Weights stay in global memory
+// (<= 64 KB each, warp-uniform float4 reads that live in L1).  Dropout is the
+// identity on this path (p = 0 in every reference launch).
+//
+// Backward: the forward is recomputed on the tile from x and the saved LN
+// statistics; the kernel produces dL/dx and the LayerNorm parameter gradients,
+// and leaves gz / h / g_pre (and u = LN(x) for ln_first) in scratch tensors laid
+// out like x, from which the weight gradients are three plain contractions.
+#include "common.cuh"
+
+namespace mimrl {
+namespace {
+
+constexpr int kTI = 32;         // columns per tile
+constexpr int kThreads = 256;   // 8 row groups x 32 columns
+constexpr int kRB = 16;         // output rows per thread and chunk (chunk = 128 rows)
+
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  if (act == 0) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));      // exact-erf GELU (Utils.py:88)
+  if (act == 1) return fmaxf(z, 0.f);
+  return tanhf(z);
+}
+__device__ __forceinline__ float act_bwd(int act, float z) {
+  if (act == 0) {
+    const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+    return cdf + z * pdf;
+  }
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  const float t = tanhf(z);
+  return 1.f - t * t;
+}
+
+struct MixDims {
+  int outer, A, H, A2, inner;
+  long long n_cols;   // outer * inner
+};
+
+// global offset of element (feature f of `F` features, column c)
+__device__ __forceinline__ size_t col_base(long long c, int inner, int F) {
+  const long long o = c / inner, i = c - o * inner;
+  return (size_t)o * F * inner + (size_t)i;
+}
+
+// tile[f][j] = src[column c0+j, feature f]   (zero for columns past the end)
+__device__ void load_tile(float *tile, const float *__restrict__ src, long long c0, int F, const MixDims &d) {
+  const int tid = threadIdx.x;
+  if (d.inner == 1) {   // the 32 fibres are one contiguous chunk of 32*F floats
+    const long long n = min((long long)kTI, d.n_cols - c0) * F;
+    for (int t = tid; t < kTI * F; t += kThreads) {
+      const int j = t / F, f = t - j * F;
+      tile[f * kTI + j] = t < n ? __ldg(src + (size_t)c0 * F + t) : 0.f;
+    }
+  } else {
+    const int j = tid & 31;
+    const long long c = c0 + j;
+    const bool ok = c < d.n_cols;
+    const size_t b = ok ? col_base(c, d.inner, F) : 0;
+    for (int f = tid >> 5; f < F; f += kThreads / 32) tile[f * kTI + j] = ok ? __ldg(src + b + (size_t)f * d.inner) : 0.f;
+  }
+}
+
+__device__ void store_tile(const float *tile, float *__restrict__ dst, long long c0, int F, const MixDims &d) {
+  const int tid = threadIdx.x;
+  if (d.inner == 1) {
+    const long long n = min((long long)kTI, d.n_cols - c0) * F;
+    for (int t = tid; t < kTI * F; t += kThreads) {
+      const int j = t / F, f = t - j * F;
+      if (t < n) dst[(size_t)c0 * F + t] = tile[f * kTI + j];
+    }
+  } else {
+    const int j = tid & 31;
+    const long long c = c0 + j;
+    if (c >= d.n_cols) return;
+    const size_t b = col_base(c, d.inner, F);
+    for (int f = tid >> 5; f < F; f += kThreads / 32) dst[b + (size_t)f * d.inner] = tile[f * kTI + j];
+  }
+}
+
+// acc[jj] += sum_a W[r0 + g*16 + jj][a] * in[a][i]          (W row-major [R, A] in global memory)
+__device__ __forceinline__ void contract_rows(const float *__restrict__ W, int R, int A, const float *in, int g, int i,
+                                              int r0, float (&acc)[kRB]) {
+  const int rbase = r0 + g * kRB;
+  if ((A & 3) == 0 && ((size_t)W & 15) == 0) {
+    for (int a = 0; a < A; a += 4) {
+      const float x0 = in[a * kTI + i], x1 = in[(a + 1) * kTI + i], x2 = in[(a + 2) * kTI + i], x3 = in[(a + 3) * kTI + i];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) {
+        const int r = rbase + jj;
+        if (r < R) {
+          const float4 w = __ldg(reinterpret_cast<const float4 *>(W + (size_t)r * A + a));
+          acc[jj] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, fmaf(w.w, x3, acc[jj]))));
+        }
+      }
+    }
+  } else {
+    for (int a = 0; a < A; ++a) {
+      const float x0 = in[a * kTI + i];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) {
+        const int r = rbase + jj;
+        if (r < R) acc[jj] = fmaf(__ldg(W + (size_t)r * A + a), x0, acc[jj]);
+      }
+    }
+  }
+}
+
+// acc[jj] += sum_r W[r][a0 + g*16 + jj] * in[r][i]          (transposed use of the same W)
+__device__ __forceinline__ void contract_cols(const float *__restrict__ W, int R, int A, const float *in, int g, int i,
+                                              int a0, float (&acc)[kRB]) {
+  const int abase = a0 + g * kRB;
+  if (abase >= A) return;
+  if ((A & 3) == 0 && ((size_t)W & 15) == 0) {
+    for (int r = 0; r < R; ++r) {
+      const float x0 = in[r * kTI + i];
+#pragma unroll
+      for (int jj = 0; jj < kRB; jj += 4) {
+        if (abase + jj < A) {
+          const float4 w = __ldg(reinterpret_cast<const float4 *>(W + (size_t)r * A + abase + jj));
+          acc[jj] = fmaf(w.x, x0, acc[jj]);
+          acc[jj + 1] = fmaf(w.y, x0, acc[jj + 1]);
+          acc[jj + 2] = fmaf(w.z, x0, acc[jj + 2]);
+          acc[jj + 3] = fmaf(w.w, x0, acc[jj + 3]);
+        }
+      }
+    }
+  } else {
+    for (int r = 0; r < R; ++r) {
+      const float x0 = in[r * kTI + i];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj)
+        if (abase + jj < A) acc[jj] = fmaf(__ldg(W + (size_t)r * A + abase + jj), x0, acc[jj]);
+    }
+  }
+}
+
+// per-column mean / rstd over F features of tile[f][j]; red is [2][8][32] scratch
+__device__ void column_stats(const float *tile, int F, float *red, float &mean, float &rstd, float eps) {
+  const int g = threadIdx.x >> 5, i = threadIdx.x & 31;
+  float s = 0.f;
+  for (int f = g; f < F; f += 8) s += tile[f * kTI + i];
+  red[g * kTI + i] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k * kTI + i];
+  mean = tot / F;
+  __syncthreads();
+  float v = 0.f;
+  for (int f = g; f < F; f += 8) {
+    const float dlt = tile[f * kTI + i] - mean;
+    v = fmaf(dlt, dlt, v);
+  }
+  red[g * kTI + i] = v;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k * kTI + i];
+  rstd = rsqrtf(tot / F + eps);
+  __syncthreads();
+}
+
+struct MixArgs {
+  const float *x, *w1, *b1, *w2, *b2, *wres, *ln_w, *ln_b;
+  int ln_first, act;
+  MixDims d;
+};
+
+// First half of the forward, shared by both kernels.  On exit: Xs = x tile, Us = LN_A(x) (ln_first) or an alias of
+// Xs, Hs = pre-activation W1 u + b1, (mean_in, rstd_in) = input LayerNorm statistics of this thread's column.
+__device__ void mix_forward_tile(const MixArgs &m, long long c0, float *Xs, float *Us, float *Hs, float *red,
+                                 float &mean_in, float &rstd_in) {
+  const MixDims &d = m.d;
+  const int g = threadIdx.x >> 5, i = threadIdx.x & 31;
+  load_tile(Xs, m.x, c0, d.A, d);
+  __syncthreads();
+  if (m.ln_first) {
+    column_stats(Xs, d.A, red, mean_in, rstd_in, 1e-6f);
+    for (int a = g; a < d.A; a += 8) Us[a * kTI + i] = (Xs[a * kTI + i] - mean_in) * rstd_in * m.ln_w[a] + m.ln_b[a];
+    __syncthreads();
+  }
+  for (int r0 = 0; r0 < d.H; r0 += 8 * kRB) {
+    float acc[kRB];
+#pragma unroll
+    for (int jj = 0; jj < kRB; ++jj) acc[jj] = 0.f;
+    contract_rows(m.w1, d.H, d.A, Us, g, i, r0, acc);
+#pragma unroll
+    for (int jj = 0; jj < kRB; ++jj) {
+      const int r = r0 + g * kRB + jj;
+      if (r < d.H) Hs[r * kTI + i] = acc[jj] + (m.b1 ? m.b1[r] : 0.f);
+    }
+  }
+  __syncthreads();
+}
+
+__host__ __device__ constexpr size_t tile_floats(int F) { return (size_t)F * kTI; }
+
+__global__ void __launch_bounds__(kThreads)
+cubemlp_mix_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict__ saved) {
+  extern __shared__ float smem[];
+  const MixDims &d = m.d;
+  float *Xs = smem;
+  float *Us = m.ln_first ? Xs + tile_floats(d.A) : Xs;
+  float *Hs = Us + tile_floats(d.A);
+  float *Zs = Hs + tile_floats(d.H);
+  float *red = Zs + tile_floats(d.A2);
+  const int g = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const long long n_tiles = (d.n_cols + kTI - 1) / kTI;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long c0 = tile * kTI;
+    float mean_in = 0.f, rstd_in = 1.f;
+    __syncthreads();
+    mix_forward_tile(m, c0, Xs, Us, Hs, red, mean_in, rstd_in);
+    // activate in place
+    for (int h = g; h < d.H; h += 8) Hs[h * kTI + i] = act_fwd(m.act, Hs[h * kTI + i]);
+    __syncthreads();
+    for (int r0 = 0; r0 < d.A2; r0 += 8 * kRB) {
+      float acc[kRB];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) acc[jj] = 0.f;
+      contract_rows(m.w2, d.A2, d.H, Hs, g, i, r0, acc);
+      if (m.wres) contract_rows(m.wres, d.A2, d.A, Xs, g, i, r0, acc);
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) {
+        const int r = r0 + g * kRB + jj;
+        if (r < d.A2) Zs[r * kTI + i] = acc[jj] + (m.b2 ? m.b2[r] : 0.f) + (m.wres ? 0.f : Xs[r * kTI + i]);
+      }
+    }
+    __syncthreads();
+    float mean = mean_in, rstd = rstd_in;
+    if (!m.ln_first) {
+      column_stats(Zs, d.A2, red, mean, rstd, 1e-6f);
+      for (int a = g; a < d.A2; a += 8) Zs[a * kTI + i] = (Zs[a * kTI + i] - mean) * rstd * m.ln_w[a] + m.ln_b[a];
+      __syncthreads();
+    }
+    if (g == 0 && c0 + i < d.n_cols) {
+      saved[2 * (c0 + i)] = mean;
+      saved[2 * (c0 + i) + 1] = rstd;
+    }
+    store_tile(Zs, y, c0, d.A2, d);
+  }
+}
+
+struct MixBwdOut {
+  float *gx, *s_gz, *s_h, *s_gpre, *s_u, *gln_w, *gln_b;
+};
+
+__global__ void __launch_bounds__(kThreads)
+cubemlp_mix_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const float *__restrict__ saved,
+                       const MixBwdOut o) {
+  extern __shared__ float smem[];
+  const MixDims &d = m.d;
+  float *Xs = smem;
+  float *Us = m.ln_first ? Xs + tile_floats(d.A) : Xs;
+  const int hx = d.H > d.A ? d.H : d.A;
+  float *Hs = Us + tile_floats(d.A);           // pre-activation [H]; ln_first parks the residual gradient [A] here
+  float *Zs = Hs + tile_floats(hx);            // zhat, then g_z [A2]
+  float *Gs = Zs + tile_floats(d.A2);          // gy tile [A2], then g_pre [H]
+  float *Ts = Gs + tile_floats(d.A2 > d.H ? d.A2 : d.H);   // g_u / g_x tile [A]
+  float *red = Ts + tile_floats(d.A);          // [2][8][32] reduction scratch
+  float *As = red + 2 * 8 * kTI;               // act(pre) [H]
+  const int g = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const long long n_tiles = (d.n_cols + kTI - 1) / kTI;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long c0 = tile * kTI;
+    const bool col_ok = c0 + i < d.n_cols;
+    float mean_in = 0.f, rstd_in = 1.f;
+    __syncthreads();
+    mix_forward_tile(m, c0, Xs, Us, Hs, red, mean_in, rstd_in);     // Hs = pre-activation
+    load_tile(Gs, gy, c0, d.A2, d);
+    __syncthreads();
+    // h = act(pre): kept in its own tile (operand of the z rebuild) and written to the scratch tensor
+    for (int h = g; h < d.H; h += 8) As[h * kTI + i] = act_fwd(m.act, Hs[h * kTI + i]);
+    __syncthreads();
+    store_tile(As, o.s_h, c0, d.H, d);
+    float mean = saved[2 * (col_ok ? c0 + i : 0)], rstd = saved[2 * (col_ok ? c0 + i : 0) + 1];
+    if (!m.ln_first) {
+      // rebuild z, normalise to zhat, LayerNorm backward
+      for (int r0 = 0; r0 < d.A2; r0 += 8 * kRB) {
+        float acc[kRB];
+#pragma unroll
+        for (int jj = 0; jj < kRB; ++jj) acc[jj] = 0.f;
+        contract_rows(m.w2, d.A2, d.H, As, g, i, r0, acc);
+        if (m.wres) contract_rows(m.wres, d.A2, d.A, Xs, g, i, r0, acc);
+#pragma unroll
+        for (int jj = 0; jj < kRB; ++jj) {
+          const int r = r0 + g * kRB + jj;
+          if (r < d.A2) {
+            const float z = acc[jj] + (m.b2 ? m.b2[r] : 0.f) + (m.wres ? 0.f : Xs[r * kTI + i]);
+            Zs[r * kTI + i] = (z - mean) * rstd;                    // zhat
+          }
+        }
+      }
+      __syncthreads();
+      // column sums of gyw and gyw*zhat, and the LN parameter gradients
+      float s1 = 0.f, s2 = 0.f;
+      for (int a = g; a < d.A2; a += 8) {
+        const float gyv = col_ok ? Gs[a * kTI + i] : 0.f, zh = Zs[a * kTI + i];
+        const float gw = gyv * m.ln_w[a];
+        s1 += gw;
+        s2 = fmaf(gw, zh, s2);
+        // d/d ln_w[a] += sum_cols gy*zhat ; d/d ln_b[a] += sum_cols gy  (warp = one feature row here)
+        float pw = gyv * zh, pb = gyv;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          pw += __shfl_xor_sync(0xffffffffu, pw, off);
+          pb += __shfl_xor_sync(0xffffffffu, pb, off);
+        }
+        if (i == 0) {
+          atomicAdd(o.gln_w + a, pw);
+          atomicAdd(o.gln_b + a, pb);
+        }
+      }
+      red[g * kTI + i] = s1;
+      red[8 * kTI + g * kTI + i] = s2;
+      __syncthreads();
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        t1 += red[k * kTI + i];
+        t2 += red[8 * kTI + k * kTI + i];
+      }
+      t1 /= d.A2;
+      t2 /= d.A2;
+      __syncthreads();
+      for (int a = g; a < d.A2; a += 8) {
+        const float gw = (col_ok ? Gs[a * kTI + i] : 0.f) * m.ln_w[a];
+        Zs[a * kTI + i] = (gw - t1 - Zs[a * kTI + i] * t2) * rstd;   // g_z
+      }
+    } else {
+      for (int a = g; a < d.A2; a += 8) Zs[a * kTI + i] = col_ok ? Gs[a * kTI + i] : 0.f;   // g_z = gy
+    }
+    __syncthreads();
+    store_tile(Zs, o.s_gz, c0, d.A2, d);
+    // ---- g_pre = (W2^T g_z) * act'(pre)
+    for (int h0 = 0; h0 < d.H; h0 += 8 * kRB) {
+      float acc[kRB];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) acc[jj] = 0.f;
+      contract_cols(m.w2, d.A2, d.H, Zs, g, i, h0, acc);
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) {
+        const int h = h0 + g * kRB + jj;
+        if (h < d.H) Gs[h * kTI + i] = acc[jj] * act_bwd(m.act, Hs[h * kTI + i]);
+      }
+    }
+    __syncthreads();
+    store_tile(Gs, o.s_gpre, c0, d.H, d);
+    if (m.ln_first) store_tile(Us, o.s_u, c0, d.A, d);
+    // ---- g_u = W1^T g_pre ; residual path R^T g_z
+    for (int a0 = 0; a0 < d.A; a0 += 8 * kRB) {
+      float acc[kRB], accr[kRB];
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) acc[jj] = 0.f, accr[jj] = 0.f;
+      contract_cols(m.w1, d.H, d.A, Gs, g, i, a0, acc);
+      if (m.wres) contract_cols(m.wres, d.A2, d.A, Zs, g, i, a0, accr);
+#pragma unroll
+      for (int jj = 0; jj < kRB; ++jj) {
+        const int a = a0 + g * kRB + jj;
+        if (a < d.A) {
+          const float res = m.wres ? accr[jj] : Zs[a * kTI + i];
+          if (m.ln_first) {
+            Ts[a * kTI + i] = acc[jj];               // g_u, LN backward below
+            Hs[a * kTI + i] = res;                   // park the residual gradient (pre-activation no longer needed)
+          } else {
+            Ts[a * kTI + i] = acc[jj] + res;         // g_x
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (m.ln_first) {
+      // LN backward on g_u with uhat = (x - mean_in) * rstd_in, then add the parked residual gradient
+      float s1 = 0.f, s2 = 0.f;
+      for (int a = g; a < d.A; a += 8) {
+        const float uh = (Xs[a * kTI + i] - mean_in) * rstd_in;
+        const float gu = col_ok ? Ts[a * kTI + i] : 0.f;
+        const float gw = gu * m.ln_w[a];
+        s1 += gw;
+        s2 = fmaf(gw, uh, s2);
+        float pw = gu * uh, pb = gu;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          pw += __shfl_xor_sync(0xffffffffu, pw, off);
+          pb += __shfl_xor_sync(0xffffffffu, pb, off);
+        }
+        if (i == 0) {
+          atomicAdd(o.gln_w + a, pw);
+          atomicAdd(o.gln_b + a, pb);
+        }
+      }
+      red[g * kTI + i] = s1;
+      red[8 * kTI + g * kTI + i] = s2;
+      __syncthreads();
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        t1 += red[k * kTI + i];
+        t2 += red[8 * kTI + k * kTI + i];
+      }
+      t1 /= d.A;
+      t2 /= d.A;
+      __syncthreads();
+      for (int a = g; a < d.A; a += 8) {
+        const float uh = (Xs[a * kTI + i] - mean_in) * rstd_in;
+        const float gw = Ts[a * kTI + i] * m.ln_w[a];
+        Ts[a * kTI + i] = (gw - t1 - uh * t2) * rstd_in + Hs[a * kTI + i];
+      }
+      __syncthreads();
+    }
+    store_tile(Ts, o.gx, c0, d.A, d);
+  }
+}
+
+size_t fwd_smem(const MixDims &d, int ln_first) {
+  return (tile_floats(d.A) * (ln_first ? 2 : 1) + tile_floats(d.H) + tile_floats(d.A2) + 2 * 8 * kTI) * sizeof(float);
+}
+size_t bwd_smem(const MixDims &d, int ln_first) {
+  const int hx = d.H > d.A ? d.H : d.A;     // Hs doubles as the parked residual gradient [A] for ln_first
+  const int gx = d.A2 > d.H ? d.A2 : d.H;
+  return (tile_floats(d.A) * (ln_first ? 2 : 1) + tile_floats(hx) + tile_floats(d.A2) + tile_floats(gx) +
+          tile_floats(d.A) + 2 * 8 * kTI + tile_floats(d.H)) * sizeof(float);
+}
+
+int fill_args(MixArgs &m, const float *x, int outer, int a_in, int inner, const float *w1, const float *b1, int a_hid,
+              const float *w2, const float *b2, int a_out, const float *wres, const float *ln_w, const float *ln_b,
+              int ln_first, int act) {
+  MIMRL_REQUIRE(outer > 0 && a_in > 0 && inner > 0 && a_hid > 0 && a_out > 0, "cubemlp_mix: empty input");
+  MIMRL_REQUIRE(act >= 0 && act <= 2, "cubemlp_mix: activation %d not supported by the fused kernel (gelu/relu/tanh)", act);
+  MIMRL_REQUIRE(wres || a_in == a_out, "cubemlp_mix: without res_project d_in must equal d_out (MLPProcess.py:46-48)");
+  MIMRL_REQUIRE(ln_w && ln_b && w1 && w2, "cubemlp_mix: missing parameters");
+  m.x = x, m.w1 = w1, m.b1 = b1, m.w2 = w2, m.b2 = b2, m.wres = wres, m.ln_w = ln_w, m.ln_b = ln_b;
+  m.ln_first = ln_first, m.act = act;
+  m.d.outer = outer, m.d.A = a_in, m.d.H = a_hid, m.d.A2 = a_out, m.d.inner = inner;
+  m.d.n_cols = (long long)outer * inner;
+  return 0;
+}
+
+}  // namespace
+}  // namespace mimrl
+
+using namespace mimrl;
+
+extern "C" size_t mimrl_cubemlp_saved_floats(int outer, int a_in, int a_hid, int a_out, int inner) {
+  (void)a_in, (void)a_hid, (void)a_out;
+  return (size_t)2 * outer * inner;
+}
+
+extern "C" int mimrl_cubemlp_mix_fwd(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
+                                     int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
+                                     const float *ln_w, const float *ln_b, int ln_first, int act, float *y,
+                                     float *saved, void *stream) {
+  MixArgs m;
+  if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
+  const size_t smem = fwd_smem(m.d, ln_first);
+  MIMRL_REQUIRE(smem <= 220 * 1024, "cubemlp_mix_fwd: axis sizes %d/%d/%d need %zu B of shared memory", a_in, a_hid, a_out, smem);
+  cudaFuncSetAttribute(cubemlp_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long n_tiles = (m.d.n_cols + kTI - 1) / kTI;
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+  int blocks = (int)(n_tiles < 148LL * per_sm ? n_tiles : 148LL * per_sm);
+  cubemlp_mix_fwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(m, y, saved);
+  return check_launch("cubemlp_mix_fwd");
+}
+
+extern "C" int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                                     const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
+                                     const float *wres, const float *ln_w, const float *ln_b, int ln_first, int act,
+                                     const float *saved, float *gx, float *s_gz, float *s_h, float *s_gpre, float *s_u,
+                                     float *gln_w, float *gln_b, void *stream) {
+  MixArgs m;
+  if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
+  MIMRL_REQUIRE(gx && s_gz && s_h && s_gpre && gln_w && gln_b && (!ln_first || s_u), "cubemlp_mix_bwd: missing outputs");
+  const size_t smem = bwd_smem(m.d, ln_first);
+  MIMRL_REQUIRE(smem <= 220 * 1024, "cubemlp_mix_bwd: axis sizes %d/%d/%d need %zu B of shared memory", a_in, a_hid, a_out, smem);
+  cudaFuncSetAttribute(cubemlp_mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long n_tiles = (m.d.n_cols + kTI - 1) / kTI;
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+  int blocks = (int)(n_tiles < 148LL * per_sm ? n_tiles : 148LL * per_sm);
+  MixBwdOut o{gx, s_gz, s_h, s_gpre, s_u, gln_w, gln_b};
+  cubemlp_mix_bwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(m, gy, saved, o);
+  return check_launch("cubemlp_mix_bwd");
+}

@@ -1,0 +1,189 @@
+"""CubeMLP fusion encoder: drop-in for the reference's ``MLPProcess.py``
+(``MLP``, ``MLPsBlock``, ``MLPEncoder`` with the same constructor arguments,
+``forward(x, mask=None)`` and parameter paths ``layers_stack.N.mlp_{l,k,d}.fc{1,2}``,
+``res_projection_{l,k,d}``, ``ln_{l,k,d}``).
+
+Each of the three axis mixes of a block (MLPProcess.py:64-122) runs as ONE
+fused kernel over ``x [bs, L, K, D]`` in place of the reference's permute ->
+Linear -> act -> Linear -> permute -> residual(-projection) -> LayerNorm chain;
+see csrc/cubemlp.cu.  The fused path covers dropout p = 0 (every reference
+launch command) or eval mode, activations gelu / relu / tanh and mask=None
+(the reference itself only warns about masks and never passes one,
+Model.py:481).  Other settings run the reference's op order with stock torch
+ops on the GPU and say so once.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+
+_ACT_IDS = {"gelu": 0, "relu": 1, "tanh": 2}
+_ACT_FNS = {  # Utils.py:85-98 get_activation_function
+    "elu": F.elu, "gelu": F.gelu, "hardshrink": F.hardshrink, "hardtanh": F.hardtanh, "leakyrelu": F.leaky_relu,
+    "prelu": F.prelu, "relu": F.relu, "rrelu": F.rrelu, "tanh": torch.tanh,
+}
+
+
+def get_activation_function(activation):
+    return _ACT_FNS[activation]
+
+
+class _AxisMix(torch.autograd.Function):
+    """y = mix along `axis` of x [bs, L, K, D]; parameters in nn.Linear layout."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, wres, ln_w, ln_b, axis, ln_first, act_id):
+        x = L.f32(x)
+        shape = list(x.shape)
+        A = shape[axis]
+        outer = 1
+        for s in shape[:axis]:
+            outer *= s
+        inner = 1
+        for s in shape[axis + 1:]:
+            inner *= s
+        H, A2 = w1.shape[0], w2.shape[0]
+        prm = [None if t is None else L.f32(t.detach()) for t in (w1, b1, w2, b2, wres, ln_w, ln_b)]
+        oshape = shape[:axis] + [A2] + shape[axis + 1:]
+        y = torch.empty(oshape, dtype=torch.float32, device=x.device)
+        saved = torch.empty(2 * outer * inner, dtype=torch.float32, device=x.device)
+        L.check(L.lib.mimrl_cubemlp_mix_fwd(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H, L.ptr(prm[2]),
+                                            L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]), L.ptr(prm[6]),
+                                            int(ln_first), act_id, L.ptr(y), L.ptr(saved), L.stream()))
+        ctx.save_for_backward(x, saved, *[p if p is not None else x.new_empty(0) for p in prm])
+        ctx.cfg = (outer, A, inner, H, A2, int(ln_first), act_id, [p is not None for p in prm])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, saved, *prm = ctx.saved_tensors
+        outer, A, inner, H, A2, ln_first, act_id, present = ctx.cfg
+        prm = [p if ok else None for p, ok in zip(prm, present)]
+        w1, b1, w2, b2, wres, ln_w, ln_b = prm
+        gy = L.f32(gy)
+        dev = x.device
+        gx = torch.empty_like(x)
+        s_gz = torch.empty(outer, A2, inner, device=dev)
+        s_h = torch.empty(outer, H, inner, device=dev)
+        s_gpre = torch.empty(outer, H, inner, device=dev)
+        s_u = torch.empty(outer, A, inner, device=dev) if ln_first else None
+        gln = torch.zeros(2, ln_w.numel(), device=dev)
+        L.check(L.lib.mimrl_cubemlp_mix_bwd(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2),
+                                            L.ptr(b2), A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), ln_first, act_id,
+                                            L.ptr(saved), L.ptr(gx), L.ptr(s_gz), L.ptr(s_h), L.ptr(s_gpre),
+                                            L.ptr(s_u), L.ptr(gln[0]), L.ptr(gln[1]), L.stream()))
+        x3 = x.view(outer, A, inner)
+        u3 = s_u if ln_first else x3
+        # weight gradients: plain contractions over (outer, inner) of tensors already laid out like x
+        gw2 = torch.einsum("oqi,ohi->qh", s_gz, s_h)
+        gw1 = torch.einsum("ohi,oai->ha", s_gpre, u3)
+        gb2 = s_gz.sum(dim=(0, 2)) if b2 is not None else None
+        gb1 = s_gpre.sum(dim=(0, 2)) if b1 is not None else None
+        gwres = torch.einsum("oqi,oai->qa", s_gz, x3) if wres is not None else None
+        return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+
+
+class MLP(nn.Module):
+    """MLPProcess.py:9-21: fc2(act(fc1(x))) on the last axis."""
+
+    def __init__(self, activate, d_in, d_hidden, d_out, bias):
+        super().__init__()
+        self.fc1 = nn.Linear(d_in, d_hidden, bias=bias)
+        self.fc2 = nn.Linear(d_hidden, d_out, bias=bias)
+        self.activate = activate
+        self.activation = get_activation_function(activate)
+
+    def forward(self, x, mask=None):
+        return self.fc2(self.activation(self.fc1(x)))
+
+
+class MLPsBlock(nn.Module):
+    """MLPProcess.py:25-122."""
+
+    def __init__(self, activate, d_ins, d_hiddens, d_outs, dropouts, bias, ln_first=False, res_project=False):
+        super().__init__()
+        self.mlp_l = MLP(activate, d_ins[0], d_hiddens[0], d_outs[0], bias)
+        self.mlp_k = MLP(activate, d_ins[1], d_hiddens[1], d_outs[1], bias)
+        self.mlp_d = MLP(activate, d_ins[2], d_hiddens[2], d_outs[2], bias)
+        self.dropout_l = nn.Dropout(p=dropouts[0])
+        self.dropout_k = nn.Dropout(p=dropouts[1])
+        self.dropout_d = nn.Dropout(p=dropouts[2])
+        dims = d_ins if ln_first else d_outs
+        self.ln_l = nn.LayerNorm(dims[0], eps=1e-6)
+        self.ln_k = nn.LayerNorm(dims[1], eps=1e-6)
+        self.ln_d = nn.LayerNorm(dims[2], eps=1e-6)
+        self.ln_fist = ln_first          # attribute name as in the reference (MLPProcess.py:43)
+        self.res_project = res_project
+        self.activate = activate
+        if not res_project:
+            for a in range(3):
+                assert d_ins[a] == d_outs[a], \
+                    "Error from MLPsBlock: If using projection for residual, d_in should be equal to d_out."
+        else:
+            self.res_projection_l = nn.Linear(d_ins[0], d_outs[0], bias=False)
+            self.res_projection_k = nn.Linear(d_ins[1], d_outs[1], bias=False)
+            self.res_projection_d = nn.Linear(d_ins[2], d_outs[2], bias=False)
+        self._warned = False
+
+    def _fusable(self, mask):
+        drop = self.training and any(d.p > 0 for d in (self.dropout_l, self.dropout_k, self.dropout_d))
+        return mask is None and not drop and self.activate in _ACT_IDS
+
+    def _mix(self, x, axis, ax):
+        mlp, ln = getattr(self, "mlp_" + ax), getattr(self, "ln_" + ax)
+        wres = getattr(self, "res_projection_" + ax).weight if self.res_project else None
+        return _AxisMix.apply(x, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, wres, ln.weight, ln.bias,
+                              axis, self.ln_fist, _ACT_IDS[self.activate])
+
+    def forward(self, x, mask=None):
+        if mask is not None:
+            print("Warning from MLPsBlock: If using mask, d_in should be equal to d_out.")   # MLPProcess.py:56-57
+        if self._fusable(mask):
+            x = self._mix(x, 1, "l")
+            x = self._mix(x, 2, "k")
+            return self._mix(x, 3, "d")
+        if not self._warned:
+            warnings.warn("MLPsBlock: dropout>0 in training / mask / this activation are outside the fused CubeMLP "
+                          "kernels; running the reference op order with torch ops")
+            self._warned = True
+        return self._forward_torch(x, mask)
+
+    def _forward_torch(self, x, mask):
+        """Op order of MLPProcess.py:64-122 for the settings the fused kernels do not cover."""
+        plan = (("l", (0, 2, 3, 1), (0, 3, 1, 2)), ("k", (0, 1, 3, 2), (0, 1, 3, 2)), ("d", None, None))
+        for ax, fwd, back in plan:
+            mlp, ln, drop = getattr(self, "mlp_" + ax), getattr(self, "ln_" + ax), getattr(self, "dropout_" + ax)
+            xp = x.permute(*fwd) if fwd else x
+            res = getattr(self, "res_projection_" + ax)(xp) if self.res_project else xp
+            h = mlp(ln(xp) if self.ln_fist else xp)
+            if back:
+                h, res = h.permute(*back), res.permute(*back)
+            if ax == "l" and mask is not None:
+                h = h.masked_fill(mask.unsqueeze(-1).unsqueeze(-1).bool(), 0.0)
+            x = drop(h) + res
+            if not self.ln_fist:
+                x = ln(x.permute(*fwd)).permute(*back) if fwd else ln(x)
+        return x
+
+
+class MLPEncoder(nn.Module):
+    """MLPProcess.py:126-137."""
+
+    def __init__(self, activate, d_in, d_hiddens, d_outs, dropouts, bias, ln_first=False,
+                 res_project=[False, False, True]):
+        super().__init__()
+        assert len(d_hiddens) == len(d_outs) == len(res_project)
+        self.layers_stack = nn.ModuleList([
+            MLPsBlock(activate=activate, d_ins=d_in if i == 0 else d_outs[i - 1], d_hiddens=d_hiddens[i],
+                      d_outs=d_outs[i], dropouts=dropouts, bias=bias, ln_first=ln_first, res_project=res_project[i])
+            for i in range(len(d_hiddens))])
+
+    def forward(self, x, mask=None):
+        for enc_layer in self.layers_stack:
+            x = enc_layer(x, mask)
+        return x
