@@ -1,0 +1,83 @@
+"""Two-GPU parity of the row-block sharded estimator: every rank must obtain
+the single-GPU global-batch value and its own rows of the gradients."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, bound, B, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from mimrl_b200 import rowblock as RB
+        from mimrl_b200.model import VMIEstimator
+        from oracle import params as P
+        torch.backends.cuda.matmul.allow_tf32 = False
+        baseline = "unnormalized" if bound == "tuba" else "constant"
+        prm = P.vmi_params(3, "separate", baseline, 128, 64, 128, 2)
+        x, y = P.features(4, B, 128, corr=0.6)
+        counts = (B // 2 + 3, B - B // 2 - 3)                       # ragged shards
+        off = sum(counts[:rank])
+        est = VMIEstimator("separate", baseline, bound, 128, 64, 128, 2, "relu", 0, 1).cuda()
+        est.load_state_dict({k: torch.tensor(v) for k, v in P.vmi_state_dict(prm).items()})
+        est.rowblock = RB.from_group(counts[rank], device=torch.device("cuda", rank))
+        xt = torch.tensor(x[off: off + counts[rank]], device="cuda", requires_grad=True)
+        yt = torch.tensor(y[off: off + counts[rank]], device="cuda", requires_grad=True)
+        mi, loss = est(xt, yt)
+        loss.backward()
+        params = list(est.parameters())
+        RB.all_reduce_param_grads(params, est.rowblock)
+        q.put((rank, float(mi), xt.grad.cpu().numpy(), yt.grad.cpu().numpy(),
+               {n: p.grad.cpu().numpy() for n, p in est.named_parameters()}))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bound", ["infonce", "nwj", "tuba", "js"])
+def test_sharded_estimator_matches_oracle(bound):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import params as P
+    from oracle import vmi_oracle as O
+    B = 700
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bound, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(len(r) == 5 for r in res), res
+    baseline = "unnormalized" if bound == "tuba" else "constant"
+    prm = P.vmi_params(3, "separate", baseline, 128, 64, 128, 2)
+    x, y = P.features(4, B, 128, corr=0.6)
+    ref = O.vmi_estimator(prm, "separate", baseline, bound, x, y)
+    gx = np.concatenate([r[2] for r in res])
+    gy = np.concatenate([r[3] for r in res])
+    for r in res:
+        assert abs(r[1] - ref["mi"]) <= 1e-4 * max(1.0, abs(ref["mi"]))
+    assert np.abs(gx - ref["gx"]).max() <= 1e-4 * np.abs(ref["gx"]).max()
+    assert np.abs(gy - ref["gy"]).max() <= 1e-4 * np.abs(ref["gy"]).max()
+    for k, v in ref["pg"].items():
+        if k.endswith("weight"):
+            assert np.abs(res[0][4][k] - v).max() <= 2e-4 * np.abs(v).max(), k
+            assert np.array_equal(res[0][4][k], res[1][4][k])

@@ -1,0 +1,75 @@
+"""Row-block sharding plumbing on the gloo backend (world_size 2, CPU): the
+same functions the NCCL path uses, minus the kernels."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, counts, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mimrl_b200 import rowblock as RB
+        n_local = counts[rank]
+        rb = RB.from_group(n_local)
+        assert rb.counts == tuple(counts) and rb.rank == rank and rb.world == world
+        assert rb.offset == sum(counts[:rank]) and rb.n_all == sum(counts) and rb.sharded
+        # every rank builds the same global matrix and keeps its block
+        g = torch.Generator().manual_seed(0)
+        full = torch.randn(sum(counts), 5, generator=g)
+        local = full[rb.offset: rb.offset + n_local].clone()
+        gathered = RB.all_gather_rows(local, rb)
+        assert torch.equal(gathered, full)
+        assert torch.equal(RB.own_slice(gathered, rb), local)
+        vec = RB.all_gather_rows(local[:, 0].contiguous(), rb)          # 1-D rows (per-row statistics)
+        assert torch.equal(vec, full[:, 0])
+        # parameter gradients are partial sums over ranks
+        p1 = torch.nn.Parameter(torch.zeros(3, 2))
+        p2 = torch.nn.Parameter(torch.zeros(4))
+        p3 = torch.nn.Parameter(torch.zeros(2))                          # no grad on purpose
+        p1.grad = torch.full((3, 2), float(rank + 1))
+        p2.grad = torch.arange(4.0) * (rank + 1)
+        RB.all_reduce_param_grads([p1, p2, p3], rb)
+        tot = sum(range(1, world + 1))
+        assert torch.equal(p1.grad, torch.full((3, 2), float(tot)))
+        assert torch.equal(p2.grad, torch.arange(4.0) * tot) and p3.grad is None
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [(4, 4), (5, 3)])
+def test_rowblock_world2(counts):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, counts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_single_process_helpers():
+    from mimrl_b200 import rowblock as RB
+    rb = RB.single(7)
+    assert not rb.sharded and rb.n_own == 7 and rb.offset == 0
+    t = torch.randn(7, 3)
+    assert RB.all_gather_rows(t, rb) is t
+    assert RB.even_split(10, 4) == (3, 3, 2, 2) and sum(RB.even_split(65536, 8)) == 65536
+    assert RB.from_group(5).counts == (5,)
