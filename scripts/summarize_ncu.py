@@ -1,0 +1,67 @@
+"""Turn gpurun_out ncu artefacts into the committed summaries under profiles/.
+
+    python scripts/summarize_ncu.py <round-tag>
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+# ---- launch list -> share of the step per kernel
+rows = list(csv.reader(open(f"gpurun_out/launches_{tag}.csv", errors="ignore")))
+hdr, agg = None, collections.OrderedDict()
+for r in rows:
+    if "Kernel Name" in r:
+        hdr = r
+        continue
+    if hdr is None or len(r) != len(hdr):
+        continue
+    d = dict(zip(hdr, r))
+    if d.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    v = float(d["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(d["Metric Unit"], 1e-3)
+    a = agg.setdefault(d["Kernel Name"][:110], [0, 0.0])
+    a[0] += 1
+    a[1] += v
+tot = sum(a[1] for a in agg.values())
+with open(f"profiles/launches_{tag}.md", "w") as f:
+    f.write(f"# ncu launch list, `bench.py --steps 2 --warmup 1 --no-cpu` ({tag})\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and\n"
+            "serialised, so read the SHARES. 3 steps (1 warm-up + 2 timed) plus the kernel-timing leg are in the window.\n\n"
+            "| total ms | share | launches | kernel |\n|---:|---:|---:|---|\n")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        f.write(f"| {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[0]} | `{k}` |\n")
+    f.write(f"\ntotal {tot / 1e3:.2f} ms over {sum(a[0] for a in agg.values())} launches\n")
+
+# ---- full capture -> key metrics per kernel
+out = subprocess.run(["ncu", "-i", f"gpurun_out/prof_sep_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True,
+                     text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr = rows[0]
+want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_wait",
+        "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
+        "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_warps_issue_stalled_no_instructions",
+        "smsp__pcsamp_warps_issue_stalled_branch_resolving", "smsp__pcsamp_warps_issue_stalled_barrier"]
+units = rows[1]
+with open(f"profiles/sep_kernels_{tag}.md", "w") as f:
+    f.write(f"# ncu --set full, tcgen05 sweep kernels at B = 65536, E = 128 ({tag})\n\n"
+            "`ncu --set full --clock-control none --import-source on -k regex:sep_wsum_tc|sep_stats_tc`\n"
+            "(numbers under the profiler are not bench values; CUDA-event timings are in bench.py's JSON line)\n\n")
+    for r in rows[2:]:
+        f.write(f"## `{r[hdr.index('Kernel Name')][:100]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for w in want:
+            if w in hdr:
+                i = hdr.index(w)
+                f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+        f.write("\n")
+print(open(f"profiles/launches_{tag}.md").read()[:2500])
+print(open(f"profiles/sep_kernels_{tag}.md").read()[:6000])
