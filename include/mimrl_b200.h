@@ -121,6 +121,20 @@ int mimrl_scores_grad(const float *scores, int n_rows, int n_cols, int own_offse
                       float *grad_scores, void *stream);
 
 /* ------------------------------------------------------------------------
+ * fp32-class GEMM on the tensor cores (fp16 hi/lo split, three products) for the
+ * relu MLP stacks of the critics, baselines and the CMI classifier.  Replaces
+ * the nn.Linear calls inside VMI.py:13-22 `mlps` and Model.py:52-57.
+ *   mode 0: C[M,N] = A[M,K] . B[N,K]^T (+ bias[N], relu)    Linear forward
+ *   mode 1: C[M,N] = A[M,K] . B[K,N]                         input gradient  dz W
+ *   mode 2: C[M,N] = A[K,M]^T . B[K,N]                       weight gradient dz^T x
+ * a_mask (nullable, same shape as A): A is multiplied by (a_mask > 0) first
+ * (ReLU backward with the saved layer output as mask).
+ * ---------------------------------------------------------------------- */
+size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K);
+int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, const float *B, int M, int N, int K,
+                     const float *bias, int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of
  * prod_knn_sample (Model.py:75-106), i.e. sklearn NearestNeighbors.kneighbors.
  * ---------------------------------------------------------------------- */

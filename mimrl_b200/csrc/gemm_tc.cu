@@ -1,0 +1,353 @@
+// fp32-class GEMM on tcgen05 for the critic / baseline / classifier MLPs
+// (reference VMI.py:13-22 `mlps`, Model.py:52-57): the three contractions of a
+// Linear layer's forward and backward, with bias + ReLU (forward) and the ReLU
+// mask (backward) fused in.
+//
+//   mode 0 (NT)  C[M,N] = A[M,K] . B[N,K]^T   Linear forward      y  = x W^T + b
+//   mode 1 (NN)  C[M,N] = A[M,K] . B[K,N]     input gradient      dx = dz W
+//   mode 2 (TN)  C[M,N] = A[K,M]^T . B[K,N]   weight gradient     dW = dz^T x   (split over K = batch rows)
+//
+// Same arithmetic as the score sweeps (sep_tc.cu): each fp32 operand is scaled
+// by a per-tensor power of two and split into fp16 hi + lo; every product runs
+// hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM.  Operands keep their
+// natural row-major layout: a matrix whose contraction index is the slow one is
+// read as an MN-major UMMA operand, so no transposed copies are made.
+// CTA: warp 0 TMA producer (3-stage ring of 64 KB), warp 1 MMA issuer, warps 2-5
+// epilogue (thread = output row).
+#include "tc_common.cuh"
+
+namespace mimrl {
+namespace {
+
+constexpr int kGemmThreads = 192;
+constexpr int kGStages = 3;
+constexpr uint32_t kOp16 = 16384;                 // one operand half (hi or lo) of a stage: 16 KB
+constexpr uint32_t kGStage = 4 * kOp16;           // A hi, A lo, B hi, B lo
+constexpr uint32_t kGemmSmem = kGStages * kGStage + 512 + 1024;
+
+// absmax[0] = max |A (masked)|, absmax[1] = max |B|
+__global__ void gemm_absmax_kernel(const float *__restrict__ a, const float *__restrict__ mask, size_t na,
+                                   const float *__restrict__ b, size_t nb, unsigned *__restrict__ out) {
+  const bool second = blockIdx.y == 1;
+  const float *src = second ? b : a;
+  const size_t n = second ? nb : na;
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = src[i];
+    if (!second && mask && !(mask[i] > 0.f)) v = 0.f;
+    m = fmaxf(m, fabsf(v));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out + blockIdx.y, __float_as_uint(m));
+}
+
+// src [rows, cols] fp32 (optionally masked) -> hi, lo [rows, ld] fp16, zero padded, scaled by 2^k
+__global__ void gemm_split_kernel(const float *__restrict__ src, const float *__restrict__ mask, int rows, int cols,
+                                  int ld, const unsigned *__restrict__ absmax, int which, __half *__restrict__ hi,
+                                  __half *__restrict__ lo) {
+  const float sc = scale_from_absmax(absmax[which]);
+  const int half_ld = ld >> 1;
+  const size_t total = (size_t)rows * half_ld;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / half_ld;
+    const int c = (int)(idx - r * half_ld) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < cols) {
+      v0 = src[r * cols + c];
+      if (mask && !(mask[r * cols + c] > 0.f)) v0 = 0.f;
+    }
+    if (c + 1 < cols) {
+      v1 = src[r * cols + c + 1];
+      if (mask && !(mask[r * cols + c + 1] > 0.f)) v1 = 0.f;
+    }
+    v0 *= sc, v1 *= sc;
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<__half2 *>(hi + r * ld + c) = h;
+    *reinterpret_cast<__half2 *>(lo + r * ld + c) = l;
+  }
+}
+
+struct GemmParams {
+  int M, N, K, kblocks_per_split, relu;
+  const unsigned *absmax;
+  const float *bias;
+  float *C;       // [M, N] when splits == 1, else partials [splits][M][N]
+};
+
+// A_MN / B_MN: operand stored with the contraction index as the SLOW one (read MN-major)
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  const uint32_t bars = base + kGStages * kGStage;
+  const uint32_t bFull = bars, bEmpty = bars + 32, bDone = bars + 64;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kGStages * kGStage + 128);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128, split = blockIdx.z;
+  const int n_kb = (p.K + 63) / 64;
+  const int kb0 = split * p.kblocks_per_split;
+  const int kb1 = min(n_kb, kb0 + p.kblocks_per_split);
+  const int T = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGStages; ++i) {
+      mbar_init(bFull + 8 * i, 1);
+      mbar_init(bEmpty + 8 * i, 1);
+    }
+    mbar_init(bDone, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + kGStages * kGStage + 128), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    if (leader) {
+      prefetch_tmap(&map_a_hi);
+      prefetch_tmap(&map_b_hi);
+      for (int i = 0; i < T; ++i) {
+        const int stage = i % kGStages, k0 = (kb0 + i) * 64;
+        mbar_wait(bEmpty + 8 * stage, ((i / kGStages) & 1) ^ 1);
+        const uint32_t fb = bFull + 8 * stage;
+        mbar_expect_tx(fb, kGStage);
+        const uint32_t dst = base + stage * kGStage;
+        if (A_MN) {   // rows = contraction index, 64 per box; two boxes cover 128 M
+          tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, m0, k0);
+          tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
+          tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
+          tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
+        } else {
+          tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, k0, m0);
+          tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, k0, m0);
+        }
+        if (B_MN) {
+          tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, n0, k0);
+          tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
+          tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, n0, k0);
+          tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
+        } else {
+          tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, k0, n0);
+          tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = instr_desc_f16(128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+    for (int i = 0; i < T; ++i) {
+      const int stage = i % kGStages;
+      mbar_wait(bFull + 8 * stage, (i / kGStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t s0 = base + stage * kGStage;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t a_base = s0 + (prod == 2 ? 1 : 0) * kOp16;          // A hi, hi, lo
+          const uint32_t b_base = s0 + (prod == 1 ? 3 : 2) * kOp16;          // B hi, lo, hi
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = A_MN ? smem_desc_sw128_mn(a_base + k * 2048, 8192, 1024) : smem_desc_sw128(a_base + k * 32);
+            const uint64_t bd = B_MN ? smem_desc_sw128_mn(b_base + k * 2048, 8192, 1024) : smem_desc_sw128(b_base + k * 32);
+            umma_f16(tmem_base, ad, bd, idesc, (i | prod | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(bEmpty + 8 * stage);
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(bDone);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int row = m0 + r;
+    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
+    float *out = p.C + ((size_t)split * p.M + row) * p.N;
+    const bool partial = gridDim.z > 1;
+    if (T > 0) {
+      mbar_wait(bDone, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v[32];
+      if (T > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (row >= p.M) continue;
+      const int c0 = n0 + ch * 32;
+      if (c0 >= p.N) continue;
+      if (c0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x = __uint_as_float(v[j + u]) * inv;
+            if (!partial) {
+              if (p.bias) x += __ldg(p.bias + c0 + j + u);
+              if (p.relu) x = fmaxf(x, 0.f);
+            }
+            o[u] = x;
+          }
+          *reinterpret_cast<float4 *>(out + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + j < p.N) {
+            float x = __uint_as_float(v[j]) * inv;
+            if (!partial) {
+              if (p.bias) x += __ldg(p.bias + c0 + j);
+              if (p.relu) x = fmaxf(x, 0.f);
+            }
+            out[c0 + j] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+__global__ void gemm_reduce_kernel(const float *__restrict__ part, int splits, size_t mn, float *__restrict__ C) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += part[(size_t)s * mn + i];
+    C[i] = a;
+  }
+}
+
+struct GemmLayout {
+  int a_rows, a_cols, b_rows, b_cols, lda, ldb, splits;
+  size_t off_absmax, off_a_hi, off_a_lo, off_b_hi, off_b_lo, off_part, total;
+};
+
+GemmLayout gemm_layout(int mode, int M, int N, int K) {
+  GemmLayout g;
+  // stored shapes of the operands (rows x cols, row-major)
+  g.a_rows = mode == 2 ? K : M;
+  g.a_cols = mode == 2 ? M : K;
+  g.b_rows = mode == 0 ? N : K;
+  g.b_cols = mode == 0 ? K : N;
+  g.lda = (g.a_cols + 63) & ~63;
+  g.ldb = (g.b_cols + 63) & ~63;
+  const int n_kb = (K + 63) / 64;
+  const int tiles = ceil_div(M, 128) * ceil_div(N, 128);
+  int splits = 1;
+  if (mode == 2) {   // few output tiles, long contraction: spread the k-blocks over the SMs
+    splits = ceil_div(2 * 148, tiles);
+    if (splits > n_kb) splits = n_kb;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    const int per = ceil_div(n_kb, splits);
+    splits = ceil_div(n_kb, per);
+  }
+  g.splits = splits;
+  size_t o = 0;
+  g.off_absmax = o, o += 256;
+  g.off_a_hi = o, o += align256((size_t)g.a_rows * g.lda * 2);
+  g.off_a_lo = o, o += align256((size_t)g.a_rows * g.lda * 2);
+  g.off_b_hi = o, o += align256((size_t)g.b_rows * g.ldb * 2);
+  g.off_b_lo = o, o += align256((size_t)g.b_rows * g.ldb * 2);
+  g.off_part = o, o += splits > 1 ? align256((size_t)splits * M * N * sizeof(float)) : 0;
+  g.total = o;
+  return g;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
+                const GemmParams &p, dim3 grid, cudaStream_t st) {
+  cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+  gemm_tc_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmem, st>>>(ah, al, bh, bl, p);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace
+}  // namespace mimrl
+
+using namespace mimrl;
+
+extern "C" size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K) {
+  if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0) return 0;
+  return gemm_layout(mode, M, N, K).total + 256;
+}
+
+extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, const float *B, int M, int N, int K,
+                                const float *bias, int relu, float *C, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+  MIMRL_REQUIRE(mode >= 0 && mode <= 2, "gemm_f32x3: unknown mode %d", mode);
+  MIMRL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f32x3: empty problem %dx%dx%d", M, N, K);
+  const GemmLayout g = gemm_layout(mode, M, N, K);
+  MIMRL_REQUIRE(workspace_bytes >= g.total, "gemm_f32x3: workspace too small");
+  MIMRL_REQUIRE(g.splits == 1 || (!bias && !relu), "gemm_f32x3: bias/relu are not available on the split-K (mode 2) path");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)workspace;
+  unsigned *absmax = reinterpret_cast<unsigned *>(ws + g.off_absmax);
+  __half *a_hi = reinterpret_cast<__half *>(ws + g.off_a_hi), *a_lo = reinterpret_cast<__half *>(ws + g.off_a_lo);
+  __half *b_hi = reinterpret_cast<__half *>(ws + g.off_b_hi), *b_lo = reinterpret_cast<__half *>(ws + g.off_b_lo);
+  cudaMemsetAsync(absmax, 0, 8, st);
+  const size_t na = (size_t)g.a_rows * g.a_cols, nb = (size_t)g.b_rows * g.b_cols;
+  int blocks = (int)(((na > nb ? na : nb) + 1023) / 1024);
+  blocks = blocks > 296 ? 296 : (blocks < 1 ? 1 : blocks);
+  gemm_absmax_kernel<<<dim3(blocks, 2), 256, 0, st>>>(A, a_mask, na, B, nb, absmax);
+  if (check_launch("gemm absmax")) return 1;
+  auto split = [&](const float *src, const float *mask, int rows, int cols, int ld, int which, __half *hi, __half *lo) {
+    const size_t total = (size_t)rows * (ld / 2);
+    int b = (int)((total + 255) / 256);
+    b = b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b);
+    gemm_split_kernel<<<b, 256, 0, st>>>(src, mask, rows, cols, ld, absmax, which, hi, lo);
+    return check_launch("gemm split");
+  };
+  if (split(A, a_mask, g.a_rows, g.a_cols, g.lda, 0, a_hi, a_lo)) return 1;
+  if (split(B, nullptr, g.b_rows, g.b_cols, g.ldb, 1, b_hi, b_lo)) return 1;
+  // tensor maps: K-major operand -> box [128 rows x 64 k]; MN-major operand -> box [64 k-rows x 64 mn]
+  const bool a_mn = mode == 2, b_mn = mode != 0;
+  CUtensorMap ah, al, bh, bl;
+  if (make_map(&ah, a_hi, g.a_cols, g.a_rows, g.lda, a_mn ? 64 : 128)) return 1;
+  if (make_map(&al, a_lo, g.a_cols, g.a_rows, g.lda, a_mn ? 64 : 128)) return 1;
+  if (make_map(&bh, b_hi, g.b_cols, g.b_rows, g.ldb, b_mn ? 64 : 128)) return 1;
+  if (make_map(&bl, b_lo, g.b_cols, g.b_rows, g.ldb, b_mn ? 64 : 128)) return 1;
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K;
+  p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.relu = relu;
+  p.absmax = absmax;
+  p.bias = bias;
+  p.C = g.splits > 1 ? reinterpret_cast<float *>(ws + g.off_part) : C;
+  dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
+  int rc;
+  if (mode == 0) rc = launch_gemm<false, false>(ah, al, bh, bl, p, grid, st);
+  else if (mode == 1) rc = launch_gemm<false, true>(ah, al, bh, bl, p, grid, st);
+  else rc = launch_gemm<true, true>(ah, al, bh, bl, p, grid, st);
+  if (rc) return rc;
+  if (g.splits > 1) {
+    const size_t mn = (size_t)M * N;
+    int b = (int)((mn + 255) / 256);
+    b = b > 148 * 8 ? 148 * 8 : b;
+    gemm_reduce_kernel<<<b, 256, 0, st>>>(p.C, g.splits, mn, C);
+    return check_launch("gemm reduce");
+  }
+  return 0;
+}

@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import rowblock as RB
+from .linear import mlp_apply
 from .vmi import (BaselineModel, CriticModel, _scores_bound, get_activation, interp_lower_bound, separable_bound)
 
 
@@ -162,7 +163,7 @@ class MLP_For_CMI(nn.Module):
         self.act_id = 0 if last_acticate == 'hardtanh' else 1
 
     def logits(self, features):
-        return self.mlp(features)
+        return mlp_apply(self.mlp, features)
 
     def forward(self, features):
         return self.final_activate(torch.clamp(self.mlp(features), -10, 10))

@@ -23,6 +23,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import rowblock as RB
+from .linear import mlp_apply
 
 _ACTIVATIONS = {  # Utils.py:70-82 get_activation
     "elu": nn.ELU, "gelu": nn.GELU, "hardshrink": nn.Hardshrink, "hardtanh": nn.Hardtanh,
@@ -292,7 +293,7 @@ class CriticModel(nn.Module):
         self.pair_chunk = 1 << 16          # pairs scored per step of the concat critic
 
     def embed(self, x, y):
-        return self.MLP_g(x), self.MLP_h(y)
+        return mlp_apply(self.MLP_g, x), mlp_apply(self.MLP_h, y)
 
     def _concat_rows(self, x_rows, y):
         """scores[i, :] = f([x_i, y_j]) for a block of rows, first layer factorised
@@ -340,7 +341,7 @@ class BaselineModel(nn.Module):
     def forward(self, y):
         n = y.shape[0]
         if self.baseline_type == 'unnormalized':
-            return self.MLP(y).reshape(n, 1)
+            return mlp_apply(self.MLP, y).reshape(n, 1)
         if self.baseline_type == 'constant':
             return torch.zeros(n, 1, device=y.device, dtype=y.dtype)
         if self.baseline_type == 'gaussain':
