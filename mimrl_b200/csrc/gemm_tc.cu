@@ -25,21 +25,44 @@ constexpr uint32_t kOp16 = 16384;                 // one operand half (hi or lo)
 constexpr uint32_t kGStage = 4 * kOp16;           // A hi, A lo, B hi, B lo
 constexpr uint32_t kGemmSmem = kGStages * kGStage + 512 + 1024;
 
-// absmax[0] = max |A (masked)|, absmax[1] = max |B|
-__global__ void gemm_absmax_kernel(const float *__restrict__ a, const float *__restrict__ mask, size_t na,
-                                   const float *__restrict__ b, size_t nb, unsigned *__restrict__ out) {
+// absmax[0] = max |A (masked)|, absmax[1] = max |B|.  float4 grid-stride loads, 4 independent chains per thread.
+__global__ void __launch_bounds__(256)
+gemm_absmax_kernel(const float *__restrict__ a, const float *__restrict__ mask, size_t na,
+                   const float *__restrict__ b, size_t nb, unsigned *__restrict__ out) {
   const bool second = blockIdx.y == 1;
   const float *src = second ? b : a;
+  const float *msk = second ? nullptr : mask;
   const size_t n = second ? nb : na;
-  float m = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float v = src[i];
-    if (!second && mask && !(mask[i] > 0.f)) v = 0.f;
-    m = fmaxf(m, fabsf(v));
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if ((((size_t)src | (size_t)msk) & 15) == 0) {
+    const size_t n4 = n >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    const float4 *k4 = reinterpret_cast<const float4 *>(msk);
+    for (size_t i = tid; i < n4; i += stride) {
+      float4 v = __ldg(s4 + i);
+      if (msk) {
+        const float4 k = __ldg(k4 + i);
+        v.x = k.x > 0.f ? v.x : 0.f, v.y = k.y > 0.f ? v.y : 0.f, v.z = k.z > 0.f ? v.z : 0.f, v.w = k.w > 0.f ? v.w : 0.f;
+      }
+      m0 = fmaxf(m0, fabsf(v.x)), m1 = fmaxf(m1, fabsf(v.y)), m2 = fmaxf(m2, fabsf(v.z)), m3 = fmaxf(m3, fabsf(v.w));
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) {
+      float v = src[i];
+      if (msk && !(msk[i] > 0.f)) v = 0.f;
+      m0 = fmaxf(m0, fabsf(v));
+    }
+  } else {
+    for (size_t i = tid; i < n; i += stride) {
+      float v = src[i];
+      if (msk && !(msk[i] > 0.f)) v = 0.f;
+      m0 = fmaxf(m0, fabsf(v));
+    }
   }
+  float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) atomicMax(out + blockIdx.y, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(m));
 }
 
 // src [rows, cols] fp32 (optionally masked) -> hi, lo [rows, ld] fp16, zero padded, scaled by 2^k
@@ -309,8 +332,8 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   __half *b_hi = reinterpret_cast<__half *>(ws + g.off_b_hi), *b_lo = reinterpret_cast<__half *>(ws + g.off_b_lo);
   cudaMemsetAsync(absmax, 0, 8, st);
   const size_t na = (size_t)g.a_rows * g.a_cols, nb = (size_t)g.b_rows * g.b_cols;
-  int blocks = (int)(((na > nb ? na : nb) + 1023) / 1024);
-  blocks = blocks > 296 ? 296 : (blocks < 1 ? 1 : blocks);
+  int blocks = (int)(((na > nb ? na : nb) + 4095) / 4096);
+  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
   gemm_absmax_kernel<<<dim3(blocks, 2), 256, 0, st>>>(A, a_mask, na, B, nb, absmax);
   if (check_launch("gemm absmax")) return 1;
   auto split = [&](const float *src, const float *mask, int rows, int cols, int ld, int which, __half *hi, __half *lo) {

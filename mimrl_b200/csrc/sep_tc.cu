@@ -32,17 +32,28 @@ namespace mimrl {
 namespace {
 
 // --------------------------------------------------------------- prepass ----
-// absmax[which] = max |v| over the tensor (float bits compare as unsigned for v >= 0)
-__global__ void absmax2_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
-                               unsigned *__restrict__ out) {
+// absmax[which] = max |v| over the tensor (float bits compare as unsigned for v >= 0); float4 grid-stride loads
+__global__ void __launch_bounds__(256)
+absmax2_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb, unsigned *__restrict__ out) {
   const float *src = blockIdx.y == 0 ? a : b;
   const size_t n = blockIdx.y == 0 ? na : nb;
-  float m = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(src[i]));
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (((size_t)src & 15) == 0) {
+    const size_t n4 = n >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 v = __ldg(s4 + i);
+      m0 = fmaxf(m0, fabsf(v.x)), m1 = fmaxf(m1, fabsf(v.y)), m2 = fmaxf(m2, fabsf(v.z)), m3 = fmaxf(m3, fabsf(v.w));
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) m0 = fmaxf(m0, fabsf(src[i]));
+  } else {
+    for (size_t i = tid; i < n; i += stride) m0 = fmaxf(m0, fabsf(src[i]));
+  }
+  float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) atomicMax(out + blockIdx.y, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(m));
 }
 
 // [n, embed] fp32 -> hi, lo [n, 128] fp16 (K padded with zeros), scaled by 2^k
@@ -599,8 +610,8 @@ int tc_prepass(const float *own, const float *all, int n_own, int n_all, int emb
   unsigned *absmax = reinterpret_cast<unsigned *>(ws + L.off_absmax);
   cudaMemsetAsync(absmax, 0, 8, st);
   const size_t na = (size_t)n_own * embed, nb = (size_t)n_all * embed;
-  int blocks = (int)(((na > nb ? na : nb) + 1023) / 1024);
-  blocks = blocks > 296 ? 296 : (blocks < 1 ? 1 : blocks);
+  int blocks = (int)(((na > nb ? na : nb) + 4095) / 4096);
+  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
   absmax2_kernel<<<dim3(blocks, 2), 256, 0, st>>>(own, na, all, nb, absmax);
   if (check_launch("tc absmax")) return 1;
   const size_t pairs = (size_t)(n_own > n_all ? n_own : n_all) * 64;

@@ -27,17 +27,17 @@ def test_modes_against_float64(M, N, K):
     bias = torch.randn(N, device="cuda", generator=g)
     want = A.double() @ Bt.double().t() + bias.double()
     got = _gemm(0, A, None, Bt, M, N, K, bias, False)
-    assert rel(got, want) < 2e-6
+    assert rel(got, want) < 1e-5
     got = _gemm(0, A, None, Bt, M, N, K, bias, True)
-    assert rel(got, want.clamp_min(0)) < 2e-6
+    assert rel(got, want.clamp_min(0)) < 1e-5
     Bn = Bt.t().contiguous()                                       # [K, N]
     mask = torch.randn(M, K, device="cuda", generator=g)
     want = (A.double() * (mask > 0)) @ Bn.double()
-    assert rel(_gemm(1, A, mask, Bn, M, N, K), want) < 2e-6
+    assert rel(_gemm(1, A, mask, Bn, M, N, K), want) < 1e-5
     At = torch.randn(K, M, device="cuda", generator=g)             # mode 2: contraction over the rows
     maskt = torch.randn(K, M, device="cuda", generator=g)
     want = (At.double() * (maskt > 0)).t() @ Bn.double()
-    assert rel(_gemm(2, At, maskt, Bn, M, N, K), want) < 2e-6
+    assert rel(_gemm(2, At, maskt, Bn, M, N, K), want) < 1e-5
 
 
 def test_mode2_long_contraction_split_k():
@@ -47,7 +47,7 @@ def test_mode2_long_contraction_split_k():
     At = torch.randn(K, M, device="cuda", generator=g)
     Bn = torch.randn(K, N, device="cuda", generator=g)
     want = At.double().t() @ Bn.double()
-    assert rel(_gemm(2, At, None, Bn, M, N, K), want) < 2e-6
+    assert rel(_gemm(2, At, None, Bn, M, N, K), want) < 2e-5
 
 
 @pytest.mark.parametrize("rows", [512, 3000])
