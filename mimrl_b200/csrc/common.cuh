@@ -64,6 +64,21 @@ __device__ __forceinline__ void lse_merge_d(double &m, double &s, double m2, dou
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// k-NN candidate (fp32 filter distance, key index) and the tensor-core filter stage (knn_tc.cu)
+struct KnnCand {
+  float d;
+  int idx;
+};
+struct KnnTcPlan {
+  int splits, tiles_per_split, n_lists, list_len;
+  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, bytes;
+};
+bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len);
+KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len);
+// per query and list: list_len candidates sorted by (d, idx), padded with (+inf, -1); lists = splits * 2
+int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
+                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st);
+
 // Partial-statistics layout shared by every score sweep (FFMA and tcgen05):
 // part[(split * n_own + row) * 3 + {0,1,2}] = {max, sum, softplus-sum}
 int combine_row_stats(const float *part, int n_splits, int n_own, float *row_max, float *row_sum, float *row_sp,

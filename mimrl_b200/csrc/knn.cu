@@ -11,6 +11,8 @@
 //      survivors in float64 with scikit-learn's formula, order by
 //      (distance, index) and emit the k nearest (ties -> lowest index).
 // Excluded keys (the rows drawn as queries, Model.py:83-84) get norm = +inf.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mimrl {
@@ -25,10 +27,7 @@ constexpr int kThreads = 256;
 constexpr int kMaxList = 64;   // K' upper bound
 constexpr int kSlack = 16;
 
-struct Cand {
-  float d;
-  int idx;
-};
+using Cand = KnnCand;
 
 __device__ __forceinline__ bool cand_less(float d1, int i1, float d2, int i2) {
   return d1 < d2 || (d1 == d2 && i1 < i2);
@@ -197,32 +196,48 @@ knn_filter_kernel(const float *__restrict__ keys, const float *__restrict__ kn, 
   }
 }
 
-// one CTA (128 threads) per query
+// one CTA (128 threads) per query.  cand holds n_lists sorted lists of list_len candidates for this query.
 __global__ void __launch_bounds__(128)
 knn_rerank_kernel(const float *__restrict__ keys, int n_keys, int width, int64_t key_offset,
-                  const float *__restrict__ queries, int n_queries, const Cand *__restrict__ cand, int n_cand,
+                  const float *__restrict__ queries, int n_queries, const Cand *__restrict__ cand, int n_lists,
                   int list_len, int k, int exact_form, int64_t *__restrict__ nbr_orig,
                   double *__restrict__ nbr_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_cand = n_lists * list_len;
   Cand *cs = reinterpret_cast<Cand *>(smem_raw);                   // [n_cand]
   int *sel = reinterpret_cast<int *>(cs + n_cand);                 // [list_len]
   double *dd = reinterpret_cast<double *>(sel + ((list_len + 1) & ~1));  // [list_len]
+  __shared__ float w_d[4];
+  __shared__ int w_i[4], w_t[4];
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < n_cand; i += blockDim.x) cs[i] = cand[(size_t)q * n_cand + i];
-  for (int i = tid; i < list_len; i += blockDim.x) sel[i] = -1;
   __syncthreads();
-  // 1. top list_len by (fp32 distance, index): rank by counting
-  for (int i = tid; i < n_cand; i += blockDim.x) {
-    const Cand x = cs[i];
-    if (x.idx < 0) continue;
-    int rank = 0;
-    for (int j = 0; j < n_cand; ++j) {
-      const Cand y = cs[j];
-      rank += (y.idx >= 0 && cand_less(y.d, y.idx, x.d, x.idx)) ? 1 : 0;
+  // 1. the list_len best by (fp32 distance, index): multi-way merge, thread t walks list t
+  int head = 0;
+  for (int it = 0; it < list_len; ++it) {
+    float d = INFINITY;
+    int idx = -1, t = tid;
+    if (tid < n_lists && head < list_len) {
+      const Cand c = cs[tid * list_len + head];
+      if (c.idx >= 0) d = c.d, idx = c.idx;
     }
-    if (rank < list_len) sel[rank] = x.idx;
+    if (idx < 0) idx = 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float d2 = __shfl_xor_sync(0xffffffffu, d, off);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, off), t2 = __shfl_xor_sync(0xffffffffu, t, off);
+      if (cand_less(d2, i2, d, idx)) d = d2, idx = i2, t = t2;
+    }
+    if (lane == 0) w_d[warp] = d, w_i[warp] = idx, w_t[warp] = t;
+    __syncthreads();
+    d = w_d[0], idx = w_i[0], t = w_t[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+      if (cand_less(w_d[w], w_i[w], d, idx)) d = w_d[w], idx = w_i[w], t = w_t[w];
+    if (tid == 0) sel[it] = idx == 0x7fffffff ? -1 : idx;
+    if (tid == t && idx != 0x7fffffff) ++head;
+    __syncthreads();
   }
-  __syncthreads();
   // 2. float64 distances of the survivors, one warp per candidate
   const float *qr = queries + (size_t)q * width;
   for (int c = warp; c < list_len; c += 4) {
@@ -297,30 +312,38 @@ __global__ void compact_index_kernel(const int64_t *__restrict__ nbr_orig, size_
 }
 
 struct Plan {
-  int list_len, splits, tiles_per_split, n_cand;
-  size_t off_kn, off_q, off_cand, total;
+  int list_len, splits, tiles_per_split, n_lists;
+  bool use_tc;
+  KnnTcPlan tc;
+  size_t off_kn, off_q, off_cand, off_tc, total;
 };
 
 Plan make_plan(int n_keys, int n_queries, int width, int k) {
   Plan p;
   p.list_len = k + kSlack;
   if (p.list_len > kMaxList) p.list_len = kMaxList;
+  p.use_tc = knn_tc_supported(n_keys, n_queries, width, p.list_len) && !getenv("MIMRL_KNN_FFMA");
   const int q_tiles = ceil_div(n_queries, kQT), k_tiles = ceil_div(n_keys, kKT);
   int splits = ceil_div(2 * 148, q_tiles);
-  const int max_by_cand = 512 / p.list_len > 1 ? 512 / p.list_len : 1;
-  if (splits > max_by_cand) splits = max_by_cand;
+  if (splits > 32) splits = 32;
   if (splits > k_tiles) splits = k_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = ceil_div(k_tiles, splits);
   p.splits = ceil_div(k_tiles, p.tiles_per_split);
-  p.n_cand = p.splits * p.list_len;
+  p.n_lists = p.splits;
+  if (p.use_tc) {
+    p.tc = knn_tc_plan(n_keys, n_queries, width, p.list_len);
+    p.n_lists = p.tc.n_lists;
+  }
   size_t o = 0;
   p.off_kn = o;
   o += ((size_t)n_keys * sizeof(float) + 255) & ~(size_t)255;
   p.off_q = o;
   o += ((size_t)n_queries * width * sizeof(float) + 255) & ~(size_t)255;
   p.off_cand = o;
-  o += ((size_t)n_queries * p.n_cand * sizeof(Cand) + 255) & ~(size_t)255;
+  o += ((size_t)n_queries * p.n_lists * p.list_len * sizeof(Cand) + 255) & ~(size_t)255;
+  p.off_tc = o;
+  o += p.use_tc ? p.tc.bytes : 0;
   p.total = o;
   return p;
 }
@@ -339,14 +362,19 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
     mark_excluded_kernel<<<ceil_div(n_excluded, 256), 256, 0, st>>>(excluded, n_excluded, key_offset, n_keys, kn);
     if (check_launch("knn mark_excluded")) return 1;
   }
-  cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem);
-  dim3 grid(ceil_div(n_queries, kQT), p.splits);
-  knn_filter_kernel<<<grid, kThreads, kFilterSmem, st>>>(keys, kn, n_keys, width, queries, n_queries, p.list_len,
-                                                        p.tiles_per_split, cand);
-  if (check_launch("knn_filter")) return 1;
-  const size_t rsmem = (size_t)p.n_cand * sizeof(Cand) + (size_t)((p.list_len + 1) & ~1) * 4 + (size_t)p.list_len * 8;
+  if (p.use_tc) {
+    if (knn_filter_tc(keys, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st)) return 1;
+  } else {
+    cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem);
+    dim3 grid(ceil_div(n_queries, kQT), p.splits);
+    knn_filter_kernel<<<grid, kThreads, kFilterSmem, st>>>(keys, kn, n_keys, width, queries, n_queries, p.list_len,
+                                                          p.tiles_per_split, cand);
+    if (check_launch("knn_filter")) return 1;
+  }
+  const size_t rsmem = (size_t)p.n_lists * p.list_len * sizeof(Cand) + (size_t)((p.list_len + 1) & ~1) * 4 +
+                       (size_t)p.list_len * 8;
   cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-  knn_rerank_kernel<<<n_queries, 128, rsmem, st>>>(keys, n_keys, width, key_offset, queries, n_queries, cand, p.n_cand,
+  knn_rerank_kernel<<<n_queries, 128, rsmem, st>>>(keys, n_keys, width, key_offset, queries, n_queries, cand, p.n_lists,
                                                   p.list_len, k, exact_form, nbr_orig, nbr_dist);
   return check_launch("knn_rerank");
 }

@@ -1,0 +1,338 @@
+// Tensor-core distance filter of the k-NN sampler (first stage of mimrl_knn_search,
+// reference Model.py:82-86): d(q, z) = |q|^2 + |z|^2 - 2 q.z with the q.z tile on
+// tcgen05 (fp16 hi/lo split, three products -> fp32-class), 128 queries parked in
+// TMEM per CTA, keys streamed by TMA through a 4-deep ring, and the selection fused
+// into the epilogue: one thread per query row compares the 128 distances of a tile
+// against its current K'-th best and inserts the rare survivors into a sorted list
+// in shared memory.  The m x N distance matrix is never written.  Exactness comes
+// from the float64 re-rank stage (knn.cu), which only needs the true neighbours to
+// be inside the K' = k + 16 candidates kept here.
+#include "tc_common.cuh"
+
+namespace mimrl {
+namespace {
+
+constexpr int kKnnThreads = 320;
+constexpr int kKnnStages = 4;
+constexpr uint32_t kKUnit = 32768;
+constexpr uint32_t kKTile16 = 128 * 128;
+constexpr int kListMax = 32;
+constexpr uint32_t kKnnSmem = kKnnStages * kKUnit + 1024 /*bars*/ + 2 * 128 * 4 /*key norms*/ +
+                              2 * 128 * kListMax * 8 /*lists*/ + 1024;
+
+__global__ void knn_absmax_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
+                                  unsigned *__restrict__ out) {
+  const float *src = blockIdx.y == 0 ? a : b;
+  const size_t n = blockIdx.y == 0 ? na : nb;
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(src + i)));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(m));
+}
+
+// [n, width] fp32 -> hi, lo [n, 128] fp16 (K zero-padded), scaled by 2^k
+__global__ void knn_split_kernel(const float *__restrict__ src, size_t n, int width, const unsigned *__restrict__ absmax,
+                                 int which, __half *__restrict__ hi, __half *__restrict__ lo) {
+  const float sc = scale_from_absmax(absmax[which]);
+  const size_t total = n * 64;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx >> 6;
+    const int e = (int)(idx & 63) * 2;
+    const float v0 = e < width ? __ldg(src + r * width + e) * sc : 0.f;
+    const float v1 = e + 1 < width ? __ldg(src + r * width + e + 1) * sc : 0.f;
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<__half2 *>(hi + r * 128 + e) = h;
+    *reinterpret_cast<__half2 *>(lo + r * 128 + e) = l;
+  }
+}
+
+__global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int width, float *__restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float *r = x + (size_t)w * width;
+  float acc = 0.f;
+  for (int e = lane; e < width; e += 32) acc = fmaf(r[e], r[e], acc);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[w] = acc;
+}
+
+struct KnnTcParams {
+  int n_keys, n_queries, tiles_per_split, list_len, n_lists;
+  const unsigned *absmax;          // [0] queries, [1] keys
+  const __half *q_hi, *q_lo;
+  const float *qn, *kn;
+  KnnCand *cand;
+};
+
+// keep `lst[0..len)` sorted ascending by (d, idx), capacity cap; returns the new threshold
+__device__ __noinline__ void knn_insert(KnnCand *lst, int &len, int cap, float &tau_d, int &tau_i, float d, int idx) {
+  int n = len;
+  if (n == cap) {
+    if (!(d < lst[n - 1].d || (d == lst[n - 1].d && idx < lst[n - 1].idx))) return;
+    --n;
+  }
+  int p = n;
+  while (p > 0 && (d < lst[p - 1].d || (d == lst[p - 1].d && idx < lst[p - 1].idx))) {
+    lst[p] = lst[p - 1];
+    --p;
+  }
+  lst[p] = KnnCand{d, idx};
+  len = n + 1;
+  if (len == cap) {
+    tau_d = lst[cap - 1].d;
+    tau_i = lst[cap - 1].idx;
+  }
+}
+
+__global__ void __launch_bounds__(kKnnThreads, 1)
+knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+                     const KnnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  const uint32_t bars = base + kKnnStages * kKUnit;
+  const uint32_t bFull = bars, bEmpty = bars + 64, bTFull = bars + 128, bTEmpty = bars + 144;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kKnnStages * kKUnit + 256);
+  float *knbuf = reinterpret_cast<float *>(gen + kKnnStages * kKUnit + 1024);                 // [2][128]
+  KnnCand *lists = reinterpret_cast<KnnCand *>(gen + kKnnStages * kKUnit + 1024 + 1024);      // [2][128][kListMax]
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128;
+  const int split = blockIdx.y;
+  const int n_tiles = (p.n_keys + 127) / 128;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(n_tiles, t0 + p.tiles_per_split);
+  const int T = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kKnnStages; ++i) {
+      mbar_init(bFull + 8 * i, 1);
+      mbar_init(bEmpty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + kKnnStages * kKUnit + 256), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // park the 128 query rows in TMEM columns [0,128): hi kb0, hi kb1, lo kb0, lo kb1 (one column = two K values)
+  if (warp >= 2 && warp < 6) {
+    const int r = (warp & 3) * 32 + lane;
+    const bool ok = row0 + r < p.n_queries;
+#pragma unroll 1
+    for (int part = 0; part < 4; ++part) {
+      const __half *src = (part < 2 ? p.q_hi : p.q_lo) + (size_t)(row0 + r) * 128 + (part & 1) * 64;
+      uint32_t v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = ok ? __ldg(reinterpret_cast<const uint4 *>(src) + j) : make_uint4(0, 0, 0, 0);
+        v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+      }
+      tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + part * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    if (leader) {
+      prefetch_tmap(&map_k_hi);
+      prefetch_tmap(&map_k_lo);
+      for (int u = 0; u < 2 * T; ++u) {
+        const int stage = u % kKnnStages;
+        const int col = (t0 + (u >> 1)) * 128;
+        mbar_wait(bEmpty + 8 * stage, ((u / kKnnStages) & 1) ^ 1);
+        mbar_expect_tx(bFull + 8 * stage, kKUnit);
+        const CUtensorMap *m = (u & 1) ? &map_k_lo : &map_k_hi;
+        tma_load_2d(base + stage * kKUnit, m, bFull + 8 * stage, 0, col);
+        tma_load_2d(base + stage * kKUnit + kKTile16, m, bFull + 8 * stage, 64, col);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = instr_desc_f16(128, 128);
+    for (int i = 0; i < T; ++i) {
+      const int buf = i & 1;
+      const uint32_t d = tmem_base + 128 + buf * 128;
+      mbar_wait(bTEmpty + 8 * buf, ((i >> 1) & 1) ^ 1);
+      int u = 2 * i, stage = u % kKnnStages;
+      mbar_wait(bFull + 8 * stage, (u / kKnnStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t b0 = base + stage * kKUnit;
+#pragma unroll
+        for (int a_sel = 0; a_sel < 4; a_sel += 2)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(d, tmem_base + (a_sel + kb) * 32 + k * 8, smem_desc_sw128(b0 + kb * kKTile16 + k * 32), idesc,
+                          (a_sel | kb | k) ? 1u : 0u);
+        umma_commit(bEmpty + 8 * stage);
+      }
+      __syncwarp();
+      u = 2 * i + 1, stage = u % kKnnStages;
+      mbar_wait(bFull + 8 * stage, (u / kKnnStages) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t b0 = base + stage * kKUnit;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(d, tmem_base + kb * 32 + k * 8, smem_desc_sw128(b0 + kb * kKTile16 + k * 32), idesc, 1u);
+        umma_commit(bEmpty + 8 * stage);
+        umma_commit(bTFull + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int wg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool row_ok = row0 + r < p.n_queries;
+    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
+    const float m2inv = -2.f * inv;
+    const float qn = row_ok ? p.qn[row0 + r] : 0.f;
+    KnnCand *lst = lists + (size_t)(wg * 128 + r) * kListMax;
+    float *kn_s = knbuf + wg * 128;
+    int len = 0, tau_i = 0x7fffffff;
+    float tau_d = INFINITY;
+    const int buf = wg;
+    float kn_next = INFINITY;
+    if (wg < T) {
+      const int gk = (t0 + wg) * 128 + r;
+      kn_next = gk < p.n_keys ? __ldg(p.kn + gk) : INFINITY;
+    }
+    for (int i = wg; i < T; i += 2) {
+      const int col0 = (t0 + i) * 128;
+      // stage |z|^2 of this tile's 128 keys (+inf = excluded / out of range); prefetch the next tile's
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");      // previous tile's readers are done
+      kn_s[r] = kn_next;
+      if (i + 2 < T) {
+        const int gk = col0 + 256 + r;
+        kn_next = gk < p.n_keys ? __ldg(p.kn + gk) : INFINITY;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+      mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + buf * 128 + ch * 32, v);
+        tmem_ld_wait();
+        const float4 *k4 = reinterpret_cast<const float4 *>(kn_s + ch * 32);
+        float dmin = INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 kk = k4[j >> 2];
+          const float d0 = fmaxf(fmaf(__uint_as_float(v[j]), m2inv, qn + kk.x), 0.f);
+          const float d1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), m2inv, qn + kk.y), 0.f);
+          const float d2 = fmaxf(fmaf(__uint_as_float(v[j + 2]), m2inv, qn + kk.z), 0.f);
+          const float d3 = fmaxf(fmaf(__uint_as_float(v[j + 3]), m2inv, qn + kk.w), 0.f);
+          v[j] = __float_as_uint(d0), v[j + 1] = __float_as_uint(d1), v[j + 2] = __float_as_uint(d2),
+          v[j + 3] = __float_as_uint(d3);
+          dmin = fminf(dmin, fminf(fminf(d0, d1), fminf(d2, d3)));
+        }
+        if (row_ok && dmin <= tau_d) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dj = __uint_as_float(v[j]);
+            if (dj <= tau_d && dj < INFINITY) knn_insert(lst, len, p.list_len, tau_d, tau_i, dj, col0 + ch * 32 + j);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
+    }
+    if (row_ok) {
+      KnnCand *o = p.cand + ((size_t)(row0 + r) * p.n_lists + (split * 2 + wg)) * p.list_len;
+      for (int u = 0; u < p.list_len; ++u) o[u] = u < len ? lst[u] : KnnCand{INFINITY, -1};
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len) {
+  return width <= 128 && list_len <= kListMax && n_keys >= 2048 && n_queries >= 1;
+}
+
+KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
+  (void)width;
+  KnnTcPlan p;
+  p.list_len = list_len;
+  const int q_tiles = ceil_div(n_queries, 128), k_tiles = ceil_div(n_keys, 128);
+  int splits = ceil_div(148, q_tiles);
+  if (splits > 64) splits = 64;                  // n_lists = 2 * splits <= 128 (one merge thread per list)
+  if (splits > k_tiles) splits = k_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = ceil_div(k_tiles, splits);
+  p.splits = ceil_div(k_tiles, p.tiles_per_split);
+  p.n_lists = 2 * p.splits;
+  size_t o = 0;
+  p.off_absmax = o, o += 256;
+  p.off_qn = o, o += align256((size_t)n_queries * 4);
+  p.off_q_hi = o, o += align256((size_t)n_queries * 128 * 2);
+  p.off_q_lo = o, o += align256((size_t)n_queries * 128 * 2);
+  p.off_k_hi = o, o += align256((size_t)n_keys * 128 * 2);
+  p.off_k_lo = o, o += align256((size_t)n_keys * 128 * 2);
+  p.bytes = o;
+  return p;
+}
+
+int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
+                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st) {
+  unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
+  float *qn = reinterpret_cast<float *>(ws + plan.off_qn);
+  __half *q_hi = reinterpret_cast<__half *>(ws + plan.off_q_hi), *q_lo = reinterpret_cast<__half *>(ws + plan.off_q_lo);
+  __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
+  cudaMemsetAsync(absmax, 0, 8, st);
+  const size_t nq = (size_t)n_queries * width, nk = (size_t)n_keys * width;
+  int blocks = (int)((nk + 2047) / 2048);
+  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
+  knn_absmax_kernel<<<dim3(blocks, 2), 256, 0, st>>>(queries, nq, keys, nk, absmax);
+  if (check_launch("knn absmax")) return 1;
+  knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
+  if (check_launch("knn split q")) return 1;
+  blocks = (int)(((size_t)n_keys * 64 + 255) / 256);
+  blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+  knn_split_kernel<<<blocks, 256, 0, st>>>(keys, n_keys, width, absmax, 1, k_hi, k_lo);
+  if (check_launch("knn split k")) return 1;
+  knn_row_norms_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(queries, n_queries, width, qn);
+  if (check_launch("knn query norms")) return 1;
+  CUtensorMap mh, ml;
+  if (make_map(&mh, k_hi, 128, n_keys, 128, 128)) return 1;
+  if (make_map(&ml, k_lo, 128, n_keys, 128, 128)) return 1;
+  KnnTcParams p;
+  p.n_keys = n_keys, p.n_queries = n_queries, p.tiles_per_split = plan.tiles_per_split, p.list_len = plan.list_len;
+  p.n_lists = plan.n_lists;
+  p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
+  cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
+  dim3 grid(ceil_div(n_queries, 128), plan.splits);
+  knn_filter_tc_kernel<<<grid, kKnnThreads, kKnnSmem, st>>>(mh, ml, p);
+  return check_launch("knn_filter_tc");
+}
+
+}  // namespace mimrl

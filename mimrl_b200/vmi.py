@@ -303,7 +303,7 @@ class CriticModel(nn.Module):
         u = F.linear(x_rows, first.weight[:, :dx], first.bias)
         v = F.linear(y, first.weight[:, dx:])
         h = (u[:, None, :] + v[None, :, :]).reshape(-1, u.shape[1])
-        h = self.MLP_f[1:](h)
+        h = mlp_apply(self.MLP_f[1:], h)          # activation of layer 1, then the hidden layers on the tensor cores
         return h.reshape(x_rows.shape[0], y.shape[0])
 
     def forward(self, x, y):

@@ -1,0 +1,75 @@
+"""Component timings at the BASELINE.json config sizes (CUDA events, median of 5 after 2 warm-ups).
+Writes one JSON line per component; not the headline bench (that is bench.py)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+torch.backends.cuda.matmul.allow_tf32 = False
+from mimrl_b200 import _lib as L
+from mimrl_b200.model import VMIEstimator, VCMIEstimator, knn_search, prod_knn_sample
+from mimrl_b200.mlp_process import MLPEncoder
+dev = torch.device("cuda:0")
+which = sys.argv[1:] or ["knn", "cubemlp", "vcmi", "concat", "sep_small"]
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+def out(**kw): print(json.dumps(kw), flush=True)
+
+if "knn" in which:      # config 4: 1M x 128 keys, batch 8192, k = 2..16
+    N = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Z = torch.randn(N, 128, device=dev, generator=g)
+    for k in (2, 16):
+        m = 8192 // k
+        ids = torch.randperm(N, device=dev, generator=g)[:m]
+        ms = timeit(lambda: knn_search(Z, ids, k), reps=3, warm=1)
+        out(component="knn_search", N=N, width=128, queries=m, k=k, ms=ms, gflops=2 * 128 * m * N / ms / 1e6,
+            key_gbs=4 * 128 * N / ms / 1e6)
+    Zl = torch.randn(N, 1, device=dev, generator=g)
+    ids = torch.randperm(N, device=dev, generator=g)[:4096]
+    out(component="knn_search_labels", N=N, width=1, queries=4096, k=2, ms=timeit(lambda: knn_search(Zl, ids, 2), 3, 1))
+
+if "cubemlp" in which:  # config 5: [1024, 100, 3, 128] -> 50-3-128 -> 10-3-128
+    enc = MLPEncoder("gelu", [100, 3, 128], [[50, 3, 128], [10, 3, 128]], [[50, 3, 128], [10, 3, 128]], [0.0] * 3, True,
+                     False, [True, True]).to(dev)
+    for bs in (128, 1024):
+        x = torch.randn(bs, 100, 3, 128, device=dev, requires_grad=True)
+        with torch.no_grad():
+            fwd = timeit(lambda: enc(x))
+        def fb():
+            x.grad = None
+            enc(x).sum().backward()
+        both = timeit(fb)
+        out(component="cubemlp", bs=bs, fwd_ms=fwd, fwd_bwd_ms=both, fwd_gbs=(bs * 100 * 384 * 4 * 1.0 + bs * 50 * 384 * 4 * 2 + bs * 10 * 384 * 4) / fwd / 1e6)
+
+if "vcmi" in which:
+    est = VCMIEstimator(128, 256, 2, "relu", 2, 1.0, "hardtanh").to(dev)
+    for bs in (128, 1024, 8192):
+        ins = [torch.randn(bs, 128, device=dev, requires_grad=True) for _ in range(6)]
+        def fb():
+            c, l = est(*ins); (c + l).backward()
+        out(component="vcmi_fwd_bwd", bs=bs, ms=timeit(fb))
+
+if "concat" in which:   # config 3 at sizes that fit one GPU quickly
+    for bound in ("nwj", "js"):
+        est = VMIEstimator("concat", "constant", bound, 128, 256, 128, 2, "relu", 0, 1).to(dev)
+        for B in (512, 2048):
+            x = torch.randn(B, 128, device=dev, requires_grad=True); y = torch.randn(B, 128, device=dev, requires_grad=True)
+            def fb():
+                mi, loss = est(x, y); loss.backward()
+            ms = timeit(fb, reps=3, warm=1)
+            out(component="concat_fwd_bwd", bound=bound, B=B, ms=ms, pairs_per_s=B * B / ms * 1e3)
+
+if "sep_small" in which:  # config 2 sweep
+    est = VMIEstimator("separate", "constant", "infonce", 128, 256, 128, 2, "relu", 0, 1).to(dev)
+    for B in (128, 512, 2048, 8192, 32768):
+        x = torch.randn(B, 128, device=dev, requires_grad=True); y = torch.randn(B, 128, device=dev, requires_grad=True)
+        def fb():
+            mi, loss = est(x, y); loss.backward()
+        ms = timeit(fb)
+        out(component="sep_infonce_fwd_bwd", B=B, ms=ms, pairs_per_s=B * B / ms * 1e3)
