@@ -62,7 +62,9 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int width, con
   }
 }
 
-// grid: (query tiles, key splits)
+// grid: (query tiles, key splits).  DIRECT: accumulate (q - z)^2 instead of q.z -- for narrow keys (the label
+// pools, width 1) neighbours are so close that the GEMM form |q|^2 + |z|^2 - 2 q.z cancels to noise in fp32.
+template <bool DIRECT>
 __global__ void __launch_bounds__(kThreads)
 knn_filter_kernel(const float *__restrict__ keys, const float *__restrict__ kn, int n_keys, int width,
                   const float *__restrict__ queries, int n_queries, int list_len, int tiles_per_split,
@@ -133,7 +135,14 @@ knn_filter_kernel(const float *__restrict__ keys, const float *__restrict__ kn, 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) {
+            if (DIRECT) {
+              const float df = av[i] - bv[j];
+              acc[i][j] = fmaf(df, df, acc[i][j]);
+            } else {
+              acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+          }
       }
     }
     // threshold test: rows ty*4+i, keys tx*4+j (j<4) and 64+tx*4+j-4
@@ -146,7 +155,7 @@ knn_filter_kernel(const float *__restrict__ keys, const float *__restrict__ kn, 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int ql = ty * 4 + i;
-        const float d = fmaxf(qn[ql] + knv - 2.f * acc[i][j], 0.f);
+        const float d = DIRECT ? acc[i][j] : fmaxf(qn[ql] + knv - 2.f * acc[i][j], 0.f);
         if (d <= tau_d[ql] && knv < INFINITY && q0 + ql < n_queries) {
           const int pos = atomicAdd(&cnt[ql], 1);
           buf[ql * kKT + pos] = Cand{d, gk};
@@ -322,7 +331,8 @@ Plan make_plan(int n_keys, int n_queries, int width, int k) {
   Plan p;
   p.list_len = k + kSlack;
   if (p.list_len > kMaxList) p.list_len = kMaxList;
-  p.use_tc = knn_tc_supported(n_keys, n_queries, width, p.list_len) && !getenv("MIMRL_KNN_FFMA");
+  // narrow keys (sklearn's kd_tree range, width <= 15) take the direct-difference CUDA-core filter
+  p.use_tc = width > 15 && knn_tc_supported(n_keys, n_queries, width, p.list_len) && !getenv("MIMRL_KNN_FFMA");
   const int q_tiles = ceil_div(n_queries, kQT), k_tiles = ceil_div(n_keys, kKT);
   int splits = ceil_div(2 * 148, q_tiles);
   if (splits > 32) splits = 32;
@@ -365,10 +375,16 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
   if (p.use_tc) {
     if (knn_filter_tc(keys, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st)) return 1;
   } else {
-    cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem);
     dim3 grid(ceil_div(n_queries, kQT), p.splits);
-    knn_filter_kernel<<<grid, kThreads, kFilterSmem, st>>>(keys, kn, n_keys, width, queries, n_queries, p.list_len,
-                                                          p.tiles_per_split, cand);
+    if (width <= 15) {
+      cudaFuncSetAttribute(knn_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem);
+      knn_filter_kernel<true><<<grid, kThreads, kFilterSmem, st>>>(keys, kn, n_keys, width, queries, n_queries,
+                                                                  p.list_len, p.tiles_per_split, cand);
+    } else {
+      cudaFuncSetAttribute(knn_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem);
+      knn_filter_kernel<false><<<grid, kThreads, kFilterSmem, st>>>(keys, kn, n_keys, width, queries, n_queries,
+                                                                   p.list_len, p.tiles_per_split, cand);
+    }
     if (check_launch("knn_filter")) return 1;
   }
   const size_t rsmem = (size_t)p.n_lists * p.list_len * sizeof(Cand) + (size_t)((p.list_len + 1) & ~1) * 4 +

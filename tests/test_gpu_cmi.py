@@ -63,7 +63,8 @@ def test_sampler_matches_reference_golden(case):
 
 
 @pytest.mark.parametrize("N,width,m,k", [(20000, 128, 300, 2), (20000, 128, 70, 16), (50000, 1, 257, 4),
-                                         (3000, 8, 64, 3), (5000, 16, 100, 32), (130, 128, 64, 2)])
+                                         (3000, 8, 64, 3), (5000, 16, 100, 32), (130, 128, 64, 2),
+                                         (400000, 1, 300, 2), (300000, 128, 200, 4), (100000, 40, 129, 8)])
 def test_knn_indices_vs_float64_oracle(N, width, m, k):
     from mimrl_b200.model import knn_search, sklearn_route
     Z = P.features(N + width, N, width)
