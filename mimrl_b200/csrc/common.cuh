@@ -71,7 +71,7 @@ struct KnnCand {
 };
 struct KnnTcPlan {
   int splits, tiles_per_split, n_lists, list_len;
-  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, bytes;
+  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, off_pub, bytes;
 };
 bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len);
 KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len);

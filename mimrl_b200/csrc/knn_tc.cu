@@ -62,7 +62,8 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
 }
 
 struct KnnTcParams {
-  int n_keys, n_queries, tiles_per_split, list_len, n_lists;
+  int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth;
+  float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
   const unsigned *absmax;          // [0] queries, [1] keys
   const __half *q_hi, *q_lo;
   const float *qn, *kn;
@@ -214,7 +215,14 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
     KnnCand *lst = lists + (size_t)(wg * 128 + r) * kListMax;
     float *kn_s = knbuf + wg * 128;
     int len = 0, tau_i = 0x7fffffff;
-    float tau_d = INFINITY;
+    float tau_d = INFINITY;          // effective threshold = min(local K'-th best, shared bound)
+    float tau_local = INFINITY, tau_shared = INFINITY, published = INFINITY;
+    // Shared bound across the key splits of this query: every part publishes the jth-smallest distance it has seen,
+    // jth = ceil(K' / parts).  If every part holds >= jth keys within t = max over parts, the union holds >= K'
+    // keys within t, so nothing beyond t can be among the K' best: the splits tighten each other's thresholds as
+    // if they were one sweep, and the (warp-divergent) insertion path stays rare.
+    const int part = split * 2 + wg;
+    float *pub_row = p.pub + (size_t)(row0 + r) * p.n_lists;
     const int buf = wg;
     float kn_next = INFINITY;
     if (wg < T) {
@@ -255,13 +263,31 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float dj = __uint_as_float(v[j]);
-            if (dj <= tau_d && dj < INFINITY) knn_insert(lst, len, p.list_len, tau_d, tau_i, dj, col0 + ch * 32 + j);
+            if (dj <= tau_d && dj < INFINITY) {
+              knn_insert(lst, len, p.list_len, tau_local, tau_i, dj, col0 + ch * 32 + j);
+              tau_d = fminf(tau_local, tau_shared);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
+      if (row_ok) {
+        if (len >= p.jth) {
+          const float mine = lst[p.jth - 1].d;
+          if (mine < published) {
+            published = mine;
+            __stcg(pub_row + part, mine);
+          }
+        }
+        if (((i >> 1) & 3) == 3) {           // every 4th tile of this warpgroup: refresh the shared bound
+          float t = 0.f;
+          for (int pp = 0; pp < p.n_lists; ++pp) t = fmaxf(t, __ldcg(pub_row + pp));
+          tau_shared = fminf(tau_shared, t);
+          tau_d = fminf(tau_local, tau_shared);
+        }
+      }
     }
     if (row_ok) {
       KnnCand *o = p.cand + ((size_t)(row0 + r) * p.n_lists + (split * 2 + wg)) * p.list_len;
@@ -284,10 +310,15 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   KnnTcPlan p;
   p.list_len = list_len;
   const int q_tiles = ceil_div(n_queries, 128), k_tiles = ceil_div(n_keys, 128);
-  int splits = ceil_div(148, q_tiles);
-  if (splits > 64) splits = 64;                  // n_lists = 2 * splits <= 128 (one merge thread per list)
-  if (splits > k_tiles) splits = k_tiles;
-  if (splits < 1) splits = 1;
+  // key splits: as few idle waves over the 148 SMs as possible (one CTA per SM); every split pays a warm-up of a few
+  // tiles while its candidate lists fill.  n_lists = 2 * splits <= 128 (one merge thread per list in the re-rank).
+  int splits = 1;
+  double best = 1e300;
+  for (int s = 1; s <= 64 && s <= k_tiles; ++s) {
+    const int per = ceil_div(k_tiles, s), eff = ceil_div(k_tiles, per);
+    const double cost = (double)ceil_div(q_tiles * eff, 148) * (per + 6.0);
+    if (cost < best - 1e-9) best = cost, splits = eff;
+  }
   p.tiles_per_split = ceil_div(k_tiles, splits);
   p.splits = ceil_div(k_tiles, p.tiles_per_split);
   p.n_lists = 2 * p.splits;
@@ -298,6 +329,7 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   p.off_q_lo = o, o += align256((size_t)n_queries * 128 * 2);
   p.off_k_hi = o, o += align256((size_t)n_keys * 128 * 2);
   p.off_k_lo = o, o += align256((size_t)n_keys * 128 * 2);
+  p.off_pub = o, o += align256((size_t)n_queries * p.n_lists * 4);
   p.bytes = o;
   return p;
 }
@@ -328,6 +360,9 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   KnnTcParams p;
   p.n_keys = n_keys, p.n_queries = n_queries, p.tiles_per_split = plan.tiles_per_split, p.list_len = plan.list_len;
   p.n_lists = plan.n_lists;
+  p.jth = ceil_div(plan.list_len, plan.n_lists);
+  p.pub = reinterpret_cast<float *>(ws + plan.off_pub);
+  cudaMemsetAsync(p.pub, 0x7f, (size_t)n_queries * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
   dim3 grid(ceil_div(n_queries, 128), plan.splits);
