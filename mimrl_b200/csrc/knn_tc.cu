@@ -70,24 +70,29 @@ struct KnnTcParams {
   KnnCand *cand;
 };
 
-// keep `lst[0..len)` sorted ascending by (d, idx), capacity cap; returns the new threshold
-__device__ __noinline__ void knn_insert(KnnCand *lst, int &len, int cap, float &tau_d, int &tau_i, float d, int idx) {
-  int n = len;
-  if (n == cap) {
-    if (!(d < lst[n - 1].d || (d == lst[n - 1].d && idx < lst[n - 1].idx))) return;
-    --n;
+// Candidate list of one (query row, warpgroup): UNSORTED, capacity cap, the thread tracks its worst entry
+// (tau_d, tau_i, worst).  An insertion overwrites the worst slot and rescans the list for the new worst: ~cap
+// independent shared-memory reads instead of a dependent shift chain (insertions are executed by one lane at a time
+// under divergence, so their latency is what matters).  Sorted once at the end of the sweep.
+__device__ __forceinline__ bool knn_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+__device__ __noinline__ void knn_insert(KnnCand *lst, int &len, int cap, float &tau_d, int &tau_i, int &worst, float d,
+                                        int idx) {
+  if (len < cap) {
+    lst[len] = KnnCand{d, idx};
+    ++len;
+    if (len < cap) return;                       // threshold stays +inf until the list is full
+  } else {
+    if (!knn_less(d, idx, tau_d, tau_i)) return;
+    lst[worst] = KnnCand{d, idx};
   }
-  int p = n;
-  while (p > 0 && (d < lst[p - 1].d || (d == lst[p - 1].d && idx < lst[p - 1].idx))) {
-    lst[p] = lst[p - 1];
-    --p;
+  float wd = -1.f;
+  int wi = -1, wp = 0;
+  for (int u = 0; u < cap; ++u) {
+    const KnnCand c = lst[u];
+    if (knn_less(wd, wi, c.d, c.idx)) wd = c.d, wi = c.idx, wp = u;
   }
-  lst[p] = KnnCand{d, idx};
-  len = n + 1;
-  if (len == cap) {
-    tau_d = lst[cap - 1].d;
-    tau_i = lst[cap - 1].idx;
-  }
+  tau_d = wd, tau_i = wi, worst = wp;
 }
 
 __global__ void __launch_bounds__(kKnnThreads, 1)
@@ -214,7 +219,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
     const float qn = row_ok ? p.qn[row0 + r] : 0.f;
     KnnCand *lst = lists + (size_t)(wg * 128 + r) * kListMax;
     float *kn_s = knbuf + wg * 128;
-    int len = 0, tau_i = 0x7fffffff;
+    int len = 0, tau_i = 0x7fffffff, worst = 0;
     float tau_d = INFINITY;          // effective threshold = min(local K'-th best, shared bound)
     float tau_local = INFINITY, tau_shared = INFINITY, published = INFINITY;
     // Shared bound across the key splits of this query: every part publishes the jth-smallest distance it has seen,
@@ -264,7 +269,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
           for (int j = 0; j < 32; ++j) {
             const float dj = __uint_as_float(v[j]);
             if (dj <= tau_d && dj < INFINITY) {
-              knn_insert(lst, len, p.list_len, tau_local, tau_i, dj, col0 + ch * 32 + j);
+              knn_insert(lst, len, p.list_len, tau_local, tau_i, worst, dj, col0 + ch * 32 + j);
               tau_d = fminf(tau_local, tau_shared);
             }
           }
@@ -274,14 +279,27 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
       if (row_ok) {
-        if (len >= p.jth) {
-          const float mine = lst[p.jth - 1].d;
+        const int it = i >> 1;               // tiles this warpgroup has finished
+        const bool refresh = it < 8 || (it & 3) == 3;     // every tile while the lists warm up, then every 4th
+        if (refresh && len >= p.jth) {
+          // jth-smallest distance of this part (jth is 1 or 2 in practice): partial selection over the unsorted list
+          float lo_d = -1.f, mine = INFINITY;
+          int lo_i = -1;
+          for (int jj = 0; jj < p.jth; ++jj) {
+            float bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int u = 0; u < len; ++u) {
+              const KnnCand c = lst[u];
+              if (knn_less(lo_d, lo_i, c.d, c.idx) && knn_less(c.d, c.idx, bd, bi)) bd = c.d, bi = c.idx;
+            }
+            lo_d = bd, lo_i = bi, mine = bd;
+          }
           if (mine < published) {
             published = mine;
             __stcg(pub_row + part, mine);
           }
         }
-        if (((i >> 1) & 3) == 3) {           // every 4th tile of this warpgroup: refresh the shared bound
+        if (refresh) {
           float t = 0.f;
           for (int pp = 0; pp < p.n_lists; ++pp) t = fmaxf(t, __ldcg(pub_row + pp));
           tau_shared = fminf(tau_shared, t);
@@ -290,6 +308,15 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       }
     }
     if (row_ok) {
+      for (int u = 1; u < len; ++u) {            // sort ascending by (d, idx): the re-rank merges sorted lists
+        const KnnCand x = lst[u];
+        int v = u;
+        while (v > 0 && knn_less(x.d, x.idx, lst[v - 1].d, lst[v - 1].idx)) {
+          lst[v] = lst[v - 1];
+          --v;
+        }
+        lst[v] = x;
+      }
       KnnCand *o = p.cand + ((size_t)(row0 + r) * p.n_lists + (split * 2 + wg)) * p.list_len;
       for (int u = 0; u < p.list_len; ++u) o[u] = u < len ? lst[u] : KnnCand{INFINITY, -1};
     }
