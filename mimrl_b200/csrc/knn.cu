@@ -25,7 +25,7 @@ constexpr int kQS = 68;        // padded strides (multiples of 4 floats for LDS.
 constexpr int kKS = 132;
 constexpr int kThreads = 256;
 constexpr int kMaxList = 64;   // K' upper bound
-constexpr int kSlack = 16;
+constexpr int kSlack = 4;    // fp32-class filter distances: the float64 re-rank only has to fix the ORDER of near-ties
 
 using Cand = KnnCand;
 

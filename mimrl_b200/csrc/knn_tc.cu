@@ -6,7 +6,7 @@
 // against its current K'-th best and inserts the rare survivors into a sorted list
 // in shared memory.  The m x N distance matrix is never written.  Exactness comes
 // from the float64 re-rank stage (knn.cu), which only needs the true neighbours to
-// be inside the K' = k + 16 candidates kept here.
+// be inside the K' = k + 4 candidates kept here.
 #include "tc_common.cuh"
 
 namespace mimrl {
@@ -88,9 +88,13 @@ __device__ __noinline__ void knn_insert(KnnCand *lst, int &len, int cap, float &
   }
   float wd = -1.f;
   int wi = -1, wp = 0;
-  for (int u = 0; u < cap; ++u) {
-    const KnnCand c = lst[u];
-    if (knn_less(wd, wi, c.d, c.idx)) wd = c.d, wi = c.idx, wp = u;
+  for (int u0 = 0; u0 < cap; u0 += 8) {          // 8 independent loads per round trip
+    KnnCand c[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) c[t] = u0 + t < cap ? lst[u0 + t] : KnnCand{-2.f, -1};
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (knn_less(wd, wi, c[t].d, c[t].idx)) wd = c[t].d, wi = c[t].idx, wp = u0 + t;
   }
   tau_d = wd, tau_i = wi, worst = wp;
 }
@@ -109,8 +113,8 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
   KnnCand *lists = reinterpret_cast<KnnCand *>(gen + kKnnStages * kKUnit + 1024 + 1024);      // [2][128][kListMax]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 128;
-  const int split = blockIdx.y;
+  const int row0 = blockIdx.y * 128;
+  const int split = blockIdx.x;                 // fast index: the splits of one query tile run together
   const int n_tiles = (p.n_keys + 127) / 128;
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(n_tiles, t0 + p.tiles_per_split);
@@ -280,7 +284,8 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
       if (row_ok) {
         const int it = i >> 1;               // tiles this warpgroup has finished
-        const bool refresh = it < 8 || (it & 3) == 3;     // every tile while the lists warm up, then every 4th
+        // refresh points: tiles 1, 2, 4, 8 of this warpgroup while the lists warm up, then every 16th
+        const bool refresh = it == 0 || it == 1 || it == 3 || it == 7 || (it & 15) == 15;
         if (refresh && len >= p.jth) {
           // jth-smallest distance of this part (jth is 1 or 2 in practice): partial selection over the unsorted list
           float lo_d = -1.f, mine = INFINITY;
@@ -300,8 +305,16 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
           }
         }
         if (refresh) {
+          // n_lists is even; 8 independent L2 loads in flight per round trip
           float t = 0.f;
-          for (int pp = 0; pp < p.n_lists; ++pp) t = fmaxf(t, __ldcg(pub_row + pp));
+          int pp = 0;
+          for (; pp + 8 <= p.n_lists; pp += 8) {
+            const float a0 = __ldcg(pub_row + pp), a1 = __ldcg(pub_row + pp + 1), a2 = __ldcg(pub_row + pp + 2),
+                        a3 = __ldcg(pub_row + pp + 3), a4 = __ldcg(pub_row + pp + 4), a5 = __ldcg(pub_row + pp + 5),
+                        a6 = __ldcg(pub_row + pp + 6), a7 = __ldcg(pub_row + pp + 7);
+            t = fmaxf(t, fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7))));
+          }
+          for (; pp < p.n_lists; pp += 2) t = fmaxf(t, fmaxf(__ldcg(pub_row + pp), __ldcg(pub_row + pp + 1)));
           tau_shared = fminf(tau_shared, t);
           tau_d = fminf(tau_local, tau_shared);
         }
@@ -392,7 +405,7 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   cudaMemsetAsync(p.pub, 0x7f, (size_t)n_queries * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
-  dim3 grid(ceil_div(n_queries, 128), plan.splits);
+  dim3 grid(plan.splits, ceil_div(n_queries, 128));
   knn_filter_tc_kernel<<<grid, kKnnThreads, kKnnSmem, st>>>(mh, ml, p);
   return check_launch("knn_filter_tc");
 }
