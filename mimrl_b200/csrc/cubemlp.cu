@@ -425,6 +425,219 @@ cubemlp_mix_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const floa
   }
 }
 
+// ---------------------------------------------------------------------------
+// Tiny mixed axis (A, H, A2 <= 8: the modality mix K = 3 of MLPProcess.py:106-112).  One thread per fibre, everything
+// in registers, parameters in shared memory; purely bandwidth-bound (one read, one write of the tensor).
+constexpr int kSmallMax = 8;
+
+struct SmallParams {
+  float w1[kSmallMax * kSmallMax], w2[kSmallMax * kSmallMax], wr[kSmallMax * kSmallMax];
+  float b1[kSmallMax], b2[kSmallMax], lw[kSmallMax], lb[kSmallMax];
+};
+
+__device__ void load_small_params(SmallParams &sp, const MixArgs &m) {
+  const MixDims &d = m.d;
+  for (int t = threadIdx.x; t < kSmallMax * kSmallMax; t += blockDim.x) {
+    const int r = t / kSmallMax, c = t % kSmallMax;
+    sp.w1[t] = (r < d.H && c < d.A) ? m.w1[r * d.A + c] : 0.f;
+    sp.w2[t] = (r < d.A2 && c < d.H) ? m.w2[r * d.H + c] : 0.f;
+    sp.wr[t] = (r < d.A2 && c < d.A) ? (m.wres ? m.wres[r * d.A + c] : (r == c ? 1.f : 0.f)) : 0.f;
+  }
+  for (int t = threadIdx.x; t < kSmallMax; t += blockDim.x) {
+    sp.b1[t] = (m.b1 && t < d.H) ? m.b1[t] : 0.f;
+    sp.b2[t] = (m.b2 && t < d.A2) ? m.b2[t] : 0.f;
+    const int nl = m.ln_first ? d.A : d.A2;
+    sp.lw[t] = t < nl ? m.ln_w[t] : 0.f;
+    sp.lb[t] = t < nl ? m.ln_b[t] : 0.f;
+  }
+}
+
+__device__ __forceinline__ void small_ln(const float *v, int n, float &mean, float &rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int a = 0; a < kSmallMax; ++a) s += a < n ? v[a] : 0.f;
+  mean = s / n;
+  float q = 0.f;
+#pragma unroll
+  for (int a = 0; a < kSmallMax; ++a) {
+    const float dlt = a < n ? v[a] - mean : 0.f;
+    q = fmaf(dlt, dlt, q);
+  }
+  rstd = rsqrtf(q / n + 1e-6f);
+}
+
+// forward of one fibre; returns everything the backward needs in registers
+__device__ __forceinline__ void small_forward(const SmallParams &sp, const MixArgs &m, const float *x, float *u, float *pre,
+                                              float *h, float *z, float &mean, float &rstd, float *y) {
+  const MixDims &d = m.d;
+  if (m.ln_first) {
+    small_ln(x, d.A, mean, rstd);
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) u[a] = a < d.A ? (x[a] - mean) * rstd * sp.lw[a] + sp.lb[a] : 0.f;
+  } else {
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) u[a] = x[a];
+  }
+#pragma unroll
+  for (int r = 0; r < kSmallMax; ++r) {
+    float acc = sp.b1[r];
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) acc = fmaf(sp.w1[r * kSmallMax + a], u[a], acc);
+    pre[r] = acc;
+    h[r] = r < d.H ? act_fwd(m.act, acc) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < kSmallMax; ++r) {
+    float acc = sp.b2[r];
+#pragma unroll
+    for (int c = 0; c < kSmallMax; ++c) acc = fmaf(sp.w2[r * kSmallMax + c], h[c], acc);
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) acc = fmaf(sp.wr[r * kSmallMax + a], x[a], acc);
+    z[r] = r < d.A2 ? acc : 0.f;
+  }
+  if (!m.ln_first) {
+    small_ln(z, d.A2, mean, rstd);
+#pragma unroll
+    for (int r = 0; r < kSmallMax; ++r) y[r] = (z[r] - mean) * rstd * sp.lw[r] + sp.lb[r];
+  } else {
+#pragma unroll
+    for (int r = 0; r < kSmallMax; ++r) y[r] = z[r];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cubemlp_small_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict__ saved) {
+  __shared__ SmallParams sp;
+  load_small_params(sp, m);
+  __syncthreads();
+  const MixDims &d = m.d;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < d.n_cols; c += (long long)gridDim.x * blockDim.x) {
+    const size_t bi = col_base(c, d.inner, d.A), bo = col_base(c, d.inner, d.A2);
+    float x[kSmallMax], u[kSmallMax], pre[kSmallMax], h[kSmallMax], z[kSmallMax], yo[kSmallMax], mean, rstd;
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) x[a] = a < d.A ? __ldg(m.x + bi + (size_t)a * d.inner) : 0.f;
+    small_forward(sp, m, x, u, pre, h, z, mean, rstd, yo);
+#pragma unroll
+    for (int r = 0; r < kSmallMax; ++r)
+      if (r < d.A2) y[bo + (size_t)r * d.inner] = yo[r];
+    saved[2 * c] = mean;
+    saved[2 * c + 1] = rstd;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cubemlp_small_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBwdOut o) {
+  __shared__ SmallParams sp;
+  __shared__ float s_glw[kSmallMax], s_glb[kSmallMax];
+  load_small_params(sp, m);
+  if (threadIdx.x < kSmallMax) s_glw[threadIdx.x] = 0.f, s_glb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const MixDims &d = m.d;
+  float glw[kSmallMax], glb[kSmallMax];
+#pragma unroll
+  for (int a = 0; a < kSmallMax; ++a) glw[a] = 0.f, glb[a] = 0.f;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < d.n_cols; c += (long long)gridDim.x * blockDim.x) {
+    const size_t bi = col_base(c, d.inner, d.A), bo = col_base(c, d.inner, d.A2), bh = col_base(c, d.inner, d.H);
+    float x[kSmallMax], u[kSmallMax], pre[kSmallMax], h[kSmallMax], z[kSmallMax], yo[kSmallMax], mean, rstd;
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) x[a] = a < d.A ? __ldg(m.x + bi + (size_t)a * d.inner) : 0.f;
+    small_forward(sp, m, x, u, pre, h, z, mean, rstd, yo);
+    float g[kSmallMax], gz[kSmallMax];
+#pragma unroll
+    for (int r = 0; r < kSmallMax; ++r) g[r] = r < d.A2 ? __ldg(gy + bo + (size_t)r * d.inner) : 0.f;
+    if (!m.ln_first) {
+      float t1 = 0.f, t2 = 0.f, zh[kSmallMax];
+#pragma unroll
+      for (int r = 0; r < kSmallMax; ++r) {
+        zh[r] = r < d.A2 ? (z[r] - mean) * rstd : 0.f;
+        const float gw = g[r] * sp.lw[r];
+        t1 += gw;
+        t2 = fmaf(gw, zh[r], t2);
+        glw[r] = fmaf(g[r], zh[r], glw[r]);
+        glb[r] += g[r];
+      }
+      t1 /= d.A2, t2 /= d.A2;
+#pragma unroll
+      for (int r = 0; r < kSmallMax; ++r) gz[r] = r < d.A2 ? (g[r] * sp.lw[r] - t1 - zh[r] * t2) * rstd : 0.f;
+    } else {
+#pragma unroll
+      for (int r = 0; r < kSmallMax; ++r) gz[r] = g[r];
+    }
+    float gpre[kSmallMax];
+#pragma unroll
+    for (int c2 = 0; c2 < kSmallMax; ++c2) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSmallMax; ++r) acc = fmaf(sp.w2[r * kSmallMax + c2], gz[r], acc);
+      gpre[c2] = c2 < d.H ? acc * act_bwd(m.act, pre[c2]) : 0.f;
+    }
+    float gu[kSmallMax], gres[kSmallMax];
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) {
+      float acc = 0.f, accr = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSmallMax; ++r) {
+        acc = fmaf(sp.w1[r * kSmallMax + a], gpre[r], acc);
+        accr = fmaf(sp.wr[r * kSmallMax + a], gz[r], accr);
+      }
+      gu[a] = acc, gres[a] = accr;
+    }
+    float gx[kSmallMax];
+    if (m.ln_first) {
+      float t1 = 0.f, t2 = 0.f, uh[kSmallMax];
+#pragma unroll
+      for (int a = 0; a < kSmallMax; ++a) {
+        uh[a] = a < d.A ? (x[a] - mean) * rstd : 0.f;
+        const float gw = gu[a] * sp.lw[a];
+        t1 += gw;
+        t2 = fmaf(gw, uh[a], t2);
+        glw[a] = fmaf(gu[a], uh[a], glw[a]);
+        glb[a] += gu[a];
+      }
+      t1 /= d.A, t2 /= d.A;
+#pragma unroll
+      for (int a = 0; a < kSmallMax; ++a) gx[a] = (gu[a] * sp.lw[a] - t1 - uh[a] * t2) * rstd + gres[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < kSmallMax; ++a) gx[a] = gu[a] + gres[a];
+    }
+#pragma unroll
+    for (int a = 0; a < kSmallMax; ++a) {
+      if (a < d.A) {
+        o.gx[bi + (size_t)a * d.inner] = gx[a];
+        if (m.ln_first) o.s_u[bi + (size_t)a * d.inner] = u[a];
+      }
+      if (a < d.A2) o.s_gz[bo + (size_t)a * d.inner] = gz[a];
+      if (a < d.H) {
+        o.s_h[bh + (size_t)a * d.inner] = h[a];
+        o.s_gpre[bh + (size_t)a * d.inner] = gpre[a];
+      }
+    }
+  }
+  // LayerNorm parameter gradients: warp reduce -> shared -> one global atomic per block and feature
+#pragma unroll
+  for (int a = 0; a < kSmallMax; ++a) {
+    float pw = glw[a], pb = glb[a];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      pw += __shfl_xor_sync(0xffffffffu, pw, off);
+      pb += __shfl_xor_sync(0xffffffffu, pb, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&s_glw[a], pw);
+      atomicAdd(&s_glb[a], pb);
+    }
+  }
+  __syncthreads();
+  const int nl = m.ln_first ? d.A : d.A2;
+  if (threadIdx.x < nl) {
+    atomicAdd(o.gln_w + threadIdx.x, s_glw[threadIdx.x]);
+    atomicAdd(o.gln_b + threadIdx.x, s_glb[threadIdx.x]);
+  }
+}
+
+bool is_small(const MixDims &d) { return d.A <= kSmallMax && d.H <= kSmallMax && d.A2 <= kSmallMax; }
+
 size_t fwd_smem(const MixDims &d, int ln_first) {
   return (tile_floats(d.A) * (ln_first ? 2 : 1) + tile_floats(d.H) + tile_floats(d.A2) + 2 * 8 * kTI) * sizeof(float);
 }
@@ -465,6 +678,11 @@ extern "C" int mimrl_cubemlp_mix_fwd(const float *x, int outer, int a_in, int in
                                      float *saved, void *stream) {
   MixArgs m;
   if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
+  if (is_small(m.d)) {
+    const long long nb = (m.d.n_cols + 255) / 256;
+    cubemlp_small_fwd_kernel<<<(int)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, (cudaStream_t)stream>>>(m, y, saved);
+    return check_launch("cubemlp_small_fwd");
+  }
   const size_t smem = fwd_smem(m.d, ln_first);
   MIMRL_REQUIRE(smem <= 220 * 1024, "cubemlp_mix_fwd: axis sizes %d/%d/%d need %zu B of shared memory", a_in, a_hid, a_out, smem);
   cudaFuncSetAttribute(cubemlp_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -483,6 +701,12 @@ extern "C" int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer,
   MixArgs m;
   if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
   MIMRL_REQUIRE(gx && s_gz && s_h && s_gpre && gln_w && gln_b && (!ln_first || s_u), "cubemlp_mix_bwd: missing outputs");
+  if (is_small(m.d)) {
+    const long long nb = (m.d.n_cols + 255) / 256;
+    MixBwdOut so{gx, s_gz, s_h, s_gpre, s_u, gln_w, gln_b};
+    cubemlp_small_bwd_kernel<<<(int)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+    return check_launch("cubemlp_small_bwd");
+  }
   const size_t smem = bwd_smem(m.d, ln_first);
   MIMRL_REQUIRE(smem <= 220 * 1024, "cubemlp_mix_bwd: axis sizes %d/%d/%d need %zu B of shared memory", a_in, a_hid, a_out, smem);
   cudaFuncSetAttribute(cubemlp_mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
