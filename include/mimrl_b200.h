@@ -133,6 +133,15 @@ int mimrl_scores_grad(const float *scores, int n_rows, int n_cols, int own_offse
 size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K);
 int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, const float *B, int M, int N, int K,
                      const float *bias, int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
+/* Same product on operands split once and reused (a layer's input serves its forward and its weight gradient, a
+ * weight serves forward and input gradient).  mimrl_split_f32 writes [scale header | fp16 hi | fp16 lo] for a
+ * row-major [rows, cols] matrix, optionally masked by (mask > 0); colsum (nullable) ACCUMULATES the column sums of
+ * the masked matrix (bias gradient).  Stored operand shapes as listed for the three modes above. */
+size_t mimrl_split_bytes(int rows, int cols);
+int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum, void *stream);
+size_t mimrl_gemm_split_workspace_bytes(int mode, int M, int N, int K);
+int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, int N, int K, const float *bias,
+                     int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of

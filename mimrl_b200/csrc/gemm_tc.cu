@@ -66,12 +66,16 @@ gemm_absmax_kernel(const float *__restrict__ a, const float *__restrict__ mask, 
 }
 
 // src [rows, cols] fp32 (optionally masked) -> hi, lo [rows, ld] fp16, zero padded, scaled by 2^k
+// colsum (nullable): column sums of the masked source are ACCUMULATED there (bias gradient); the launch makes the
+// grid stride a multiple of ld/2 so that every thread stays on one column pair.
 __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__restrict__ mask, int rows, int cols,
                                   int ld, const unsigned *__restrict__ absmax, int which, __half *__restrict__ hi,
-                                  __half *__restrict__ lo) {
+                                  __half *__restrict__ lo, float *__restrict__ colsum) {
   const float sc = scale_from_absmax(absmax[which]);
   const int half_ld = ld >> 1;
   const size_t total = (size_t)rows * half_ld;
+  float cs0 = 0.f, cs1 = 0.f;
+  int my_c = -1;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t r = idx / half_ld;
     const int c = (int)(idx - r * half_ld) * 2;
@@ -84,12 +88,17 @@ __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__
       v1 = src[r * cols + c + 1];
       if (mask && !(mask[r * cols + c + 1] > 0.f)) v1 = 0.f;
     }
+    cs0 += v0, cs1 += v1, my_c = c;
     v0 *= sc, v1 *= sc;
     const __half2 h = __floats2half2_rn(v0, v1);
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     *reinterpret_cast<__half2 *>(hi + r * ld + c) = h;
     *reinterpret_cast<__half2 *>(lo + r * ld + c) = l;
+  }
+  if (colsum && my_c >= 0) {
+    if (my_c < cols) atomicAdd(colsum + my_c, cs0);
+    if (my_c + 1 < cols) atomicAdd(colsum + my_c + 1, cs1);
   }
 }
 
@@ -312,6 +321,106 @@ int launch_gemm(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap 
 
 using namespace mimrl;
 
+namespace {
+struct SplitLayout {
+  int ld;
+  size_t off_hi, off_lo, total;
+};
+SplitLayout split_layout(int rows, int cols) {
+  SplitLayout L;
+  L.ld = (cols + 63) & ~63;
+  L.off_hi = 256;
+  L.off_lo = 256 + align256((size_t)rows * L.ld * 2);
+  L.total = L.off_lo + align256((size_t)rows * L.ld * 2);
+  return L;
+}
+}  // namespace
+
+extern "C" size_t mimrl_split_bytes(int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return split_layout(rows, cols).total;
+}
+
+extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum,
+                               void *stream) {
+  MIMRL_REQUIRE(rows > 0 && cols > 0 && src && out, "split_f32: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SplitLayout L = split_layout(rows, cols);
+  unsigned char *o = (unsigned char *)out;
+  unsigned *absmax = reinterpret_cast<unsigned *>(o);
+  cudaMemsetAsync(absmax, 0, 8, st);
+  const size_t n = (size_t)rows * cols;
+  int blocks = (int)((n + 4095) / 4096);
+  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
+  gemm_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(src, mask, n, nullptr, 0, absmax);
+  if (check_launch("split absmax")) return 1;
+  // grid stride (blocks * 256 threads) must be a multiple of ld/2 (64, 128 or 192 for the widths in use): 3k blocks
+  const size_t total = (size_t)rows * (L.ld / 2);
+  int b = (int)((total + 255) / 256);
+  b = b > 148 * 6 ? 148 * 6 : b;
+  if (colsum) {
+    const int unit = (L.ld / 2) / 64 > 0 ? 3 * (L.ld / 2) : 3;     // generous multiple; exact check below
+    (void)unit;
+    while (b > 1 && ((size_t)b * 256) % (size_t)(L.ld / 2) != 0) --b;
+    MIMRL_REQUIRE(((size_t)b * 256) % (size_t)(L.ld / 2) == 0, "split_f32: column sums need ld/2 to divide the grid stride");
+  }
+  gemm_split_kernel<<<b, 256, 0, st>>>(src, mask, rows, cols, L.ld, absmax, 0, reinterpret_cast<__half *>(o + L.off_hi),
+                                     reinterpret_cast<__half *>(o + L.off_lo), colsum);
+  return check_launch("split_f32");
+}
+
+// GEMM on operands already split by mimrl_split_f32.  Stored shapes: mode 0: A [M,K], B [N,K]; mode 1: A [M,K],
+// B [K,N]; mode 2: A [K,M], B [K,N].
+extern "C" size_t mimrl_gemm_split_workspace_bytes(int mode, int M, int N, int K) {
+  if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0) return 0;
+  const GemmLayout g = gemm_layout(mode, M, N, K);
+  return (g.splits > 1 ? align256((size_t)g.splits * M * N * sizeof(float)) : 0) + 256;
+}
+
+extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, int N, int K,
+                                const float *bias, int relu, float *C, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+  MIMRL_REQUIRE(mode >= 0 && mode <= 2, "gemm_split: unknown mode %d", mode);
+  MIMRL_REQUIRE(M > 0 && N > 0 && K > 0 && a_split && b_split, "gemm_split: empty problem");
+  const GemmLayout g = gemm_layout(mode, M, N, K);
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_gemm_split_workspace_bytes(mode, M, N, K), "gemm_split: workspace too small");
+  MIMRL_REQUIRE(g.splits == 1 || (!bias && !relu), "gemm_split: bias/relu are not available on the split-K (mode 2) path");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SplitLayout la = split_layout(g.a_rows, g.a_cols), lb = split_layout(g.b_rows, g.b_cols);
+  const unsigned char *pa = (const unsigned char *)a_split, *pb = (const unsigned char *)b_split;
+  // the kernel reads absmax[0] (A) and absmax[1] (B) from one array: gather the two headers
+  unsigned *absmax = reinterpret_cast<unsigned *>((unsigned char *)workspace + workspace_bytes - 256);
+  cudaMemcpyAsync(absmax, pa, 4, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(absmax + 1, pb, 4, cudaMemcpyDeviceToDevice, st);
+  const bool a_mn = mode == 2, b_mn = mode != 0;
+  CUtensorMap ah, al, bh, bl;
+  if (make_map(&ah, pa + la.off_hi, g.a_cols, g.a_rows, la.ld, a_mn ? 64 : 128)) return 1;
+  if (make_map(&al, pa + la.off_lo, g.a_cols, g.a_rows, la.ld, a_mn ? 64 : 128)) return 1;
+  if (make_map(&bh, pb + lb.off_hi, g.b_cols, g.b_rows, lb.ld, b_mn ? 64 : 128)) return 1;
+  if (make_map(&bl, pb + lb.off_lo, g.b_cols, g.b_rows, lb.ld, b_mn ? 64 : 128)) return 1;
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K;
+  p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.relu = relu;
+  p.absmax = absmax;
+  p.bias = bias;
+  p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
+  dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
+  int rc;
+  if (mode == 0) rc = launch_gemm<false, false>(ah, al, bh, bl, p, grid, st);
+  else if (mode == 1) rc = launch_gemm<false, true>(ah, al, bh, bl, p, grid, st);
+  else rc = launch_gemm<true, true>(ah, al, bh, bl, p, grid, st);
+  if (rc) return rc;
+  if (g.splits > 1) {
+    const size_t mn = (size_t)M * N;
+    int b = (int)((mn + 255) / 256);
+    b = b > 148 * 8 ? 148 * 8 : b;
+    gemm_reduce_kernel<<<b, 256, 0, st>>>(p.C, g.splits, mn, C);
+    return check_launch("gemm reduce");
+  }
+  return 0;
+}
+
 extern "C" size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K) {
   if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0) return 0;
   return gemm_layout(mode, M, N, K).total + 256;
@@ -340,7 +449,7 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
     const size_t total = (size_t)rows * (ld / 2);
     int b = (int)((total + 255) / 256);
     b = b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b);
-    gemm_split_kernel<<<b, 256, 0, st>>>(src, mask, rows, cols, ld, absmax, which, hi, lo);
+    gemm_split_kernel<<<b, 256, 0, st>>>(src, mask, rows, cols, ld, absmax, which, hi, lo, nullptr);
     return check_launch("gemm split");
   };
   if (split(A, a_mask, g.a_rows, g.a_cols, g.lda, 0, a_hi, a_lo)) return 1;

@@ -27,33 +27,47 @@ def _gemm(mode, A, mask, B, M, N, K, bias=None, relu=False):
     return C
 
 
+def _split(t, mask=None, colsum=None):
+    """fp16 hi/lo split of a row-major fp32 matrix (optionally masked), reusable by several products."""
+    rows, cols = t.shape
+    buf = torch.empty(L.lib.mimrl_split_bytes(rows, cols), dtype=torch.uint8, device=t.device)
+    L.check(L.lib.mimrl_split_f32(L.ptr(t), L.ptr(mask), rows, cols, L.ptr(buf), L.ptr(colsum), L.stream()))
+    return buf
+
+
+def _gemm_split(mode, a_buf, b_buf, M, N, K, bias=None, relu=False):
+    C = torch.empty(M, N, dtype=torch.float32, device=a_buf.device)
+    ws = torch.empty(L.lib.mimrl_gemm_split_workspace_bytes(mode, M, N, K), dtype=torch.uint8, device=a_buf.device)
+    L.check(L.lib.mimrl_gemm_split(mode, L.ptr(a_buf), L.ptr(b_buf), M, N, K, L.ptr(bias), int(relu), L.ptr(C),
+                                   L.ptr(ws), ws.numel(), L.stream()))
+    return C
+
+
 class _LinearTC(torch.autograd.Function):
+    """x [M,K], w [N,K]: the split of x serves the forward and the weight gradient, the split of w the forward and
+    the input gradient, the split of the masked output gradient both backward products and the bias gradient."""
+
     @staticmethod
     def forward(ctx, x, w, b, relu):
         x, w = L.f32(x), L.f32(w)
         b = L.f32(b) if b is not None else None
         M, K = x.shape
         N = w.shape[0]
-        y = _gemm(0, x, None, w, M, N, K, b, relu)
-        ctx.save_for_backward(x, w, y if relu else x.new_empty(0))
-        ctx.cfg = (relu, b is not None)
+        xs, wsp = _split(x), _split(w)
+        y = _gemm_split(0, xs, wsp, M, N, K, b, relu)
+        ctx.save_for_backward(xs, wsp, y if relu else x.new_empty(0))
+        ctx.cfg = (relu, b is not None, M, N, K)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
-        relu, has_b = ctx.cfg
+        xs, wsp, y = ctx.saved_tensors
+        relu, has_b, M, N, K = ctx.cfg
         gy = L.f32(gy)
-        mask = y if relu else None
-        M, K = x.shape
-        N = w.shape[0]
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = _gemm(1, gy, mask, w, M, K, N)            # dz [M,N] . W [N,K]
-        if ctx.needs_input_grad[1]:
-            gw = _gemm(2, gy, mask, x, N, K, M)            # dz^T [N,M] . x [M,K]
-        if has_b and ctx.needs_input_grad[2]:
-            gb = (gy * (y > 0) if relu else gy).sum(dim=0)
+        gb = torch.zeros(N, dtype=torch.float32, device=gy.device) if has_b and ctx.needs_input_grad[2] else None
+        dzs = _split(gy, y if relu else None, gb)
+        gx = _gemm_split(1, dzs, wsp, M, K, N) if ctx.needs_input_grad[0] else None       # dz [M,N] . W [N,K]
+        gw = _gemm_split(2, dzs, xs, N, K, M) if ctx.needs_input_grad[1] else None        # dz^T [N,M] . x [M,K]
         return gx, gw, gb, None
 
 
