@@ -8,7 +8,7 @@ from mimrl_b200 import _lib as L
 from mimrl_b200.model import VMIEstimator, VCMIEstimator, knn_search, prod_knn_sample
 from mimrl_b200.mlp_process import MLPEncoder
 dev = torch.device("cuda:0")
-which = sys.argv[1:] or ["knn", "cubemlp", "vcmi", "concat", "sep_small"]
+which = sys.argv[1:] or ["knn", "cubemlp", "vcmi", "concat", "sep_small", "step"]
 
 def timeit(fn, reps=5, warm=2):
     for _ in range(warm): fn()
@@ -73,3 +73,32 @@ if "sep_small" in which:  # config 2 sweep
             mi, loss = est(x, y); loss.backward()
         ms = timeit(fb)
         out(component="sep_infonce_fwd_bwd", B=B, ms=ms, pairs_per_s=B * B / ms * 1e3)
+
+if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of the MI/CMI path on synthetic features
+    from types import SimpleNamespace
+    from mimrl_b200.model import MIHeads
+    from mimrl_b200.train_step import FeaturePool, TwoStageStep
+    for bs, N in ((128, 1284), (1024, 16326)):
+        opt = SimpleNamespace(critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2,
+                              radius=1.0, cmi_last_acticate="hardtanh", d_common=128)
+        heads = MIHeads(opt).to(dev)
+        enc = torch.nn.Linear(128, 4 * 128).to(dev)          # stand-in for the encoders: features from one projection
+        cls = torch.nn.Linear(128, 1).to(dev)
+        def features(batch):
+            f = enc(batch).view(-1, 4, 128)
+            return cls(f[:, 0]), f[:, 0].contiguous(), f[:, 1].contiguous(), f[:, 2].contiguous(), f[:, 3].contiguous()
+        main_params = list(enc.parameters()) + list(cls.parameters())
+        step = TwoStageStep(heads, features, torch.nn.L1Loss(), torch.optim.Adam(main_params, 1e-4),
+                            torch.optim.Adam(heads.parameters(), 1e-4), clip_params=main_params + list(heads.parameters()))
+        pool = FeaturePool()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        pool.C = torch.randn(N, 1, device=dev, generator=g).clamp(-3, 3)
+        pool.F, pool.T, pool.A, pool.V = (torch.randn(N, 128, device=dev, generator=g) for _ in range(4))
+        batch = torch.randn(bs, 128, device=dev, generator=g)
+        labels = torch.randn(bs, device=dev, generator=g).clamp(-3, 3)
+        np.random.seed(0)
+        def one():
+            step.stage1(batch, labels, pool); step.stage2(batch, labels, pool)
+        ms = timeit(one, reps=5, warm=2)
+        out(component="two_stage_step_mi_cmi", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
+            note="5 VMI + 6 k-NN samplers + 6 VCMI per stage, Adam on both optimisers; encoders replaced by one Linear")
