@@ -213,6 +213,16 @@ int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer, int a_in, 
                           const float *saved, float *gx, float *s_gz, float *s_h, float *s_gpre, float *s_u,
                           float *gln_w, float *gln_b, void *stream);
 
+/* Tensor-core forward of the same mix (ln_first = 0, axis sizes <= 128, not the tiny-axis case): fibres in TMEM
+ * lanes, W1 / W2 / Wres resident in shared memory, LayerNorm thread-local in the epilogue.  Writes the same
+ * `saved` statistics, so mimrl_cubemlp_mix_bwd applies unchanged. */
+int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln_first, int act);
+size_t mimrl_cubemlp_tc_workspace_bytes(int a_in, int a_hid, int a_out);
+int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
+                             int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
+                             const float *ln_w, const float *ln_b, int act, float *y, float *saved, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

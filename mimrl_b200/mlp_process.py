@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from . import _lib as L
 
 _ACT_IDS = {"gelu": 0, "relu": 1, "tanh": 2}
+USE_TC = True        # tensor-core forward for the large mixes (set False to force the CUDA-core kernels)
 _ACT_FNS = {  # Utils.py:85-98 get_activation_function
     "elu": F.elu, "gelu": F.gelu, "hardshrink": F.hardshrink, "hardtanh": F.hardtanh, "leakyrelu": F.leaky_relu,
     "prelu": F.prelu, "relu": F.relu, "rrelu": F.rrelu, "tanh": torch.tanh,
@@ -52,9 +53,18 @@ class _AxisMix(torch.autograd.Function):
         oshape = shape[:axis] + [A2] + shape[axis + 1:]
         y = torch.empty(oshape, dtype=torch.float32, device=x.device)
         saved = torch.empty(2 * outer * inner, dtype=torch.float32, device=x.device)
-        L.check(L.lib.mimrl_cubemlp_mix_fwd(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H, L.ptr(prm[2]),
-                                            L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]), L.ptr(prm[6]),
-                                            int(ln_first), act_id, L.ptr(y), L.ptr(saved), L.stream()))
+        if (USE_TC and outer * inner >= 1024
+                and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id)):
+            ws = torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=x.device)
+            L.check(L.lib.mimrl_cubemlp_mix_fwd_tc(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
+                                                   L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
+                                                   L.ptr(prm[6]), act_id, L.ptr(y), L.ptr(saved), L.ptr(ws), ws.numel(),
+                                                   L.stream()))
+        else:
+            L.check(L.lib.mimrl_cubemlp_mix_fwd(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
+                                                L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
+                                                L.ptr(prm[6]), int(ln_first), act_id, L.ptr(y), L.ptr(saved),
+                                                L.stream()))
         ctx.save_for_backward(x, saved, *[p if p is not None else x.new_empty(0) for p in prm])
         ctx.cfg = (outer, A, inner, H, A2, int(ln_first), act_id, [p is not None for p in prm])
         return y

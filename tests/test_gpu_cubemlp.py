@@ -87,3 +87,27 @@ def test_state_dict_names():
     enc = MLPEncoder("gelu", [10, 3, 16], [[5, 3, 16]], [[5, 3, 16]], [0.0] * 3, True, False, [True])
     want = set(P.cubemlp_state_dict(P.cubemlp_params(0, [10, 3, 16], [[5, 3, 16]], [[5, 3, 16]], True, False, [True])))
     assert set(enc.state_dict()) == want
+
+
+@pytest.mark.parametrize("bs,d_in,d_h,d_out,act,res", [
+    (16, [100, 3, 128], [[50, 3, 128]], [[50, 3, 128]], "gelu", True),          # README block 1: L-mix and D-mix on tcgen05
+    (16, [50, 3, 128], [[10, 3, 128]], [[10, 3, 128]], "gelu", True),           # README block 2
+    (9, [40, 3, 72], [[24, 3, 100]], [[40, 3, 72]], "relu", False),             # identity residual, odd sizes
+    (7, [33, 4, 20], [[17, 4, 40]], [[21, 4, 12]], "tanh", True)])
+def test_tensor_core_forward_vs_oracle(bs, d_in, d_h, d_out, act, res):
+    """Shapes large enough (>= 1024 fibres per mix) to take the tcgen05 forward; backward is the recompute kernel."""
+    c = dict(act=act, d_in=d_in, d_hiddens=d_h, d_outs=d_out, bias=True, ln_first=False, res=[res])
+    blocks = P.cubemlp_params(91, d_in, d_h, d_out, True, False, [res])
+    x = P.features(92, bs * d_in[0] * d_in[1], d_in[2]).reshape(bs, *d_in)
+    oshape = (bs, *d_out[-1])
+    w = P.features(93, int(np.prod(oshape[:-1])), oshape[-1]).reshape(oshape)
+    enc = build(c, blocks)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    y = enc(xt)
+    (y * torch.tensor(w, device="cuda")).sum().backward()
+    yo, caches = C.encoder_forward(blocks, x, act, False, [res])
+    gxo, pgo = C.encoder_backward(caches, w.astype(np.float64), False, [res])
+    assert rel_err(y.detach().cpu().numpy(), yo) < TOL, rel_err(y.detach().cpu().numpy(), yo)
+    assert rel_err(xt.grad.cpu().numpy(), gxo) < 2 * TOL
+    for n, p in enc.named_parameters():
+        assert np.abs(p.grad.cpu().numpy() - pgo[n]).max() <= 2 * TOL * np.abs(pgo[n]).max() + 2e-6, n
