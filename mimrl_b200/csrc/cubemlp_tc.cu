@@ -24,7 +24,7 @@ namespace {
 constexpr int kCubeThreads = 192;                      // warp 0 TMA, warp 1 MMA, warps 2-5 compute (thread = fibre)
 constexpr uint32_t kW16 = 128 * 128;                   // one 128-row x 64-K block: 16 KB
 constexpr uint32_t kWMat = 4 * kW16;                   // hi kb0, hi kb1, lo kb0, lo kb1
-constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 1024;
+constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, alignment
 // TMEM columns
 constexpr uint32_t kTX = 0, kTD1 = 128, kTH = 256, kTD2 = 384;
 
@@ -76,6 +76,13 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
   const uint32_t bars = base + 3 * kWMat;
   const uint32_t bWFull = bars, bXReady = bars + 8, bD1Full = bars + 16, bHReady = bars + 24, bD2Full = bars + 32;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + 3 * kWMat + 128);
+  float *s_b1 = reinterpret_cast<float *>(gen + 3 * kWMat + 256), *s_b2 = s_b1 + 128, *s_lw = s_b1 + 256, *s_lb = s_b1 + 384;
+  for (int t = threadIdx.x; t < 128; t += blockDim.x) {
+    s_b1[t] = (p.b1 && t < p.H) ? p.b1[t] : 0.f;
+    s_b2[t] = (p.b2 && t < p.A2) ? p.b2[t] : 0.f;
+    s_lw[t] = t < p.A2 ? p.ln_w[t] : 0.f;
+    s_lb[t] = t < p.A2 ? p.ln_b[t] : 0.f;
+  }
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const long long n_tiles = (p.n_cols + 127) / 128;
@@ -188,8 +195,16 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       float *yf = p.y + (size_t)o * p.A2 * p.inner + (size_t)i;
       // ---- 1. fibre -> TMEM (own power-of-two scale, fp16 hi/lo)
       float amax = 0.f;
-      if (ok)
-        for (int a = 0; a < p.A; ++a) amax = fmaxf(amax, fabsf(__ldg(xf + (size_t)a * p.inner)));
+      if (ok) {          // 8 independent loads in flight per round trip
+        float m8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int a = 0;
+        for (; a + 8 <= p.A; a += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) m8[u] = fmaxf(m8[u], fabsf(__ldg(xf + (size_t)(a + u) * p.inner)));
+        }
+        for (; a < p.A; ++a) m8[0] = fmaxf(m8[0], fabsf(__ldg(xf + (size_t)a * p.inner)));
+        amax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      }
       const float sx = pow2_scale(amax), inv_x = 1.f / sx;
       for (int ch = 0; ch * 32 < ks1 * 16; ++ch) {
         float v[32];
@@ -219,7 +234,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int h = ch * 32 + j;
-          if (h < p.H) hmax = fmaxf(hmax, fabsf(fmaf(__uint_as_float(v[j]), s1, p.b1 ? __ldg(p.b1 + h) : 0.f)));
+          if (h < p.H) hmax = fmaxf(hmax, fabsf(fmaf(__uint_as_float(v[j]), s1, s_b1[h])));
         }
       }
       const float sh = pow2_scale(hmax), inv_h = 1.f / sh;
@@ -231,7 +246,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int h = ch * 32 + j;
-          hv[j] = h < p.H ? cube_act(p.act, fmaf(__uint_as_float(v[j]), s1, p.b1 ? __ldg(p.b1 + h) : 0.f)) * sh : 0.f;
+          hv[j] = h < p.H ? cube_act(p.act, fmaf(__uint_as_float(v[j]), s1, s_b1[h])) * sh : 0.f;
         }
         uint32_t hi[16], lo[16];
         split32(hv, hi, lo);
@@ -256,7 +271,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           const int a2 = ch * 32 + j;
           float t = 0.f;
           if (a2 < p.A2) {
-            t = fmaf(__uint_as_float(v[j]), s2, p.b2 ? __ldg(p.b2 + a2) : 0.f);
+            t = fmaf(__uint_as_float(v[j]), s2, s_b2[a2]);
             if (p.has_res) t = fmaf(__uint_as_float(w[j]), s3, t);
             else if (ok) t += __ldg(xf + (size_t)a2 * p.inner);
           }
@@ -289,7 +304,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int a2 = ch * 32 + j;
-            if (a2 < p.A2) yf[(size_t)a2 * p.inner] = (z[j] - mean) * rstd * __ldg(p.ln_w + a2) + __ldg(p.ln_b + a2);
+            if (a2 < p.A2) yf[(size_t)a2 * p.inner] = (z[j] - mean) * rstd * s_lw[a2] + s_lb[a2];
           }
         }
       }
