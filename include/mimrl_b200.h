@@ -223,6 +223,24 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
                              const float *ln_w, const float *ln_b, int act, float *y, float *saved, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* ---- concat critic, all pairs on the tensor cores (reference VMI.py:58-65 with mlps of VMI.py:13-22) ----
+ * The first layer factorises over the concatenation: u = x W1x^T + b1 [n_own, 256], vt = (y W1y^T)^T [256, ldv]
+ * (both from the caller).  scores[i, j] = w4 . relu(W3 relu(W2 relu(u_i + v_j) + b2) + b3) + b4 for every pair,
+ * without the [n_own * n_all, 256] activations ever reaching HBM.  hidden = 256, layers = 2 only. */
+int mimrl_concat_tc_supported(int hidden, int layers);
+size_t mimrl_concat_workspace_bytes(int hidden);
+int mimrl_concat_scores(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden, const float *w2,
+                        const float *b2, const float *w3, const float *b3, const float *w4, const float *b4,
+                        float *scores, void *workspace, size_t workspace_bytes, void *stream);
+/* Backward for g = dL/dscores.  Accumulates (+=) into g_u [n_own,256], g_vt [256,ldv], g_b2, g_b3, g_w4 [256] and
+ * writes the weight-gradient operands h1, h2, g2, g3 (mimrl_split_f32 format of a [256, mimrl_concat_pair_rows()]
+ * matrix, feature-major): gW2 = g2 h1^T and gW3 = g3 h2^T through mimrl_gemm_split(mode 0). */
+long long mimrl_concat_pair_rows(int n_own, int n_all);
+int mimrl_concat_grad(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden, const float *w2,
+                      const float *b2, const float *w3, const float *b3, const float *w4, const float *g, float *g_u,
+                      float *g_vt, float *g_b2, float *g_b3, float *g_w4, void *op_h1, void *op_h2, void *op_g2,
+                      void *op_g3, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

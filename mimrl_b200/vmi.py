@@ -269,6 +269,68 @@ def interp_lower_bound(scores, baseline, alpha_logit):
 
 
 # --------------------------------------------------------------------------
+# concat critic, all pairs (VMI.py:58-65) on the tensor cores: csrc/concat_tc.cu
+# --------------------------------------------------------------------------
+
+CONCAT_GRAD_PAIRS = 1 << 21      # pairs per backward pass (4 KB of weight-gradient operands each)
+
+
+class _ConcatPairMLP(torch.autograd.Function):
+    """scores[i, j] = w4 . relu(W3 relu(W2 relu(u_i + v_j) + b2) + b3) + b4 for every pair.
+
+    Forward: mimrl_concat_scores (activations stay in TMEM).  Backward: row chunks of mimrl_concat_grad
+    (recompute + both data-gradient contractions) followed by the two split-K weight-gradient GEMMs."""
+
+    @staticmethod
+    def forward(ctx, u, v, w2, b2, w3, b3, w4, b4):
+        u, w2, w3 = L.f32(u), L.f32(w2), L.f32(w3)
+        vt = L.f32(v).t().contiguous()
+        w4 = L.f32(w4).reshape(-1)
+        n_own, n_all, hid = u.shape[0], vt.shape[1], u.shape[1]
+        scores = torch.empty(n_own, n_all, device=u.device, dtype=torch.float32)
+        wsb = L.lib.mimrl_concat_workspace_bytes(hid)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=u.device)
+        L.check(L.lib.mimrl_concat_scores(L.ptr(u), L.ptr(vt), n_own, n_all, n_all, hid, L.ptr(w2), L.ptr(b2), L.ptr(w3),
+                                          L.ptr(b3), L.ptr(w4), L.ptr(b4), L.ptr(scores), L.ptr(ws), wsb, L.stream()))
+        ctx.save_for_backward(u, vt, w2, b2, w3, b3, w4)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        u, vt, w2, b2, w3, b3, w4 = ctx.saved_tensors
+        g = L.f32(g)
+        dev = u.device
+        n_own, n_all, hid = u.shape[0], vt.shape[1], u.shape[1]
+        g_u = torch.zeros_like(u)
+        g_vt = torch.zeros_like(vt)
+        g_b2, g_b3, g_w4 = (torch.zeros(hid, device=dev) for _ in range(3))
+        g_w2, g_w3 = torch.zeros_like(w2), torch.zeros_like(w3)
+        rows = max(4, (CONCAT_GRAD_PAIRS // max(n_all, 1)) // 4 * 4)
+        rows = min(rows, n_own)
+        pair_rows = L.lib.mimrl_concat_pair_rows(rows, n_all)
+        opb = L.lib.mimrl_split_bytes(hid, pair_rows)
+        ops = [torch.empty(opb, dtype=torch.uint8, device=dev) for _ in range(4)]
+        wsb = L.lib.mimrl_concat_workspace_bytes(hid)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        gwb = L.lib.mimrl_gemm_split_workspace_bytes(0, hid, hid, pair_rows)
+        gws = torch.empty(gwb, dtype=torch.uint8, device=dev)
+        tmp = torch.empty_like(w2)
+        st = L.stream()
+        for r0 in range(0, n_own, rows):
+            r = min(rows, n_own - r0)
+            pr = L.lib.mimrl_concat_pair_rows(r, n_all)
+            L.check(L.lib.mimrl_concat_grad(L.ptr(u[r0:r0 + r]), L.ptr(vt), r, n_all, n_all, hid, L.ptr(w2), L.ptr(b2), L.ptr(w3),
+                                            L.ptr(b3), L.ptr(w4), L.ptr(g[r0:r0 + r]), L.ptr(g_u[r0:r0 + r]), L.ptr(g_vt),
+                                            L.ptr(g_b2), L.ptr(g_b3), L.ptr(g_w4), L.ptr(ops[0]), L.ptr(ops[1]), L.ptr(ops[2]),
+                                            L.ptr(ops[3]), L.ptr(ws), wsb, st))
+            for a, b, acc in ((ops[2], ops[0], g_w2), (ops[3], ops[1], g_w3)):
+                L.check(L.lib.mimrl_gemm_split(0, L.ptr(a), L.ptr(b), hid, hid, pr, None, 0, L.ptr(tmp), L.ptr(gws), gwb, st))
+                acc += tmp
+        return (g_u, g_vt.t(), g_w2, g_b2 if b2 is not None else None, g_w3, g_b3 if b3 is not None else None,
+                g_w4.reshape(1, -1), g.sum().reshape(1))
+
+
+# --------------------------------------------------------------------------
 # modules (VMI.py:25-110)
 # --------------------------------------------------------------------------
 
@@ -290,7 +352,7 @@ class CriticModel(nn.Module):
             _zero_biases(self.MLP_f)
         else:
             raise NotImplementedError
-        self.pair_chunk = 1 << 16          # pairs scored per step of the concat critic
+        self.pair_chunk = 1 << 20          # pairs scored per step of the concat critic
 
     def embed(self, x, y):
         return mlp_apply(self.MLP_g, x), mlp_apply(self.MLP_h, y)
@@ -302,15 +364,27 @@ class CriticModel(nn.Module):
         dx = x_rows.shape[1]
         u = F.linear(x_rows, first.weight[:, :dx], first.bias)
         v = F.linear(y, first.weight[:, dx:])
+        if self._fused_pairs():
+            f = self.MLP_f
+            return _ConcatPairMLP.apply(u, v, f[2].weight, f[2].bias, f[4].weight, f[4].bias, f[6].weight, f[6].bias)
         h = (u[:, None, :] + v[None, :, :]).reshape(-1, u.shape[1])
         h = mlp_apply(self.MLP_f[1:], h)          # activation of layer 1, then the hidden layers on the tensor cores
         return h.reshape(x_rows.shape[0], y.shape[0])
+
+    def _fused_pairs(self):
+        """The tensor-core all-pairs kernels cover the reference default: ReLU, hidden 256, two hidden layers."""
+        f = self.MLP_f
+        return (f[0].weight.is_cuda and len(f) == 7 and all(isinstance(f[i], nn.ReLU) for i in (1, 3, 5))
+                and L.lib.mimrl_concat_tc_supported(f[2].weight.shape[0], 2) and f[2].weight.shape == (256, 256)
+                and f[4].weight.shape == (256, 256) and f[6].weight.shape == (1, 256))
 
     def forward(self, x, y):
         if self.critic_type == 'separate':
             x_, y_ = self.embed(x, y)
             return torch.matmul(y_, x_.t())
         if self.critic_type == 'concat':
+            if self._fused_pairs():
+                return self._concat_rows(x, y)
             from torch.utils.checkpoint import checkpoint
             n = x.shape[0]
             rows = max(1, self.pair_chunk // max(n, 1))
