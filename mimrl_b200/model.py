@@ -14,7 +14,8 @@ import torch.nn as nn
 from . import _lib as L
 from . import rowblock as RB
 from .linear import mlp_apply
-from .vmi import (BaselineModel, CriticModel, _scores_bound, get_activation, interp_lower_bound, separable_bound)
+from .vmi import (BaselineModel, CriticModel, _scores_bound, gather_rows, get_activation, interp_lower_bound,
+                  separable_bound)
 
 
 # --------------------------------------------------------------------------
@@ -108,12 +109,16 @@ class VMIEstimator(nn.Module):
             x_, y_ = self.critic_model.embed(features_x, features_y)
             base = self.baseline_model(features_y) if needs_base else None
             return separable_bound(x_, y_, bound, base, self.rowblock, self.impl)
-        scores = self.critic_model(features_x, features_y)
         if bound == 'interpolate':
+            if self.rowblock is not None and self.rowblock.sharded:
+                raise NotImplementedError("the interpolated bound needs the whole score matrix on one rank")
+            scores = self.critic_model(features_x, features_y)
             mi = interp_lower_bound(scores, self.baseline_model(features_y), alpha_logit)
             return mi, -mi
+        # materialised scores: this rank's rows (its x against every rank's y, Model.py global-batch semantics)
+        scores = self.critic_model(features_x, gather_rows(features_y, self.rowblock))
         base = self.baseline_model(features_y) if needs_base else None
-        return _scores_bound(scores, bound, base)
+        return _scores_bound(scores, bound, base, self.rowblock)
 
 
 # --------------------------------------------------------------------------

@@ -153,48 +153,85 @@ def separable_bound(x_emb, y_emb, bound_type, log_baseline=None, rowblock=None, 
 
 
 class _ScoresBound(torch.autograd.Function):
-    """Bound over a materialised score matrix [n, n] (API parity with VMI.py:136-198)."""
+    """Bound over a materialised score matrix (API parity with VMI.py:136-198).
+
+    Single rank: scores is [n, n].  Under a sharded RowBlock each rank passes its own rows [n_own, n_all] of the
+    global matrix; per-row statistics are all-gathered so every rank obtains the global-batch value and the
+    gradient of its own rows."""
 
     @staticmethod
-    def forward(ctx, scores, log_baseline, bound_id):
+    def forward(ctx, scores, log_baseline, bound_id, rb=None):
         scores = L.f32(scores)
-        n = scores.shape[0]
-        if scores.dim() != 2 or scores.shape[1] != n:
-            raise ValueError("scores must be a square [batch, batch] matrix")
+        if scores.dim() != 2:
+            raise ValueError("scores must be a [batch, batch] matrix")
+        n_own, n_all = scores.shape
+        if rb is None:
+            rb = RB.single(n_own)
+        if n_all != rb.n_all or n_own != rb.n_own:
+            raise ValueError("scores must be a square [batch, batch] matrix (or this rank's rows of it)")
         fam, inc, flags = _family(bound_id)
         st = L.stream()
-        stats = torch.empty(4, n, dtype=torch.float32, device=scores.device)
-        L.check(L.lib.mimrl_scores_row_stats(L.ptr(scores), n, n, 0, flags, L.ptr(stats[0]), L.ptr(stats[1]),
-                                             L.ptr(stats[2]), L.ptr(stats[3]), st))
-        base = L.f32(log_baseline).reshape(-1) if log_baseline is not None else None
+        stats = torch.empty(4, n_own, dtype=torch.float32, device=scores.device)
+        L.check(L.lib.mimrl_scores_row_stats(L.ptr(scores), n_own, n_all, rb.offset, flags, L.ptr(stats[0]),
+                                             L.ptr(stats[1]), L.ptr(stats[2]), L.ptr(stats[3]), st))
+        base = None
+        if log_baseline is not None:
+            base = RB.all_gather_rows(L.f32(log_baseline).reshape(-1), rb)
+        all_stats = RB.all_gather_rows(stats.t().contiguous(), rb).t().contiguous() if rb.sharded else stats
         result = torch.zeros(16, dtype=torch.float32, device=scores.device)
-        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(stats[2]), L.ptr(stats[3]),
-                                           L.ptr(base), n, L.ptr(result), st))
-        ctx.save_for_backward(scores, stats, result, base if base is not None else result.new_empty(0))
-        ctx.cfg = (bound_id, fam, inc, base is not None)
+        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(all_stats[0]), L.ptr(all_stats[1]), L.ptr(all_stats[2]),
+                                           L.ptr(all_stats[3]), L.ptr(base), n_all, L.ptr(result), st))
+        ctx.save_for_backward(scores, all_stats, result, base if base is not None else result.new_empty(0))
+        ctx.cfg = (bound_id, fam, inc, base is not None, rb)
         return result[0].clone(), result[1].clone()
 
     @staticmethod
     def backward(ctx, g_mi, g_loss):
         scores, stats, result, base = ctx.saved_tensors
-        bound_id, fam, inc, has_base = ctx.cfg
+        bound_id, fam, inc, has_base, rb = ctx.cfg
         base = base if has_base else None
-        n = scores.shape[0]
+        n_own, n_all = scores.shape
         st = L.stream()
         grad = _grad_pair(g_mi, g_loss, result)
         coef = torch.empty(1, dtype=torch.float32, device=scores.device)
-        vec = torch.empty(3, n, dtype=torch.float32, device=scores.device)
+        vec = torch.empty(3, n_all, dtype=torch.float32, device=scores.device)
         L.check(L.lib.mimrl_bound_backward_coef(bound_id, L.ptr(result), L.ptr(grad), L.ptr(stats[0]), L.ptr(stats[1]),
-                                                L.ptr(stats[3]), L.ptr(base), n, L.ptr(coef), L.ptr(vec[0]),
+                                                L.ptr(stats[3]), L.ptr(base), n_all, L.ptr(coef), L.ptr(vec[0]),
                                                 L.ptr(vec[1]), L.ptr(vec[2]) if has_base else None, st))
+        own = slice(rb.offset, rb.offset + n_own)
+        shift_own, dcoef_own = vec[0, own].contiguous(), vec[1, own].contiguous()
         g = torch.empty_like(scores)
-        L.check(L.lib.mimrl_scores_grad(L.ptr(scores), n, n, 0, fam, inc, L.ptr(vec[0]), L.ptr(coef), L.ptr(vec[1]),
-                                        L.ptr(g), st))
-        return g, (vec[2].reshape(n, 1).clone() if has_base else None), None
+        L.check(L.lib.mimrl_scores_grad(L.ptr(scores), n_own, n_all, rb.offset, fam, inc, L.ptr(shift_own), L.ptr(coef),
+                                        L.ptr(dcoef_own), L.ptr(g), st))
+        return g, (vec[2, own].reshape(n_own, 1).clone() if has_base else None), None, None
 
 
-def _scores_bound(scores, bound_type, log_baseline=None):
-    return _ScoresBound.apply(scores, log_baseline, L.BOUND_IDS[bound_type])
+def _scores_bound(scores, bound_type, log_baseline=None, rowblock=None):
+    return _ScoresBound.apply(scores, log_baseline, L.BOUND_IDS[bound_type], rowblock)
+
+
+class _GatherRows(torch.autograd.Function):
+    """All-gather of row blocks that is differentiable: the backward sums every rank's gradient of the gathered
+    matrix and keeps the rows this rank owns (the swept operand of a row-block sharded score matrix)."""
+
+    @staticmethod
+    def forward(ctx, local, rb):
+        ctx.rb = rb
+        return RB.all_gather_rows(local, rb)
+
+    @staticmethod
+    def backward(ctx, g):
+        rb = ctx.rb
+        g = g.contiguous()
+        if rb.sharded:
+            torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM, group=rb.group)
+        return RB.own_slice(g, rb).contiguous(), None
+
+
+def gather_rows(local, rowblock):
+    if rowblock is None or not rowblock.sharded:
+        return local
+    return _GatherRows.apply(local, rowblock)
 
 
 # --------------------------------------------------------------------------

@@ -34,6 +34,14 @@ def _worker(rank, world, port, counts, q):
         assert torch.equal(RB.own_slice(gathered, rb), local)
         vec = RB.all_gather_rows(local[:, 0].contiguous(), rb)          # 1-D rows (per-row statistics)
         assert torch.equal(vec, full[:, 0])
+        # differentiable gather: the backward sums every rank's gradient of the gathered matrix, own rows kept
+        from mimrl_b200.vmi import gather_rows
+        loc = local.clone().requires_grad_(True)
+        got = gather_rows(loc, rb)
+        assert torch.equal(got.detach(), full)
+        w = torch.arange(full.numel(), dtype=torch.float32).reshape(full.shape)
+        (got * w * (rank + 1)).sum().backward()
+        assert torch.equal(loc.grad, RB.own_slice(w * sum(range(1, world + 1)), rb))
         # parameter gradients are partial sums over ranks
         p1 = torch.nn.Parameter(torch.zeros(3, 2))
         p2 = torch.nn.Parameter(torch.zeros(4))
