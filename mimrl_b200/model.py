@@ -81,6 +81,88 @@ def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
     return batch_x.requires_grad_(True), batch_y.requires_grad_(True), batch_z.requires_grad_(True)
 
 
+def _sum_over_ranks(t, rb):
+    if rb.sharded:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=rb.group)
+    return t
+
+
+def _rows_from_shards(local, ids, rb):
+    """rows ``ids`` (global row numbers) of a matrix whose row blocks live on different ranks: every rank
+    contributes the rows it owns, one all-reduce assembles them everywhere."""
+    out = torch.zeros(ids.numel(), local.shape[1], dtype=torch.float32, device=local.device)
+    mine = (ids >= rb.offset) & (ids < rb.offset + rb.n_own)
+    out[mine] = L.f32(local)[ids[mine] - rb.offset]
+    return _sum_over_ranks(out, rb)
+
+
+def knn_search_sharded(Z_local, ids, k, rb, return_distance=False):
+    """``knn_search`` with the key pool row-sharded over ranks (BASELINE config 4): each rank searches its own
+    key block for every query (mimrl_knn_search_rows returns global indices and float64 distances), the
+    world * k candidates per query are all-gathered and merged by (distance, index) -- the same total order the
+    single-GPU search uses, so the result is bit-identical to it.  ``ids`` are global row numbers, the same on
+    every rank.  Returns (nbr_orig, nbr_comp[, dist]) replicated on every rank."""
+    Z_local = L.f32(Z_local)
+    dev = Z_local.device
+    width = Z_local.shape[1]
+    N, m = rb.n_all, int(ids.numel())
+    if k > N - m:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {k}, n_samples_fit = {N - m}")
+    ids = ids.to(device=dev, dtype=torch.int64).contiguous()
+    queries = _rows_from_shards(Z_local, ids, rb)
+    excluded = torch.sort(ids).values.contiguous()
+    n_keys = Z_local.shape[0]
+    nbr = torch.full((m, k), -1, dtype=torch.int64, device=dev)
+    dist = torch.full((m, k), float("inf"), dtype=torch.float64, device=dev)
+    if n_keys > 0:
+        ws_bytes = L.lib.mimrl_knn_workspace_bytes(n_keys, m, width, k)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        exact = 1 if sklearn_route(width, k, N - m) == "brute" else 0
+        L.check(L.lib.mimrl_knn_search_rows(L.ptr(Z_local), n_keys, width, rb.offset, L.ptr(queries), m, L.ptr(excluded), m,
+                                            k, exact, L.ptr(nbr), L.ptr(dist), L.ptr(ws), ws.numel(), L.stream()))
+        dist = torch.where(nbr < 0, torch.full_like(dist, float("inf")), dist)
+    if rb.sharded:
+        all_nbr = [torch.empty_like(nbr) for _ in range(rb.world)]
+        all_dist = [torch.empty_like(dist) for _ in range(rb.world)]
+        torch.distributed.all_gather(all_nbr, nbr, group=rb.group)
+        torch.distributed.all_gather(all_dist, dist, group=rb.group)
+        nbr, dist = torch.cat(all_nbr, dim=1), torch.cat(all_dist, dim=1)
+        # order by (distance, index): stable sort by index, then stable sort by distance
+        o = torch.sort(torch.where(nbr < 0, torch.full_like(nbr, N), nbr), dim=1, stable=True).indices
+        nbr, dist = nbr.gather(1, o), dist.gather(1, o)
+        o = torch.sort(dist, dim=1, stable=True).indices[:, :k]
+        nbr, dist = nbr.gather(1, o).contiguous(), dist.gather(1, o).contiguous()
+    comp = nbr - torch.searchsorted(excluded, nbr.reshape(-1)).reshape(m, k)      # index with the query rows removed
+    return (nbr, comp, dist) if return_distance else (nbr, comp)
+
+
+def prod_knn_sample_sharded(X_local, Y_local, Z_local, batch_size, k_neighbor, radius, rb):
+    """``prod_knn_sample`` (Model.py:75-106) with the pools row-sharded over ranks.  Every rank draws the ids from
+    numpy's global RNG exactly as the reference does (rank 0's draw is broadcast so differently seeded ranks
+    still agree) and receives the full, replicated product batch."""
+    N = rb.n_all
+    m = batch_size // k_neighbor
+    if m > N:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    dev = Z_local.device
+    ids = torch.from_numpy(np.random.permutation(N)[:m].astype(np.int64)).to(dev)
+    if rb.sharded:
+        torch.distributed.broadcast(ids, src=torch.distributed.get_global_rank(rb.group, 0) if rb.group is not None else 0,
+                                    group=rb.group)
+    nbr, _ = knn_search_sharded(Z_local.detach(), ids, k_neighbor, rb)
+    wmax = max(X_local.shape[1], Y_local.shape[1], Z_local.shape[1])
+
+    def tiled(rows, repeat):
+        width = rows.shape[1]
+        rows = rows.repeat(1, wmax // width) if width < wmax else rows          # Model.py:98-104
+        return rows.repeat_interleave(repeat, dim=0).contiguous().requires_grad_(True)
+
+    batch_x = tiled(_rows_from_shards(X_local.detach(), nbr.reshape(-1), rb), 1)
+    batch_y = tiled(_rows_from_shards(Y_local.detach(), ids, rb), k_neighbor)
+    batch_z = tiled(_rows_from_shards(Z_local.detach(), ids, rb), k_neighbor)
+    return batch_x, batch_y, batch_z
+
+
 # --------------------------------------------------------------------------
 # variational MI estimator (Model.py:108-148)
 # --------------------------------------------------------------------------
