@@ -223,6 +223,17 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
                              const float *ln_w, const float *ln_b, int act, float *y, float *saved, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* Tensor-core backward of the same mix.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
+ * writes the weight-gradient operands op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R]
+ * (R = mimrl_cubemlp_tc_fibre_rows(outer, inner), mimrl_split_f32 format, feature-major):
+ * gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T through mimrl_gemm_split(mode 0). */
+long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner);
+int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                             const float *b1, int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
+                             const float *ln_w, const float *ln_b, int act, const float *saved, float *gx, float *g_b1,
+                             float *g_b2, float *gln_w, float *gln_b, void *op_x, void *op_h, void *op_gz, void *op_gpre,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- concat critic, all pairs on the tensor cores (reference VMI.py:58-65 with mlps of VMI.py:13-22) ----
  * The first layer factorises over the concatenation: u = x W1x^T + b1 [n_own, 256], vt = (y W1y^T)^T [256, ldv]
  * (both from the caller).  scores[i, j] = w4 . relu(W3 relu(W2 relu(u_i + v_j) + b2) + b3) + b4 for every pair,

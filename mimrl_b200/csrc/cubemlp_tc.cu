@@ -320,6 +320,486 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---- backward on the tensor cores -------------------------------------------------------------------------
+// Same tile (128 fibres in the TMEM lanes, W1 / W2 / Wres resident in shared memory), two epilogue warpgroups
+// that split the 32-feature chunks of a fibre between them.  One pass per tile:
+//
+//   x -> X            pre = X W1^T -> D1        h = act(pre + b1) -> H          o = H W2^T -> D2,  r = X Wres^T -> H
+//   z = o + r + b2 (+x), zhat from the saved statistics, LayerNorm backward -> gz -> X (over x)
+//   gh = GZ W2 -> D2  (the SAME shared-memory tiles, read MN-major)            gpre = gh act'(pre) -> H
+//   gx = GPRE W1 -> D1  +  GZ Wres -> D2  (+ gz)                               one write of dL/dx
+//
+// The weight gradients contract over fibres (the lane axis): x, h, gz, gpre are written once as fp16 hi/lo
+// operands, feature-major (coalesced: one feature of 32 consecutive fibres per store), and three split-K GEMMs
+// (gemm_tc.cu) finish gW1 = gpre x^T, gW2 = gz h^T, gWres = gz x^T.  Bias and LayerNorm parameter gradients are sums
+// over fibres: 32x32 butterfly transposes, accumulated in registers over the CTA's tiles.
+// Operand scales are powers of two from bounds known before the launch (absmax of x and gy, max rstd of the saved
+// statistics, L1 norms of the weights): |gz| <= rstd (2 + sqrt(A')) max|gy ln_w|.
+constexpr int kCubeBwdThreads = 320;
+constexpr uint32_t kCbVec = 3 * kWMat + 256;                   // b1 | b2 | ln_w (3 x 128 floats)
+constexpr uint32_t kCbPart = kCbVec + 3 * 128 * 4;             // [2 warpgroups][128 fibres][2] partial LN sums
+constexpr uint32_t kCubeBwdSmem = kCbPart + 2 * 128 * 2 * 4 + 1024;
+
+struct CubeBwdParams {
+  CubeTcParams f;
+  const float *gy;
+  float *gx, *g_b1, *g_b2, *g_lnw, *g_lnb;
+  __half *op[4][2];          // x, h, gz, gpre: hi / lo, [features][ld]
+  size_t ld;
+  const float *scales;       // [0] x [1] h [2] gz [3] gpre
+};
+
+__device__ __forceinline__ float cube_dact(int act, float z) {
+  if (act == 0) return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  const float t = tanhf(z);
+  return 1.f - t * t;
+}
+
+// sum over the 32 lanes of v[t] for every t; lane t returns the total of entry t
+__device__ __forceinline__ float cube_lane_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = lane & s;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float keep = upper ? v[k + n / 2] : v[k];
+      const float send = upper ? v[k] : v[k + n / 2];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// features [f0, f0 + 32) of one fibre -> feature-major operand (rows past n_feat do not exist)
+__device__ __forceinline__ void cube_store_op(__half *hi_base, __half *lo_base, size_t ld, size_t row, int f0, int n_feat,
+                                              const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+  unsigned short *h = reinterpret_cast<unsigned short *>(hi_base) + (size_t)f0 * ld + row;
+  unsigned short *l = reinterpret_cast<unsigned short *>(lo_base) + (size_t)f0 * ld + row;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (f0 + 2 * t < n_feat) {
+      h[(size_t)(2 * t) * ld] = (unsigned short)(hi[t] & 0xffffu);
+      l[(size_t)(2 * t) * ld] = (unsigned short)(lo[t] & 0xffffu);
+    }
+    if (f0 + 2 * t + 1 < n_feat) {
+      h[(size_t)(2 * t + 1) * ld] = (unsigned short)(hi[t] >> 16);
+      l[(size_t)(2 * t + 1) * ld] = (unsigned short)(lo[t] >> 16);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCubeBwdThreads, 1)
+cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                      const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                      const __grid_constant__ CUtensorMap map_wr_hi, const __grid_constant__ CUtensorMap map_wr_lo,
+                      const CubeBwdParams bp) {
+  const CubeTcParams &p = bp.f;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  const uint32_t sW1 = base, sW2 = base + kWMat, sWr = base + 2 * kWMat;
+  const uint32_t bars = base + 3 * kWMat;
+  // barriers: weights | x ready | pre full | h ready | o full (mid) | o,r full | gz ready | gh full | gpre ready | gx full
+  const uint32_t bW = bars, bX = bars + 8, bD1 = bars + 16, bH = bars + 24, bMid = bars + 32, bD2 = bars + 40, bGz = bars + 48,
+                 bD3 = bars + 56, bGp = bars + 64, bD4 = bars + 72;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + 3 * kWMat + 128);
+  float *s_b1 = reinterpret_cast<float *>(gen + kCbVec), *s_b2 = s_b1 + 128, *s_lw = s_b1 + 256;
+  float *s_part = reinterpret_cast<float *>(gen + kCbPart);
+  for (int t = threadIdx.x; t < 128; t += blockDim.x) {
+    s_b1[t] = (p.b1 && t < p.H) ? p.b1[t] : 0.f;
+    s_b2[t] = (p.b2 && t < p.A2) ? p.b2[t] : 0.f;
+    s_lw[t] = t < p.A2 ? p.ln_w[t] : 0.f;
+  }
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const long long n_tiles = (p.n_cols + 127) / 128;
+  const int ks_a = (p.A + 15) / 16, ks_h = (p.H + 15) / 16, ks_q = (p.A2 + 15) / 16;       // k-steps over A, H, A'
+  const int n_a = (p.A + 15) & ~15, n_h = (p.H + 15) & ~15, n_q = (p.A2 + 15) & ~15;         // MMA N
+
+  if (threadIdx.x == 0) {
+    mbar_init(bW, 1);
+    mbar_init(bX, 8);
+    mbar_init(bD1, 1);
+    mbar_init(bH, 8);
+    mbar_init(bMid, 1);
+    mbar_init(bD2, 1);
+    mbar_init(bGz, 8);
+    mbar_init(bD3, 1);
+    mbar_init(bGp, 8);
+    mbar_init(bD4, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + 3 * kWMat + 128), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bW, (p.has_res ? 3 : 2) * kWMat);
+      const CUtensorMap *maps[6] = {&map_w1_hi, &map_w1_lo, &map_w2_hi, &map_w2_lo, &map_wr_hi, &map_wr_lo};
+      for (int m = 0; m < (p.has_res ? 3 : 2); ++m)
+        for (int half = 0; half < 2; ++half)
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(base + m * kWMat + (half * 2 + kb) * kW16, maps[m * 2 + half], bW, kb * 64, 0);
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one();
+    mbar_wait(bW, 0);
+    // K-major product set: D (+)= A . W^T with W [n rows, k cols] as loaded
+    auto mma_k = [&](uint32_t d, uint32_t a, uint32_t sw, int ksteps, uint32_t idesc) {
+      uint32_t acc = 0;
+      for (int prod = 0; prod < 3; ++prod) {
+        const uint32_t a_off = prod == 2 ? 64 : 0, b_off = prod == 1 ? 2 * kW16 : 0;
+        for (int k = 0; k < ksteps; ++k) {
+          umma_f16_ts(d, a + a_off + k * 8, smem_desc_sw128(sw + b_off + (k >> 2) * kW16 + (k & 3) * 32), idesc, acc);
+          acc = 1;
+        }
+      }
+    };
+    // MN-major product set: D (+)= A . W with the contraction over the ROWS of the same tiles
+    auto mma_mn = [&](uint32_t d, uint32_t a, uint32_t sw, int ksteps, uint32_t idesc) {
+      uint32_t acc = 0;
+      for (int prod = 0; prod < 3; ++prod) {
+        const uint32_t a_off = prod == 2 ? 64 : 0, b_off = prod == 1 ? 2 * kW16 : 0;
+        for (int k = 0; k < ksteps; ++k) {
+          umma_f16_ts(d, a + a_off + k * 8, smem_desc_sw128_mn(sw + b_off + k * 2048, kW16, 1024), idesc, acc);
+          acc = 1;
+        }
+      }
+    };
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const uint32_t tX = tmem_base + kTX, tD1 = tmem_base + kTD1, tH = tmem_base + kTH, tD2 = tmem_base + kTD2;
+      mbar_wait(bX, ph);
+      tc_fence_after();
+      if (leader) {
+        mma_k(tD1, tX, sW1, ks_a, instr_desc_f16(128, n_h));
+        umma_commit(bD1);
+      }
+      __syncwarp();
+      mbar_wait(bH, ph);
+      tc_fence_after();
+      if (leader) {
+        mma_k(tD2, tH, sW2, ks_h, instr_desc_f16(128, n_q));
+        umma_commit(bMid);
+      }
+      __syncwarp();
+      mbar_wait(bMid, ph);               // the h operand has been consumed: its columns become the accumulator of r
+      tc_fence_after();
+      if (leader) {
+        if (p.has_res) mma_k(tH, tX, sWr, ks_a, instr_desc_f16(128, n_q));
+        umma_commit(bD2);
+      }
+      __syncwarp();
+      mbar_wait(bGz, ph);
+      tc_fence_after();
+      if (leader) {
+        mma_mn(tD2, tX, sW2, ks_q, instr_desc_f16_bmn(128, n_h));
+        umma_commit(bD3);
+      }
+      __syncwarp();
+      mbar_wait(bGp, ph);
+      tc_fence_after();
+      if (leader) {
+        mma_mn(tD1, tH, sW1, ks_h, instr_desc_f16_bmn(128, n_a));
+        if (p.has_res) mma_mn(tD2, tX, sWr, ks_q, instr_desc_f16_bmn(128, n_a));
+        umma_commit(bD4);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int e = warp - 2, q = warp & 3, g = e >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tX = tmem_base + lane_off + kTX, tD1 = tmem_base + lane_off + kTD1, tH = tmem_base + lane_off + kTH,
+                   tD2 = tmem_base + lane_off + kTD2;
+    const float sx = bp.scales[0], sh = bp.scales[1], sgz = bp.scales[2], sgp = bp.scales[3];
+    const float sw1 = scale_from_absmax(p.sc_w1[0]), sw2 = scale_from_absmax(p.sc_w2[0]);
+    const float swr = p.has_res ? scale_from_absmax(p.sc_wr[0]) : 1.f;
+    const float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr), i_gh = 1.f / (sgz * sw2),
+                i_gx1 = 1.f / (sgp * sw1), i_gx2 = 1.f / (sgz * swr), i_gz = 1.f / sgz;
+    float acc_lnw[2] = {0.f, 0.f}, acc_lnb[2] = {0.f, 0.f}, acc_b2[2] = {0.f, 0.f}, acc_b1[2] = {0.f, 0.f};
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const long long c = tile * 128 + r;
+      const bool ok = c < p.n_cols;
+      const long long o = ok ? c / p.inner : 0, i = ok ? c - o * p.inner : 0;
+      const float *xf = p.x + (size_t)o * p.A * p.inner + (size_t)i;
+      const float *gyf = bp.gy + (size_t)o * p.A2 * p.inner + (size_t)i;
+      float *gxf = bp.gx + (size_t)o * p.A * p.inner + (size_t)i;
+      const size_t row = (size_t)c;
+      const float mean = ok ? p.saved[2 * c] : 0.f, rstd = ok ? p.saved[2 * c + 1] : 0.f;
+      // ---- x -> X operand (+ feature-major copy for the weight gradients)
+      for (int ch = g; ch * 32 < ks_a * 16; ch += 2) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int a = ch * 32 + j;
+          v[j] = (ok && a < p.A) ? __ldg(xf + (size_t)a * p.inner) * sx : 0.f;
+        }
+        uint32_t hi[16], lo[16];
+        split32(v, hi, lo);
+        tmem_st16(tX + ch * 16, hi);
+        tmem_st16(tX + 64 + ch * 16, lo);
+        cube_store_op(bp.op[0][0], bp.op[0][1], bp.ld, row, ch * 32, p.A, hi, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bX);
+      // ---- h = act(pre + b1) -> H operand
+      mbar_wait(bD1, ph);
+      tc_fence_after();
+      for (int ch = g; ch * 32 < ks_h * 16; ch += 2) {
+        uint32_t d[32];
+        tmem_ld32(tD1 + ch * 32, d);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int h = ch * 32 + j;
+          v[j] = h < p.H ? cube_act(p.act, fmaf(__uint_as_float(d[j]), i_pre, s_b1[h])) * sh : 0.f;
+        }
+        uint32_t hi[16], lo[16];
+        split32(v, hi, lo);
+        tmem_st16(tH + ch * 16, hi);
+        tmem_st16(tH + 64 + ch * 16, lo);
+        cube_store_op(bp.op[1][0], bp.op[1][1], bp.ld, row, ch * 32, p.H, hi, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bH);
+      // ---- z, LayerNorm backward -> gz -> X operand
+      mbar_wait(bD2, ph);
+      tc_fence_after();
+      auto z_chunk = [&](int ch, float (&z)[32]) {
+        uint32_t d[32], w[32];
+        tmem_ld32(tD2 + ch * 32, d);
+        if (p.has_res) tmem_ld32(tH + ch * 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int a2 = ch * 32 + j;
+          float t = 0.f;
+          if (a2 < p.A2) {
+            t = fmaf(__uint_as_float(d[j]), i_o, s_b2[a2]);
+            if (p.has_res) t = fmaf(__uint_as_float(w[j]), i_r, t);
+            else if (ok) t += __ldg(xf + (size_t)a2 * p.inner);
+          }
+          z[j] = t;
+        }
+      };
+      float sum_g = 0.f, sum_gz = 0.f;
+      {
+        int cc = 0;
+        for (int ch = g; ch * 32 < n_q; ch += 2, ++cc) {
+          float z[32], t1[32], t2[32];
+          z_chunk(ch, z);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int a2 = ch * 32 + j;
+            const float gyv = (ok && a2 < p.A2) ? __ldg(gyf + (size_t)a2 * p.inner) : 0.f;
+            const float zh = (z[j] - mean) * rstd;
+            const float gh_ = gyv * s_lw[a2 < p.A2 ? a2 : 0];
+            sum_g += gh_;
+            sum_gz = fmaf(gh_, zh, sum_gz);
+            t1[j] = gyv * zh;
+            t2[j] = gyv;
+          }
+          const float a1 = cube_lane_sum(t1, lane), a2s = cube_lane_sum(t2, lane);
+          if (cc == 0) acc_lnw[0] += a1, acc_lnb[0] += a2s;
+          else acc_lnw[1] += a1, acc_lnb[1] += a2s;
+        }
+      }
+      s_part[(g * 128 + r) * 2] = sum_g;
+      s_part[(g * 128 + r) * 2 + 1] = sum_gz;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m1 = (sum_g + s_part[((g ^ 1) * 128 + r) * 2]) / p.A2;
+      const float m2 = (sum_gz + s_part[((g ^ 1) * 128 + r) * 2 + 1]) / p.A2;
+      {
+        int cc = 0;
+        for (int ch = g; ch * 32 < ks_q * 16; ch += 2, ++cc) {
+          float z[32], v[32], t1[32];
+          z_chunk(ch, z);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int a2 = ch * 32 + j;
+            const float gyv = (ok && a2 < p.A2) ? __ldg(gyf + (size_t)a2 * p.inner) : 0.f;
+            const float zh = (z[j] - mean) * rstd;
+            const float gzv = a2 < p.A2 ? rstd * (gyv * s_lw[a2 < p.A2 ? a2 : 0] - m1 - zh * m2) : 0.f;
+            t1[j] = gzv;
+            v[j] = gzv * sgz;
+          }
+          uint32_t hi[16], lo[16];
+          split32(v, hi, lo);
+          tmem_st16(tX + ch * 16, hi);
+          tmem_st16(tX + 64 + ch * 16, lo);
+          cube_store_op(bp.op[2][0], bp.op[2][1], bp.ld, row, ch * 32, p.A2, hi, lo);
+          const float a1 = cube_lane_sum(t1, lane);
+          if (cc == 0) acc_b2[0] += a1;
+          else acc_b2[1] += a1;
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bGz);
+      // ---- gpre = gh act'(pre) -> H operand
+      mbar_wait(bD3, ph);
+      tc_fence_after();
+      {
+        int cc = 0;
+        for (int ch = g; ch * 32 < ks_h * 16; ch += 2, ++cc) {
+          uint32_t d[32], w[32];
+          tmem_ld32(tD2 + ch * 32, d);
+          tmem_ld32(tD1 + ch * 32, w);
+          tmem_ld_wait();
+          float v[32], t1[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int h = ch * 32 + j;
+            const float pre = fmaf(__uint_as_float(w[j]), i_pre, s_b1[h < p.H ? h : 0]);
+            const float gp = h < p.H ? __uint_as_float(d[j]) * i_gh * cube_dact(p.act, pre) : 0.f;
+            t1[j] = gp;
+            v[j] = gp * sgp;
+          }
+          uint32_t hi[16], lo[16];
+          split32(v, hi, lo);
+          tmem_st16(tH + ch * 16, hi);
+          tmem_st16(tH + 64 + ch * 16, lo);
+          cube_store_op(bp.op[3][0], bp.op[3][1], bp.ld, row, ch * 32, p.H, hi, lo);
+          const float a1 = cube_lane_sum(t1, lane);
+          if (cc == 0) acc_b1[0] += a1;
+          else acc_b1[1] += a1;
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bGp);
+      // ---- gx = gpre W1 + gz Wres (+ gz)
+      mbar_wait(bD4, ph);
+      tc_fence_after();
+      for (int ch = g; ch * 32 < n_a; ch += 2) {
+        uint32_t d[32], w[32];
+        tmem_ld32(tD1 + ch * 32, d);
+        if (p.has_res) tmem_ld32(tD2 + ch * 32, w);
+        else {                                         // identity residual: gz itself, back from its operand columns
+          uint32_t hi[16], lo[16];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                       : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]),
+                         "=r"(hi[8]), "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
+                       : "r"(tX + ch * 16) : "memory");
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                       : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]),
+                         "=r"(lo[8]), "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15])
+                       : "r"(tX + 64 + ch * 16) : "memory");
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&hi[t]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&lo[t]));
+            w[2 * t] = __float_as_uint((a.x + b.x) * i_gz);
+            w[2 * t + 1] = __float_as_uint((a.y + b.y) * i_gz);
+          }
+        }
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int a = ch * 32 + j;
+            if (a < p.A) {
+              float t = __uint_as_float(d[j]) * i_gx1;
+              t += p.has_res ? __uint_as_float(w[j]) * i_gx2 : __uint_as_float(w[j]);
+              gxf[(size_t)a * p.inner] = t;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int f = 32 * (g + 2 * cc) + lane;
+      if (f < p.A2) {
+        atomicAdd(bp.g_lnw + f, acc_lnw[cc]);
+        atomicAdd(bp.g_lnb + f, acc_lnb[cc]);
+        if (bp.g_b2) atomicAdd(bp.g_b2 + f, acc_b2[cc]);
+      }
+      if (f < p.H && bp.g_b1) atomicAdd(bp.g_b1 + f, acc_b1[cc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- scales of the backward operands ------------------------------------------------------------------------
+// absmax: [0] x  [1] gy  [2] rstd (saved[2c+1])
+__global__ void cube_absmax_kernel(const float *x, size_t nx, const float *gy, size_t ngy, const float *saved, size_t n_cols,
+                                   unsigned *out) {
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = t0; t < nx; t += st) m0 = fmaxf(m0, fabsf(x[t]));
+  for (size_t t = t0; t < ngy; t += st) m1 = fmaxf(m1, fabsf(gy[t]));
+  for (size_t t = t0; t < n_cols; t += st) m2 = fmaxf(m2, fabsf(saved[2 * t + 1]));
+  for (int o = 16; o; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, __float_as_uint(m0));
+    atomicMax(out + 1, __float_as_uint(m1));
+    atomicMax(out + 2, __float_as_uint(m2));
+  }
+}
+
+// one block of 128 threads
+__global__ void cube_scales_kernel(const unsigned *absmax, const float *w1, const float *b1, const float *w2, const float *ln_w,
+                                   int A, int H, int A2, float *scales, unsigned *hdr_x, unsigned *hdr_h, unsigned *hdr_gz,
+                                   unsigned *hdr_gp) {
+  __shared__ float red[128];
+  const int n = threadIdx.x;
+  auto block_max = [&](float v) {
+    __syncthreads();
+    red[n] = v;
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+      if (n < o) red[n] = fmaxf(red[n], red[n + o]);
+      __syncthreads();
+    }
+    return red[0];
+  };
+  float row1 = 0.f, col2 = 0.f;
+  if (n < H) {
+    for (int a = 0; a < A; ++a) row1 += fabsf(w1[(size_t)n * A + a]);          // sum_a |W1[h, a]|
+    for (int q = 0; q < A2; ++q) col2 += fabsf(w2[(size_t)q * H + n]);         // sum_q |W2[q, h]|
+  }
+  const float row1_max = block_max(row1), col2_max = block_max(col2);
+  const float b1_max = block_max((b1 && n < H) ? fabsf(b1[n]) : 0.f), lw_max = block_max(n < A2 ? fabsf(ln_w[n]) : 0.f);
+  if (n == 0) {
+    const float m_x = __uint_as_float(absmax[0]), m_gy = __uint_as_float(absmax[1]), m_rstd = __uint_as_float(absmax[2]);
+    const float m_h = m_x * row1_max + b1_max;                                 // |act(z)| <= |z| for gelu, relu, tanh
+    const float m_gz = m_rstd * (2.f + sqrtf((float)A2)) * m_gy * lw_max;
+    const float m_gp = 1.2f * m_gz * col2_max;                                 // |gelu'| < 1.13
+    scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h), scales[2] = pow2_scale(m_gz), scales[3] = pow2_scale(m_gp);
+    *hdr_x = __float_as_uint(m_x), *hdr_h = __float_as_uint(m_h), *hdr_gz = __float_as_uint(m_gz), *hdr_gp = __float_as_uint(m_gp);
+  }
+}
+
 }  // namespace
 }  // namespace mimrl
 
@@ -379,4 +859,81 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   cubemlp_tc_fwd_kernel<<<blocks, kCubeThreads, kCubeSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, p);
   return check_launch("cubemlp_tc_fwd");
+}
+
+// rows (fibres, whole tiles) of the feature-major weight-gradient operands
+extern "C" long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner) {
+  if (outer <= 0 || inner <= 0) return 0;
+  return (((long long)outer * inner + 127) / 128) * 128;
+}
+
+// Backward of mimrl_cubemlp_mix_fwd_tc.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
+// writes op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R] (R = mimrl_cubemlp_tc_fibre_rows,
+// mimrl_split_f32 format): gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T via mimrl_gemm_split(mode 0).
+extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                                        const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
+                                        const float *wres, const float *ln_w, const float *ln_b, int act,
+                                        const float *saved, float *gx, float *g_b1, float *g_b2, float *gln_w, float *gln_b,
+                                        void *op_x, void *op_h, void *op_gz, void *op_gpre, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+  MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in, a_hid, a_out, 0, act), "cubemlp_mix_bwd_tc: sizes %d/%d/%d act %d not supported",
+                a_in, a_hid, a_out, act);
+  MIMRL_REQUIRE(outer > 0 && inner > 0 && x && gy && saved && gx && w1 && w2 && ln_w && gln_w && gln_b && op_x && op_h && op_gz &&
+                    op_gpre,
+                "cubemlp_mix_bwd_tc: bad arguments");
+  MIMRL_REQUIRE(wres || a_in == a_out, "cubemlp_mix: without res_project d_in must equal d_out (MLPProcess.py:46-48)");
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_cubemlp_tc_workspace_bytes(a_in, a_hid, a_out), "cubemlp_mix_bwd_tc: workspace too small");
+  (void)ln_b;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)workspace;
+  unsigned char *s1 = ws, *s2 = s1 + mimrl_split_bytes(a_hid, a_in), *s3 = s2 + mimrl_split_bytes(a_out, a_hid);
+  unsigned char *tail = s3 + mimrl_split_bytes(a_out, a_in);           // 256 spare bytes: absmax[3] | scales[4]
+  unsigned *absmax = reinterpret_cast<unsigned *>(tail);
+  float *scales = reinterpret_cast<float *>(tail + 64);
+  if (int rc = mimrl_split_f32(w1, nullptr, a_hid, a_in, s1, nullptr, stream)) return rc;
+  if (int rc = mimrl_split_f32(w2, nullptr, a_out, a_hid, s2, nullptr, stream)) return rc;
+  if (wres)
+    if (int rc = mimrl_split_f32(wres, nullptr, a_out, a_in, s3, nullptr, stream)) return rc;
+  const long long n_cols = (long long)outer * inner;
+  cudaMemsetAsync(absmax, 0, 16, st);
+  cube_absmax_kernel<<<148 * 2, 256, 0, st>>>(x, (size_t)n_cols * a_in, gy, (size_t)n_cols * a_out, saved, (size_t)n_cols, absmax);
+  if (check_launch("cubemlp absmax")) return 1;
+  cube_scales_kernel<<<1, 128, 0, st>>>(absmax, w1, b1, w2, ln_w, a_in, a_hid, a_out, scales, (unsigned *)op_x, (unsigned *)op_h,
+                                        (unsigned *)op_gz, (unsigned *)op_gpre);
+  if (check_launch("cubemlp scales")) return 1;
+  auto maps = [&](unsigned char *s, int rows, int cols, CUtensorMap *hi, CUtensorMap *lo) {
+    const int ld = (cols + 63) & ~63;
+    const size_t off_lo = 256 + align256((size_t)rows * ld * 2);
+    if (make_map(hi, s + 256, cols, rows, ld, 128)) return 1;
+    return make_map(lo, s + off_lo, cols, rows, ld, 128);
+  };
+  CUtensorMap m1h, m1l, m2h, m2l, mrh, mrl;
+  if (maps(s1, a_hid, a_in, &m1h, &m1l)) return 1;
+  if (maps(s2, a_out, a_hid, &m2h, &m2l)) return 1;
+  if (wres) {
+    if (maps(s3, a_out, a_in, &mrh, &mrl)) return 1;
+  } else {
+    mrh = m1h, mrl = m1l;
+  }
+  CubeBwdParams bp;
+  CubeTcParams &p = bp.f;
+  p.x = x, p.b1 = b1, p.b2 = b2, p.ln_w = ln_w, p.ln_b = ln_b, p.y = nullptr, p.saved = const_cast<float *>(saved);
+  p.sc_w1 = reinterpret_cast<const unsigned *>(s1), p.sc_w2 = reinterpret_cast<const unsigned *>(s2);
+  p.sc_wr = reinterpret_cast<const unsigned *>(s3);
+  p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
+  p.n_cols = n_cols;
+  bp.gy = gy, bp.gx = gx, bp.g_b1 = g_b1, bp.g_b2 = g_b2, bp.g_lnw = gln_w, bp.g_lnb = gln_b;
+  bp.scales = scales;
+  const long long n_tiles = (n_cols + 127) / 128;
+  bp.ld = (size_t)n_tiles * 128;
+  void *ops[4] = {op_x, op_h, op_gz, op_gpre};
+  const int feats[4] = {a_in, a_hid, a_out, a_hid};
+  for (int t = 0; t < 4; ++t) {
+    bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
+    bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256 + align256((size_t)feats[t] * bp.ld * 2));
+  }
+  cudaFuncSetAttribute(cubemlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);
+  const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
+  cubemlp_tc_bwd_kernel<<<blocks, kCubeBwdThreads, kCubeBwdSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, bp);
+  return check_launch("cubemlp_tc_bwd");
 }

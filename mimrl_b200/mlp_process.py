@@ -67,6 +67,8 @@ class _AxisMix(torch.autograd.Function):
                                                 L.stream()))
         ctx.save_for_backward(x, saved, *[p if p is not None else x.new_empty(0) for p in prm])
         ctx.cfg = (outer, A, inner, H, A2, int(ln_first), act_id, [p is not None for p in prm])
+        ctx.use_tc = bool(USE_TC and outer * inner >= 1024
+                          and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id))
         return y
 
     @staticmethod
@@ -78,6 +80,8 @@ class _AxisMix(torch.autograd.Function):
         gy = L.f32(gy)
         dev = x.device
         gx = torch.empty_like(x)
+        if ctx.use_tc:
+            return _AxisMix._backward_tc(x, gy, saved, prm, ctx.cfg, gx)
         s_gz = torch.empty(outer, A2, inner, device=dev)
         s_h = torch.empty(outer, H, inner, device=dev)
         s_gpre = torch.empty(outer, H, inner, device=dev)
@@ -96,6 +100,40 @@ class _AxisMix(torch.autograd.Function):
         gb1 = s_gpre.sum(dim=(0, 2)) if b1 is not None else None
         gwres = torch.einsum("oqi,oai->qa", s_gz, x3) if wres is not None else None
         return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+
+
+def _backward_tc(x, gy, saved, prm, cfg, gx):
+    """Tensor-core backward: one fused data-gradient kernel, then three split-K GEMMs over the feature-major
+    fp16 hi/lo operands it leaves behind (csrc/cubemlp_tc.cu)."""
+    outer, A, inner, H, A2, ln_first, act_id, present = cfg
+    w1, b1, w2, b2, wres, ln_w, ln_b = prm
+    dev = x.device
+    st = L.stream()
+    R = L.lib.mimrl_cubemlp_tc_fibre_rows(outer, inner)
+    ops = [torch.empty(L.lib.mimrl_split_bytes(n, R), dtype=torch.uint8, device=dev) for n in (A, H, A2, H)]
+    ws = torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=dev)
+    gb1 = torch.zeros(H, device=dev) if b1 is not None else None
+    gb2 = torch.zeros(A2, device=dev) if b2 is not None else None
+    gln = torch.zeros(2, A2, device=dev)
+    L.check(L.lib.mimrl_cubemlp_mix_bwd_tc(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2), L.ptr(b2),
+                                           A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), act_id, L.ptr(saved), L.ptr(gx),
+                                           L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(ops[0]), L.ptr(ops[1]),
+                                           L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), ws.numel(), st))
+
+    def wgrad(a, b, m, n):
+        out = torch.empty(m, n, device=dev)
+        gwb = L.lib.mimrl_gemm_split_workspace_bytes(0, m, n, R)
+        gws = torch.empty(gwb, dtype=torch.uint8, device=dev)
+        L.check(L.lib.mimrl_gemm_split(0, L.ptr(a), L.ptr(b), m, n, R, None, 0, L.ptr(out), L.ptr(gws), gwb, st))
+        return out
+
+    gw1 = wgrad(ops[3], ops[0], H, A)
+    gw2 = wgrad(ops[2], ops[1], A2, H)
+    gwres = wgrad(ops[2], ops[0], A2, A) if wres is not None else None
+    return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+
+
+_AxisMix._backward_tc = staticmethod(_backward_tc)
 
 
 class MLP(nn.Module):
