@@ -213,6 +213,15 @@ int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer, int a_in, 
                           const float *saved, float *gx, float *s_gz, float *s_h, float *s_gpre, float *s_u,
                           float *gln_w, float *gln_b, void *stream);
 
+/* Tiny mixed axis (all three sizes <= 4, the modality mix K = 3 of MLPProcess.py:106-112): the complete backward in
+ * one register-resident kernel.  Writes gx; accumulates (+=) gw1 [a_hid,a_in], gb1, gw2 [a_out,a_hid], gb2,
+ * gwres [a_out,a_in] (NULL without res_projection), gln_w, gln_b. */
+int mimrl_cubemlp_small_supported(int a_in, int a_hid, int a_out);
+int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                            const float *b1, int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
+                            const float *ln_w, const float *ln_b, int ln_first, int act, float *gx, float *gw1, float *gb1,
+                            float *gw2, float *gb2, float *gwres, float *gln_w, float *gln_b, void *stream);
+
 /* Tensor-core forward of the same mix (ln_first = 0, axis sizes <= 128, not the tiny-axis case): fibres in TMEM
  * lanes, W1 / W2 / Wres resident in shared memory, LayerNorm thread-local in the epilogue.  Writes the same
  * `saved` statistics, so mimrl_cubemlp_mix_bwd applies unchanged. */

@@ -65,6 +65,9 @@ _SIGS = {
                                          _P, c_size_t, _P]),
     "mimrl_cubemlp_mix_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int,
                                       c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mimrl_cubemlp_small_supported": (c_int, [c_int, c_int, c_int]),
+    "mimrl_cubemlp_small_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, c_int,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mimrl_cubemlp_tc_fibre_rows": (c_int64, [c_int, c_int]),
     "mimrl_cubemlp_mix_bwd_tc": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P,
                                          _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -256,6 +256,7 @@ cubemlp_mix_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict
 
 struct MixBwdOut {
   float *gx, *s_gz, *s_h, *s_gpre, *s_u, *gln_w, *gln_b;
+  float *gw1 = nullptr, *gw2 = nullptr, *gwr = nullptr, *gb1 = nullptr, *gb2 = nullptr;   // tiny-axis kernel, WG > 0
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -525,10 +526,23 @@ cubemlp_small_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restri
   }
 }
 
+// WG > 0 (axis sizes <= WG): the weight and bias gradients are accumulated here as well (registers -> warp
+// shuffles -> shared -> one global atomic per block and entry) and the scratch tensors are not written.
+template <int WG>
 __global__ void __launch_bounds__(256)
 cubemlp_small_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBwdOut o) {
   __shared__ SmallParams sp;
   __shared__ float s_glw[kSmallMax], s_glb[kSmallMax];
+  constexpr int NW = WG > 0 ? WG : 1;
+  __shared__ float s_w[3 * NW * NW + 2 * NW];
+  float aw1[NW * NW], aw2[NW * NW], awr[NW * NW], ab1[NW], ab2[NW];
+  if (WG > 0) {
+    for (int t = threadIdx.x; t < 3 * NW * NW + 2 * NW; t += blockDim.x) s_w[t] = 0.f;
+#pragma unroll
+    for (int t = 0; t < NW * NW; ++t) aw1[t] = 0.f, aw2[t] = 0.f, awr[t] = 0.f;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) ab1[t] = 0.f, ab2[t] = 0.f;
+  }
   load_small_params(sp, m);
   if (threadIdx.x < kSmallMax) s_glw[threadIdx.x] = 0.f, s_glb[threadIdx.x] = 0.f;
   __syncthreads();
@@ -601,17 +615,64 @@ cubemlp_small_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const Mi
 #pragma unroll
       for (int a = 0; a < kSmallMax; ++a) gx[a] = gu[a] + gres[a];
     }
+    if (WG > 0) {
 #pragma unroll
-    for (int a = 0; a < kSmallMax; ++a) {
-      if (a < d.A) {
-        o.gx[bi + (size_t)a * d.inner] = gx[a];
-        if (m.ln_first) o.s_u[bi + (size_t)a * d.inner] = u[a];
+      for (int a = 0; a < kSmallMax; ++a)
+        if (a < d.A) o.gx[bi + (size_t)a * d.inner] = gx[a];
+      // gW1[h, a] += gpre[h] u[a];  gW2[q, h] += gz[q] h[h];  gWres[q, a] += gz[q] x[a]   (entries past the sizes are 0)
+#pragma unroll
+      for (int r = 0; r < NW; ++r) {
+#pragma unroll
+        for (int c2 = 0; c2 < NW; ++c2) {
+          aw1[r * NW + c2] = fmaf(gpre[r], m.ln_first ? u[c2] : x[c2], aw1[r * NW + c2]);
+          aw2[r * NW + c2] = fmaf(gz[r], h[c2], aw2[r * NW + c2]);
+          awr[r * NW + c2] = fmaf(gz[r], x[c2], awr[r * NW + c2]);
+        }
+        ab1[r] += gpre[r];
+        ab2[r] += gz[r];
       }
-      if (a < d.A2) o.s_gz[bo + (size_t)a * d.inner] = gz[a];
-      if (a < d.H) {
-        o.s_h[bh + (size_t)a * d.inner] = h[a];
-        o.s_gpre[bh + (size_t)a * d.inner] = gpre[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < kSmallMax; ++a) {
+        if (a < d.A) {
+          o.gx[bi + (size_t)a * d.inner] = gx[a];
+          if (m.ln_first) o.s_u[bi + (size_t)a * d.inner] = u[a];
+        }
+        if (a < d.A2) o.s_gz[bo + (size_t)a * d.inner] = gz[a];
+        if (a < d.H) {
+          o.s_h[bh + (size_t)a * d.inner] = h[a];
+          o.s_gpre[bh + (size_t)a * d.inner] = gpre[a];
+        }
       }
+    }
+  }
+  if (WG > 0) {
+    auto warp_sum = [](float v) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      return v;
+    };
+    const bool lead = (threadIdx.x & 31) == 0;
+#pragma unroll
+    for (int t = 0; t < NW * NW; ++t) {
+      const float v1 = warp_sum(aw1[t]), v2 = warp_sum(aw2[t]), v3 = warp_sum(awr[t]);
+      if (lead) atomicAdd(&s_w[t], v1), atomicAdd(&s_w[NW * NW + t], v2), atomicAdd(&s_w[2 * NW * NW + t], v3);
+    }
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const float v1 = warp_sum(ab1[t]), v2 = warp_sum(ab2[t]);
+      if (lead) atomicAdd(&s_w[3 * NW * NW + t], v1), atomicAdd(&s_w[3 * NW * NW + NW + t], v2);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NW * NW; t += blockDim.x) {
+      const int r = t / NW, c2 = t % NW;
+      if (r < d.H && c2 < d.A) atomicAdd(o.gw1 + r * d.A + c2, s_w[t]);
+      if (r < d.A2 && c2 < d.H) atomicAdd(o.gw2 + r * d.H + c2, s_w[NW * NW + t]);
+      if (o.gwr && r < d.A2 && c2 < d.A) atomicAdd(o.gwr + r * d.A + c2, s_w[2 * NW * NW + t]);
+    }
+    if (threadIdx.x < NW) {
+      if (o.gb1 && threadIdx.x < d.H) atomicAdd(o.gb1 + threadIdx.x, s_w[3 * NW * NW + threadIdx.x]);
+      if (o.gb2 && threadIdx.x < d.A2) atomicAdd(o.gb2 + threadIdx.x, s_w[3 * NW * NW + NW + threadIdx.x]);
     }
   }
   // LayerNorm parameter gradients: warp reduce -> shared -> one global atomic per block and feature
@@ -704,7 +765,7 @@ extern "C" int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer,
   if (is_small(m.d)) {
     const long long nb = (m.d.n_cols + 255) / 256;
     MixBwdOut so{gx, s_gz, s_h, s_gpre, s_u, gln_w, gln_b};
-    cubemlp_small_bwd_kernel<<<(int)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+    cubemlp_small_bwd_kernel<0><<<(int)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, (cudaStream_t)stream>>>(m, gy, so);
     return check_launch("cubemlp_small_bwd");
   }
   const size_t smem = bwd_smem(m.d, ln_first);
@@ -716,4 +777,25 @@ extern "C" int mimrl_cubemlp_mix_bwd(const float *x, const float *gy, int outer,
   MixBwdOut o{gx, s_gz, s_h, s_gpre, s_u, gln_w, gln_b};
   cubemlp_mix_bwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(m, gy, saved, o);
   return check_launch("cubemlp_mix_bwd");
+}
+
+// Tiny axis (all three sizes <= 4, the modality mix K = 3): complete backward in one kernel.  Writes gx; accumulates
+// (+=) gw1 [a_hid, a_in], gb1, gw2 [a_out, a_hid], gb2, gwres [a_out, a_in] (nullable), gln_w, gln_b.
+extern "C" int mimrl_cubemlp_small_supported(int a_in, int a_hid, int a_out) { return a_in <= 4 && a_hid <= 4 && a_out <= 4; }
+
+extern "C" int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
+                                       const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
+                                       const float *wres, const float *ln_w, const float *ln_b, int ln_first, int act,
+                                       float *gx, float *gw1, float *gb1, float *gw2, float *gb2, float *gwres, float *gln_w,
+                                       float *gln_b, void *stream) {
+  MixArgs m;
+  if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
+  MIMRL_REQUIRE(mimrl_cubemlp_small_supported(a_in, a_hid, a_out), "cubemlp_small_bwd: axis sizes %d/%d/%d exceed 4", a_in, a_hid,
+                a_out);
+  MIMRL_REQUIRE(gx && gw1 && gw2 && gln_w && gln_b && (!wres || gwres), "cubemlp_small_bwd: missing outputs");
+  MixBwdOut so{gx, nullptr, nullptr, nullptr, nullptr, gln_w, gln_b};
+  so.gw1 = gw1, so.gw2 = gw2, so.gwr = wres ? gwres : nullptr, so.gb1 = gb1, so.gb2 = gb2;
+  const long long nb = (m.d.n_cols + 255) / 256;
+  cubemlp_small_bwd_kernel<4><<<(int)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+  return check_launch("cubemlp_small_bwd (with weight gradients)");
 }

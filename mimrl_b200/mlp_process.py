@@ -82,6 +82,18 @@ class _AxisMix(torch.autograd.Function):
         gx = torch.empty_like(x)
         if ctx.use_tc:
             return _AxisMix._backward_tc(x, gy, saved, prm, ctx.cfg, gx)
+        if L.lib.mimrl_cubemlp_small_supported(A, H, A2):
+            # the modality mix: data, weight, bias and LayerNorm gradients from one register-resident kernel
+            gw1, gw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+            gb1 = torch.zeros_like(b1) if b1 is not None else None
+            gb2 = torch.zeros_like(b2) if b2 is not None else None
+            gwres = torch.zeros_like(wres) if wres is not None else None
+            gln = torch.zeros(2, ln_w.numel(), device=dev)
+            L.check(L.lib.mimrl_cubemlp_small_bwd(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2),
+                                                  L.ptr(b2), A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), ln_first, act_id,
+                                                  L.ptr(gx), L.ptr(gw1), L.ptr(gb1), L.ptr(gw2), L.ptr(gb2), L.ptr(gwres),
+                                                  L.ptr(gln[0]), L.ptr(gln[1]), L.stream()))
+            return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
         s_gz = torch.empty(outer, A2, inner, device=dev)
         s_h = torch.empty(outer, H, inner, device=dev)
         s_gpre = torch.empty(outer, H, inner, device=dev)
