@@ -21,10 +21,11 @@
 namespace mimrl {
 namespace {
 
-constexpr int kCubeThreads = 192;                      // warp 0 TMA, warp 1 MMA, warps 2-5 compute (thread = fibre)
+constexpr int kCubeThreads = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-9: two compute warpgroups that
+                                                       // split the 32-feature chunks of a fibre (thread = fibre x chunk parity)
 constexpr uint32_t kW16 = 128 * 128;                   // one 128-row x 64-K block: 16 KB
 constexpr uint32_t kWMat = 4 * kW16;                   // hi kb0, hi kb1, lo kb0, lo kb1
-constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, alignment
+constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + 2 * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, LN partials, alignment
 // TMEM columns
 constexpr uint32_t kTX = 0, kTD1 = 128, kTH = 256, kTD2 = 384;
 
@@ -32,6 +33,7 @@ struct CubeTcParams {
   const float *x, *b1, *b2, *ln_w, *ln_b;
   float *y, *saved;
   const unsigned *sc_w1, *sc_w2, *sc_wr;               // absmax headers of the split weights
+  const float *scales;                                 // forward: [0] scale of x, [1] scale of h (powers of two)
   int outer, A, H, A2, inner, act, has_res;
   long long n_cols;
 };
@@ -91,9 +93,9 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(bWFull, 1);
-    mbar_init(bXReady, 4);
+    mbar_init(bXReady, 8);
     mbar_init(bD1Full, 1);
-    mbar_init(bHReady, 4);
+    mbar_init(bHReady, 8);
     mbar_init(bD2Full, 1);
     fence_barrier_init();
   }
@@ -180,11 +182,13 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3, g = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const float inv_w1 = 1.f / scale_from_absmax(p.sc_w1[0]), inv_w2 = 1.f / scale_from_absmax(p.sc_w2[0]);
-    const float inv_wr = p.has_res ? 1.f / scale_from_absmax(p.sc_wr[0]) : 0.f;
+    float *s_part = s_lb + 128;                                  // [2 warpgroups][128 fibres]
+    const float sx = p.scales[0], sh = p.scales[1];
+    const float s1 = 1.f / (sx * scale_from_absmax(p.sc_w1[0])), s2 = 1.f / (sh * scale_from_absmax(p.sc_w2[0]));
+    const float s3 = p.has_res ? 1.f / (sx * scale_from_absmax(p.sc_wr[0])) : 0.f;
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -193,20 +197,8 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       const long long o = ok ? c / p.inner : 0, i = ok ? c - o * p.inner : 0;
       const float *xf = p.x + (size_t)o * p.A * p.inner + (size_t)i;
       float *yf = p.y + (size_t)o * p.A2 * p.inner + (size_t)i;
-      // ---- 1. fibre -> TMEM (own power-of-two scale, fp16 hi/lo)
-      float amax = 0.f;
-      if (ok) {          // 8 independent loads in flight per round trip
-        float m8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int a = 0;
-        for (; a + 8 <= p.A; a += 8) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) m8[u] = fmaxf(m8[u], fabsf(__ldg(xf + (size_t)(a + u) * p.inner)));
-        }
-        for (; a < p.A; ++a) m8[0] = fmaxf(m8[0], fabsf(__ldg(xf + (size_t)a * p.inner)));
-        amax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-      }
-      const float sx = pow2_scale(amax), inv_x = 1.f / sx;
-      for (int ch = 0; ch * 32 < ks1 * 16; ++ch) {
+      // ---- 1. fibre -> TMEM (one power-of-two scale for the tensor, fp16 hi/lo)
+      for (int ch = g; ch * 32 < ks1 * 16; ch += 2) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -222,23 +214,10 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bXReady);
-      // ---- 2. pre-activation -> h (bound |act(z)| <= |z| gives the scale without a second activation pass)
+      // ---- 2. h = act(pre + b1) (scale from the bound |act(z)| <= |z| <= max|x| max_h sum_a |W1[h,a]| + max|b1|)
       mbar_wait(bD1Full, ph);
       tc_fence_after();
-      const float s1 = inv_x * inv_w1;
-      float hmax = 0.f;
-      for (int ch = 0; ch * 32 < n1; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + kTD1 + ch * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int h = ch * 32 + j;
-          if (h < p.H) hmax = fmaxf(hmax, fabsf(fmaf(__uint_as_float(v[j]), s1, s_b1[h])));
-        }
-      }
-      const float sh = pow2_scale(hmax), inv_h = 1.f / sh;
-      for (int ch = 0; ch * 32 < ks2 * 16; ++ch) {
+      for (int ch = g; ch * 32 < ks2 * 16; ch += 2) {
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + kTD1 + ch * 32, v);
         tmem_ld_wait();
@@ -257,62 +236,69 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bHReady);
-      // ---- 3. z = o + r + b2 (+ x), LayerNorm over A' thread-locally, one write
+      // ---- 3. z = o + r + b2 (+ x), LayerNorm over A' (this thread's chunks stay in registers; the two
+      //         warpgroups exchange their partial sums through shared memory), one write
       mbar_wait(bD2Full, ph);
       tc_fence_after();
-      const float s2 = inv_h * inv_w2, s3 = inv_x * inv_wr;
-      auto z_chunk = [&](int ch, float (&z)[32]) {
-        uint32_t v[32], w[32];
-        tmem_ld32(tmem_base + lane_off + kTD2 + ch * 32, v);
-        if (p.has_res) tmem_ld32(tmem_base + lane_off + kTD1 + ch * 32, w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int a2 = ch * 32 + j;
-          float t = 0.f;
-          if (a2 < p.A2) {
-            t = fmaf(__uint_as_float(v[j]), s2, s_b2[a2]);
-            if (p.has_res) t = fmaf(__uint_as_float(w[j]), s3, t);
-            else if (ok) t += __ldg(xf + (size_t)a2 * p.inner);
-          }
-          z[j] = t;
-        }
-      };
+      float z[2][32];
       float sum = 0.f;
-      for (int ch = 0; ch * 32 < n2; ++ch) {
-        float z[32];
-        z_chunk(ch, z);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += z[j];            // entries past A2 are zero
-      }
-      const float mean = sum / p.A2;
-      float var = 0.f;
-      for (int ch = 0; ch * 32 < n2; ++ch) {
-        float z[32];
-        z_chunk(ch, z);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float dlt = (ch * 32 + j < p.A2) ? z[j] - mean : 0.f;
-          var = fmaf(dlt, dlt, var);
-        }
-      }
-      const float rstd = rsqrtf(var / p.A2 + 1e-6f);
-      for (int ch = 0; ch * 32 < n2; ++ch) {
-        float z[32];
-        z_chunk(ch, z);
-        if (ok) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = g + 2 * cc;
+        if (ch * 32 < n2) {
+          uint32_t v[32], w[32];
+          tmem_ld32(tmem_base + lane_off + kTD2 + ch * 32, v);
+          if (p.has_res) tmem_ld32(tmem_base + lane_off + kTD1 + ch * 32, w);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int a2 = ch * 32 + j;
-            if (a2 < p.A2) yf[(size_t)a2 * p.inner] = (z[j] - mean) * rstd * s_lw[a2] + s_lb[a2];
+            float t = 0.f;
+            if (a2 < p.A2) {
+              t = fmaf(__uint_as_float(v[j]), s2, s_b2[a2]);
+              if (p.has_res) t = fmaf(__uint_as_float(w[j]), s3, t);
+              else if (ok) t += __ldg(xf + (size_t)a2 * p.inner);
+            }
+            z[cc][j] = t;
+            sum += t;                                            // entries past A2 are zero
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[cc][j] = 0.f;
         }
       }
-      if (ok) {
-        p.saved[2 * c] = mean;
-        p.saved[2 * c + 1] = rstd;
+      tc_fence_before();
+      s_part[g * 128 + r] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = (sum + s_part[(g ^ 1) * 128 + r]) / p.A2;
+      float var = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dlt = ((g + 2 * cc) * 32 + j < p.A2) ? z[cc][j] - mean : 0.f;
+          var = fmaf(dlt, dlt, var);
+        }
       }
-      tc_fence_before();        // TMEM reads of this tile are done before the next tile's stores / MMAs
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // everyone has read the sums
+      s_part[g * 128 + r] = var;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float rstd = rsqrtf((var + s_part[(g ^ 1) * 128 + r]) / p.A2 + 1e-6f);
+      if (ok) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int a2 = (g + 2 * cc) * 32 + j;
+            if (a2 < p.A2) yf[(size_t)a2 * p.inner] = (z[cc][j] - mean) * rstd * s_lw[a2] + s_lb[a2];
+          }
+        }
+        if (g == 0) {
+          p.saved[2 * c] = mean;
+          p.saved[2 * c + 1] = rstd;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // partial-sum slots are free for the next tile
     }
   }
   tc_fence_before();
@@ -752,8 +738,21 @@ __global__ void cube_absmax_kernel(const float *x, size_t nx, const float *gy, s
                                    unsigned *out) {
   float m0 = 0.f, m1 = 0.f, m2 = 0.f;
   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = t0; t < nx; t += st) m0 = fmaxf(m0, fabsf(x[t]));
-  for (size_t t = t0; t < ngy; t += st) m1 = fmaxf(m1, fabsf(gy[t]));
+  auto amax4 = [&](const float *p, size_t n, float m) {          // 16-byte loads where the pointer allows it
+    size_t head = 0;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(p);
+      for (size_t t = t0; t < n / 4; t += st) {
+        const float4 v = __ldg(p4 + t);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+      head = (n / 4) * 4;
+    }
+    for (size_t t = head + t0; t < n; t += st) m = fmaxf(m, fabsf(p[t]));
+    return m;
+  };
+  m0 = amax4(x, nx, m0);
+  m1 = amax4(gy, ngy, m1);
   for (size_t t = t0; t < n_cols; t += st) m2 = fmaxf(m2, fabsf(saved[2 * t + 1]));
   for (int o = 16; o; o >>= 1) {
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
@@ -796,7 +795,7 @@ __global__ void cube_scales_kernel(const unsigned *absmax, const float *w1, cons
     const float m_gz = m_rstd * (2.f + sqrtf((float)A2)) * m_gy * lw_max;
     const float m_gp = 1.2f * m_gz * col2_max;                                 // |gelu'| < 1.13
     scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h), scales[2] = pow2_scale(m_gz), scales[3] = pow2_scale(m_gp);
-    *hdr_x = __float_as_uint(m_x), *hdr_h = __float_as_uint(m_h), *hdr_gz = __float_as_uint(m_gz), *hdr_gp = __float_as_uint(m_gp);
+    if (hdr_x) *hdr_x = __float_as_uint(m_x), *hdr_h = __float_as_uint(m_h), *hdr_gz = __float_as_uint(m_gz), *hdr_gp = __float_as_uint(m_gp);
   }
 }
 
@@ -848,7 +847,15 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   } else {
     mrh = m1h, mrl = m1l;
   }
+  unsigned *x_absmax = reinterpret_cast<unsigned *>(s3 + mimrl_split_bytes(a_out, a_in));      // the 256 spare bytes
+  float *scales = reinterpret_cast<float *>(x_absmax + 16);
+  cudaMemsetAsync(x_absmax, 0, 16, st);
+  cube_absmax_kernel<<<148 * 8, 256, 0, st>>>(x, (size_t)outer * inner * a_in, nullptr, 0, nullptr, 0, x_absmax);
+  if (check_launch("cubemlp absmax")) return 1;
+  cube_scales_kernel<<<1, 128, 0, st>>>(x_absmax, w1, b1, w2, ln_w, a_in, a_hid, a_out, scales, nullptr, nullptr, nullptr, nullptr);
+  if (check_launch("cubemlp scales")) return 1;
   CubeTcParams p;
+  p.scales = scales;
   p.x = x, p.b1 = b1, p.b2 = b2, p.ln_w = ln_w, p.ln_b = ln_b, p.y = y, p.saved = saved;
   p.sc_w1 = reinterpret_cast<const unsigned *>(s1), p.sc_w2 = reinterpret_cast<const unsigned *>(s2);
   p.sc_wr = reinterpret_cast<const unsigned *>(s3);
@@ -896,7 +903,7 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
     if (int rc = mimrl_split_f32(wres, nullptr, a_out, a_in, s3, nullptr, stream)) return rc;
   const long long n_cols = (long long)outer * inner;
   cudaMemsetAsync(absmax, 0, 16, st);
-  cube_absmax_kernel<<<148 * 2, 256, 0, st>>>(x, (size_t)n_cols * a_in, gy, (size_t)n_cols * a_out, saved, (size_t)n_cols, absmax);
+  cube_absmax_kernel<<<148 * 8, 256, 0, st>>>(x, (size_t)n_cols * a_in, gy, (size_t)n_cols * a_out, saved, (size_t)n_cols, absmax);
   if (check_launch("cubemlp absmax")) return 1;
   cube_scales_kernel<<<1, 128, 0, st>>>(absmax, w1, b1, w2, ln_w, a_in, a_hid, a_out, scales, (unsigned *)op_x, (unsigned *)op_h,
                                         (unsigned *)op_gz, (unsigned *)op_gpre);
@@ -917,6 +924,7 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   }
   CubeBwdParams bp;
   CubeTcParams &p = bp.f;
+  p.scales = scales;
   p.x = x, p.b1 = b1, p.b2 = b2, p.ln_w = ln_w, p.ln_b = ln_b, p.y = nullptr, p.saved = const_cast<float *>(saved);
   p.sc_w1 = reinterpret_cast<const unsigned *>(s1), p.sc_w2 = reinterpret_cast<const unsigned *>(s2);
   p.sc_wr = reinterpret_cast<const unsigned *>(s3);
