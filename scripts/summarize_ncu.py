@@ -35,12 +35,8 @@ with open(f"profiles/launches_{tag}.md", "w") as f:
         f.write(f"| {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[0]} | `{k}` |\n")
     f.write(f"\ntotal {tot / 1e3:.2f} ms over {sum(a[0] for a in agg.values())} launches\n")
 
-# ---- full capture -> key metrics per kernel
-out = subprocess.run(["ncu", "-i", f"gpurun_out/prof_sep_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True,
-                     text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr = rows[0]
-want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+# ---- full captures -> key metrics per kernel
+WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -51,17 +47,38 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cyc
         "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
         "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_warps_issue_stalled_no_instructions",
         "smsp__pcsamp_warps_issue_stalled_branch_resolving", "smsp__pcsamp_warps_issue_stalled_barrier"]
-units = rows[1]
-with open(f"profiles/sep_kernels_{tag}.md", "w") as f:
-    f.write(f"# ncu --set full, tcgen05 sweep kernels at B = 65536, E = 128 ({tag})\n\n"
-            "`ncu --set full --clock-control none --import-source on -k regex:sep_wsum_tc|sep_stats_tc`\n"
-            "(numbers under the profiler are not bench values; CUDA-event timings are in bench.py's JSON line)\n\n")
-    for r in rows[2:]:
-        f.write(f"## `{r[hdr.index('Kernel Name')][:100]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
-        for w in want:
-            if w in hdr:
-                i = hdr.index(w)
-                f.write(f"| {w} | {r[i]} | {units[i]} |\n")
-        f.write("\n")
+
+
+def summarize(rep, dst, title, how):
+    import os
+    if not os.path.exists(rep):
+        return
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# {title} ({tag})\n\n`{how}`\n"
+                "(numbers under the profiler are not bench values; CUDA-event timings are in bench.py's JSON line and\n"
+                "scripts/bench_components.py)\n\n")
+        for r in rows[2:]:
+            f.write(f"## `{r[hdr.index('Kernel Name')][:100]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+            f.write("\n")
+
+
+summarize(f"gpurun_out/prof_sep_{tag}.ncu-rep", f"profiles/sep_kernels_{tag}.md",
+          "ncu --set full, tcgen05 sweep kernels at B = 65536, E = 128",
+          "ncu --set full --clock-control none --import-source on -k regex:sep_wsum_tc|sep_stats_tc python bench.py ...")
+summarize(f"gpurun_out/prof_concat_{tag}.ncu-rep", f"profiles/concat_kernels_{tag}.md",
+          "ncu --set full, fused concat-critic kernels, 2048 x 4096 pairs",
+          "ncu --set full --clock-control none --import-source on -k regex:concat_(fwd|bwd)_kernel -c 2 python scripts/prof_concat.py")
+summarize(f"gpurun_out/prof_cube_{tag}.ncu-rep", f"profiles/cubemlp_kernels_{tag}.md",
+          "ncu --set full, CubeMLP tensor-core mixes, [1024,100,3,128] -> 50-3-128 -> 10-3-128",
+          "ncu --set full --clock-control none --import-source on -k regex:cubemlp_tc_(fwd|bwd)_kernel -c 8 python scripts/cube_prof.py")
+summarize(f"gpurun_out/prof_knn_{tag}.ncu-rep", f"profiles/knn_kernels_{tag}.md",
+          "ncu --set full, k-NN filter / re-rank kernels, 4096 queries x 1M x 128 keys",
+          "ncu --set full --clock-control none --import-source on -k regex:knn python scripts/bench_components.py knn")
 print(open(f"profiles/launches_{tag}.md").read()[:2500])
-print(open(f"profiles/sep_kernels_{tag}.md").read()[:6000])
