@@ -58,6 +58,9 @@ def _gather(src, idx, repeat, out_width):
     return out
 
 
+_ID_SOURCE = None          # set by graphs.GraphedCallable while it warms up / captures a step
+
+
 def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
     """Model.py:75-106.  Draws m = batch_size // k query rows with numpy's GLOBAL
     RNG (same draw and same RNG state afterwards as the reference's
@@ -71,8 +74,11 @@ def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
     m = batch_size // k_neighbor
     if m > N:
         raise ValueError("Cannot take a larger sample than population when 'replace=False'")
-    ids_host = np.random.permutation(N)[:m]
-    ids = torch.from_numpy(ids_host.astype(np.int64)).to(Z.device, non_blocking=True)
+    if _ID_SOURCE is not None:            # CUDA-graph capture (graphs.py): same draw, staged through a pinned buffer
+        ids = _ID_SOURCE.next(N, m, Z.device)
+    else:
+        ids_host = np.random.permutation(N)[:m]
+        ids = torch.from_numpy(ids_host.astype(np.int64)).to(Z.device, non_blocking=True)
     nbr_orig, _ = knn_search(Z, ids, k_neighbor, radius)
     wmax = max(X.shape[1], Y.shape[1], Z.shape[1])
     batch_x = _gather(X, nbr_orig.reshape(-1), 1, wmax)

@@ -91,3 +91,63 @@ class TwoStageStep:
         self._clip()
         self.opt_main.step()
         return loss.detach(), [m.detach() for m in mis]
+
+
+class GraphedTwoStageStep:
+    """``TwoStageStep`` with each stage captured into one CUDA graph (graphs.py): the launch-bound small-batch regime.
+
+    The pool tensors are static for an epoch (Solver.py:244 swaps them at the epoch boundary): call ``recapture`` after
+    ``pool.roll()``.  Optimisers must be built with ``capturable=True``.  The k-NN query ids are drawn on the host from
+    numpy's global RNG before every replay, in the reference's call order."""
+
+    def __init__(self, step: TwoStageStep, batch: torch.Tensor, labels: torch.Tensor, pool: FeaturePool):
+        self.step, self.pool = step, pool
+        self.recapture(batch, labels)
+
+    def recapture(self, batch, labels):
+        from .graphs import GraphedCallable, HostIdSource
+        step, pool = self.step, self.pool
+        frozen = FeaturePool(C=pool.C, F=pool.F, T=pool.T, A=pool.A, V=pool.V)     # appends go to a scratch list
+        self._feats = None
+
+        def s1(b, l):
+            loss, mis = step.stage1(b, l, frozen)
+            return (loss,) + tuple(mis)
+
+        def s2(b, l):
+            frozen._next = {k: [] for k in "CFTAV"}
+            loss, mis = step.stage2(b, l, frozen)
+            feats = tuple(frozen._next[k][-1] for k in "CFTAV")
+            return (loss,) + tuple(mis) + feats
+
+        # warm-up and capture run real optimiser steps and consume numpy's RNG: put everything back afterwards
+        # (in place -- the graphs hold the addresses of the parameters and of the optimiser state)
+        import numpy as np
+        opts = (step.opt_main, step.opt_vmi)
+        params = [p for o in opts for gr in o.param_groups for p in gr["params"]]
+        p_saved = [p.detach().clone() for p in params]
+        o_saved = [{id(p): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in o.state.items()}
+                   for o in opts]
+        rng = np.random.get_state()
+        self.g1 = GraphedCallable(s1, [batch, labels], id_source=HostIdSource())
+        self.g2 = GraphedCallable(s2, [batch, labels], id_source=HostIdSource())
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, v in zip(params, p_saved):
+                p.copy_(v)
+            for o, saved in zip(opts, o_saved):
+                for p, st in o.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(saved[id(p)][k]) if id(p) in saved and k in saved[id(p)] else v.zero_()
+        np.random.set_state(rng)
+
+    def stage1(self, batch, labels):
+        out = self.g1(batch, labels)
+        return out[0], list(out[1:])
+
+    def stage2(self, batch, labels):
+        out = self.g2(batch, labels)
+        feats = out[-5:]
+        self.pool.append(feats[0].clone(), *(f.clone() for f in feats[1:]))      # next epoch's pool (Solver.py:237-241)
+        return out[0], list(out[1:-5])

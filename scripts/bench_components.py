@@ -74,6 +74,31 @@ if "sep_small" in which:  # config 2 sweep
         ms = timeit(fb)
         out(component="sep_infonce_fwd_bwd", B=B, ms=ms, pairs_per_s=B * B / ms * 1e3)
 
+if "sep_graph" in which or "sep_small" in which:   # config 2, small end of the sweep: one CUDA graph per estimator step
+    from mimrl_b200.graphs import GraphedCallable
+    for B in (128, 512, 2048, 8192):
+        est = VMIEstimator("separate", "constant", "infonce", 128, 256, 128, 2, "relu", 0, 1).to(dev)
+        params = list(est.parameters())
+        def fb(x, y):
+            for p in params:
+                p.grad = None
+            x.grad = y.grad = None
+            mi, loss = est(x, y)
+            loss.backward()
+            return mi, x.grad, y.grad
+        x0 = torch.randn(B, 128, device=dev).requires_grad_(True); y0 = torch.randn(B, 128, device=dev).requires_grad_(True)
+        class Wrap:
+            def __init__(self):
+                self.g = None
+            def build(self):
+                def fn(xs, ys):
+                    xs.requires_grad_(True); ys.requires_grad_(True)
+                    return fb(xs, ys)
+                self.g = GraphedCallable(fn, [x0, y0])
+        w = Wrap(); w.build()
+        ms = timeit(lambda: w.g(x0, y0))
+        out(component="sep_infonce_fwd_bwd_cuda_graph", B=B, ms=ms, pairs_per_s=B * B / ms * 1e3)
+
 if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of the MI/CMI path on synthetic features
     from types import SimpleNamespace
     from mimrl_b200.model import MIHeads
@@ -88,8 +113,9 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
             f = enc(batch).view(-1, 4, 128)
             return cls(f[:, 0]), f[:, 0].contiguous(), f[:, 1].contiguous(), f[:, 2].contiguous(), f[:, 3].contiguous()
         main_params = list(enc.parameters()) + list(cls.parameters())
-        step = TwoStageStep(heads, features, torch.nn.L1Loss(), torch.optim.Adam(main_params, 1e-4),
-                            torch.optim.Adam(heads.parameters(), 1e-4), clip_params=main_params + list(heads.parameters()))
+        step = TwoStageStep(heads, features, torch.nn.L1Loss(), torch.optim.Adam(main_params, 1e-4, capturable=True),
+                            torch.optim.Adam(heads.parameters(), 1e-4, capturable=True),
+                            clip_params=main_params + list(heads.parameters()))
         pool = FeaturePool()
         g = torch.Generator(device="cuda").manual_seed(0)
         pool.C = torch.randn(N, 1, device=dev, generator=g).clamp(-3, 3)
@@ -102,3 +128,10 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
         ms = timeit(one, reps=5, warm=2)
         out(component="two_stage_step_mi_cmi", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
             note="5 VMI + 6 k-NN samplers + 6 VCMI per stage, Adam on both optimisers; encoders replaced by one Linear")
+        from mimrl_b200.train_step import GraphedTwoStageStep
+        graphed = GraphedTwoStageStep(step, batch, labels, pool)
+        def one_g():
+            graphed.stage1(batch, labels); graphed.stage2(batch, labels)
+        ms = timeit(one_g, reps=5, warm=2)
+        out(component="two_stage_step_mi_cmi_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
+            note="same step, one CUDA graph per stage; k-NN ids drawn on the host before each replay")

@@ -55,3 +55,60 @@ def test_two_stage_step_updates_the_right_groups():
     assert len(mis) == 8 and torch.isfinite(loss)
     assert any(not torch.equal(a, b.detach()) for a, b in zip(m0, main))                    # main model moved
     assert all(torch.equal(a, b.detach()) for a, b in zip(h1, heads.parameters()))          # estimators did not
+
+
+def test_graphed_two_stage_step_matches_eager():
+    """One CUDA graph per stage (graphs.py) reproduces the eager step: same numpy RNG stream for the k-NN query ids,
+    same losses, same parameters after three steps."""
+    import copy
+    from types import SimpleNamespace
+    from mimrl_b200.model import MIHeads
+    from mimrl_b200.train_step import FeaturePool, GraphedTwoStageStep, TwoStageStep
+    dev = torch.device("cuda:0")
+    opt = SimpleNamespace(critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2,
+                          radius=1.0, cmi_last_acticate="hardtanh", d_common=128)
+    torch.manual_seed(0)
+    heads0 = MIHeads(opt).to(dev)
+    enc0 = torch.nn.Linear(128, 4 * 128).to(dev)
+    cls0 = torch.nn.Linear(128, 1).to(dev)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    N, bs = 700, 96
+    pool_t = [torch.randn(N, 1, device=dev, generator=g).clamp(-3, 3)] + [torch.randn(N, 128, device=dev, generator=g)
+                                                                           for _ in range(4)]
+    batches = [(torch.randn(bs, 128, device=dev, generator=g), torch.randn(bs, device=dev, generator=g).clamp(-3, 3))
+               for _ in range(3)]
+
+    def make():
+        heads, enc, cls = copy.deepcopy(heads0), copy.deepcopy(enc0), copy.deepcopy(cls0)
+
+        def features(batch):
+            f = enc(batch).view(-1, 4, 128)
+            return cls(f[:, 0]), f[:, 0].contiguous(), f[:, 1].contiguous(), f[:, 2].contiguous(), f[:, 3].contiguous()
+        main = list(enc.parameters()) + list(cls.parameters())
+        step = TwoStageStep(heads, features, torch.nn.L1Loss(), torch.optim.Adam(main, 1e-3, capturable=True),
+                            torch.optim.Adam(heads.parameters(), 1e-3, capturable=True),
+                            clip_params=main + list(heads.parameters()))
+        pool = FeaturePool(C=pool_t[0], F=pool_t[1], T=pool_t[2], A=pool_t[3], V=pool_t[4])
+        return step, pool, list(heads.parameters()) + main
+
+    step_e, pool_e, params_e = make()
+    np.random.seed(3)
+    eager = []
+    for b, l in batches:
+        l1, _ = step_e.stage1(b, l, pool_e)
+        l2, mis = step_e.stage2(b, l, pool_e)
+        eager.append((float(l1), float(l2), [float(m) for m in mis]))
+    step_g, pool_g, params_g = make()
+    graphed = GraphedTwoStageStep(step_g, batches[0][0], batches[0][1], pool_g)
+    np.random.seed(3)
+    got = []
+    for b, l in batches:
+        l1, _ = graphed.stage1(b, l)
+        l2, mis = graphed.stage2(b, l)
+        got.append((float(l1), float(l2), [float(m) for m in mis]))
+    for (a1, a2, am), (b1, b2, bm) in zip(eager, got):
+        assert abs(a1 - b1) <= 1e-4 * max(1.0, abs(a1)) and abs(a2 - b2) <= 1e-4 * max(1.0, abs(a2))
+        assert np.allclose(am, bm, rtol=1e-4, atol=1e-5)
+    for pe, pg in zip(params_e, params_g):
+        assert torch.allclose(pe, pg, rtol=1e-4, atol=1e-6)
+    assert len(pool_g._next["C"]) == 3 and pool_g._next["F"][0].shape == (bs, 128)
