@@ -413,4 +413,22 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly one JSON line: libraries that write to fd 1 themselves (NCCL prints its version
+    # there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*a, **k):          # noqa: A001  (the two JSON prints above resolve this name at call time)
+        _buf.append(" ".join(str(x) for x in a))
+
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        for _l in _buf:
+            _print(_l, flush=True)
