@@ -103,7 +103,7 @@ __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__
 }
 
 struct GemmParams {
-  int M, N, K, kblocks_per_split, relu;
+  int M, N, K, kblocks_per_split, relu, splits;
   const unsigned *absmax;
   const float *bias;
   float *C;       // [M, N] when splits == 1, else partials [splits][M][N]
@@ -120,26 +120,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - raw);
   const uint32_t bars = base + kGStages * kGStage;
-  const uint32_t bFull = bars, bEmpty = bars + 32, bDone = bars + 64;
+  const uint32_t bFull = bars, bEmpty = bars + 32;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kGStages * kGStage + 128);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128, split = blockIdx.z;
+  // Persistent over work items (m tile, n tile, k split): the ring keeps streaming across items and the two TMEM
+  // accumulators alternate, so the epilogue of one item overlaps the loads and MMAs of the next.
   const int n_kb = (p.K + 63) / 64;
-  const int kb0 = split * p.kblocks_per_split;
-  const int kb1 = min(n_kb, kb0 + p.kblocks_per_split);
-  const int T = kb1 - kb0;
+  const int tiles_m = (p.M + 127) / 128, tiles_n = (p.N + 127) / 128;
+  const long long n_items = (long long)tiles_m * tiles_n * p.splits;
+  const uint32_t bAccFull = bars + 64, bAccEmpty = bars + 80;
+  auto item_of = [&](long long it, int &m0, int &n0, int &split, int &kb0, int &T) {
+    split = (int)(it / ((long long)tiles_m * tiles_n));
+    const int rem = (int)(it - (long long)split * tiles_m * tiles_n);
+    m0 = (rem / tiles_n) * 128, n0 = (rem % tiles_n) * 128;
+    kb0 = split * p.kblocks_per_split;
+    const int kb1 = min(n_kb, kb0 + p.kblocks_per_split);
+    T = kb1 > kb0 ? kb1 - kb0 : 0;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGStages; ++i) {
       mbar_init(bFull + 8 * i, 1);
       mbar_init(bEmpty + 8 * i, 1);
     }
-    mbar_init(bDone, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bAccFull + 8 * i, 1);
+      mbar_init(bAccEmpty + 8 * i, 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(gen + kGStages * kGStage + 128), 128);
+    tmem_alloc(smem_u32(gen + kGStages * kGStage + 128), 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -152,115 +164,135 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (leader) {
       prefetch_tmap(&map_a_hi);
       prefetch_tmap(&map_b_hi);
-      for (int i = 0; i < T; ++i) {
-        const int stage = i % kGStages, k0 = (kb0 + i) * 64;
-        mbar_wait(bEmpty + 8 * stage, ((i / kGStages) & 1) ^ 1);
-        const uint32_t fb = bFull + 8 * stage;
-        mbar_expect_tx(fb, kGStage);
-        const uint32_t dst = base + stage * kGStage;
-        if (A_MN) {   // rows = contraction index, 64 per box; two boxes cover 128 M
-          tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, m0, k0);
-          tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
-          tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
-          tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
-        } else {
-          tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, k0, m0);
-          tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, k0, m0);
-        }
-        if (B_MN) {
-          tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, n0, k0);
-          tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
-          tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, n0, k0);
-          tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
-        } else {
-          tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, k0, n0);
-          tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, k0, n0);
+      uint32_t n = 0;
+      for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+        int m0, n0, split, kb0, T;
+        item_of(it, m0, n0, split, kb0, T);
+        for (int i = 0; i < T; ++i, ++n) {
+          const int stage = n % kGStages, k0 = (kb0 + i) * 64;
+          mbar_wait(bEmpty + 8 * stage, ((n / kGStages) & 1) ^ 1);
+          const uint32_t fb = bFull + 8 * stage;
+          mbar_expect_tx(fb, kGStage);
+          const uint32_t dst = base + stage * kGStage;
+          if (A_MN) {   // rows = contraction index, 64 per box; two boxes cover 128 M
+            tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, m0, k0);
+            tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
+            tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
+            tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
+          } else {
+            tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, k0, m0);
+            tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, k0, m0);
+          }
+          if (B_MN) {
+            tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, n0, k0);
+            tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
+            tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, n0, k0);
+            tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
+          } else {
+            tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, k0, n0);
+            tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc = instr_desc_f16(128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-    for (int i = 0; i < T; ++i) {
-      const int stage = i % kGStages;
-      mbar_wait(bFull + 8 * stage, (i / kGStages) & 1);
+    uint32_t n = 0, j = 0;
+    for (long long it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      int m0, n0, split, kb0, T;
+      item_of(it, m0, n0, split, kb0, T);
+      const uint32_t acc = j & 1, tacc = tmem_base + acc * 128;
+      mbar_wait(bAccEmpty + 8 * acc, ((j >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
       tc_fence_after();
-      if (leader) {
-        const uint32_t s0 = base + stage * kGStage;
+      for (int i = 0; i < T; ++i, ++n) {
+        const int stage = n % kGStages;
+        mbar_wait(bFull + 8 * stage, (n / kGStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t s0 = base + stage * kGStage;
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t a_base = s0 + (prod == 2 ? 1 : 0) * kOp16;          // A hi, hi, lo
-          const uint32_t b_base = s0 + (prod == 1 ? 3 : 2) * kOp16;          // B hi, lo, hi
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t a_base = s0 + (prod == 2 ? 1 : 0) * kOp16;          // A hi, hi, lo
+            const uint32_t b_base = s0 + (prod == 1 ? 3 : 2) * kOp16;          // B hi, lo, hi
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = A_MN ? smem_desc_sw128_mn(a_base + k * 2048, 8192, 1024) : smem_desc_sw128(a_base + k * 32);
-            const uint64_t bd = B_MN ? smem_desc_sw128_mn(b_base + k * 2048, 8192, 1024) : smem_desc_sw128(b_base + k * 32);
-            umma_f16(tmem_base, ad, bd, idesc, (i | prod | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = A_MN ? smem_desc_sw128_mn(a_base + k * 2048, 8192, 1024) : smem_desc_sw128(a_base + k * 32);
+              const uint64_t bd = B_MN ? smem_desc_sw128_mn(b_base + k * 2048, 8192, 1024) : smem_desc_sw128(b_base + k * 32);
+              umma_f16(tacc, ad, bd, idesc, (i | prod | k) ? 1u : 0u);
+            }
           }
+          umma_commit(bEmpty + 8 * stage);
         }
-        umma_commit(bEmpty + 8 * stage);
+        __syncwarp();
       }
+      if (leader) umma_commit(bAccFull + 8 * acc);
       __syncwarp();
     }
-    if (leader) umma_commit(bDone);
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int row = m0 + r;
     const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
-    float *out = p.C + ((size_t)split * p.M + row) * p.N;
-    const bool partial = gridDim.z > 1;
-    if (T > 0) {
-      mbar_wait(bDone, 0);
+    const bool partial = p.splits > 1;
+    uint32_t j = 0;
+    for (long long it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      int m0, n0, split, kb0, T;
+      item_of(it, m0, n0, split, kb0, T);
+      const uint32_t acc = j & 1;
+      const int row = m0 + r;
+      float *out = p.C + ((size_t)split * p.M + row) * p.N;
+      mbar_wait(bAccFull + 8 * acc, (j >> 1) & 1);
       tc_fence_after();
-    }
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      uint32_t v[32];
-      if (T > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
-        tmem_ld_wait();
-      } else {
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        if (T > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 32, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (row >= p.M) continue;
-      const int c0 = n0 + ch * 32;
-      if (c0 >= p.N) continue;
-      if (c0 + 32 <= p.N && (p.N & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float x = __uint_as_float(v[j + u]) * inv;
-            if (!partial) {
-              if (p.bias) x += __ldg(p.bias + c0 + j + u);
-              if (p.relu) x = fmaxf(x, 0.f);
-            }
-            o[u] = x;
-          }
-          *reinterpret_cast<float4 *>(out + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
         }
-      } else {
+        if (row >= p.M) continue;
+        const int c0 = n0 + ch * 32;
+        if (c0 >= p.N) continue;
+        if (c0 + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (c0 + j < p.N) {
-            float x = __uint_as_float(v[j]) * inv;
-            if (!partial) {
-              if (p.bias) x += __ldg(p.bias + c0 + j);
-              if (p.relu) x = fmaxf(x, 0.f);
+          for (int jj = 0; jj < 32; jj += 4) {
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float x = __uint_as_float(v[jj + u]) * inv;
+              if (!partial) {
+                if (p.bias) x += __ldg(p.bias + c0 + jj + u);
+                if (p.relu) x = fmaxf(x, 0.f);
+              }
+              o[u] = x;
             }
-            out[c0 + j] = x;
+            *reinterpret_cast<float4 *>(out + c0 + jj) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            if (c0 + jj < p.N) {
+              float x = __uint_as_float(v[jj]) * inv;
+              if (!partial) {
+                if (p.bias) x += __ldg(p.bias + c0 + jj);
+                if (p.relu) x = fmaxf(x, 0.f);
+              }
+              out[c0 + jj] = x;
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bAccEmpty + 8 * acc);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 __global__ void gemm_reduce_kernel(const float *__restrict__ part, int splits, size_t mn, int N, const float *__restrict__ bias,
@@ -330,7 +362,8 @@ template <bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
                 const GemmParams &p, dim3 grid, cudaStream_t st) {
   cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-  gemm_tc_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmem, st>>>(ah, al, bh, bl, p);
+  const long long items = (long long)grid.x * grid.y * grid.z;          // persistent: one CTA per SM walks the items
+  gemm_tc_kernel<A_MN, B_MN><<<(int)(items < 148 ? items : 148), kGemmThreads, kGemmSmem, st>>>(ah, al, bh, bl, p);
   return check_launch("gemm_tc");
 }
 
@@ -418,6 +451,7 @@ extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_spl
   GemmParams p;
   p.M = M, p.N = N, p.K = K;
   p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.splits = g.splits;
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
   p.bias = g.splits > 1 ? nullptr : bias;
@@ -480,6 +514,7 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   GemmParams p;
   p.M = M, p.N = N, p.K = K;
   p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.splits = g.splits;
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
   p.bias = g.splits > 1 ? nullptr : bias;
