@@ -142,6 +142,12 @@ int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, voi
 size_t mimrl_gemm_split_workspace_bytes(int mode, int M, int N, int K);
 int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, int N, int K, const float *bias,
                      int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
+/* C[M,N] = A[M,K] . B[N,K]^T with both operands in BLOCKED-K order: tiles of 64 consecutive k, each [rows][64]
+ * contiguous (same header, hi / lo offsets and total size as mimrl_split_f32 of a [rows, K] matrix; K % 64 == 0).
+ * Every TMA box is then one contiguous run in memory: the layout for contractions over millions of entries (the
+ * weight gradients over pairs / fibres).  Workspace: mimrl_gemm_split_workspace_bytes(0, M, N, K). */
+int mimrl_gemm_split_blocked(const void *a_split, const void *b_split, int M, int N, int K, float *C, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of
@@ -234,8 +240,8 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
 
 /* Tensor-core backward of the same mix.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
  * writes the weight-gradient operands op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R]
- * (R = mimrl_cubemlp_tc_fibre_rows(outer, inner), mimrl_split_f32 format, feature-major):
- * gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T through mimrl_gemm_split(mode 0). */
+ * (R = mimrl_cubemlp_tc_fibre_rows(outer, inner), mimrl_split_f32 sizes, feature-major in blocked-K order):
+ * gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T through mimrl_gemm_split_blocked. */
 long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner);
 int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
                              const float *b1, int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
@@ -254,7 +260,7 @@ int mimrl_concat_scores(const float *u, const float *vt, int n_own, int n_all, i
                         float *scores, void *workspace, size_t workspace_bytes, void *stream);
 /* Backward for g = dL/dscores.  Accumulates (+=) into g_u [n_own,256], g_vt [256,ldv], g_b2, g_b3, g_w4 [256] and
  * writes the weight-gradient operands h1, h2, g2, g3 (mimrl_split_f32 format of a [256, mimrl_concat_pair_rows()]
- * matrix, feature-major): gW2 = g2 h1^T and gW3 = g3 h2^T through mimrl_gemm_split(mode 0). */
+ * matrix, feature-major in blocked-K order): gW2 = g2 h1^T and gW3 = g3 h2^T through mimrl_gemm_split_blocked. */
 long long mimrl_concat_pair_rows(int n_own, int n_all);
 int mimrl_concat_grad(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden, const float *w2,
                       const float *b2, const float *w3, const float *b3, const float *w4, const float *g, float *g_u,

@@ -242,7 +242,7 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
 //
 // The weight gradients contract over PAIRS (the TMEM lane axis), so they cannot share this kernel's
 // accumulators: h1, h2, g2, g3 are written once to HBM as fp16 hi/lo operands (4 KB per pair, feature-major) and
-// two split-K GEMMs (gemm_tc.cu, mode 0) finish gW2 = g2 h1^T and gW3 = g3 h2^T.  Bias and w4 gradients are column sums over
+// two split-K GEMMs (gemm_tc.cu, blocked-K operands) finish gW2 = g2 h1^T and gW3 = g3 h2^T.  Bias and w4 gradients are column sums over
 // pairs: 32x32 butterfly transposes leave lane t with feature 32c+t, accumulated in registers over the tiles.
 constexpr uint32_t kCbGvOff = kCcPartOff + 128 * 4;                // g_v accumulator [256 f][32 j] fp32
 constexpr uint32_t kCbSmem = kCbGvOff + kHid * 32 * 4 + 1024;
@@ -272,18 +272,21 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-// operands are stored TRANSPOSED, [256 features][pair rows]: for one feature the 32 lanes of a warp (32 consecutive
-// pairs) write 64 contiguous bytes -- one LSU wavefront per store instead of 32 with a pair-major layout
-__device__ __forceinline__ void store_op32(__half *dst_hi, __half *dst_lo, size_t ld, const uint32_t (&hi)[16],
+// Operands are stored feature-major in the blocked-K layout of make_map_blocked: tiles of 64 consecutive pairs, each
+// [256 features][64 pairs] contiguous.  For one feature the 32 lanes of a warp (32 consecutive pairs) write 64
+// contiguous bytes (one LSU wavefront per store instead of 32 with a pair-major layout), and the weight-gradient GEMM
+// reads every [128 features x 64 pairs] box as one contiguous 16 KB run.
+__device__ __forceinline__ void store_op32(__half *base_hi, __half *base_lo, size_t row, int f0, const uint32_t (&hi)[16],
                                            const uint32_t (&lo)[16], int dbg) {
   if (dbg & 1) return;
-  unsigned short *h = reinterpret_cast<unsigned short *>(dst_hi), *l = reinterpret_cast<unsigned short *>(dst_lo);
+  const size_t off = ((row >> 6) * kHid + f0) * 64 + (row & 63);
+  unsigned short *h = reinterpret_cast<unsigned short *>(base_hi) + off, *l = reinterpret_cast<unsigned short *>(base_lo) + off;
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
-    h[(size_t)(2 * t) * ld] = (unsigned short)(hi[t] & 0xffffu);
-    h[(size_t)(2 * t + 1) * ld] = (unsigned short)(hi[t] >> 16);
-    l[(size_t)(2 * t) * ld] = (unsigned short)(lo[t] & 0xffffu);
-    l[(size_t)(2 * t + 1) * ld] = (unsigned short)(lo[t] >> 16);
+    h[(2 * t) * 64] = (unsigned short)(hi[t] & 0xffffu);
+    h[(2 * t + 1) * 64] = (unsigned short)(hi[t] >> 16);
+    l[(2 * t) * 64] = (unsigned short)(lo[t] & 0xffffu);
+    l[(2 * t + 1) * 64] = (unsigned short)(lo[t] >> 16);
   }
 }
 
@@ -403,7 +406,6 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
     const float inv12 = 1.f / (s1 * sw2), inv23 = 1.f / (s2 * sw3), inv_c = 1.f / (sg3 * sw3), inv_d = 1.f / (sg2 * sw2);
     float acc_b2[4] = {0.f, 0.f, 0.f, 0.f}, acc_b3[4] = {0.f, 0.f, 0.f, 0.f}, acc_w4[4] = {0.f, 0.f, 0.f, 0.f};
     asm volatile("bar.sync 1, 256;" ::: "memory");      // s_gv zeroed (the block-wide barrier above already ordered it; cheap)
-    const size_t op_ld = (size_t)p.n_tiles * 128;
     long long cur_jb = -1;
     uint32_t it = 0;
     auto flush_gv = [&](long long jb) {
@@ -454,7 +456,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR0 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR0 + 32 * c + 16, lo);
-        store_op32(bp.op[0][0] + (size_t)(32 * c) * op_ld + row, bp.op[0][1] + (size_t)(32 * c) * op_ld + row, op_ld, hi, lo, bp.dbg);
+        store_op32(bp.op[0][0], bp.op[0][1], row, 32 * c, hi, lo, bp.dbg);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -481,7 +483,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c + 16, lo);
-        store_op32(bp.op[1][0] + (size_t)(32 * c) * op_ld + row, bp.op[1][1] + (size_t)(32 * c) * op_ld + row, op_ld, hi, lo, bp.dbg);
+        store_op32(bp.op[1][0], bp.op[1][1], row, 32 * c, hi, lo, bp.dbg);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -514,7 +516,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
           split32h(v, hi, lo);
           tmem_st16(tmem_base + lane_off + kR0 + 32 * c, hi);
           tmem_st16(tmem_base + lane_off + kR0 + 32 * c + 16, lo);
-          store_op32(bp.op[3][0] + (size_t)(32 * c) * op_ld + row, bp.op[3][1] + (size_t)(32 * c) * op_ld + row, op_ld, hi, lo, bp.dbg);
+          store_op32(bp.op[3][0], bp.op[3][1], row, 32 * c, hi, lo, bp.dbg);
         }
         acc_b3[cc] += lane_transpose_sum(gb, lane);
       }
@@ -541,7 +543,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c + 16, lo);
-        store_op32(bp.op[2][0] + (size_t)(32 * c) * op_ld + row, bp.op[2][1] + (size_t)(32 * c) * op_ld + row, op_ld, hi, lo, bp.dbg);
+        store_op32(bp.op[2][0], bp.op[2][1], row, 32 * c, hi, lo, bp.dbg);
         acc_b2[cc] += lane_transpose_sum(gb, lane);
       }
       tmem_st_wait();

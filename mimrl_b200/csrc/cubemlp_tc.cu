@@ -358,20 +358,21 @@ __device__ __forceinline__ float cube_lane_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-// features [f0, f0 + 32) of one fibre -> feature-major operand (rows past n_feat do not exist)
-__device__ __forceinline__ void cube_store_op(__half *hi_base, __half *lo_base, size_t ld, size_t row, int f0, int n_feat,
+// features [f0, f0 + 32) of one fibre -> feature-major operand in the blocked-K layout of make_map_blocked (tiles of
+// 64 consecutive fibres, each [n_feat][64] contiguous); features past n_feat do not exist
+__device__ __forceinline__ void cube_store_op(__half *hi_base, __half *lo_base, size_t row, int f0, int n_feat,
                                               const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
-  unsigned short *h = reinterpret_cast<unsigned short *>(hi_base) + (size_t)f0 * ld + row;
-  unsigned short *l = reinterpret_cast<unsigned short *>(lo_base) + (size_t)f0 * ld + row;
+  const size_t off = ((row >> 6) * n_feat + f0) * 64 + (row & 63);
+  unsigned short *h = reinterpret_cast<unsigned short *>(hi_base) + off, *l = reinterpret_cast<unsigned short *>(lo_base) + off;
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     if (f0 + 2 * t < n_feat) {
-      h[(size_t)(2 * t) * ld] = (unsigned short)(hi[t] & 0xffffu);
-      l[(size_t)(2 * t) * ld] = (unsigned short)(lo[t] & 0xffffu);
+      h[(2 * t) * 64] = (unsigned short)(hi[t] & 0xffffu);
+      l[(2 * t) * 64] = (unsigned short)(lo[t] & 0xffffu);
     }
     if (f0 + 2 * t + 1 < n_feat) {
-      h[(size_t)(2 * t + 1) * ld] = (unsigned short)(hi[t] >> 16);
-      l[(size_t)(2 * t + 1) * ld] = (unsigned short)(lo[t] >> 16);
+      h[(2 * t + 1) * 64] = (unsigned short)(hi[t] >> 16);
+      l[(2 * t + 1) * 64] = (unsigned short)(lo[t] >> 16);
     }
   }
 }
@@ -538,7 +539,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         split32(v, hi, lo);
         tmem_st16(tX + ch * 16, hi);
         tmem_st16(tX + 64 + ch * 16, lo);
-        cube_store_op(bp.op[0][0], bp.op[0][1], bp.ld, row, ch * 32, p.A, hi, lo);
+        cube_store_op(bp.op[0][0], bp.op[0][1], row, ch * 32, p.A, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -561,7 +562,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         split32(v, hi, lo);
         tmem_st16(tH + ch * 16, hi);
         tmem_st16(tH + 64 + ch * 16, lo);
-        cube_store_op(bp.op[1][0], bp.op[1][1], bp.ld, row, ch * 32, p.H, hi, lo);
+        cube_store_op(bp.op[1][0], bp.op[1][1], row, ch * 32, p.H, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -632,7 +633,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           split32(v, hi, lo);
           tmem_st16(tX + ch * 16, hi);
           tmem_st16(tX + 64 + ch * 16, lo);
-          cube_store_op(bp.op[2][0], bp.op[2][1], bp.ld, row, ch * 32, p.A2, hi, lo);
+          cube_store_op(bp.op[2][0], bp.op[2][1], row, ch * 32, p.A2, hi, lo);
           const float a1 = cube_lane_sum(t1, lane);
           if (cc == 0) acc_b2[0] += a1;
           else acc_b2[1] += a1;
@@ -665,7 +666,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           split32(v, hi, lo);
           tmem_st16(tH + ch * 16, hi);
           tmem_st16(tH + 64 + ch * 16, lo);
-          cube_store_op(bp.op[3][0], bp.op[3][1], bp.ld, row, ch * 32, p.H, hi, lo);
+          cube_store_op(bp.op[3][0], bp.op[3][1], row, ch * 32, p.H, hi, lo);
           const float a1 = cube_lane_sum(t1, lane);
           if (cc == 0) acc_b1[0] += a1;
           else acc_b1[1] += a1;
@@ -876,7 +877,8 @@ extern "C" long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner) {
 
 // Backward of mimrl_cubemlp_mix_fwd_tc.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
 // writes op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R] (R = mimrl_cubemlp_tc_fibre_rows,
-// mimrl_split_f32 format): gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T via mimrl_gemm_split(mode 0).
+// mimrl_split_f32 sizes, blocked-K order): gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T via
+// mimrl_gemm_split_blocked.
 extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
                                         const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
                                         const float *wres, const float *ln_w, const float *ln_b, int act,

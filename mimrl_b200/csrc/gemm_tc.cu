@@ -110,7 +110,8 @@ struct GemmParams {
 };
 
 // A_MN / B_MN: operand stored with the contraction index as the SLOW one (read MN-major)
-template <bool A_MN, bool B_MN>
+// BLK: both operands K-major in the blocked-K layout of make_map_blocked (3-D tensor maps)
+template <bool A_MN, bool B_MN, bool BLK = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -179,6 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
             tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
             tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
+          } else if (BLK) {
+            tma_load_3d(dst + 0 * kOp16, &map_a_hi, fb, 0, m0, kb0 + i);
+            tma_load_3d(dst + 1 * kOp16, &map_a_lo, fb, 0, m0, kb0 + i);
           } else {
             tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, k0, m0);
             tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, k0, m0);
@@ -188,6 +192,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
             tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, n0, k0);
             tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
+          } else if (BLK) {
+            tma_load_3d(dst + 2 * kOp16, &map_b_hi, fb, 0, n0, kb0 + i);
+            tma_load_3d(dst + 3 * kOp16, &map_b_lo, fb, 0, n0, kb0 + i);
           } else {
             tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, k0, n0);
             tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, k0, n0);
@@ -358,12 +365,12 @@ GemmLayout gemm_layout(int mode, int M, int N, int K) {
   return g;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool BLK = false>
 int launch_gemm(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
                 const GemmParams &p, dim3 grid, cudaStream_t st) {
-  cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+  cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
   const long long items = (long long)grid.x * grid.y * grid.z;          // persistent: one CTA per SM walks the items
-  gemm_tc_kernel<A_MN, B_MN><<<(int)(items < 148 ? items : 148), kGemmThreads, kGemmSmem, st>>>(ah, al, bh, bl, p);
+  gemm_tc_kernel<A_MN, B_MN, BLK><<<(int)(items < 148 ? items : 148), kGemmThreads, kGemmSmem, st>>>(ah, al, bh, bl, p);
   return check_launch("gemm_tc");
 }
 
@@ -467,6 +474,46 @@ extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_spl
     int b = (int)((mn + 255) / 256);
     b = b > 148 * 8 ? 148 * 8 : b;
     gemm_reduce_kernel<<<b, 256, 0, st>>>(p.C, g.splits, mn, N, bias, relu, C);
+    return check_launch("gemm reduce");
+  }
+  return 0;
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T with both operands in the blocked-K layout (tiles of 64 consecutive k, each [rows][64]
+// contiguous; same header / hi / lo placement and total size as mimrl_split_f32 of a [rows, K] matrix, K % 64 == 0).
+// For contractions over millions of entries (weight gradients over pairs or fibres): every TMA box is one
+// contiguous run in memory.  Workspace: mimrl_gemm_split_workspace_bytes(0, M, N, K).
+extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split, int M, int N, int K, float *C,
+                                        void *workspace, size_t workspace_bytes, void *stream) {
+  MIMRL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 64) == 0 && a_split && b_split && C, "gemm_split_blocked: bad arguments");
+  const GemmLayout g = gemm_layout(0, M, N, K);
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_gemm_split_workspace_bytes(0, M, N, K), "gemm_split_blocked: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SplitLayout la = split_layout(M, K), lb = split_layout(N, K);
+  const unsigned char *pa = (const unsigned char *)a_split, *pb = (const unsigned char *)b_split;
+  unsigned *absmax = reinterpret_cast<unsigned *>((unsigned char *)workspace + workspace_bytes - 256);
+  cudaMemcpyAsync(absmax, pa, 4, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(absmax + 1, pb, 4, cudaMemcpyDeviceToDevice, st);
+  CUtensorMap ah, al, bh, bl;
+  const uint64_t kt = (uint64_t)K / 64;
+  if (make_map_blocked(&ah, pa + la.off_hi, M, kt, 128) || make_map_blocked(&al, pa + la.off_lo, M, kt, 128) ||
+      make_map_blocked(&bh, pb + lb.off_hi, N, kt, 128) || make_map_blocked(&bl, pb + lb.off_lo, N, kt, 128))
+    return 1;
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K;
+  p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.splits = g.splits;
+  p.relu = 0;
+  p.absmax = absmax;
+  p.bias = nullptr;
+  p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
+  dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
+  if (int rc = launch_gemm<false, false, true>(ah, al, bh, bl, p, grid, st)) return rc;
+  if (g.splits > 1) {
+    const size_t mn = (size_t)M * N;
+    int b = (int)((mn + 255) / 256);
+    b = b > 148 * 8 ? 148 * 8 : b;
+    gemm_reduce_kernel<<<b, 256, 0, st>>>(p.C, g.splits, mn, N, nullptr, 0, C);
     return check_launch("gemm reduce");
   }
   return 0;

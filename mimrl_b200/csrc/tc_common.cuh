@@ -49,6 +49,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -223,6 +229,29 @@ inline int make_map(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t ro
   return 0;
 }
 
+// Blocked-K fp16 matrix [rows, K]: tiles of 64 consecutive k, each tile [rows][64] contiguous (tile t at
+// t * rows * 64 elements).  A [box_rows x 64] box of one tile is ONE contiguous run of box_rows * 128 bytes in
+// memory -- the layout for operands whose K runs over millions of entries (weight gradients over pairs / fibres).
+inline int make_map_blocked(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t k_tiles, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return 1;
+  }
+  cuuint64_t dims[3] = {64, rows, k_tiles};
+  cuuint64_t strides[2] = {64 * sizeof(__half), rows * 64 * sizeof(__half)};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (blocked) failed with %d (rows=%llu k_tiles=%llu)", (int)r, (unsigned long long)rows,
+              (unsigned long long)k_tiles);
+    return 1;
+  }
+  return 0;
+}
 
 }  // namespace
 }  // namespace mimrl

@@ -136,7 +136,7 @@ def _backward_tc(x, gy, saved, prm, cfg, gx):
         out = torch.empty(m, n, device=dev)
         gwb = L.lib.mimrl_gemm_split_workspace_bytes(0, m, n, R)
         gws = torch.empty(gwb, dtype=torch.uint8, device=dev)
-        L.check(L.lib.mimrl_gemm_split(0, L.ptr(a), L.ptr(b), m, n, R, None, 0, L.ptr(out), L.ptr(gws), gwb, st))
+        L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(a), L.ptr(b), m, n, R, L.ptr(out), L.ptr(gws), gwb, st))
         return out
 
     gw1 = wgrad(ops[3], ops[0], H, A)

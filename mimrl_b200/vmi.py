@@ -361,7 +361,7 @@ class _ConcatPairMLP(torch.autograd.Function):
                                             L.ptr(g_b2), L.ptr(g_b3), L.ptr(g_w4), L.ptr(ops[0]), L.ptr(ops[1]), L.ptr(ops[2]),
                                             L.ptr(ops[3]), L.ptr(ws), wsb, st))
             for a, b, acc in ((ops[2], ops[0], g_w2), (ops[3], ops[1], g_w3)):
-                L.check(L.lib.mimrl_gemm_split(0, L.ptr(a), L.ptr(b), hid, hid, pr, None, 0, L.ptr(tmp), L.ptr(gws), gwb, st))
+                L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(a), L.ptr(b), hid, hid, pr, L.ptr(tmp), L.ptr(gws), gwb, st))
                 acc += tmp
         return (g_u, g_vt.t(), g_w2, g_b2 if b2 is not None else None, g_w3, g_b3 if b3 is not None else None,
                 g_w4.reshape(1, -1), g.sum().reshape(1))

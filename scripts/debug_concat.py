@@ -75,8 +75,8 @@ def run_bwd(n_own, n_all, time_it=False, check=True):
                                         L.ptr(ops[0]), L.ptr(ops[1]), L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), wsb, L.stream()))
         if not parts[1]:
             return
-        L.check(L.lib.mimrl_gemm_split(0, L.ptr(ops[2]), L.ptr(ops[0]), H, H, rows, None, 0, L.ptr(gW2), L.ptr(gws), gws_b, L.stream()))
-        L.check(L.lib.mimrl_gemm_split(0, L.ptr(ops[3]), L.ptr(ops[1]), H, H, rows, None, 0, L.ptr(gW3), L.ptr(gws), gws_b, L.stream()))
+        L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(ops[2]), L.ptr(ops[0]), H, H, rows, L.ptr(gW2), L.ptr(gws), gws_b, L.stream()))
+        L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(ops[3]), L.ptr(ops[1]), H, H, rows, L.ptr(gW3), L.ptr(gws), gws_b, L.stream()))
         return g_u, g_vt, gW2, gb2, gW3, gb3, gw4
     outs = call(); torch.cuda.synchronize()
     if check:
