@@ -65,6 +65,41 @@ __device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[16]
   }
 }
 
+// 32 consecutive features [a0, a0 + 32) of one fibre (element a at base[a * stride]); entries past n are 0.  When the
+// mixed axis is the innermost one (stride 1, the D mix) the fibre is a contiguous row: 16-byte accesses.
+__device__ __forceinline__ void fibre_load32(const float *base, int a0, int n, size_t stride, bool vec, bool ok, float (&v)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int a = a0 + 4 * t;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && a < n) q = __ldg(reinterpret_cast<const float4 *>(base + a));          // n % 4 == 0 on this path
+      v[4 * t] = q.x, v[4 * t + 1] = q.y, v[4 * t + 2] = q.z, v[4 * t + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int a = a0 + j;
+      v[j] = (ok && a < n) ? __ldg(base + (size_t)a * stride) : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void fibre_store32(float *base, int a0, int n, size_t stride, bool vec, const float (&v)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int a = a0 + 4 * t;
+      if (a < n) *reinterpret_cast<float4 *>(base + a) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int a = a0 + j;
+      if (a < n) base[(size_t)a * stride] = v[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kCubeThreads, 1)
 cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
                       const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
@@ -189,6 +224,8 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
     const float sx = p.scales[0], sh = p.scales[1];
     const float s1 = 1.f / (sx * scale_from_absmax(p.sc_w1[0])), s2 = 1.f / (sh * scale_from_absmax(p.sc_w2[0]));
     const float s3 = p.has_res ? 1.f / (sx * scale_from_absmax(p.sc_wr[0])) : 0.f;
+    const bool vec_in = p.inner == 1 && (p.A & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+    const bool vec_out = p.inner == 1 && (p.A2 & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -200,11 +237,9 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       // ---- 1. fibre -> TMEM (one power-of-two scale for the tensor, fp16 hi/lo)
       for (int ch = g; ch * 32 < ks1 * 16; ch += 2) {
         float v[32];
+        fibre_load32(xf, ch * 32, p.A, p.inner, vec_in, ok, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int a = ch * 32 + j;
-          v[j] = (ok && a < p.A) ? __ldg(xf + (size_t)a * p.inner) * sx : 0.f;
-        }
+        for (int j = 0; j < 32; ++j) v[j] *= sx;
         uint32_t hi[16], lo[16];
         split32(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kTX + ch * 16, hi);
@@ -287,11 +322,13 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       if (ok) {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
+          float yv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int a2 = (g + 2 * cc) * 32 + j;
-            if (a2 < p.A2) yf[(size_t)a2 * p.inner] = (z[cc][j] - mean) * rstd * s_lw[a2] + s_lb[a2];
+            yv[j] = a2 < p.A2 ? (z[cc][j] - mean) * rstd * s_lw[a2] + s_lb[a2] : 0.f;
           }
+          fibre_store32(yf, (g + 2 * cc) * 32, p.A2, p.inner, vec_out, yv);
         }
         if (g == 0) {
           p.saved[2 * c] = mean;
@@ -516,6 +553,8 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
     const float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr), i_gh = 1.f / (sgz * sw2),
                 i_gx1 = 1.f / (sgp * sw1), i_gx2 = 1.f / (sgz * swr), i_gz = 1.f / sgz;
     float acc_lnw[2] = {0.f, 0.f}, acc_lnb[2] = {0.f, 0.f}, acc_b2[2] = {0.f, 0.f}, acc_b1[2] = {0.f, 0.f};
+    const bool vec_in = p.inner == 1 && (p.A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(bp.gx)) & 15) == 0;
+    const bool vec_out = p.inner == 1 && (p.A2 & 3) == 0 && (reinterpret_cast<uintptr_t>(bp.gy) & 15) == 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -530,11 +569,9 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       // ---- x -> X operand (+ feature-major copy for the weight gradients)
       for (int ch = g; ch * 32 < ks_a * 16; ch += 2) {
         float v[32];
+        fibre_load32(xf, ch * 32, p.A, p.inner, vec_in, ok, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int a = ch * 32 + j;
-          v[j] = (ok && a < p.A) ? __ldg(xf + (size_t)a * p.inner) * sx : 0.f;
-        }
+        for (int j = 0; j < 32; ++j) v[j] *= sx;
         uint32_t hi[16], lo[16];
         split32(v, hi, lo);
         tmem_st16(tX + ch * 16, hi);
@@ -594,10 +631,11 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         for (int ch = g; ch * 32 < n_q; ch += 2, ++cc) {
           float z[32], t1[32], t2[32];
           z_chunk(ch, z);
+          fibre_load32(gyf, ch * 32, p.A2, p.inner, vec_out, ok, t2);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int a2 = ch * 32 + j;
-            const float gyv = (ok && a2 < p.A2) ? __ldg(gyf + (size_t)a2 * p.inner) : 0.f;
+            const float gyv = t2[j];
             const float zh = (z[j] - mean) * rstd;
             const float gh_ = gyv * s_lw[a2 < p.A2 ? a2 : 0];
             sum_g += gh_;
@@ -620,10 +658,11 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         for (int ch = g; ch * 32 < ks_q * 16; ch += 2, ++cc) {
           float z[32], v[32], t1[32];
           z_chunk(ch, z);
+          fibre_load32(gyf, ch * 32, p.A2, p.inner, vec_out, ok, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int a2 = ch * 32 + j;
-            const float gyv = (ok && a2 < p.A2) ? __ldg(gyf + (size_t)a2 * p.inner) : 0.f;
+            const float gyv = v[j];
             const float zh = (z[j] - mean) * rstd;
             const float gzv = a2 < p.A2 ? rstd * (gyv * s_lw[a2 < p.A2 ? a2 : 0] - m1 - zh * m2) : 0.f;
             t1[j] = gzv;
@@ -704,15 +743,14 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         }
         tmem_ld_wait();
         if (ok) {
+          float gv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int a = ch * 32 + j;
-            if (a < p.A) {
-              float t = __uint_as_float(d[j]) * i_gx1;
-              t += p.has_res ? __uint_as_float(w[j]) * i_gx2 : __uint_as_float(w[j]);
-              gxf[(size_t)a * p.inner] = t;
-            }
+            float t = __uint_as_float(d[j]) * i_gx1;
+            t += p.has_res ? __uint_as_float(w[j]) * i_gx2 : __uint_as_float(w[j]);
+            gv[j] = t;
           }
+          fibre_store32(gxf, ch * 32, p.A, p.inner, vec_in, gv);
         }
       }
       tc_fence_before();

@@ -135,3 +135,42 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
         ms = timeit(one_g, reps=5, warm=2)
         out(component="two_stage_step_mi_cmi_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
             note="same step, one CUDA graph per stage; k-NN ids drawn on the host before each replay")
+
+if "step5" in which or "step" in which:   # config 5 shape: the same two-stage step with the CubeMLP fusion encoder in the loop
+    from types import SimpleNamespace
+    from mimrl_b200.model import MIHeads
+    from mimrl_b200.train_step import FeaturePool, GraphedTwoStageStep, TwoStageStep
+    bs, N = 1024, 16326
+    opt = SimpleNamespace(critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2,
+                          radius=1.0, cmi_last_acticate="hardtanh", d_common=128)
+    heads = MIHeads(opt).to(dev)
+    fusion = MLPEncoder("gelu", [100, 3, 128], [[50, 3, 128], [10, 3, 128]], [[50, 3, 128], [10, 3, 128]], [0.0] * 3, True,
+                        False, [True, True]).to(dev)                          # README: --d_hiddens 50-3-128=10-3-128
+    cls = torch.nn.Linear(128, 1).to(dev)
+    def features(batch):                                                      # batch: stacked encoder outputs [bs, 100, 3, 128]
+        z = fusion(batch).mean(dim=1)                                         # [bs, 3, 128]
+        T_F, A_F, V_F = z[:, 0].contiguous(), z[:, 1].contiguous(), z[:, 2].contiguous()
+        F_F = z.mean(dim=1)
+        return cls(F_F), F_F, T_F, A_F, V_F
+    main_params = list(fusion.parameters()) + list(cls.parameters())
+    step = TwoStageStep(heads, features, torch.nn.L1Loss(), torch.optim.Adam(main_params, 1e-4, capturable=True),
+                        torch.optim.Adam(heads.parameters(), 1e-4, capturable=True),
+                        clip_params=main_params + list(heads.parameters()))
+    pool = FeaturePool()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pool.C = torch.randn(N, 1, device=dev, generator=g).clamp(-3, 3)
+    pool.F, pool.T, pool.A, pool.V = (torch.randn(N, 128, device=dev, generator=g) for _ in range(4))
+    batch = torch.randn(bs, 100, 3, 128, device=dev, generator=g)
+    labels = torch.randn(bs, device=dev, generator=g).clamp(-3, 3)
+    np.random.seed(0)
+    def one():
+        step.stage1(batch, labels, pool); step.stage2(batch, labels, pool)
+    ms = timeit(one, reps=5, warm=2)
+    out(component="two_stage_step_cubemlp_mi_cmi", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
+        note="config 5 without BERT/GRU: CubeMLP 50-3-128=10-3-128 on [bs,100,3,128] + 5 VMI + 6 k-NN + 6 VCMI per stage, Adam x2")
+    graphed = GraphedTwoStageStep(step, batch, labels, pool)
+    def one_g():
+        graphed.stage1(batch, labels); graphed.stage2(batch, labels)
+    ms = timeit(one_g, reps=5, warm=2)
+    out(component="two_stage_step_cubemlp_mi_cmi_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
+        note="same, one CUDA graph per stage")
