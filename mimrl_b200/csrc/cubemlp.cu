@@ -427,9 +427,9 @@ cubemlp_mix_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const floa
 }
 
 // ---------------------------------------------------------------------------
-// Tiny mixed axis (A, H, A2 <= 8: the modality mix K = 3 of MLPProcess.py:106-112).  One thread per fibre, everything
+// Tiny mixed axis (A, H, A2 <= 4: the modality mix K = 3 of MLPProcess.py:106-112).  One thread per fibre, everything
 // in registers, parameters in shared memory; purely bandwidth-bound (one read, one write of the tensor).
-constexpr int kSmallMax = 8;
+constexpr int kSmallMax = 4;
 
 struct SmallParams {
   float w1[kSmallMax * kSmallMax], w2[kSmallMax * kSmallMax], wr[kSmallMax * kSmallMax];

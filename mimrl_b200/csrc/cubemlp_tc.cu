@@ -848,7 +848,7 @@ extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, in
                                void *stream);
 
 extern "C" int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln_first, int act) {
-  const bool small = a_in <= 8 && a_hid <= 8 && a_out <= 8;
+  const bool small = a_in <= 4 && a_hid <= 4 && a_out <= 4;      // the register-resident kernel of cubemlp.cu
   return !ln_first && !small && a_in <= 128 && a_hid <= 128 && a_out <= 128 && act >= 0 && act <= 2;
 }
 
