@@ -100,6 +100,7 @@ __device__ __forceinline__ void fibre_store32(float *base, int a0, int n, size_t
   }
 }
 
+template <int ACT>      // activation as a template parameter: only its own code is unrolled into the epilogues
 __global__ void __launch_bounds__(kCubeThreads, 1)
 cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
                       const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
@@ -260,7 +261,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int h = ch * 32 + j;
-          hv[j] = h < p.H ? cube_act(p.act, fmaf(__uint_as_float(v[j]), s1, s_b1[h])) * sh : 0.f;
+          hv[j] = h < p.H ? cube_act(ACT, fmaf(__uint_as_float(v[j]), s1, s_b1[h])) * sh : 0.f;
         }
         uint32_t hi[16], lo[16];
         split32(hv, hi, lo);
@@ -401,6 +402,16 @@ __device__ __forceinline__ void cube_store_op(__half *hi_base, __half *lo_base, 
                                               const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
   const size_t off = ((row >> 6) * n_feat + f0) * 64 + (row & 63);
   unsigned short *h = reinterpret_cast<unsigned short *>(hi_base) + off, *l = reinterpret_cast<unsigned short *>(lo_base) + off;
+  if (f0 + 32 <= n_feat) {            // whole chunk in range: no per-element predicates
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      h[(2 * t) * 64] = (unsigned short)(hi[t] & 0xffffu);
+      l[(2 * t) * 64] = (unsigned short)(lo[t] & 0xffffu);
+      h[(2 * t + 1) * 64] = (unsigned short)(hi[t] >> 16);
+      l[(2 * t + 1) * 64] = (unsigned short)(lo[t] >> 16);
+    }
+    return;
+  }
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     if (f0 + 2 * t < n_feat) {
@@ -414,6 +425,7 @@ __device__ __forceinline__ void cube_store_op(__half *hi_base, __half *lo_base, 
   }
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(kCubeBwdThreads, 1)
 cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
                       const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
@@ -593,7 +605,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int h = ch * 32 + j;
-          v[j] = h < p.H ? cube_act(p.act, fmaf(__uint_as_float(d[j]), i_pre, s_b1[h])) * sh : 0.f;
+          v[j] = h < p.H ? cube_act(ACT, fmaf(__uint_as_float(d[j]), i_pre, s_b1[h])) * sh : 0.f;
         }
         uint32_t hi[16], lo[16];
         split32(v, hi, lo);
@@ -697,7 +709,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           for (int j = 0; j < 32; ++j) {
             const int h = ch * 32 + j;
             const float pre = fmaf(__uint_as_float(w[j]), i_pre, s_b1[h < p.H ? h : 0]);
-            const float gp = h < p.H ? __uint_as_float(d[j]) * i_gh * cube_dact(p.act, pre) : 0.f;
+            const float gp = h < p.H ? __uint_as_float(d[j]) * i_gh * cube_dact(ACT, pre) : 0.f;
             t1[j] = gp;
             v[j] = gp * sgp;
           }
@@ -901,9 +913,14 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
   p.n_cols = (long long)outer * inner;
   const long long n_tiles = (p.n_cols + 127) / 128;
-  cudaFuncSetAttribute(cubemlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeSmem);
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
-  cubemlp_tc_fwd_kernel<<<blocks, kCubeThreads, kCubeSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, p);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeSmem);
+    kern<<<blocks, kCubeThreads, kCubeSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, p);
+  };
+  if (act == 0) launch(cubemlp_tc_fwd_kernel<0>);
+  else if (act == 1) launch(cubemlp_tc_fwd_kernel<1>);
+  else launch(cubemlp_tc_fwd_kernel<2>);
   return check_launch("cubemlp_tc_fwd");
 }
 
@@ -980,8 +997,13 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
     bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
     bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256 + align256((size_t)feats[t] * bp.ld * 2));
   }
-  cudaFuncSetAttribute(cubemlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
-  cubemlp_tc_bwd_kernel<<<blocks, kCubeBwdThreads, kCubeBwdSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, bp);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);
+    kern<<<blocks, kCubeBwdThreads, kCubeBwdSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, bp);
+  };
+  if (act == 0) launch(cubemlp_tc_bwd_kernel<0>);
+  else if (act == 1) launch(cubemlp_tc_bwd_kernel<1>);
+  else launch(cubemlp_tc_bwd_kernel<2>);
   return check_launch("cubemlp_tc_bwd");
 }
