@@ -244,6 +244,9 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
 // accumulators: h1, h2, g2, g3 are written once to HBM as fp16 hi/lo operands (4 KB per pair, feature-major) and
 // two split-K GEMMs (gemm_tc.cu, blocked-K operands) finish gW2 = g2 h1^T and gW3 = g3 h2^T.  Bias and w4 gradients are column sums over
 // pairs: 32x32 butterfly transposes leave lane t with feature 32c+t, accumulated in registers over the tiles.
+constexpr int kBwdWG = 4;                           // epilogue warpgroups of the backward kernel (2 chunks of 32 features each)
+constexpr int kBwdCh = 8 / kBwdWG;
+constexpr int kBwdThreads = 64 + 128 * kBwdWG;
 constexpr uint32_t kCbGvOff = kCcPartOff + 128 * 4;                // g_v accumulator [256 f][32 j] fp32
 constexpr uint32_t kCbSmem = kCbGvOff + kHid * 32 * 4 + 1024;
 
@@ -290,7 +293,7 @@ __device__ __forceinline__ void store_op32(__half *base_hi, __half *base_lo, siz
   }
 }
 
-__global__ void __launch_bounds__(kCcThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                   const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo,
                   const __grid_constant__ CUtensorMap mn_w2_hi, const __grid_constant__ CUtensorMap mn_w2_lo,
@@ -324,7 +327,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       mbar_init(bEmpty + 8 * s, 1);
     }
     for (int s = 0; s < 4; ++s) {
-      mbar_init(bReady + 8 * s, 8);
+      mbar_init(bReady + 8 * s, 4 * kBwdWG);
       mbar_init(bAcc + 8 * s, 1);
     }
     fence_barrier_init();
@@ -404,20 +407,20 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
     const float s1 = p.scales[0], s2 = p.scales[1], sg3 = p.scales[4], sg2 = p.scales[5];
     const float sw2 = scale_from_absmax(p.sc_w2[0]), sw3 = scale_from_absmax(p.sc_w3[0]);
     const float inv12 = 1.f / (s1 * sw2), inv23 = 1.f / (s2 * sw3), inv_c = 1.f / (sg3 * sw3), inv_d = 1.f / (sg2 * sw2);
-    float acc_b2[4] = {0.f, 0.f, 0.f, 0.f}, acc_b3[4] = {0.f, 0.f, 0.f, 0.f}, acc_w4[4] = {0.f, 0.f, 0.f, 0.f};
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // s_gv zeroed (the block-wide barrier above already ordered it; cheap)
+    float acc_b2[kBwdCh] = {}, acc_b3[kBwdCh] = {}, acc_w4[kBwdCh] = {};
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * kBwdWG) : "memory");      // s_gv zeroed (the block-wide barrier above already ordered it; cheap)
     long long cur_jb = -1;
     uint32_t it = 0;
     auto flush_gv = [&](long long jb) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int t = (e * 32 + lane); t < kHid * 32; t += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kBwdWG) : "memory");
+      for (int t = (e * 32 + lane); t < kHid * 32; t += 128 * kBwdWG) {
         const int f = t >> 5, jj = t & 31;
         const long long j = jb * 32 + jj;
         const float val = s_gv[t];
         if (j < p.n_all && val != 0.f) atomicAdd(bp.g_vt + (size_t)f * p.ldv + j, val);
         s_gv[t] = 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kBwdWG) : "memory");
     };
     for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
       const uint32_t par = it & 1;
@@ -433,10 +436,10 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       const float *vj = p.vt + (j < p.n_all ? j : 0);
       const float gp = ok ? __ldg(bp.g + (size_t)i * p.n_all + j) : 0.f;
       const size_t row = (size_t)(tile - 0) * 128 + q * 32 + lane;        // operand row of this pair
-      uint32_t mask1[4], mask2[4];
+      uint32_t mask1[kBwdCh], mask2[kBwdCh];
       // ---- phase 0 operand: h1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * g + cc;
+      for (int cc = 0; cc < kBwdCh; ++cc) {
+        const int c = kBwdCh * g + cc;
         float v[32];
         uint32_t m = 0;
 #pragma unroll
@@ -465,8 +468,8 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- phase 1 operand: h2 in place over D2
       mbar_wait(bAcc + 0, par);
       tc_fence_after();
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * g + cc;
+      for (int cc = 0; cc < kBwdCh; ++cc) {
+        const int c = kBwdCh * g + cc;
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR1 + 32 * c, d);
         tmem_ld_wait();
@@ -492,8 +495,8 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- phase 2 operand: g3 = G w4 [pre3 > 0] in place over D3; w4 and b3 gradients
       mbar_wait(bAcc + 8, par);
       tc_fence_after();
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * g + cc;
+      for (int cc = 0; cc < kBwdCh; ++cc) {
+        const int c = kBwdCh * g + cc;
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR0 + 32 * c, d);
         tmem_ld_wait();
@@ -527,8 +530,8 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- phase 3 operand: g2 = g_h2 [h2 > 0] in place (region 1); b2 gradient
       mbar_wait(bAcc + 16, par);
       tc_fence_after();
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * g + cc;
+      for (int cc = 0; cc < kBwdCh; ++cc) {
+        const int c = kBwdCh * g + cc;
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR1 + 32 * c, d);
         tmem_ld_wait();
@@ -553,8 +556,8 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- g1 = g_h1 [h1 > 0]: row sums to g_u, column sums to the shared g_v accumulator
       mbar_wait(bAcc + 24, par);
       tc_fence_after();
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * g + cc;
+      for (int cc = 0; cc < kBwdCh; ++cc) {
+        const int c = kBwdCh * g + cc;
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR0 + 32 * c, d);
         tmem_ld_wait();
@@ -571,8 +574,8 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
     }
     if (cur_jb >= 0) flush_gv(cur_jb);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int f = 32 * (4 * g + cc) + lane;
+    for (int cc = 0; cc < kBwdCh; ++cc) {
+      const int f = 32 * (kBwdCh * g + cc) + lane;
       atomicAdd(bp.g_b2 + f, acc_b2[cc]);
       atomicAdd(bp.g_b3 + f, acc_b3[cc]);
       atomicAdd(bp.g_w4 + f, acc_w4[cc]);
@@ -766,6 +769,6 @@ extern "C" int mimrl_concat_grad(const float *u, const float *vt, int n_own, int
   }
   cudaFuncSetAttribute(concat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCbSmem);
   const int blocks = (int)(bp.f.n_tiles < 148 ? bp.f.n_tiles : 148);
-  concat_bwd_kernel<<<blocks, kCcThreads, kCbSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, h.m2h, h.m2l, h.m3h, h.m3l, bp);
+  concat_bwd_kernel<<<blocks, kBwdThreads, kCbSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, h.m2h, h.m2l, h.m3h, h.m3l, bp);
   return check_launch("concat_bwd");
 }
