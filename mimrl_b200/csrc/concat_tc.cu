@@ -19,14 +19,16 @@
 namespace mimrl {
 namespace {
 
-constexpr int kCcThreads = 320;                    // warp 0 TMA, warp 1 MMA, warps 2-9 two epilogue warpgroups
+constexpr int kFwdWG = 4;                           // epilogue warpgroups of the forward kernel
+constexpr int kFwdCh = 8 / kFwdWG;                  // 32-feature chunks per epilogue thread
+constexpr int kCcThreads = 64 + 128 * kFwdWG;       // warp 0 TMA, warp 1 MMA, then the epilogue warpgroups
 constexpr int kHid = 256;
 constexpr uint32_t kCcUnit = 256 * 128;            // ring unit: 64 k of a 256 x 256 weight, hi OR lo half, 32 KB
 constexpr int kCcStages = 5;                       // units in flight (hi and lo of a k-block are separate units)
 constexpr uint32_t kCcRing = kCcStages * kCcUnit;
 constexpr uint32_t kCcVecOff = kCcRing + 256;                       // b2 | b3 | w4 (3 x 256 floats)
 constexpr uint32_t kCcPartOff = kCcVecOff + 3 * kHid * 4;           // 128 partial dot products
-constexpr uint32_t kCcSmem = kCcPartOff + 128 * 4 + 1024;
+constexpr uint32_t kCcSmem = kCcPartOff + 4 * 128 * 4 + 1024;
 constexpr uint32_t kR0 = 0, kR1 = 256;             // TMEM regions
 
 struct ConcatParams {
@@ -86,9 +88,9 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       mbar_init(bFull + 8 * s, 1);
       mbar_init(bEmpty + 8 * s, 1);
     }
-    mbar_init(bH1, 8);
+    mbar_init(bH1, 4 * kFwdWG);
     mbar_init(bD2, 1);
-    mbar_init(bH2, 8);
+    mbar_init(bH2, 4 * kFwdWG);
     mbar_init(bD3, 1);
     fence_barrier_init();
   }
@@ -151,7 +153,7 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       }
     }
   } else {
-    const int e = warp - 2;                 // 0..7
+    const int e = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const int g = e >> 2;                   // feature half handled by this warpgroup
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -168,7 +170,7 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       const float *ui = p.u + (size_t)(i < p.n_own ? i : 0) * kHid;
       const float *vj = p.vt + (j < p.n_all ? j : 0);
       // ---- h1 = relu(u_i + v_j) -> TMEM region 0
-      for (int c = 4 * g; c < 4 * g + 4; ++c) {
+      for (int c = kFwdCh * g; c < kFwdCh * g + kFwdCh; ++c) {
         float v[32];
 #pragma unroll
         for (int t4 = 0; t4 < 8; ++t4) {
@@ -192,7 +194,7 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- h2 = relu(D2 + b2), in place over D2 (region 1)
       mbar_wait(bD2, ph);
       tc_fence_after();
-      for (int c = 4 * g; c < 4 * g + 4; ++c) {
+      for (int c = kFwdCh * g; c < kFwdCh * g + kFwdCh; ++c) {
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR1 + 32 * c, d);
         tmem_ld_wait();
@@ -212,7 +214,7 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       mbar_wait(bD3, ph);
       tc_fence_after();
       float dot = 0.f;
-      for (int c = 4 * g; c < 4 * g + 4; ++c) {
+      for (int c = kFwdCh * g; c < kFwdCh * g + kFwdCh; ++c) {
         uint32_t d[32];
         tmem_ld32(tmem_base + lane_off + kR0 + 32 * c, d);
         tmem_ld_wait();
@@ -221,9 +223,13 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
           dot = fmaf(fmaxf(fmaf(__uint_as_float(d[t]), inv23, s_b3[32 * c + t]), 0.f), s_w4[32 * c + t], dot);
       }
       tc_fence_before();
-      if (g == 1) s_part[q * 32 + lane] = dot;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (g == 0 && ok) p.scores[(size_t)i * p.n_all + j] = dot + s_part[q * 32 + lane] + b4;
+      if (g > 0) s_part[(g - 1) * 128 + q * 32 + lane] = dot;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kFwdWG) : "memory");
+      if (g == 0 && ok) {
+#pragma unroll
+        for (int w = 0; w < kFwdWG - 1; ++w) dot += s_part[w * 128 + q * 32 + lane];
+        p.scores[(size_t)i * p.n_all + j] = dot + b4;
+      }
     }
   }
   tc_fence_before();
