@@ -21,11 +21,13 @@
 namespace mimrl {
 namespace {
 
-constexpr int kCubeThreads = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-9: two compute warpgroups that
+constexpr int kCubeWG = 4;                             // compute warpgroups
+constexpr int kCubeCh = 4 / kCubeWG;                   // 32-feature chunks of a fibre per compute thread
+constexpr int kCubeThreads = 64 + 128 * kCubeWG;       // warp 0 TMA, warp 1 MMA, then the compute warpgroups that
                                                        // split the 32-feature chunks of a fibre (thread = fibre x chunk parity)
 constexpr uint32_t kW16 = 128 * 128;                   // one 128-row x 64-K block: 16 KB
 constexpr uint32_t kWMat = 4 * kW16;                   // hi kb0, hi kb1, lo kb0, lo kb1
-constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + 2 * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, LN partials, alignment
+constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + kCubeWG * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, LN partials, alignment
 // TMEM columns
 constexpr uint32_t kTX = 0, kTD1 = 128, kTH = 256, kTD2 = 384;
 
@@ -129,9 +131,9 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(bWFull, 1);
-    mbar_init(bXReady, 8);
+    mbar_init(bXReady, 4 * kCubeWG);
     mbar_init(bD1Full, 1);
-    mbar_init(bHReady, 8);
+    mbar_init(bHReady, 4 * kCubeWG);
     mbar_init(bD2Full, 1);
     fence_barrier_init();
   }
@@ -236,7 +238,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       const float *xf = p.x + (size_t)o * p.A * p.inner + (size_t)i;
       float *yf = p.y + (size_t)o * p.A2 * p.inner + (size_t)i;
       // ---- 1. fibre -> TMEM (one power-of-two scale for the tensor, fp16 hi/lo)
-      for (int ch = g; ch * 32 < ks1 * 16; ch += 2) {
+      for (int ch = g; ch * 32 < ks1 * 16; ch += kCubeWG) {
         float v[32];
         fibre_load32(xf, ch * 32, p.A, p.inner, vec_in, ok, v);
 #pragma unroll
@@ -253,7 +255,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       // ---- 2. h = act(pre + b1) (scale from the bound |act(z)| <= |z| <= max|x| max_h sum_a |W1[h,a]| + max|b1|)
       mbar_wait(bD1Full, ph);
       tc_fence_after();
-      for (int ch = g; ch * 32 < ks2 * 16; ch += 2) {
+      for (int ch = g; ch * 32 < ks2 * 16; ch += kCubeWG) {
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + kTD1 + ch * 32, v);
         tmem_ld_wait();
@@ -276,11 +278,11 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       //         warpgroups exchange their partial sums through shared memory), one write
       mbar_wait(bD2Full, ph);
       tc_fence_after();
-      float z[2][32];
+      float z[kCubeCh][32];
       float sum = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = g + 2 * cc;
+      for (int cc = 0; cc < kCubeCh; ++cc) {
+        const int ch = g + kCubeWG * cc;
         if (ch * 32 < n2) {
           uint32_t v[32], w[32];
           tmem_ld32(tmem_base + lane_off + kTD2 + ch * 32, v);
@@ -305,38 +307,44 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       }
       tc_fence_before();
       s_part[g * 128 + r] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mean = (sum + s_part[(g ^ 1) * 128 + r]) / p.A2;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeWG) : "memory");
+      float sum_all = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCubeWG; ++w) sum_all += s_part[w * 128 + r];
+      const float mean = sum_all / p.A2;
       float var = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < kCubeCh; ++cc) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float dlt = ((g + 2 * cc) * 32 + j < p.A2) ? z[cc][j] - mean : 0.f;
+          const float dlt = ((g + kCubeWG * cc) * 32 + j < p.A2) ? z[cc][j] - mean : 0.f;
           var = fmaf(dlt, dlt, var);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");             // everyone has read the sums
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeWG) : "memory");             // everyone has read the sums
       s_part[g * 128 + r] = var;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float rstd = rsqrtf((var + s_part[(g ^ 1) * 128 + r]) / p.A2 + 1e-6f);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeWG) : "memory");
+      float var_all = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCubeWG; ++w) var_all += s_part[w * 128 + r];
+      const float rstd = rsqrtf(var_all / p.A2 + 1e-6f);
       if (ok) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < kCubeCh; ++cc) {
           float yv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int a2 = (g + 2 * cc) * 32 + j;
+            const int a2 = (g + kCubeWG * cc) * 32 + j;
             yv[j] = a2 < p.A2 ? (z[cc][j] - mean) * rstd * s_lw[a2] + s_lb[a2] : 0.f;
           }
-          fibre_store32(yf, (g + 2 * cc) * 32, p.A2, p.inner, vec_out, yv);
+          fibre_store32(yf, (g + kCubeWG * cc) * 32, p.A2, p.inner, vec_out, yv);
         }
         if (g == 0) {
           p.saved[2 * c] = mean;
           p.saved[2 * c + 1] = rstd;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");             // partial-sum slots are free for the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeWG) : "memory");             // partial-sum slots are free for the next tile
     }
   }
   tc_fence_before();
@@ -360,10 +368,12 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 // over fibres: 32x32 butterfly transposes, accumulated in registers over the CTA's tiles.
 // Operand scales are powers of two from bounds known before the launch (absmax of x and gy, max rstd of the saved
 // statistics, L1 norms of the weights): |gz| <= rstd (2 + sqrt(A')) max|gy ln_w|.
-constexpr int kCubeBwdThreads = 320;
+constexpr int kCubeBwdWG = 2;                          // (four warpgroups spill: 96 registers per thread are too few here)
+constexpr int kCubeBwdCh = 4 / kCubeBwdWG;
+constexpr int kCubeBwdThreads = 64 + 128 * kCubeBwdWG;
 constexpr uint32_t kCbVec = 3 * kWMat + 256;                   // b1 | b2 | ln_w (3 x 128 floats)
-constexpr uint32_t kCbPart = kCbVec + 3 * 128 * 4;             // [2 warpgroups][128 fibres][2] partial LN sums
-constexpr uint32_t kCubeBwdSmem = kCbPart + 2 * 128 * 2 * 4 + 1024;
+constexpr uint32_t kCbPart = kCbVec + 3 * 128 * 4;             // [warpgroups][128 fibres][2] partial LN sums
+constexpr uint32_t kCubeBwdSmem = kCbPart + kCubeBwdWG * 128 * 2 * 4 + 1024;
 
 struct CubeBwdParams {
   CubeTcParams f;
@@ -457,14 +467,14 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(bW, 1);
-    mbar_init(bX, 8);
+    mbar_init(bX, 4 * kCubeBwdWG);
     mbar_init(bD1, 1);
-    mbar_init(bH, 8);
+    mbar_init(bH, 4 * kCubeBwdWG);
     mbar_init(bMid, 1);
     mbar_init(bD2, 1);
-    mbar_init(bGz, 8);
+    mbar_init(bGz, 4 * kCubeBwdWG);
     mbar_init(bD3, 1);
-    mbar_init(bGp, 8);
+    mbar_init(bGp, 4 * kCubeBwdWG);
     mbar_init(bD4, 1);
     fence_barrier_init();
   }
@@ -564,7 +574,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
     const float swr = p.has_res ? scale_from_absmax(p.sc_wr[0]) : 1.f;
     const float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr), i_gh = 1.f / (sgz * sw2),
                 i_gx1 = 1.f / (sgp * sw1), i_gx2 = 1.f / (sgz * swr), i_gz = 1.f / sgz;
-    float acc_lnw[2] = {0.f, 0.f}, acc_lnb[2] = {0.f, 0.f}, acc_b2[2] = {0.f, 0.f}, acc_b1[2] = {0.f, 0.f};
+    float acc_lnw[kCubeBwdCh] = {}, acc_lnb[kCubeBwdCh] = {}, acc_b2[kCubeBwdCh] = {}, acc_b1[kCubeBwdCh] = {};
     const bool vec_in = p.inner == 1 && (p.A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(bp.gx)) & 15) == 0;
     const bool vec_out = p.inner == 1 && (p.A2 & 3) == 0 && (reinterpret_cast<uintptr_t>(bp.gy) & 15) == 0;
     int it = 0;
@@ -579,7 +589,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       const size_t row = (size_t)c;
       const float mean = ok ? p.saved[2 * c] : 0.f, rstd = ok ? p.saved[2 * c + 1] : 0.f;
       // ---- x -> X operand (+ feature-major copy for the weight gradients)
-      for (int ch = g; ch * 32 < ks_a * 16; ch += 2) {
+      for (int ch = g; ch * 32 < ks_a * 16; ch += kCubeBwdWG) {
         float v[32];
         fibre_load32(xf, ch * 32, p.A, p.inner, vec_in, ok, v);
 #pragma unroll
@@ -597,7 +607,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       // ---- h = act(pre + b1) -> H operand
       mbar_wait(bD1, ph);
       tc_fence_after();
-      for (int ch = g; ch * 32 < ks_h * 16; ch += 2) {
+      for (int ch = g; ch * 32 < ks_h * 16; ch += kCubeBwdWG) {
         uint32_t d[32];
         tmem_ld32(tD1 + ch * 32, d);
         tmem_ld_wait();
@@ -640,7 +650,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       float sum_g = 0.f, sum_gz = 0.f;
       {
         int cc = 0;
-        for (int ch = g; ch * 32 < n_q; ch += 2, ++cc) {
+        for (int ch = g; ch * 32 < n_q; ch += kCubeBwdWG, ++cc) {
           float z[32], t1[32], t2[32];
           z_chunk(ch, z);
           fibre_load32(gyf, ch * 32, p.A2, p.inner, vec_out, ok, t2);
@@ -656,18 +666,21 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
             t2[j] = gyv;
           }
           const float a1 = cube_lane_sum(t1, lane), a2s = cube_lane_sum(t2, lane);
-          if (cc == 0) acc_lnw[0] += a1, acc_lnb[0] += a2s;
-          else acc_lnw[1] += a1, acc_lnb[1] += a2s;
+#pragma unroll
+          for (int w = 0; w < kCubeBwdCh; ++w)
+            if (cc == w) acc_lnw[w] += a1, acc_lnb[w] += a2s;
         }
       }
       s_part[(g * 128 + r) * 2] = sum_g;
       s_part[(g * 128 + r) * 2 + 1] = sum_gz;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m1 = (sum_g + s_part[((g ^ 1) * 128 + r) * 2]) / p.A2;
-      const float m2 = (sum_gz + s_part[((g ^ 1) * 128 + r) * 2 + 1]) / p.A2;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeBwdWG) : "memory");
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCubeBwdWG; ++w) m1 += s_part[(w * 128 + r) * 2], m2 += s_part[(w * 128 + r) * 2 + 1];
+      m1 /= p.A2, m2 /= p.A2;
       {
         int cc = 0;
-        for (int ch = g; ch * 32 < ks_q * 16; ch += 2, ++cc) {
+        for (int ch = g; ch * 32 < ks_q * 16; ch += kCubeBwdWG, ++cc) {
           float z[32], v[32], t1[32];
           z_chunk(ch, z);
           fibre_load32(gyf, ch * 32, p.A2, p.inner, vec_out, ok, v);
@@ -686,8 +699,9 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           tmem_st16(tX + 64 + ch * 16, lo);
           cube_store_op(bp.op[2][0], bp.op[2][1], row, ch * 32, p.A2, hi, lo);
           const float a1 = cube_lane_sum(t1, lane);
-          if (cc == 0) acc_b2[0] += a1;
-          else acc_b2[1] += a1;
+#pragma unroll
+          for (int w = 0; w < kCubeBwdCh; ++w)
+            if (cc == w) acc_b2[w] += a1;
         }
       }
       tmem_st_wait();
@@ -699,7 +713,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       tc_fence_after();
       {
         int cc = 0;
-        for (int ch = g; ch * 32 < ks_h * 16; ch += 2, ++cc) {
+        for (int ch = g; ch * 32 < ks_h * 16; ch += kCubeBwdWG, ++cc) {
           uint32_t d[32], w[32];
           tmem_ld32(tD2 + ch * 32, d);
           tmem_ld32(tD1 + ch * 32, w);
@@ -719,8 +733,9 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
           tmem_st16(tH + 64 + ch * 16, lo);
           cube_store_op(bp.op[3][0], bp.op[3][1], row, ch * 32, p.H, hi, lo);
           const float a1 = cube_lane_sum(t1, lane);
-          if (cc == 0) acc_b1[0] += a1;
-          else acc_b1[1] += a1;
+#pragma unroll
+          for (int w = 0; w < kCubeBwdCh; ++w)
+            if (cc == w) acc_b1[w] += a1;
         }
       }
       tmem_st_wait();
@@ -730,7 +745,7 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       // ---- gx = gpre W1 + gz Wres (+ gz)
       mbar_wait(bD4, ph);
       tc_fence_after();
-      for (int ch = g; ch * 32 < n_a; ch += 2) {
+      for (int ch = g; ch * 32 < n_a; ch += kCubeBwdWG) {
         uint32_t d[32], w[32];
         tmem_ld32(tD1 + ch * 32, d);
         if (p.has_res) tmem_ld32(tD2 + ch * 32, w);
@@ -768,8 +783,8 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
       tc_fence_before();
     }
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int f = 32 * (g + 2 * cc) + lane;
+    for (int cc = 0; cc < kCubeBwdCh; ++cc) {
+      const int f = 32 * (g + kCubeBwdWG * cc) + lane;
       if (f < p.A2) {
         atomicAdd(bp.g_lnw + f, acc_lnw[cc]);
         atomicAdd(bp.g_lnb + f, acc_lnb[cc]);
