@@ -42,6 +42,8 @@ enum mimrl_bound {
 /* statistics requested from the score sweep */
 #define MIMRL_STAT_CLAMP 1    /* exp-sum runs on clamp(S,-1,1)  (smile, VMI.py:186-191) */
 #define MIMRL_STAT_SOFTPLUS 2 /* also accumulate sum softplus(S) (js_fgan/js/smile, VMI.py:169-174) */
+#define MIMRL_STAT_MAXONLY 4  /* tcgen05 path: row_max only, from ONE fp16 product (approximate, ~2^-11 |y||x|): the
+                                reference point of mimrl_sep_fused_forward; row_sum / row_sp come back as 0 */
 
 /* per-pair weight families of the backward sweep */
 #define MIMRL_WEIGHT_EXP 0     /* w_ij = exp(S_ij - shift) */
@@ -83,6 +85,15 @@ int mimrl_sep_row_stats(const float *own_emb, const float *all_emb, int n_own, i
  * (shift[i], i < n_own) or, with shift_by_swept, by the swept row (shift[j],
  * j < n_all).  Called twice per backward: rows = h(y) to get d/dh(y), then with
  * the operands swapped to get d/dg(x). */
+/* Fused forward sweep (tcgen05 path): for every owned row i, in ONE pass over the score tiles,
+ *   row_sum[i] = sum_{j != i} exp(S_ij - shift[i])          (the off-diagonal statistic of mimrl_sep_row_stats)
+ *   wsum[i,:]  = sum_j exp(S_ij - shift[i]) all_emb[j,:]    (j = i included iff include_diag)
+ * shift is any per-row reference point near the row maximum (MIMRL_STAT_MAXONLY pre-pass).  For the exp-family bounds
+ * (dv, mine, tuba, nwj, infonce) this replaces the exact statistics sweep and the owned-row gradient sweep
+ * (the gradient is wsum rescaled by exp(shift - final shift)): 4 1/3 tensor-core units per step instead of 5. */
+int mimrl_sep_fused_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                            int own_offset, int include_diag, const float *shift, float *wsum, float *row_sum,
+                            void *workspace, size_t workspace_bytes, void *stream);
 int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                            int own_offset, int weight_family, int include_diag, const float *shift,
                            int shift_by_swept, const float *coef, const float *dcoef, int impl, float *out,

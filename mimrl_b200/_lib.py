@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmimrl_b200.so")
 
 BOUND_IDS = {"dv": 0, "mine": 1, "tuba": 2, "nwj": 3, "infonce": 4, "js_fgan": 5, "js": 6, "smile": 7,
              "interpolate": 8}
-STAT_CLAMP, STAT_SOFTPLUS = 1, 2
+STAT_CLAMP, STAT_SOFTPLUS, STAT_MAXONLY = 1, 2, 4
 WEIGHT_EXP, WEIGHT_SIGMOID = 0, 1
 IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05 = 0, 1, 2
 
@@ -36,6 +36,7 @@ _SIGS = {
     "mimrl_sep_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mimrl_sep_selected_impl": (c_int, [c_int, c_int, c_int, c_int]),
     "mimrl_sep_row_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mimrl_sep_fused_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_weighted_sum": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P,
                                        _P, c_size_t, _P]),
     "mimrl_bound_finalize": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P, _P]),

@@ -327,6 +327,8 @@ extern "C" int mimrl_sep_row_stats(const float *own_emb, const float *all_emb, i
   MIMRL_REQUIRE(workspace_bytes >= mimrl_sep_workspace_bytes(n_own, n_all, embed), "sep_row_stats: workspace too small");
   MIMRL_REQUIRE(impl != MIMRL_IMPL_TCGEN05 || sep_tc_supported(n_own, n_all, embed),
                 "sep_row_stats: tcgen05 path needs embed <= 128 (got %d)", embed);
+  MIMRL_REQUIRE(!(flags & MIMRL_STAT_MAXONLY) || use_tc(impl, n_own, n_all, embed),
+                "sep_row_stats: MIMRL_STAT_MAXONLY exists on the tcgen05 path only");
   if (diag) {
     sep_diag_kernel<<<ceil_div(n_own * 32, 256), 256, 0, st>>>(own_emb, all_emb, n_own, n_all, embed, own_offset, diag);
     if (check_launch("sep_diag")) return 1;
@@ -344,6 +346,22 @@ extern "C" int mimrl_sep_row_stats(const float *own_emb, const float *all_emb, i
   else rc = launch_row_stats<256>(own_emb, all_emb, n_own, n_all, embed, own_offset, flags, part, splits, st);
   if (rc) return rc;
   return combine_row_stats(part, splits, n_own, row_max, row_sum, row_sp, st);
+}
+
+// Fused forward sweep (tcgen05 path only): one pass over the own x swept score tiles gives BOTH the row statistic
+// row_sum[i] = sum_{j != i} exp(S_ij - shift[i]) and the weighted sum wsum[i] = sum_j w_ij all_j (w includes the
+// diagonal when include_diag).  With shift = an approximate row maximum (MIMRL_STAT_MAXONLY pre-pass) this replaces the
+// exact statistics sweep AND the owned-row gradient sweep of the exp-family bounds: 4 1/3 tensor-core units instead of 5.
+extern "C" int mimrl_sep_fused_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                                       int own_offset, int include_diag, const float *shift, float *wsum, float *row_sum,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MIMRL_REQUIRE(n_own > 0 && n_all > 0 && embed > 0 && shift && wsum && row_sum, "sep_fused_forward: bad arguments");
+  MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "sep_fused_forward: row block outside the batch");
+  MIMRL_REQUIRE(sep_tc_supported(n_own, n_all, embed), "sep_fused_forward: tcgen05 path needs embed <= 128 (got %d)", embed);
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_sep_workspace_bytes(n_own, n_all, embed), "sep_fused_forward: workspace too small");
+  return sep_weighted_sum_tc(own_emb, all_emb, n_own, n_all, embed, own_offset, MIMRL_WEIGHT_EXP, include_diag, shift, 0,
+                             /*coef = 1*/ nullptr, nullptr, wsum, workspace, workspace_bytes, st, row_sum);
 }
 
 extern "C" int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,

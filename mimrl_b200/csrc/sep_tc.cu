@@ -166,17 +166,20 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
   __syncthreads();
   tc_fence_after();
 
+  // FLAGS & 4 (MIMRL_STAT_MAXONLY): approximate row maxima only -- one product (own_hi . x_hi, 11-bit operands) instead
+  // of three and no exponentials: the reference point of the fused forward sweep, which does not need to be exact.
+  constexpr bool kMaxOnly = (FLAGS & 4) != 0;
   if (warp == 0) {
     const uint32_t leader = elect_one();
     if (leader) {
       prefetch_tmap(&map_all_hi);
       prefetch_tmap(&map_all_lo);
-      for (int u = 0; u < 2 * T; ++u) {
+      for (int u = 0; u < (kMaxOnly ? T : 2 * T); ++u) {
         const int stage = u % kStages;
-        const int col = (t0 + (u >> 1)) * 128;
+        const int col = (t0 + (kMaxOnly ? u : (u >> 1))) * 128;
         mbar_wait(bEmpty + 8 * stage, ((u / kStages) & 1) ^ 1);
         mbar_expect_tx(bFull + 8 * stage, kUnit);
-        const CUtensorMap *m = (u & 1) ? &map_all_lo : &map_all_hi;
+        const CUtensorMap *m = (!kMaxOnly && (u & 1)) ? &map_all_lo : &map_all_hi;
         tma_load_2d(base + stage * kUnit, m, bFull + 8 * stage, 0, col);
         tma_load_2d(base + stage * kUnit + kTile16, m, bFull + 8 * stage, 64, col);
       }
@@ -188,6 +191,23 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
       const int buf = i & 1;
       const uint32_t d = tmem_base + 128 + buf * 128;
       mbar_wait(bTEmpty + 8 * buf, ((i >> 1) & 1) ^ 1);
+      if (kMaxOnly) {
+        const int stage = i % kStages;
+        mbar_wait(bFull + 8 * stage, (i / kStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t b0 = base + stage * kUnit;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(d, tmem_a + kb * 32 + k * 8, smem_desc_sw128(b0 + kb * kTile16 + k * 32), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(bEmpty + 8 * stage);
+          umma_commit(bTFull + 8 * buf);
+        }
+        __syncwarp();
+        continue;
+      }
       // hi half of the swept tile: own_hi . x_hi and own_lo . x_hi
       int u = 2 * i, stage = u % kStages;
       mbar_wait(bFull + 8 * stage, (u / kStages) & 1);
@@ -237,7 +257,7 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
     const int buf = wg;
     for (int i = wg; i < T; i += 2) {
       const int col0 = (t0 + i) * 128;
-      const bool clean = FLAGS == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
+      const bool clean = (FLAGS & 3) == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
       mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -266,6 +286,10 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
 #pragma unroll
           for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(v[j + u]));
         const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (kMaxOnly) {
+          m2 = fmaxf(m2, cmax);
+          continue;
+        }
         if (cmax > m2) {                      // also false when the whole chunk is masked (-inf)
           s *= ex2((m2 - cmax) * c2);
           m2 = cmax;
@@ -305,6 +329,7 @@ struct WsumParams {
   const __half *own_hi, *own_lo;
   const float *shift;
   float *part;  // [split][n_own][128]
+  float *rsum_part;   // nullable: [split * 2 + warpgroup][n_own] sum of the off-diagonal weights of the row
 };
 
 template <int FAMILY>
@@ -458,10 +483,13 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       const int gc = t0 * 64 + et;
       sh_next = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
     }
+    const bool want_rsum = p.rsum_part != nullptr;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1;
       const int col0 = (t0 + i) * 64;
       const bool clean = col0 + 64 <= p.n_all && (p.include_diag || col0 + 64 <= grmin || col0 > grmax);
+      const bool clean_stat = col0 + 64 <= p.n_all && (col0 + 64 <= grmin || col0 > grmax);
       if (by_swept) {
         if (et < 64) {
           sh_smem[buf * 64 + et] = sh_next;
@@ -497,6 +525,14 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
             if (!(gc < p.n_all && (p.include_diag || gc != gr))) wv = 0.f;
           }
           w[u] = wv;
+          if (want_rsum) {                      // the statistic always leaves the diagonal out
+            float add = wv;
+            if (!clean_stat) {
+              const int gc = col0 + wg * 32 + j + u;
+              if (gc == gr || gc >= p.n_all) add = 0.f;
+            }
+            rs[u] += add;
+          }
         }
         // hi = w truncated to 11 significant bits (exactly representable in fp16), lo = w - hi
         float wh[4], wl[4];
@@ -519,6 +555,8 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(bWFull + 8 * buf);
     }
+    if (want_rsum && row_ok)
+      p.rsum_part[(size_t)(split * 2 + wg) * p.n_own + row0 + r] = ((rs[0] + rs[1]) + (rs[2] + rs[3])) * (1.f / 16384.f);
     if (T > 0) {
       mbar_wait(bOFull, 0);
       tc_fence_after();
@@ -546,12 +584,20 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+__global__ void rsum_reduce_tc_kernel(const float *__restrict__ part, int n_parts, int n_own, float *__restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_own) return;
+  float a = 0.f;
+  for (int s = 0; s < n_parts; ++s) a += part[(size_t)s * n_own + r];
+  out[r] = a;
+}
+
 // out[r][e] = coef * sum_splits part[s][r][e] + dcoef[r] * all[own_offset + r][e]     (part rows are 128 wide)
 __global__ void wsum_reduce_tc_kernel(const float *__restrict__ part, int n_splits, int n_own, int embed,
                                       const float *__restrict__ all, int own_offset, const float *__restrict__ coef,
                                       const float *__restrict__ dcoef, float *__restrict__ out) {
   const size_t total = (size_t)n_own * embed;
-  const float c = coef[0];
+  const float c = coef ? coef[0] : 1.f;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx / embed), e = (int)(idx - (size_t)r * embed);
     float a = 0.f;
@@ -563,7 +609,7 @@ __global__ void wsum_reduce_tc_kernel(const float *__restrict__ part, int n_spli
 
 // ------------------------------------------------------------------ host ----
 struct TcLayout {
-  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_part, total;
+  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_part, off_rsum, total;
 };
 
 
@@ -584,6 +630,8 @@ TcLayout tc_layout(int n_own, int n_all) {
   o += align256((size_t)n_all * 128 * 2);
   L.off_part = o;
   o += align256((size_t)tc_max_splits() * n_own * 128 * sizeof(float));
+  L.off_rsum = o;
+  o += align256((size_t)2 * tc_max_splits() * n_own * sizeof(float));
   L.total = o;
   return L;
 }
@@ -660,11 +708,12 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
     cudaFuncSetAttribute(sep_stats_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);    \
     sep_stats_tc_kernel<F><<<grid, kTcThreads, kRingSmem, st>>>(m_all_hi, m_all_lo, p);                           \
   } while (0)
-  switch (flags & 3) {
+  switch (flags & 7) {
     case 0: LAUNCH_STATS(0); break;
     case 1: LAUNCH_STATS(1); break;
     case 2: LAUNCH_STATS(2); break;
-    default: LAUNCH_STATS(3); break;
+    case 3: LAUNCH_STATS(3); break;
+    default: LAUNCH_STATS(4); break;          // MIMRL_STAT_MAXONLY (clamp / softplus do not apply)
   }
 #undef LAUNCH_STATS
   if (check_launch("sep_stats_tc")) return 1;
@@ -673,7 +722,8 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
 
 int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
                         int family, int include_diag, const float *shift, int shift_by_swept, const float *coef,
-                        const float *dcoef, float *out, void *workspace, size_t ws_bytes, cudaStream_t st) {
+                        const float *dcoef, float *out, void *workspace, size_t ws_bytes, cudaStream_t st,
+                        float *row_sum) {
   const TcLayout L = tc_layout(n_own, n_all);
   MIMRL_REQUIRE(ws_bytes >= L.total, "sep_weighted_sum(tcgen05): workspace too small");
   unsigned char *ws = (unsigned char *)workspace;
@@ -695,6 +745,7 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
   p.shift = shift;
   p.part = reinterpret_cast<float *>(ws + L.off_part);
+  p.rsum_part = row_sum ? reinterpret_cast<float *>(ws + L.off_rsum) : nullptr;
   dim3 grid(row_tiles, splits);
   if (family == MIMRL_WEIGHT_EXP) {
     cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);
@@ -709,7 +760,12 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   int blocks = (int)((total + 255) / 256);
   blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
   wsum_reduce_tc_kernel<<<blocks, 256, 0, st>>>(p.part, splits, n_own, embed, all, own_offset, coef, dcoef, out);
-  return check_launch("wsum_reduce_tc");
+  if (check_launch("wsum_reduce_tc")) return 1;
+  if (row_sum) {
+    rsum_reduce_tc_kernel<<<ceil_div(n_own, 256), 256, 0, st>>>(p.rsum_part, 2 * splits, n_own, row_sum);
+    return check_launch("rsum_reduce_tc");
+  }
+  return 0;
 }
 
 }  // namespace mimrl

@@ -143,12 +143,107 @@ class _SeparableBound(torch.autograd.Function):
         return dx, dy, dbase, None, None, None
 
 
+FUSED_FORWARD = True      # exp-family bounds: statistics and the owned-row gradient sum from ONE sweep (see below)
+_FUSED_BOUNDS = ("dv", "mine", "tuba", "nwj", "infonce")
+
+
+class _SeparableBoundFused(torch.autograd.Function):
+    """Same contract as ``_SeparableBound`` for the exp-family bounds when a gradient is wanted.
+
+    The backward of these bounds weights row i's swept embeddings by exp(S_ij - shift_i); up to a per-row factor
+    that is exp(S_ij - ref_i) for ANY reference point ref_i.  So the forward takes an approximate row maximum from a
+    cheap pre-pass (one fp16 product, no exponentials: MIMRL_STAT_MAXONLY) and then ONE sweep (mimrl_sep_fused_forward)
+    returns both the exact row statistic sum_{j != i} exp(S_ij - ref_i) and O_i = sum_j exp(S_ij - ref_i) x_j.  The
+    backward rescales O_i and only has to sweep for the swept side: 1/3 + 2 + 2 tensor-core units instead of 1 + 2 + 2."""
+
+    @staticmethod
+    def forward(ctx, x_emb, y_emb, log_baseline, bound_id, impl, rb):
+        x_emb, y_emb = L.f32(x_emb), L.f32(y_emb)
+        n_own, embed = y_emb.shape
+        if rb is None:
+            rb = RB.single(n_own)
+        fam, inc, flags = _family(bound_id)
+        all_x = RB.all_gather_rows(x_emb, rb)
+        n_all = all_x.shape[0]
+        dev = y_emb.device
+        st = L.stream()
+        ws = torch.empty(max(L.lib.mimrl_sep_workspace_bytes(n_own, n_all, embed), 16), dtype=torch.uint8, device=dev)
+        # InfoNCE: sweep the CENTRED embeddings (see _SeparableBound.backward); S_ij = y_i.(x_j - mu) + y_i.mu
+        centred = bound_id == L.BOUND_IDS["infonce"]
+        if centred:
+            mu = all_x.mean(dim=0)
+            swept = (all_x - mu).contiguous()
+            ymu = y_emb @ mu
+        else:
+            swept, ymu = all_x, None
+        pre = torch.empty(4, n_own, dtype=torch.float32, device=dev)      # approx off-diag max, -, -, diag of y.swept
+        L.check(L.lib.mimrl_sep_row_stats(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, L.STAT_MAXONLY, impl,
+                                          L.ptr(pre[0]), L.ptr(pre[1]), L.ptr(pre[2]), L.ptr(pre[3]), L.ptr(ws), ws.numel(),
+                                          st))
+        ref = torch.maximum(pre[0], pre[3]) if inc else pre[0]
+        ref = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref)).contiguous()
+        wsum = torch.empty(n_own, embed, dtype=torch.float32, device=dev)
+        stats = torch.zeros(4, n_own, dtype=torch.float32, device=dev)      # max, sum, softplus, diag (true S units)
+        L.check(L.lib.mimrl_sep_fused_forward(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, inc, L.ptr(ref),
+                                              L.ptr(wsum), L.ptr(stats[1]), L.ptr(ws), ws.numel(), st))
+        stats[0] = ref if ymu is None else ref + ymu
+        stats[3] = pre[3] if ymu is None else pre[3] + ymu
+        base = None
+        if log_baseline is not None:
+            base = RB.all_gather_rows(L.f32(log_baseline).reshape(-1), rb)
+        all_stats = RB.all_gather_rows(stats.t().contiguous(), rb).t().contiguous() if rb.sharded else stats
+        result = torch.zeros(16, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(all_stats[0]), L.ptr(all_stats[1]), L.ptr(all_stats[2]),
+                                           L.ptr(all_stats[3]), L.ptr(base), n_all, L.ptr(result), st))
+        own_rows = swept[rb.offset: rb.offset + n_own]
+        ctx.save_for_backward(x_emb, y_emb, all_stats, result, base if base is not None else result.new_empty(0), wsum,
+                              own_rows)
+        ctx.cfg = (bound_id, impl, rb, fam, inc, log_baseline is not None, ws)
+        return result[0].clone(), result[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_mi, g_loss):
+        x_emb, y_emb, all_stats, result, base, wsum, own_rows = ctx.saved_tensors
+        bound_id, impl, rb, fam, inc, has_base, ws = ctx.cfg
+        base = base if has_base else None
+        n_own, embed = y_emb.shape
+        n_all = all_stats.shape[1]
+        dev = y_emb.device
+        st = L.stream()
+        grad = _grad_pair(g_mi, g_loss, result)
+        coef = torch.empty(1, dtype=torch.float32, device=dev)
+        vec = torch.empty(3, n_all, dtype=torch.float32, device=dev)            # shift, dcoef, dbaseline
+        L.check(L.lib.mimrl_bound_backward_coef(bound_id, L.ptr(result), L.ptr(grad), L.ptr(all_stats[0]),
+                                                L.ptr(all_stats[1]), L.ptr(all_stats[3]), L.ptr(base), n_all,
+                                                L.ptr(coef), L.ptr(vec[0]), L.ptr(vec[1]),
+                                                L.ptr(vec[2]) if has_base else None, st))
+        own = slice(rb.offset, rb.offset + n_own)
+        # d/d h(y): the forward's weighted sum, moved from its reference point to the final shift
+        scale = coef * torch.exp(all_stats[0, own] - vec[0, own])
+        dy = scale[:, None] * wsum + vec[1, own][:, None] * own_rows
+        # d/d g(x): columns are owned, y is swept, shift indexed by the swept row
+        all_y = RB.all_gather_rows(y_emb, rb)
+        dx = torch.empty_like(x_emb)
+        dcoef_own = vec[1, own].contiguous()
+        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(x_emb), L.ptr(all_y), n_own, n_all, embed, rb.offset, fam, inc,
+                                             L.ptr(vec[0]), 1, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dx),
+                                             L.ptr(ws), ws.numel(), st))
+        dbase = vec[2, own].reshape(n_own, 1).clone() if has_base else None
+        return dx, dy, dbase, None, None, None
+
+
 def separable_bound(x_emb, y_emb, bound_type, log_baseline=None, rowblock=None, impl=L.IMPL_AUTO):
     """Fused ``bound(h(y) @ g(x).T)`` for every bound with a single-sweep form
     (all of VMI.py:136-198 plus the MINE branch of Model.py:121-124).
     Returns ``(mi, mi_loss)`` exactly as ``VMIEstimator.forward`` does."""
     if bound_type not in L.BOUND_IDS:
         raise NotImplementedError
+    if (FUSED_FORWARD and bound_type in _FUSED_BOUNDS and torch.is_grad_enabled()
+            and (x_emb.requires_grad or y_emb.requires_grad)):
+        n_own = y_emb.shape[0]
+        n_all = rowblock.n_all if rowblock is not None else n_own
+        if L.lib.mimrl_sep_selected_impl(n_own, n_all, y_emb.shape[1], impl) == L.IMPL_TCGEN05:
+            return _SeparableBoundFused.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
     return _SeparableBound.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
 
 
