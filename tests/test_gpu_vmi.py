@@ -195,3 +195,26 @@ def test_full_size_properties():
     Gs[torch.arange(2048, device=dev()), idx] -= 1.0 / B
     want = (Gs @ xe.double()).cpu().numpy()            # d loss / d y_emb rows
     assert rel_err(gy0[rows].cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("bound", ["infonce", "dv", "mine", "tuba", "nwj"])
+@pytest.mark.parametrize("B,scale", [(700, 1.0), (1500, 6.0)])
+def test_fused_forward_matches_three_sweep_path(bound, B, scale, monkeypatch):
+    """mimrl_sep_fused_forward (approximate-max pre-pass + one sweep for the statistics and the owned-row gradient
+    sum) against the exact-statistics path it replaces, and both against the float64 oracle.  scale = 6 makes the
+    scores large (|S| ~ 100s), where the one-product row maxima are off by ~0.1 and must not matter."""
+    import mimrl_b200.vmi as V
+    baseline = "unnormalized" if bound == "tuba" else "constant"
+    c = dict(critic="separate", baseline=baseline, bound=bound, d=128, hidden=64, embed=128, layers=2)
+    prm = P.vmi_params(17, "separate", baseline, 128, 64, 128, 2)
+    x, y = P.features(18, B, 128, scale=scale, corr=0.6)
+    out = {}
+    for fused in (True, False):
+        monkeypatch.setattr(V, "FUSED_FORWARD", fused)
+        out[fused] = run(make_estimator(c, prm), x, y)
+    ref = O.vmi_estimator(prm, "separate", baseline, bound, x, y)
+    for fused in (True, False):
+        mi, loss, gx, gy, pg = out[fused]
+        assert close_scalar(mi, ref["mi"]), (fused, mi, ref["mi"])
+        assert rel_err(gx, ref["gx"]) < TOL and rel_err(gy, ref["gy"]) < TOL, fused
+    assert rel_err(out[True][2], out[False][2]) < 2e-5 and rel_err(out[True][3], out[False][3]) < 2e-5
