@@ -150,6 +150,9 @@ int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, const float 
  * the masked matrix (bias gradient).  Stored operand shapes as listed for the three modes above. */
 size_t mimrl_split_bytes(int rows, int cols);
 int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum, void *stream);
+/* mask from the hi half of another split buffer of the same shape (entries with hi <= 0 are zeroed) */
+int mimrl_split_f32_hmask(const float *src, const void *mask_split, int rows, int cols, void *out, float *colsum,
+                          void *stream);
 size_t mimrl_gemm_split_workspace_bytes(int mode, int M, int N, int K);
 int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, int N, int K, const float *bias,
                      int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
@@ -259,6 +262,18 @@ int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_i
                              const float *ln_w, const float *ln_b, int act, const float *saved, float *gx, float *g_b1,
                              float *g_b2, float *gln_w, float *gln_b, void *op_x, void *op_h, void *op_gz, void *op_gpre,
                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- the critic MLP in one forward kernel (reference VMI.py:13-22 `mlps(dim, 256, out, layers=2, 'relu')`) ----
+ * y = W4 relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3) + b4 for x [M, d_in], d_in <= 128, hidden 256, d_out <= 128:
+ * activations stay in TMEM between the layers.  Also written (caller-allocated with mimrl_split_bytes, mimrl_split_f32
+ * format): op_x [M,d_in], op_h1..3 [M,256] (weight-gradient operands; the hi half of op_h* is the ReLU mask for
+ * mimrl_split_f32_hmask) and ws_w1..4 (the split weights, reusable by mimrl_gemm_split in the backward).
+ * scratch256: 256 bytes of device scratch. */
+int mimrl_mlp4_supported(int d_in, int hidden, int d_out);
+int mimrl_mlp4_fwd(const float *x, int M, int d_in, const float *w1, const float *b1, const float *w2, const float *b2,
+                   const float *w3, const float *b3, const float *w4, const float *b4, int d_out, float *y, void *op_x,
+                   void *op_h1, void *op_h2, void *op_h3, void *ws_w1, void *ws_w2, void *ws_w3, void *ws_w4,
+                   void *scratch256, void *stream);
 
 /* ---- concat critic, all pairs on the tensor cores (reference VMI.py:58-65 with mlps of VMI.py:13-22) ----
  * The first layer factorises over the concatenation: u = x W1x^T + b1 [n_own, 256], vt = (y W1y^T)^T [256, ldv]

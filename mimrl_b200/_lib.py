@@ -50,6 +50,10 @@ _SIGS = {
     "mimrl_split_f32": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "mimrl_gemm_split_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_gemm_split": (c_int, [c_int, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P]),
+    "mimrl_split_f32_hmask": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "mimrl_mlp4_supported": (c_int, [c_int, c_int, c_int]),
+    "mimrl_mlp4_fwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               _P, _P]),
     "mimrl_gemm_split_blocked": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "mimrl_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_knn_search": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),

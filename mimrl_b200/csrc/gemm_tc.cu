@@ -68,9 +68,11 @@ gemm_absmax_kernel(const float *__restrict__ a, const float *__restrict__ mask, 
 // src [rows, cols] fp32 (optionally masked) -> hi, lo [rows, ld] fp16, zero padded, scaled by 2^k
 // colsum (nullable): column sums of the masked source are ACCUMULATED there (bias gradient); the launch makes the
 // grid stride a multiple of ld/2 so that every thread stays on one column pair.
+// hmask (nullable, [rows, ld] fp16): alternative mask source -- the hi half of an activation split by mlp_tc.cu
 __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__restrict__ mask, int rows, int cols,
                                   int ld, const unsigned *__restrict__ absmax, int which, __half *__restrict__ hi,
-                                  __half *__restrict__ lo, float *__restrict__ colsum) {
+                                  __half *__restrict__ lo, float *__restrict__ colsum,
+                                  const __half *__restrict__ hmask = nullptr) {
   const float sc = scale_from_absmax(absmax[which]);
   const int half_ld = ld >> 1;
   const size_t total = (size_t)rows * half_ld;
@@ -83,10 +85,12 @@ __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__
     if (c < cols) {
       v0 = src[r * cols + c];
       if (mask && !(mask[r * cols + c] > 0.f)) v0 = 0.f;
+      if (hmask && !(__half2float(hmask[r * ld + c]) > 0.f)) v0 = 0.f;
     }
     if (c + 1 < cols) {
       v1 = src[r * cols + c + 1];
       if (mask && !(mask[r * cols + c + 1] > 0.f)) v1 = 0.f;
+      if (hmask && !(__half2float(hmask[r * ld + c + 1]) > 0.f)) v1 = 0.f;
     }
     cs0 += v0, cs1 += v1, my_c = c;
     v0 *= sc, v1 *= sc;
@@ -399,8 +403,8 @@ extern "C" size_t mimrl_split_bytes(int rows, int cols) {
   return split_layout(rows, cols).total;
 }
 
-extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum,
-                               void *stream) {
+static int split_f32_impl(const float *src, const float *mask, const __half *hmask, int rows, int cols, void *out,
+                          float *colsum, void *stream) {
   MIMRL_REQUIRE(rows > 0 && cols > 0 && src && out, "split_f32: empty input");
   cudaStream_t st = (cudaStream_t)stream;
   const SplitLayout L = split_layout(rows, cols);
@@ -423,8 +427,23 @@ extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, in
     MIMRL_REQUIRE(((size_t)b * 256) % (size_t)(L.ld / 2) == 0, "split_f32: column sums need ld/2 to divide the grid stride");
   }
   gemm_split_kernel<<<b, 256, 0, st>>>(src, mask, rows, cols, L.ld, absmax, 0, reinterpret_cast<__half *>(o + L.off_hi),
-                                     reinterpret_cast<__half *>(o + L.off_lo), colsum);
+                                     reinterpret_cast<__half *>(o + L.off_lo), colsum, hmask);
   return check_launch("split_f32");
+}
+
+extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum,
+                               void *stream) {
+  return split_f32_impl(src, mask, nullptr, rows, cols, out, colsum, stream);
+}
+
+// Same, with the mask taken from another split buffer of the same shape: entries whose hi half is not positive are
+// zeroed (ReLU backward against an activation that only exists as the fp16 operand written by mimrl_mlp4_fwd).
+extern "C" int mimrl_split_f32_hmask(const float *src, const void *mask_split, int rows, int cols, void *out, float *colsum,
+                                     void *stream) {
+  MIMRL_REQUIRE(mask_split, "split_f32_hmask: no mask operand");
+  const SplitLayout L = split_layout(rows, cols);
+  return split_f32_impl(src, nullptr, reinterpret_cast<const __half *>((const unsigned char *)mask_split + L.off_hi), rows, cols,
+                        out, colsum, stream);
 }
 
 // GEMM on operands already split by mimrl_split_f32.  Stored shapes: mode 0: A [M,K], B [N,K]; mode 1: A [M,K],

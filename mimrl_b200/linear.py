@@ -71,6 +71,74 @@ class _LinearTC(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+USE_FUSED_MLP = True      # mlps(dim<=128, 256, out<=128, layers=2, relu) in one forward kernel (csrc/mlp_tc.cu)
+
+
+class _MLP4TC(torch.autograd.Function):
+    """Linear+ReLU, Linear+ReLU, Linear+ReLU, Linear with hidden width 256 (the critic MLP of VMI.py:13-22).
+
+    Forward: mimrl_mlp4_fwd, activations in TMEM between the layers.  Backward: the per-layer tensor-core products of
+    ``_LinearTC`` on the operands the forward left behind (the hi half of an activation operand is its ReLU mask)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
+        x = L.f32(x)
+        ws = [L.f32(w) for w in (w1, w2, w3, w4)]
+        bs = [L.f32(b) if b is not None else None for b in (b1, b2, b3, b4)]
+        M, d_in = x.shape
+        d_out = ws[3].shape[0]
+        dev = x.device
+        buf = lambda r, c: torch.empty(L.lib.mimrl_split_bytes(r, c), dtype=torch.uint8, device=dev)
+        ops = [buf(M, d_in), buf(M, 256), buf(M, 256), buf(M, 256)]
+        wsp = [buf(256, d_in), buf(256, 256), buf(256, 256), buf(d_out, 256)]
+        scratch = torch.empty(256, dtype=torch.uint8, device=dev)
+        y = torch.empty(M, d_out, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_mlp4_fwd(L.ptr(x), M, d_in, L.ptr(ws[0]), L.ptr(bs[0]), L.ptr(ws[1]), L.ptr(bs[1]), L.ptr(ws[2]),
+                                     L.ptr(bs[2]), L.ptr(ws[3]), L.ptr(bs[3]), d_out, L.ptr(y), L.ptr(ops[0]), L.ptr(ops[1]),
+                                     L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(wsp[0]), L.ptr(wsp[1]), L.ptr(wsp[2]),
+                                     L.ptr(wsp[3]), L.ptr(scratch), L.stream()))
+        ctx.save_for_backward(*ops, *wsp)
+        ctx.cfg = (M, d_in, d_out, [b is not None for b in bs])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        saved = ctx.saved_tensors
+        ops, wsp = saved[:4], saved[4:]
+        M, d_in, d_out, has_b = ctx.cfg
+        dims = [(256, d_in), (256, 256), (256, 256), (d_out, 256)]          # (N_l, K_l) of layer l
+        g = L.f32(gy)
+        grads_w, grads_b = [None] * 4, [None] * 4
+        for l in (3, 2, 1, 0):
+            N, K = dims[l]
+            gb = torch.zeros(N, dtype=torch.float32, device=g.device) if has_b[l] else None
+            dzs = torch.empty(L.lib.mimrl_split_bytes(M, N), dtype=torch.uint8, device=g.device)
+            if l == 3:
+                L.check(L.lib.mimrl_split_f32(L.ptr(g), None, M, N, L.ptr(dzs), L.ptr(gb), L.stream()))
+            else:          # ReLU backward: the mask is the sign of this layer's activation operand
+                L.check(L.lib.mimrl_split_f32_hmask(L.ptr(g), L.ptr(ops[l + 1]), M, N, L.ptr(dzs), L.ptr(gb), L.stream()))
+            grads_b[l] = gb
+            if ctx.needs_input_grad[1 + 2 * l]:
+                grads_w[l] = _gemm_split(2, dzs, ops[l], N, K, M)          # dz^T [N,M] . input [M,K]
+            if l > 0 or ctx.needs_input_grad[0]:
+                g = _gemm_split(1, dzs, wsp[l], M, K, N)                   # dz [M,N] . W [N,K]
+            else:
+                g = None
+        return (g, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2], grads_w[3], grads_b[3])
+
+
+def _is_mlp4(mods, x):
+    if not (USE_FUSED_MLP and len(mods) == 7 and x.dim() == 2 and x.is_cuda and x.shape[0] >= MIN_ROWS):
+        return False
+    if not all(isinstance(mods[i], nn.Linear) for i in (0, 2, 4, 6)) or not all(isinstance(mods[i], nn.ReLU) for i in (1, 3, 5)):
+        return False
+    l1, l2, l3, l4 = mods[0], mods[2], mods[4], mods[6]
+    return (l1.out_features == 256 and l2.in_features == 256 and l2.out_features == 256 and l3.in_features == 256
+            and l3.out_features == 256 and l4.in_features == 256 and l4.out_features >= MIN_WIDTH
+            and l1.in_features >= MIN_WIDTH and l1.in_features == x.shape[1]
+            and bool(L.lib.mimrl_mlp4_supported(l1.in_features, 256, l4.out_features)))
+
+
 def linear(x, weight, bias=None, relu=False):
     """y = relu?(x W^T + b) for 2-D x; tensor-core path when the shape qualifies."""
     if (x.dim() == 2 and x.is_cuda and x.shape[0] >= MIN_ROWS and weight.shape[0] >= MIN_WIDTH
@@ -83,6 +151,9 @@ def linear(x, weight, bias=None, relu=False):
 def mlp_apply(seq: nn.Sequential, x):
     """Evaluate a Linear/activation stack; Linear+ReLU pairs run as one fused call."""
     mods = list(seq)
+    if _is_mlp4(mods, x):
+        l1, l2, l3, l4 = mods[0], mods[2], mods[4], mods[6]
+        return _MLP4TC.apply(x, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias, l4.weight, l4.bias)
     i = 0
     while i < len(mods):
         m = mods[i]
