@@ -73,3 +73,44 @@ def test_mlp_stack_matches_torch(rows):
     want = [y64.detach(), x64.grad] + [p.grad for p in seq64.parameters()]
     for a, b in zip(got, want):
         assert rel(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("M,d_in,d_out", [(512, 128, 128), (700, 128, 128), (1000, 64, 32), (3001, 100, 96)])
+def test_fused_mlp4_vs_float64(M, d_in, d_out):
+    """mimrl_mlp4_fwd (the critic MLP of VMI.py:13-22 in one kernel) + the per-layer backward on its operands against
+    float64.  Rows with a pre-activation within 1e-5 of a ReLU kink get a zero upstream gradient (their mask is
+    decided by rounding in any fp32 implementation); the forward is checked on every row."""
+    import mimrl_b200.linear as LN
+    torch.manual_seed(M)
+    dev = "cuda"
+    mods = [torch.nn.Linear(d_in, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+            torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, d_out)]
+    m = torch.nn.Sequential(*mods).to(dev)
+    for p in m.parameters():
+        if p.dim() == 1:
+            torch.nn.init.normal_(p, std=0.1)
+    x = torch.randn(M, d_in, device=dev) * 1.5
+    assert LN._is_mlp4(list(m), x)
+    m64 = torch.nn.Sequential(*[torch.nn.Linear(l.in_features, l.out_features) if isinstance(l, torch.nn.Linear)
+                                else torch.nn.ReLU() for l in mods]).double().to(dev)
+    m64.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        h, near = x.double(), torch.zeros(M, dtype=torch.bool, device=dev)
+        for i, l in enumerate(m64):
+            h = l(h)
+            if isinstance(l, torch.nn.Linear) and i < 6:
+                near |= (h.abs() < 1e-5).any(dim=1)
+    assert float(near.double().mean()) < 0.05
+    w = torch.randn(M, d_out, device=dev).abs()
+    w[near] = 0
+    xt = x.clone().requires_grad_(True)
+    y = LN.mlp_apply(m, xt)
+    (y * w).sum().backward()
+    x64 = x.double().requires_grad_(True)
+    y64 = m64(x64)
+    (y64 * w.double()).sum().backward()
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
+    assert rel(y.detach(), y64.detach()) < 1e-5
+    assert rel(xt.grad, x64.grad) < 1e-4
+    for (n, p), p64 in zip(m.named_parameters(), m64.parameters()):
+        assert rel(p.grad, p64.grad) < 1e-4, n
