@@ -275,6 +275,14 @@ int mimrl_mlp4_fwd(const float *x, int M, int d_in, const float *w1, const float
                    void *op_h1, void *op_h2, void *op_h3, void *ws_w1, void *ws_w2, void *ws_w3, void *ws_w4,
                    void *scratch256, void *stream);
 
+/* Data-gradient pass of mimrl_mlp4_fwd in one kernel: gx [M,d_in] (nullable), the row-major operands dz1..3 [M,256] and
+ * dz4 [M,d_out] (mimrl_split_f32 format, caller-allocated; gW_l = dz_l^T input_l through mimrl_gemm_split mode 2) and
+ * the bias gradients g_b1..4 (+=, nullable).  ws_w*, op_h* as left by the forward. */
+int mimrl_mlp4_bwd(const float *gy, int M, int d_in, int d_out, const float *w2, const float *w3, const float *w4,
+                   const void *ws_w1, const void *ws_w2, const void *ws_w3, const void *ws_w4, const void *op_h1,
+                   const void *op_h2, const void *op_h3, float *gx, void *dz1, void *dz2, void *dz3, void *dz4, float *g_b1,
+                   float *g_b2, float *g_b3, float *g_b4, void *scratch256, void *stream);
+
 /* ---- concat critic, all pairs on the tensor cores (reference VMI.py:58-65 with mlps of VMI.py:13-22) ----
  * The first layer factorises over the concatenation: u = x W1x^T + b1 [n_own, 256], vt = (y W1y^T)^T [256, ldv]
  * (both from the caller).  scores[i, j] = w4 . relu(W3 relu(W2 relu(u_i + v_j) + b2) + b3) + b4 for every pair,

@@ -54,6 +54,8 @@ _SIGS = {
     "mimrl_mlp4_supported": (c_int, [c_int, c_int, c_int]),
     "mimrl_mlp4_fwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P]),
+    "mimrl_mlp4_bwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               _P, _P, _P, _P]),
     "mimrl_gemm_split_blocked": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "mimrl_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_knn_search": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),

@@ -322,6 +322,282 @@ __global__ void mlp4_scales_kernel(const unsigned *absmax_x, const float *w1, co
   }
 }
 
+
+// ---- backward (data gradients) -----------------------------------------------------------------------------------
+// g_out -> TMEM; g_h3 = g_out W4, g_pre3 = g_h3 [h3 > 0] in place; ... ; g_x = g_pre1 W1: four contractions per tile with
+// the split weights read MN-major (rows = contraction index) from the same global buffers the forward used.  The ReLU
+// masks are the hi halves of the activation operands the forward wrote.  dz4 = g_out, dz3, dz2, dz1 are left behind as
+// row-major fp16 hi/lo operands for the weight-gradient GEMMs (gemm_tc.cu mode 2); bias gradients are butterfly lane
+// sums accumulated in registers over the CTA's tiles.  Scales from bounds: |dz_{l-1}| <= |dz_l|max max_k sum_n |W_l[n,k]|.
+struct Mlp4BwdParams {
+  const float *gy;           // [M, OUT]
+  float *gx;                 // [M, K0] (nullable)
+  const __half *mask[3];     // hi halves of h1, h2, h3 [M, 256]
+  __half *dz[4][2];          // split (hi, lo) of dz1, dz2, dz3 [M, 256] and dz4 [M, ldo], row-major
+  float *g_b[4];             // += (nullable)
+  const float *scales;       // [0] dz1 [1] dz2 [2] dz3 [3] dz4
+  const unsigned *sc_w[4];
+  int M, K0, ld0, OUT, ldo;
+  long long n_tiles;
+};
+
+__device__ __forceinline__ float m_lane_sum(float (&v)[32], int lane) {      // lane t returns sum over lanes of v[t]
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = lane & s;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float keep = upper ? v[k + n / 2] : v[k];
+      const float send = upper ? v[k] : v[k + n / 2];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kMThreads, 1)
+mlp4_bwd_kernel(const __grid_constant__ CUtensorMap mn_w1_hi, const __grid_constant__ CUtensorMap mn_w1_lo,
+                const __grid_constant__ CUtensorMap mn_w2_hi, const __grid_constant__ CUtensorMap mn_w2_lo,
+                const __grid_constant__ CUtensorMap mn_w3_hi, const __grid_constant__ CUtensorMap mn_w3_lo,
+                const __grid_constant__ CUtensorMap mn_w4_hi, const __grid_constant__ CUtensorMap mn_w4_lo,
+                const Mlp4BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - raw);
+  const uint32_t bars = base + kMRing;
+  const uint32_t bFull = bars, bEmpty = bars + 40, bReady = bars + 80, bAcc = bars + 112;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kMRing + 160);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // steps s = 0..3 walk the layers backwards: W4, W3, W2, W1
+  // contraction length (rows of W): ldo, 256, 256, 256; output width (cols of W): 256, 256, 256, ld0
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMStages; ++s) {
+      mbar_init(bFull + 8 * s, 1);
+      mbar_init(bEmpty + 8 * s, 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bReady + 8 * s, 4 * kMWG);
+      mbar_init(bAcc + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(gen + kMRing + 160), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    uint32_t n = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < 4; ++s) {
+        const int n_kb = s == 0 ? p.ldo / 64 : 4;
+        const int n_nb = s == 3 ? p.ld0 / 64 : 4;             // 64-column blocks of the output
+        for (int un = 0; un < 2 * n_kb; ++un, ++n) {
+          const int kb = un >> 1, lo = un & 1;
+          const uint32_t st = n % kMStages, round = n / kMStages;
+          if (round > 0) mbar_wait(bEmpty + 8 * st, (round - 1) & 1);
+          if (leader) {
+            const CUtensorMap *m = s == 0 ? (lo ? &mn_w4_lo : &mn_w4_hi)
+                                   : s == 1 ? (lo ? &mn_w3_lo : &mn_w3_hi)
+                                   : s == 2 ? (lo ? &mn_w2_lo : &mn_w2_hi) : (lo ? &mn_w1_lo : &mn_w1_hi);
+            mbar_expect_tx(bFull + 8 * st, (uint32_t)n_nb * 8192u);
+            for (int nb = 0; nb < n_nb; ++nb) tma_load_2d(base + st * kMUnit + nb * 8192, m, bFull + 8 * st, nb * 64, kb * 64);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one();
+    uint32_t n = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      for (int s = 0; s < 4; ++s) {
+        mbar_wait(bReady + 8 * s, par);
+        tc_fence_after();
+        const uint32_t ra = tmem_base + ((s & 1) ? kMR1 : kMR0), rd = tmem_base + ((s & 1) ? kMR0 : kMR1);
+        const int n_kb = s == 0 ? p.ldo / 64 : 4;
+        const uint32_t idesc = instr_desc_f16_bmn(128, s == 3 ? p.ld0 : 256);
+        for (int un = 0; un < 2 * n_kb; ++un, ++n) {
+          const int kb = un >> 1, lo = un & 1;
+          const uint32_t st = n % kMStages, round = n / kMStages;
+          mbar_wait(bFull + 8 * st, round & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t b0 = base + st * kMUnit;
+            for (int a_lo = 0; a_lo < (lo ? 1 : 2); ++a_lo) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(rd, ra + m_a_col(kb * 4 + k, a_lo), smem_desc_sw128_mn(b0 + k * 2048, 8192, 1024), idesc,
+                            (un | a_lo | k) ? 1u : 0u);
+            }
+            umma_commit(bEmpty + 8 * st);
+          }
+          __syncwarp();
+        }
+        if (leader) umma_commit(bAcc + 8 * s);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int e = warp - 2, q = warp & 3, g = e >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    // step s multiplies by W_{4-s}: accumulator = dz operand (scale of step s) x split weight
+    float inv[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) inv[s] = 1.f / (p.scales[3 - s] * scale_from_absmax(p.sc_w[3 - s][0]));
+    const bool vec = (p.OUT & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gy) & 15) == 0;
+    float acc_b4 = 0.f, acc_b[3][kMCh] = {};
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const long long row = tile * 128 + q * 32 + lane;
+      const bool ok = row < p.M;
+      const float *gr = p.gy + (size_t)(ok ? row : 0) * p.OUT;
+      // ---- dz4 = g_out -> TMEM region 0
+      if (g * 32 < p.ldo) {
+        const int c = g;
+        float v[32];
+        if (vec) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int a = 32 * c + 4 * t;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && a < p.OUT) f = __ldg(reinterpret_cast<const float4 *>(gr + a));
+            v[4 * t] = f.x, v[4 * t + 1] = f.y, v[4 * t + 2] = f.z, v[4 * t + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (ok && 32 * c + j < p.OUT) ? __ldg(gr + 32 * c + j) : 0.f;
+        }
+        float sc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc[j] = v[j] * p.scales[3];
+        uint32_t hi[16], lo[16];
+        m_split32(sc, hi, lo);
+        tmem_st16(tmem_base + lane_off + kMR0 + 32 * c, hi);
+        tmem_st16(tmem_base + lane_off + kMR0 + 32 * c + 16, lo);
+        if (ok) {
+          m_store64(p.dz[3][0] + (size_t)row * p.ldo + 32 * c, hi);
+          m_store64(p.dz[3][1] + (size_t)row * p.ldo + 32 * c, lo);
+        }
+        acc_b4 += m_lane_sum(v, lane);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bReady + 0);
+      // ---- dz3, dz2, dz1: previous product masked by the ReLU of the layer, in place
+      for (int s = 0; s < 3; ++s) {
+        const int layer = 2 - s;                                 // hidden layer index 2, 1, 0 (h3, h2, h1)
+        mbar_wait(bAcc + 8 * s, par);
+        tc_fence_after();
+        const uint32_t reg = (s & 1) ? kMR0 : kMR1;
+        const float iv = inv[s], sn = p.scales[layer];
+        for (int cc = 0; cc < kMCh; ++cc) {
+          const int c = kMCh * g + cc;
+          uint32_t d[32];
+          tmem_ld32(tmem_base + lane_off + reg + 32 * c, d);
+          uint4 mk[4];
+          if (ok) {
+            const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask[layer] + (size_t)row * kHidden + 32 * c);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) mk[t] = __ldg(mp + t);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) mk[t] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          tmem_ld_wait();
+          const uint32_t *mw = reinterpret_cast<const uint32_t *>(mk);
+          float v[32], sc[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            // positive fp16 <=> sign bit clear and magnitude bits non-zero
+            const uint32_t hbits = (mw[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+            const bool on = hbits != 0u && hbits < 0x8000u;
+            v[t] = on ? __uint_as_float(d[t]) * iv : 0.f;
+            sc[t] = v[t] * sn;
+          }
+          uint32_t hi[16], lo[16];
+          m_split32(sc, hi, lo);
+          tmem_st16(tmem_base + lane_off + reg + 32 * c, hi);
+          tmem_st16(tmem_base + lane_off + reg + 32 * c + 16, lo);
+          if (ok) {
+            m_store64(p.dz[layer][0] + (size_t)row * kHidden + 32 * c, hi);
+            m_store64(p.dz[layer][1] + (size_t)row * kHidden + 32 * c, lo);
+          }
+          acc_b[layer][cc] += m_lane_sum(v, lane);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bReady + 8 * (s + 1));
+      }
+      // ---- g_x = dz1 W1 (accumulator in region 0, ld0 columns)
+      mbar_wait(bAcc + 24, par);
+      tc_fence_after();
+      if (g * 32 < p.ld0) {
+        const int c = g;
+        uint32_t d[32];
+        tmem_ld32(tmem_base + lane_off + kMR0 + 32 * c, d);
+        tmem_ld_wait();
+        if (ok && p.gx) {
+          float *xr = p.gx + (size_t)row * p.K0;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (32 * c + t < p.K0) xr[32 * c + t] = __uint_as_float(d[t]) * inv[3];
+        }
+      }
+      tc_fence_before();
+    }
+    if (p.g_b[3] && g * 32 < p.ldo && 32 * g + lane < p.OUT) atomicAdd(p.g_b[3] + 32 * g + lane, acc_b4);
+#pragma unroll
+    for (int layer = 0; layer < 3; ++layer)
+#pragma unroll
+      for (int cc = 0; cc < kMCh; ++cc)
+        if (p.g_b[layer]) atomicAdd(p.g_b[layer] + 32 * (kMCh * g + cc) + lane, acc_b[layer][cc]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// one block of 256 threads: gradient bounds -> scales and headers.  Thread k owns column k of W3, W2 (and W4).
+__global__ void mlp4_bwd_scales_kernel(const unsigned *absmax_g, const float *w2, const float *w3, const float *w4, int OUT,
+                                       float *scales, unsigned *hdr1, unsigned *hdr2, unsigned *hdr3, unsigned *hdr4) {
+  __shared__ float red[256];
+  const int k = threadIdx.x;
+  auto block_max = [&](float v) {
+    __syncthreads();
+    red[k] = v;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+      if (k < o) red[k] = fmaxf(red[k], red[k + o]);
+      __syncthreads();
+    }
+    return red[0];
+  };
+  float c4 = 0.f, c3 = 0.f, c2 = 0.f;
+  for (int n = 0; n < OUT; ++n) c4 += fabsf(w4[(size_t)n * kHidden + k]);
+  for (int n = 0; n < kHidden; ++n) {
+    c3 += fabsf(w3[(size_t)n * kHidden + k]);
+    c2 += fabsf(w2[(size_t)n * kHidden + k]);
+  }
+  const float c4m = block_max(c4), c3m = block_max(c3), c2m = block_max(c2);
+  if (k == 0) {
+    const float m4 = __uint_as_float(absmax_g[0]);
+    const float m3 = m4 * c4m, m2 = m3 * c3m, m1 = m2 * c2m;
+    scales[0] = m_pow2_for(m1), scales[1] = m_pow2_for(m2), scales[2] = m_pow2_for(m3), scales[3] = m_pow2_for(m4);
+    *hdr1 = __float_as_uint(m1), *hdr2 = __float_as_uint(m2), *hdr3 = __float_as_uint(m3), *hdr4 = __float_as_uint(m4);
+  }
+}
+
 }  // namespace
 }  // namespace mimrl
 
@@ -392,4 +668,60 @@ extern "C" int mimrl_mlp4_fwd(const float *x, int M, int d_in, const float *w1, 
   const int grid = (int)(p.n_tiles < 148 ? p.n_tiles : 148);
   mlp4_fwd_kernel<<<grid, kMThreads, kMSmem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
   return check_launch("mlp4_fwd");
+}
+
+// Data-gradient pass of mimrl_mlp4_fwd.  gy [M, d_out]; ws_w1..4 and op_h1..3 as left by the forward.  Writes gx [M, d_in]
+// (nullable) and the row-major operands dz1, dz2, dz3 [M, 256], dz4 [M, d_out] (mimrl_split_f32 format, caller-allocated):
+// gW_l = dz_l^T input_l through mimrl_gemm_split(mode 2).  Accumulates (+=) the bias gradients g_b1..4 (nullable).
+extern "C" int mimrl_mlp4_bwd(const float *gy, int M, int d_in, int d_out, const float *w2, const float *w3, const float *w4,
+                              const void *ws_w1, const void *ws_w2, const void *ws_w3, const void *ws_w4, const void *op_h1,
+                              const void *op_h2, const void *op_h3, float *gx, void *dz1, void *dz2, void *dz3, void *dz4,
+                              float *g_b1, float *g_b2, float *g_b3, float *g_b4, void *scratch256, void *stream) {
+  MIMRL_REQUIRE(mimrl_mlp4_supported(d_in, kHidden, d_out), "mlp4_bwd: sizes %d -> 256 -> %d not supported", d_in, d_out);
+  MIMRL_REQUIRE(M > 0 && gy && w2 && w3 && w4 && ws_w1 && ws_w2 && ws_w3 && ws_w4 && op_h1 && op_h2 && op_h3 && dz1 && dz2 &&
+                    dz3 && dz4 && scratch256,
+                "mlp4_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned *absmax = reinterpret_cast<unsigned *>(scratch256);
+  float *scales = reinterpret_cast<float *>((unsigned char *)scratch256 + 64);
+  cudaMemsetAsync(absmax, 0, 16, st);
+  const size_t ng = (size_t)M * d_out;
+  int blocks = (int)((ng + 4095) / 4096);
+  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
+  mlp4_absmax_kernel<<<blocks, 256, 0, st>>>(gy, ng, absmax);
+  if (check_launch("mlp4 absmax (gy)")) return 1;
+  mlp4_bwd_scales_kernel<<<1, 256, 0, st>>>(absmax, w2, w3, w4, d_out, scales, (unsigned *)dz1, (unsigned *)dz2, (unsigned *)dz3,
+                                            (unsigned *)dz4);
+  if (check_launch("mlp4 bwd scales")) return 1;
+  const int ld0 = (d_in + 63) & ~63, ldo = (d_out + 63) & ~63;
+  auto maps = [&](const void *s, int rows, int cols, CUtensorMap *hi, CUtensorMap *lo) {
+    const int ld = (cols + 63) & ~63;
+    const unsigned char *b = (const unsigned char *)s;
+    const size_t off_lo = 256 + align256((size_t)rows * ld * 2);
+    if (make_map(hi, b + 256, cols, rows, ld, 64)) return 1;
+    return make_map(lo, b + off_lo, cols, rows, ld, 64);
+  };
+  CUtensorMap m[8];
+  if (maps(ws_w1, kHidden, d_in, &m[0], &m[1]) || maps(ws_w2, kHidden, kHidden, &m[2], &m[3]) ||
+      maps(ws_w3, kHidden, kHidden, &m[4], &m[5]) || maps(ws_w4, d_out, kHidden, &m[6], &m[7]))
+    return 1;
+  Mlp4BwdParams p;
+  p.gy = gy, p.gx = gx, p.M = M, p.K0 = d_in, p.ld0 = ld0, p.OUT = d_out, p.ldo = ldo;
+  const void *hs[3] = {op_h1, op_h2, op_h3};
+  for (int t = 0; t < 3; ++t) p.mask[t] = reinterpret_cast<const __half *>((const unsigned char *)hs[t] + 256);
+  void *dzs[4] = {dz1, dz2, dz3, dz4};
+  const void *wsp[4] = {ws_w1, ws_w2, ws_w3, ws_w4};
+  for (int t = 0; t < 4; ++t) {
+    const int ld = t == 3 ? ldo : kHidden;
+    p.dz[t][0] = reinterpret_cast<__half *>((unsigned char *)dzs[t] + 256);
+    p.dz[t][1] = reinterpret_cast<__half *>((unsigned char *)dzs[t] + 256 + align256((size_t)M * ld * 2));
+    p.sc_w[t] = reinterpret_cast<const unsigned *>(wsp[t]);
+  }
+  p.g_b[0] = g_b1, p.g_b[1] = g_b2, p.g_b[2] = g_b3, p.g_b[3] = g_b4;
+  p.scales = scales;
+  p.n_tiles = ((long long)M + 127) / 128;
+  cudaFuncSetAttribute(mlp4_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMSmem);
+  const int grid = (int)(p.n_tiles < 148 ? p.n_tiles : 148);
+  mlp4_bwd_kernel<<<grid, kMThreads, kMSmem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
+  return check_launch("mlp4_bwd");
 }

@@ -97,34 +97,31 @@ class _MLP4TC(torch.autograd.Function):
                                      L.ptr(bs[2]), L.ptr(ws[3]), L.ptr(bs[3]), d_out, L.ptr(y), L.ptr(ops[0]), L.ptr(ops[1]),
                                      L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(wsp[0]), L.ptr(wsp[1]), L.ptr(wsp[2]),
                                      L.ptr(wsp[3]), L.ptr(scratch), L.stream()))
-        ctx.save_for_backward(*ops, *wsp)
+        ctx.save_for_backward(*ops, *wsp, ws[1], ws[2], ws[3])
         ctx.cfg = (M, d_in, d_out, [b is not None for b in bs])
         return y
 
     @staticmethod
     def backward(ctx, gy):
         saved = ctx.saved_tensors
-        ops, wsp = saved[:4], saved[4:]
+        ops, wsp, wts = saved[:4], saved[4:8], saved[8:]
         M, d_in, d_out, has_b = ctx.cfg
         dims = [(256, d_in), (256, 256), (256, 256), (d_out, 256)]          # (N_l, K_l) of layer l
         g = L.f32(gy)
-        grads_w, grads_b = [None] * 4, [None] * 4
-        for l in (3, 2, 1, 0):
-            N, K = dims[l]
-            gb = torch.zeros(N, dtype=torch.float32, device=g.device) if has_b[l] else None
-            dzs = torch.empty(L.lib.mimrl_split_bytes(M, N), dtype=torch.uint8, device=g.device)
-            if l == 3:
-                L.check(L.lib.mimrl_split_f32(L.ptr(g), None, M, N, L.ptr(dzs), L.ptr(gb), L.stream()))
-            else:          # ReLU backward: the mask is the sign of this layer's activation operand
-                L.check(L.lib.mimrl_split_f32_hmask(L.ptr(g), L.ptr(ops[l + 1]), M, N, L.ptr(dzs), L.ptr(gb), L.stream()))
-            grads_b[l] = gb
-            if ctx.needs_input_grad[1 + 2 * l]:
-                grads_w[l] = _gemm_split(2, dzs, ops[l], N, K, M)          # dz^T [N,M] . input [M,K]
-            if l > 0 or ctx.needs_input_grad[0]:
-                g = _gemm_split(1, dzs, wsp[l], M, K, N)                   # dz [M,N] . W [N,K]
-            else:
-                g = None
-        return (g, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2], grads_w[3], grads_b[3])
+        dev = g.device
+        buf = lambda r, c: torch.empty(L.lib.mimrl_split_bytes(r, c), dtype=torch.uint8, device=dev)
+        dzs = [buf(M, 256), buf(M, 256), buf(M, 256), buf(M, d_out)]
+        gbs = [torch.zeros(n, dtype=torch.float32, device=dev) if hb else None for (n, _), hb in zip(dims, has_b)]
+        gx = torch.empty(M, d_in, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        scratch = torch.empty(256, dtype=torch.uint8, device=dev)
+        # one kernel: the four data-gradient products, ReLU masks from the activation operands, bias gradients
+        L.check(L.lib.mimrl_mlp4_bwd(L.ptr(g), M, d_in, d_out, L.ptr(wts[0]), L.ptr(wts[1]), L.ptr(wts[2]), L.ptr(wsp[0]),
+                                     L.ptr(wsp[1]), L.ptr(wsp[2]), L.ptr(wsp[3]), L.ptr(ops[1]), L.ptr(ops[2]), L.ptr(ops[3]),
+                                     L.ptr(gx), L.ptr(dzs[0]), L.ptr(dzs[1]), L.ptr(dzs[2]), L.ptr(dzs[3]), L.ptr(gbs[0]),
+                                     L.ptr(gbs[1]), L.ptr(gbs[2]), L.ptr(gbs[3]), L.ptr(scratch), L.stream()))
+        gws = [_gemm_split(2, dzs[l], ops[l], dims[l][0], dims[l][1], M) if ctx.needs_input_grad[1 + 2 * l] else None
+               for l in range(4)]                                            # dz^T [N,M] . input [M,K]
+        return (gx, gws[0], gbs[0], gws[1], gbs[1], gws[2], gbs[2], gws[3], gbs[3])
 
 
 def _is_mlp4(mods, x):
