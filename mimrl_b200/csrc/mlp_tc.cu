@@ -305,11 +305,26 @@ __global__ void mlp4_scales_kernel(const unsigned *absmax_x, const float *w1, co
     }
     return red[0];
   };
+  // row L1 norms, one warp per row (coalesced): lane sums its columns, the warp reduces, lane 0 keeps the running max
   float r1 = 0.f, r2 = 0.f, r3 = 0.f;
-  for (int k = 0; k < K0; ++k) r1 += fabsf(w1[(size_t)n * K0 + k]);
-  for (int k = 0; k < kHidden; ++k) {
-    r2 += fabsf(w2[(size_t)n * kHidden + k]);
-    r3 += fabsf(w3[(size_t)n * kHidden + k]);
+  {
+    const int w = n >> 5, lane = n & 31;
+    for (int row = w; row < kHidden; row += 8) {
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int k = lane; k < K0; k += 32) a1 += fabsf(w1[(size_t)row * K0 + k]);
+#pragma unroll
+      for (int k = lane; k < kHidden; k += 32) {
+        a2 += fabsf(w2[(size_t)row * kHidden + k]);
+        a3 += fabsf(w3[(size_t)row * kHidden + k]);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+      }
+      r1 = fmaxf(r1, a1), r2 = fmaxf(r2, a2), r3 = fmaxf(r3, a3);
+    }
   }
   const float r1m = block_max(r1), r2m = block_max(r2), r3m = block_max(r3);
   const float b1m = block_max(b1 ? fabsf(b1[n]) : 0.f), b2m = block_max(b2 ? fabsf(b2[n]) : 0.f),
