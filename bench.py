@@ -348,18 +348,19 @@ def run_gpu(args):
     impl_name = ("tcgen05 fp16x3 split (fp32-class)"
                  if L.lib.mimrl_sep_selected_impl(n_own, n_all, EMBED, 0) == L.IMPL_TCGEN05 else "fp32 FFMA (CUDA cores)")
     roofline = {
-        "kernel": "mimrl_sep_weighted_sum (backward sweep, 2 launches per step)", "bound": "tensor",
+        "kernel": "sep_wsum_tc_kernel via mimrl_sep_weighted_sum / mimrl_sep_fused_forward (2 launches per step: the "
+                  "fused forward sweep and the swept-side gradient sweep)", "bound": "tensor",
         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, profiles/sep_kernels_r1.md
         # (operands are L2-resident fp16 hi/lo copies; the 32 MiB partial-output buffer dominates the writes)
-        "traffic": 128574464 if (world == 1 and B == B_SINGLE) else None,
+        "traffic": 127135040 if (world == 1 and B == B_SINGLE) else None,
         "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)",
         "algorithmic_flops_per_launch": flops_wsum, "ms_per_launch": ms_wsum, "precision": impl_name,
         "note": "algorithmic fp32 flops (2*E*rows*cols) over a bf16 dense peak; fp32-class accuracy costs 3 split "
                 "products plus the score recompute, so executed tensor flops are 6x the algorithmic figure and the "
                 "ceiling for frac is 1/6 (weighted sum) or 1/3 (row stats)",
         "executed_tflops": 6.0 * achieved, "executed_frac_of_peak": 6.0 * achieved / pk["bf16_tflops"],
-        "tensor_pipe_active_pct_ncu": 80.6,
+        "tensor_pipe_active_pct_ncu": 76.4,           # profiles/sep_kernels_r1.md (74.0 with the row-sum epilogue, 76.4 without)
         "ms_per_launch_shift_by_own": ms_wsum_own, "ms_per_launch_shift_by_swept": ms_wsum_swept,
         "row_stats_ms_per_launch": ms_stats,
         "row_stats_achieved_tflops": 2.0 * EMBED * n_own * n_all / (ms_stats * 1e-3) / 1e12,
