@@ -353,7 +353,7 @@ def run_gpu(args):
         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, profiles/sep_kernels_r1.md
         # (operands are L2-resident fp16 hi/lo copies; the 32 MiB partial-output buffer dominates the writes)
-        "traffic": 127135040 if (world == 1 and B == B_SINGLE) else None,
+        "traffic": 127134976 if (world == 1 and B == B_SINGLE) else None,
         "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)",
         "algorithmic_flops_per_launch": flops_wsum, "ms_per_launch": ms_wsum, "precision": impl_name,
         "note": "algorithmic fp32 flops (2*E*rows*cols) over a bf16 dense peak; fp32-class accuracy costs 3 split "
