@@ -364,6 +364,10 @@ def run_gpu(args):
         "ms_per_launch_shift_by_own": ms_wsum_own, "ms_per_launch_shift_by_swept": ms_wsum_swept,
         "row_stats_ms_per_launch": ms_stats,
         "row_stats_achieved_tflops": 2.0 * EMBED * n_own * n_all / (ms_stats * 1e-3) / 1e12,
+        # one ex2 per score in each sweep; MUFU peak = 16 per clock per SM
+        "exp_per_s_in_sweep": float(n_own) * n_all / (ms_wsum * 1e-3),
+        "mufu_peak_per_s": 16.0 * 148 * 1.965e9,
+        "mufu_frac": float(n_own) * n_all / (ms_wsum * 1e-3) / (16.0 * 148 * 1.965e9),
     }
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample ---
