@@ -484,6 +484,10 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       sh_next = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
     }
     const bool want_rsum = p.rsum_part != nullptr;
+    // weights are carried as w * 2^wexp in fp16 hi/lo.  With an exact shift w <= 1 and 2^14 uses the whole fp16 range;
+    // the fused forward's reference point is approximate (w can exceed 1), so it leaves 2^6 of headroom, and the
+    // exponent is capped so that even a wildly wrong reference point cannot overflow fp16.
+    const float wexp = (FAMILY == MIMRL_WEIGHT_EXP && want_rsum) ? 10.f : (float)kWExp;
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1;
@@ -518,7 +522,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         for (int u = 0; u < 4; ++u) {
           const float a = __uint_as_float(v[j + u]);
           float wv;
-          if (FAMILY == MIMRL_WEIGHT_EXP) wv = ex2(fmaf(fmaf(a, inv, -shv[u]), kLog2e, (float)kWExp));
+          if (FAMILY == MIMRL_WEIGHT_EXP) wv = ex2(fminf(fmaf(fmaf(a, inv, -shv[u]), kLog2e, wexp), 15.9f));
           else wv = __fdividef(16384.f, 1.f + ex2(-a * c2));
           if (!clean) {
             const int gc = col0 + wg * 32 + j + u;
@@ -556,11 +560,11 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       if (lane == 0) mbar_arrive(bWFull + 8 * buf);
     }
     if (want_rsum && row_ok)
-      p.rsum_part[(size_t)(split * 2 + wg) * p.n_own + row0 + r] = ((rs[0] + rs[1]) + (rs[2] + rs[3])) * (1.f / 16384.f);
+      p.rsum_part[(size_t)(split * 2 + wg) * p.n_own + row0 + r] = ((rs[0] + rs[1]) + (rs[2] + rs[3])) * ex2(-wexp);
     if (T > 0) {
       mbar_wait(bOFull, 0);
       tc_fence_after();
-      const float oscale = 1.f / (16384.f * s_all);
+      const float oscale = ex2(-wexp) / s_all;
 #pragma unroll 1
       for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
         uint32_t v[32];

@@ -181,6 +181,9 @@ class _SeparableBoundFused(torch.autograd.Function):
                                           L.ptr(pre[0]), L.ptr(pre[1]), L.ptr(pre[2]), L.ptr(pre[3]), L.ptr(ws), ws.numel(),
                                           st))
         ref = torch.maximum(pre[0], pre[3]) if inc else pre[0]
+        # the one-product scores are off by at most 2^-11 |y_i| |x_j| (11-bit operands, Cauchy-Schwarz): lift the
+        # reference point by twice that, so it is a true upper bound of the row and every weight stays <= 1
+        ref = ref + (2.0 ** -10) * y_emb.norm(dim=1) * swept.norm(dim=1).max()
         ref = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref)).contiguous()
         wsum = torch.empty(n_own, embed, dtype=torch.float32, device=dev)
         stats = torch.zeros(4, n_own, dtype=torch.float32, device=dev)      # max, sum, softplus, diag (true S units)

@@ -198,12 +198,15 @@ def test_full_size_properties():
 
 
 @pytest.mark.parametrize("bound", ["infonce", "dv", "mine", "tuba", "nwj"])
-@pytest.mark.parametrize("B,scale", [(700, 1.0), (1500, 6.0)])
+@pytest.mark.parametrize("B,scale", [(700, 1.0), (1500, 6.0), (900, 40.0)])
 def test_fused_forward_matches_three_sweep_path(bound, B, scale, monkeypatch):
     """mimrl_sep_fused_forward (approximate-max pre-pass + one sweep for the statistics and the owned-row gradient
     sum) against the exact-statistics path it replaces, and both against the float64 oracle.  scale = 6 makes the
     scores large (|S| ~ 100s), where the one-product row maxima are off by ~0.1 and must not matter."""
     import mimrl_b200.vmi as V
+    if bound not in ("infonce", "dv") and scale > 10:
+        pytest.skip("mine / tuba / nwj exponentiate the scores unshifted (VMI.py:148-159, Model.py:121-124): at |S| ~ 1e4 "
+                    "they overflow in the reference itself; only the log-domain bounds are meaningful here")
     baseline = "unnormalized" if bound == "tuba" else "constant"
     c = dict(critic="separate", baseline=baseline, bound=bound, d=128, hidden=64, embed=128, layers=2)
     prm = P.vmi_params(17, "separate", baseline, 128, 64, 128, 2)
@@ -217,4 +220,4 @@ def test_fused_forward_matches_three_sweep_path(bound, B, scale, monkeypatch):
         mi, loss, gx, gy, pg = out[fused]
         assert close_scalar(mi, ref["mi"]), (fused, mi, ref["mi"])
         assert rel_err(gx, ref["gx"]) < TOL and rel_err(gy, ref["gy"]) < TOL, fused
-    assert rel_err(out[True][2], out[False][2]) < 2e-5 and rel_err(out[True][3], out[False][3]) < 2e-5
+    assert rel_err(out[True][2], out[False][2]) < TOL and rel_err(out[True][3], out[False][3]) < TOL
