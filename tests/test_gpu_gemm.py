@@ -75,7 +75,8 @@ def test_mlp_stack_matches_torch(rows):
         assert rel(a, b) < 1e-5
 
 
-@pytest.mark.parametrize("M,d_in,d_out", [(512, 128, 128), (700, 128, 128), (1000, 64, 32), (3001, 100, 96)])
+@pytest.mark.parametrize("M,d_in,d_out", [(512, 128, 128), (700, 128, 128), (1000, 64, 32), (3001, 100, 96),
+                                          (600, 36, 40), (513, 33, 34)])
 def test_fused_mlp4_vs_float64(M, d_in, d_out):
     """mimrl_mlp4_fwd (the critic MLP of VMI.py:13-22 in one kernel) + the per-layer backward on its operands against
     float64.  Rows with a pre-activation within 1e-5 of a ReLU kink get a zero upstream gradient (their mask is

@@ -221,3 +221,42 @@ def test_fused_forward_matches_three_sweep_path(bound, B, scale, monkeypatch):
         assert close_scalar(mi, ref["mi"]), (fused, mi, ref["mi"])
         assert rel_err(gx, ref["gx"]) < TOL and rel_err(gy, ref["gy"]) < TOL, fused
     assert rel_err(out[True][2], out[False][2]) < TOL and rel_err(out[True][3], out[False][3]) < TOL
+
+
+@pytest.mark.parametrize("n_own,n_all,offset,inc", [(300, 300, 0, 1), (200, 517, 130, 0), (129, 700, 571, 1)])
+def test_fused_forward_abi_row_block(n_own, n_all, offset, inc):
+    """mimrl_sep_row_stats(MIMRL_STAT_MAXONLY) + mimrl_sep_fused_forward on a row block of a larger batch, straight
+    through the C ABI, against float64: approximate off-diagonal row maxima, exact off-diagonal weight sums and the
+    weighted sum (diagonal included iff include_diag) relative to the given reference point."""
+    from mimrl_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    E = 128
+    own = rng.standard_normal((n_own, E)).astype(np.float32)
+    swept = rng.standard_normal((n_all, E)).astype(np.float32)
+    T = lambda a: torch.tensor(a, device=dev())
+    o, a = T(own), T(swept)
+    ws_b = L.lib.mimrl_sep_workspace_bytes(n_own, n_all, E)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device=dev())
+    pre = torch.empty(4, n_own, device=dev())
+    L.check(L.lib.mimrl_sep_row_stats(L.ptr(o), L.ptr(a), n_own, n_all, E, offset, L.STAT_MAXONLY, L.IMPL_TCGEN05, L.ptr(pre[0]),
+                                      L.ptr(pre[1]), L.ptr(pre[2]), L.ptr(pre[3]), L.ptr(ws), ws_b, L.stream()))
+    S = own.astype(np.float64) @ swept.astype(np.float64).T
+    rows = np.arange(n_own)
+    diag = S[rows, offset + rows]
+    off = S.copy()
+    off[rows, offset + rows] = -np.inf
+    approx = pre[0].cpu().numpy()
+    bound = 2.0 ** -11 * np.linalg.norm(own, axis=1) * np.linalg.norm(swept, axis=1).max()
+    assert np.all(np.abs(approx - off.max(axis=1)) <= bound + 1e-4)
+    assert np.allclose(pre[3].cpu().numpy(), diag, rtol=1e-5, atol=1e-4)
+    ref = (off.max(axis=1) + 0.3).astype(np.float32)                      # any reference point near the maximum
+    wsum = torch.empty(n_own, E, device=dev())
+    rsum = torch.empty(n_own, device=dev())
+    L.check(L.lib.mimrl_sep_fused_forward(L.ptr(o), L.ptr(a), n_own, n_all, E, offset, inc, L.ptr(T(ref)), L.ptr(wsum),
+                                          L.ptr(rsum), L.ptr(ws), ws_b, L.stream()))
+    W = np.exp(S - ref.astype(np.float64)[:, None])
+    Woff = W.copy()
+    Woff[rows, offset + rows] = 0.0
+    assert rel_err(rsum.cpu().numpy(), Woff.sum(axis=1)) < 5e-5          # fp32 ulp of a score ~ 40 is 4e-6
+    want = (W if inc else Woff) @ swept.astype(np.float64)
+    assert rel_err(wsum.cpu().numpy(), want) < 5e-5
