@@ -263,7 +263,6 @@ struct ConcatBwdParams {
   float *g_vt;               // [256, ldv]     (+=)
   float *g_b2, *g_b3, *g_w4; // [256] each     (+=)
   __half *op[4][2];          // h1, h2, g2, g3 operands: hi / lo, [256, n_tiles * 128]
-  int dbg;
 };
 
 // sum over the 32 lanes of v[t] for every t; lane t returns the total of entry t
@@ -286,8 +285,7 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
 // contiguous bytes (one LSU wavefront per store instead of 32 with a pair-major layout), and the weight-gradient GEMM
 // reads every [128 features x 64 pairs] box as one contiguous 16 KB run.
 __device__ __forceinline__ void store_op32(__half *base_hi, __half *base_lo, size_t row, int f0, const uint32_t (&hi)[16],
-                                           const uint32_t (&lo)[16], int dbg) {
-  if (dbg & 1) return;
+                                           const uint32_t (&lo)[16]) {
   const size_t off = ((row >> 6) * kHid + f0) * 64 + (row & 63);
   unsigned short *h = reinterpret_cast<unsigned short *>(base_hi) + off, *l = reinterpret_cast<unsigned short *>(base_lo) + off;
 #pragma unroll
@@ -465,7 +463,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR0 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR0 + 32 * c + 16, lo);
-        store_op32(bp.op[0][0], bp.op[0][1], row, 32 * c, hi, lo, bp.dbg);
+        store_op32(bp.op[0][0], bp.op[0][1], row, 32 * c, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -492,7 +490,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c + 16, lo);
-        store_op32(bp.op[1][0], bp.op[1][1], row, 32 * c, hi, lo, bp.dbg);
+        store_op32(bp.op[1][0], bp.op[1][1], row, 32 * c, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -525,7 +523,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
           split32h(v, hi, lo);
           tmem_st16(tmem_base + lane_off + kR0 + 32 * c, hi);
           tmem_st16(tmem_base + lane_off + kR0 + 32 * c + 16, lo);
-          store_op32(bp.op[3][0], bp.op[3][1], row, 32 * c, hi, lo, bp.dbg);
+          store_op32(bp.op[3][0], bp.op[3][1], row, 32 * c, hi, lo);
         }
         acc_b3[cc] += lane_transpose_sum(gb, lane);
       }
@@ -552,7 +550,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
         split32h(v, hi, lo);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c, hi);
         tmem_st16(tmem_base + lane_off + kR1 + 32 * c + 16, lo);
-        store_op32(bp.op[2][0], bp.op[2][1], row, 32 * c, hi, lo, bp.dbg);
+        store_op32(bp.op[2][0], bp.op[2][1], row, 32 * c, hi, lo);
         acc_b2[cc] += lane_transpose_sum(gb, lane);
       }
       tmem_st_wait();
@@ -571,9 +569,9 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           v[t] = ((mask1[cc] >> t) & 1u) ? __uint_as_float(d[t]) * inv_d : 0.f;
-          if (v[t] != 0.f && !(bp.dbg & 2)) atomicAdd(s_gv + (32 * c + t) * 32 + lane, v[t]);
+          if (v[t] != 0.f) atomicAdd(s_gv + (32 * c + t) * 32 + lane, v[t]);
         }
-        const float su = (bp.dbg & 4) ? v[lane & 31] : lane_transpose_sum(v, lane);
+        const float su = lane_transpose_sum(v, lane);
         if (i < p.n_own && su != 0.f) atomicAdd(bp.g_u + (size_t)i * kHid + 32 * c + lane, su);
       }
       tc_fence_before();
@@ -764,7 +762,6 @@ extern "C" int mimrl_concat_grad(const float *u, const float *vt, int n_own, int
   if (check_launch("concat scales")) return 1;
   ConcatBwdParams bp;
   concat_fill(bp.f, h, u, vt, n_own, n_all, ldv, b2, b3, w4, nullptr, nullptr);
-  bp.dbg = getenv("MIMRL_CONCAT_DBG") ? atoi(getenv("MIMRL_CONCAT_DBG")) : 0;
   bp.g = g, bp.g_u = g_u, bp.g_vt = g_vt, bp.g_b2 = g_b2, bp.g_b3 = g_b3, bp.g_w4 = g_w4;
   const size_t rows = (size_t)bp.f.n_tiles * 128;
   const size_t off_lo = 256 + align256((size_t)kHid * rows * 2);
