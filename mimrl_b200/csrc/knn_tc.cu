@@ -62,7 +62,7 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
 }
 
 struct KnnTcParams {
-  int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth;
+  int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group;
   float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
   const unsigned *absmax;          // [0] queries, [1] keys
   const __half *q_hi, *q_lo;
@@ -113,8 +113,19 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
   KnnCand *lists = reinterpret_cast<KnnCand *>(gen + kKnnStages * kKUnit + 1024 + 1024);      // [2][128][kListMax]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int row0 = blockIdx.y * 128;
-  const int split = blockIdx.x;                 // fast index: the splits of one query tile run together
+  // 1-D grid over (query tile, key split).  Query tiles are taken in groups of q_group; inside a group the query
+  // tile is the fast index, so q_group CTAs stream the same key range at the same time (L2 reuse of the keys) while
+  // all splits of a query tile still run in the same window (they tighten each other's thresholds through `pub`).
+  int split, qt;
+  {
+    const int per_group = p.splits * p.q_group;
+    const int grp = blockIdx.x / per_group, rr = blockIdx.x % per_group;
+    const int gsz = min(p.q_group, p.q_tiles - grp * p.q_group);
+    split = rr / gsz;
+    qt = grp * p.q_group + rr % gsz;
+    if (split >= p.splits) return;             // tail of a short last group
+  }
+  const int row0 = qt * 128;
   const int n_tiles = (p.n_keys + 127) / 128;
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(n_tiles, t0 + p.tiles_per_split);
@@ -405,8 +416,12 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   cudaMemsetAsync(p.pub, 0x7f, (size_t)n_queries * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
-  dim3 grid(plan.splits, ceil_div(n_queries, 128));
-  knn_filter_tc_kernel<<<grid, kKnnThreads, kKnnSmem, st>>>(mh, ml, p);
+  p.splits = plan.splits;
+  p.q_tiles = ceil_div(n_queries, 128);
+  p.q_group = getenv("MIMRL_KNN_QGROUP") ? atoi(getenv("MIMRL_KNN_QGROUP")) : 32;
+  if (p.q_group < 1) p.q_group = 1;
+  const int groups = ceil_div(p.q_tiles, p.q_group);
+  knn_filter_tc_kernel<<<groups * plan.splits * p.q_group, kKnnThreads, kKnnSmem, st>>>(mh, ml, p);
   return check_launch("knn_filter_tc");
 }
 
