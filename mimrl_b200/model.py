@@ -102,6 +102,24 @@ def _rows_from_shards(local, ids, rb):
     return _sum_over_ranks(out, rb)
 
 
+def merge_knn_candidates(nbr, dist, k, n_total, rb):
+    """All-gather every rank's k candidates per query ([m, k] global indices, -1 = none, and float64 distances) and
+    keep the k best by (distance, index) -- the total order of the single-GPU search.  Pure torch + the process
+    group, so it runs on gloo in the CPU tests."""
+    if not rb.sharded:
+        return nbr, dist
+    all_nbr = [torch.empty_like(nbr) for _ in range(rb.world)]
+    all_dist = [torch.empty_like(dist) for _ in range(rb.world)]
+    torch.distributed.all_gather(all_nbr, nbr.contiguous(), group=rb.group)
+    torch.distributed.all_gather(all_dist, dist.contiguous(), group=rb.group)
+    nbr, dist = torch.cat(all_nbr, dim=1), torch.cat(all_dist, dim=1)
+    # order by (distance, index): stable sort by index, then stable sort by distance
+    o = torch.sort(torch.where(nbr < 0, torch.full_like(nbr, n_total), nbr), dim=1, stable=True).indices
+    nbr, dist = nbr.gather(1, o), dist.gather(1, o)
+    o = torch.sort(dist, dim=1, stable=True).indices[:, :k]
+    return nbr.gather(1, o).contiguous(), dist.gather(1, o).contiguous()
+
+
 def knn_search_sharded(Z_local, ids, k, rb, return_distance=False):
     """``knn_search`` with the key pool row-sharded over ranks (BASELINE config 4): each rank searches its own
     key block for every query (mimrl_knn_search_rows returns global indices and float64 distances), the
@@ -127,17 +145,7 @@ def knn_search_sharded(Z_local, ids, k, rb, return_distance=False):
         L.check(L.lib.mimrl_knn_search_rows(L.ptr(Z_local), n_keys, width, rb.offset, L.ptr(queries), m, L.ptr(excluded), m,
                                             k, exact, L.ptr(nbr), L.ptr(dist), L.ptr(ws), ws.numel(), L.stream()))
         dist = torch.where(nbr < 0, torch.full_like(dist, float("inf")), dist)
-    if rb.sharded:
-        all_nbr = [torch.empty_like(nbr) for _ in range(rb.world)]
-        all_dist = [torch.empty_like(dist) for _ in range(rb.world)]
-        torch.distributed.all_gather(all_nbr, nbr, group=rb.group)
-        torch.distributed.all_gather(all_dist, dist, group=rb.group)
-        nbr, dist = torch.cat(all_nbr, dim=1), torch.cat(all_dist, dim=1)
-        # order by (distance, index): stable sort by index, then stable sort by distance
-        o = torch.sort(torch.where(nbr < 0, torch.full_like(nbr, N), nbr), dim=1, stable=True).indices
-        nbr, dist = nbr.gather(1, o), dist.gather(1, o)
-        o = torch.sort(dist, dim=1, stable=True).indices[:, :k]
-        nbr, dist = nbr.gather(1, o).contiguous(), dist.gather(1, o).contiguous()
+    nbr, dist = merge_knn_candidates(nbr, dist, k, N, rb)
     comp = nbr - torch.searchsorted(excluded, nbr.reshape(-1)).reshape(m, k)      # index with the query rows removed
     return (nbr, comp, dist) if return_distance else (nbr, comp)
 
