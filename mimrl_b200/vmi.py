@@ -222,15 +222,20 @@ class _SeparableBoundFused(torch.autograd.Function):
                                                 L.ptr(vec[2]) if has_base else None, st))
         own = slice(rb.offset, rb.offset + n_own)
         # d/d h(y): the forward's weighted sum, moved from its reference point to the final shift
-        scale = coef * torch.exp(all_stats[0, own] - vec[0, own])
-        dy = scale[:, None] * wsum + vec[1, own][:, None] * own_rows
-        # d/d g(x): columns are owned, y is swept, shift indexed by the swept row
+        dy = None
+        if ctx.needs_input_grad[1]:
+            scale = coef * torch.exp(all_stats[0, own] - vec[0, own])
+            dy = scale[:, None] * wsum + vec[1, own][:, None] * own_rows
+        # d/d g(x): columns are owned, y is swept, shift indexed by the swept row.  Under sharding every rank must take
+        # part in the gather, so only the sweep itself is skipped when x needs no gradient.
         all_y = RB.all_gather_rows(y_emb, rb)
-        dx = torch.empty_like(x_emb)
-        dcoef_own = vec[1, own].contiguous()
-        L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(x_emb), L.ptr(all_y), n_own, n_all, embed, rb.offset, fam, inc,
-                                             L.ptr(vec[0]), 1, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dx),
-                                             L.ptr(ws), ws.numel(), st))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_emb)
+            dcoef_own = vec[1, own].contiguous()
+            L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(x_emb), L.ptr(all_y), n_own, n_all, embed, rb.offset, fam, inc,
+                                                 L.ptr(vec[0]), 1, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dx),
+                                                 L.ptr(ws), ws.numel(), st))
         dbase = vec[2, own].reshape(n_own, 1).clone() if has_base else None
         return dx, dy, dbase, None, None, None
 

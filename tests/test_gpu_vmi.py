@@ -260,3 +260,20 @@ def test_fused_forward_abi_row_block(n_own, n_all, offset, inc):
     assert rel_err(rsum.cpu().numpy(), Woff.sum(axis=1)) < 5e-5          # fp32 ulp of a score ~ 40 is 4e-6
     want = (W if inc else Woff) @ swept.astype(np.float64)
     assert rel_err(wsum.cpu().numpy(), want) < 5e-5
+
+
+def test_fused_forward_one_sided_gradients():
+    """Only one of the two embeddings requires a gradient (stage 1 trains the critics on detached features of one
+    side in some configurations): the other gradient is None and the computed one is unchanged."""
+    import mimrl_b200.vmi as V
+    x, y = P.features(21, 640, 128, corr=0.5)
+    full = {}
+    for gx, gy in ((True, True), (True, False), (False, True)):
+        xe = torch.tensor(x, device=dev(), requires_grad=gx)
+        ye = torch.tensor(y, device=dev(), requires_grad=gy)
+        mi, loss = V.separable_bound(xe, ye, "infonce")
+        loss.backward()
+        full[(gx, gy)] = (xe.grad, ye.grad)
+    assert full[(True, False)][1] is None and full[(False, True)][0] is None
+    assert torch.equal(full[(True, False)][0], full[(True, True)][0])
+    assert torch.equal(full[(False, True)][1], full[(True, True)][1])
