@@ -301,6 +301,21 @@ int mimrl_concat_grad(const float *u, const float *vt, int n_own, int n_all, int
                       float *g_vt, float *g_b2, float *g_b3, float *g_w4, void *op_h1, void *op_h2, void *op_g2,
                       void *op_g3, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- feature heads either side of the fusion encoder (reference Model.py:466-475 and 489-507) ----
+ * stack: t [bs,len_t,d], a [bs,len_a,d], v [bs,len_v,d] (len_* <= time_len) ->
+ *   mean_t/a/v [bs,d] = the unmasked temporal means T_F, A_F, V_F (Model.py:466) and
+ *   x [bs,time_len,3,d] = stack of the three sequences zero-padded to time_len (Model.py:468-475), in one pass.
+ * Backward: g_src[b,l,:] = g_x[b,l,m,:] + g_mean_m[b,:] / len_m; g_x, g_mean_* and g_t/g_a/g_v may be NULL. */
+int mimrl_feature_stack_fwd(const float *t, const float *a, const float *v, int bs, int len_t, int len_a, int len_v,
+                            int time_len, int d, float *x, float *mean_t, float *mean_a, float *mean_v, void *stream);
+int mimrl_feature_stack_bwd(const float *g_x, const float *g_mean_t, const float *g_mean_a, const float *g_mean_v, int bs,
+                            int len_t, int len_a, int len_v, int time_len, int d, float *g_t, float *g_a, float *g_v,
+                            void *stream);
+/* reduce: out[b,:] = scale * sum_r x[b,r,:] over the rows = L' * K' (time x modality) rows of the encoder output:
+ * features_compose_k / features_compose_t in {mean, sum} (Model.py:489-504) with scale = 1 / (L' K'), 1 / L', 1 / K' or 1. */
+int mimrl_feature_reduce_fwd(const float *x, int bs, int rows, int d, float scale, float *out, void *stream);
+int mimrl_feature_reduce_bwd(const float *g_out, int bs, int rows, int d, float scale, float *g_x, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

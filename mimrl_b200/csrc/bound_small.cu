@@ -31,7 +31,7 @@ namespace {
 constexpr int kFinThreads = 1024;
 
 // result[] slots
-enum { R_MI = 0, R_LOSS = 1, R_L = 2, R_MARG = 3, R_MA = 4, R_N = 5 };
+enum { R_MI = 0, R_LOSS = 1, R_L = 2, R_MARG = 3, R_MA = 4, R_N = 5, R_GMAX = 6 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -90,7 +90,8 @@ bound_finalize_kernel(int bound, const float *__restrict__ row_max, const float 
   double sum_d = 0, sum_a = 0, sum_nce = 0, sum_sp = 0, sum_spneg = 0;
   double gm = -INFINITY, gs = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double d = diag[i], a = base ? (double)base[i] : 0.0;
+    // a log-baseline only exists for TUBA (VMI.py:148-154); it is ignored for every other bound
+    const double d = diag[i], a = (base && bound == MIMRL_BOUND_TUBA) ? (double)base[i] : 0.0;
     const double m = row_max[i], s = row_sum[i];
     sum_d += d;
     sum_a += a;
@@ -156,6 +157,7 @@ bound_finalize_kernel(int bound, const float *__restrict__ row_max, const float 
   result[R_MARG] = (float)marg;
   result[R_MA] = (float)ma;
   result[R_N] = (float)nn;
+  result[R_GMAX] = (float)gm;   // max over rows of (row_max - baseline): the weight reference of the backward sweeps
 }
 
 __global__ void bound_backward_coef_kernel(int bound, const float *__restrict__ result,
@@ -177,11 +179,20 @@ __global__ void bound_backward_coef_kernel(int bound, const float *__restrict__ 
     case MIMRL_BOUND_NWJ: c = -g * exp(L - 1.0 - log(n_off)); break;
     default: c = -g / n_off; break;  // sigmoid family: js_fgan, js, smile
   }
+  // Global-LSE bounds (dv, mine, tuba, nwj): the pair weights are exp(S_ij - a_i - L) ~ 1 / (n (n - 1)).  The tensor-core
+  // sweeps carry a weight as w * 2^14 in an fp16 hi/lo pair, so at n = 65536 such a weight would be fp16-subnormal
+  // (about 6 significant bits).  Reference the weights to the global maximum G >= every S_ij - a_i instead
+  // (w' = exp(S_ij - a_i - G) in (0, 1], the dominant pairs keep full precision) and move exp(G - L) into the fp32
+  // coefficient: the product coef' * w' is unchanged.
+  const bool global_lse = bound == MIMRL_BOUND_DV || bound == MIMRL_BOUND_MINE || bound == MIMRL_BOUND_TUBA ||
+                          bound == MIMRL_BOUND_NWJ;
+  const double gmax = result[R_GMAX];
+  const double ref = (global_lse && isfinite(gmax) && isfinite(L)) ? gmax : L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) coef[0] = (float)c;
+  if (i == 0) coef[0] = (float)(global_lse ? c * exp(ref - L) : c);
   if (i >= n) return;
-  const double d = diag[i], a = base ? (double)base[i] : 0.0;
-  double sh = L, dc = g / nn;
+  const double d = diag[i], a = (base && bound == MIMRL_BOUND_TUBA) ? (double)base[i] : 0.0;
+  double sh = ref, dc = g / nn;
   switch (bound) {
     case MIMRL_BOUND_INFONCE: {
       const double s = row_sum[i], m = row_max[i];
@@ -189,7 +200,7 @@ __global__ void bound_backward_coef_kernel(int bound, const float *__restrict__ 
       break;
     }
     case MIMRL_BOUND_MINE: dc = (g_mi + g_loss) / nn; break;
-    case MIMRL_BOUND_TUBA: sh = a + L; break;
+    case MIMRL_BOUND_TUBA: sh = a + ref; break;
     case MIMRL_BOUND_JS_FGAN:
     case MIMRL_BOUND_JS:
     case MIMRL_BOUND_SMILE: dc = g / (nn * (1.0 + exp(d))); break;  // g * sigmoid(-d) / n

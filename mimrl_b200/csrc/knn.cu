@@ -415,13 +415,15 @@ extern "C" int mimrl_gather_rows(const float *src, int n_src, int width, const i
   return check_launch("gather_rows");
 }
 
-static int knn_check(int n_keys, int width, int n_queries, int k, int n_excluded) {
+// whole_pool: the keys are the complete pool, so sklearn's n_neighbors <= n_samples_fit applies here
+// (sklearn/neighbors/_base.py:840-851).  A key SHARD may hold fewer than k keys (other shards fill in): the global
+// check is the caller's (model.knn_search_sharded), unfilled slots come back as (-1, +huge).
+static int knn_check(int n_keys, int width, int n_queries, int k, int n_excluded, bool whole_pool) {
   MIMRL_REQUIRE(n_keys > 0 && width > 0 && n_queries > 0 && k > 0, "knn_search: empty input");
-  MIMRL_REQUIRE(k + kSlack <= kMaxList || k <= kMaxList, "knn_search: k=%d too large (max %d)", k, kMaxList);
   MIMRL_REQUIRE(k <= kMaxList, "knn_search: k=%d too large (max %d)", k, kMaxList);
-  // sklearn/neighbors/_base.py:840-851: n_neighbors <= n_samples_fit
-  MIMRL_REQUIRE(k <= n_keys - n_excluded, "Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d",
-                k, n_keys - n_excluded);
+  if (whole_pool)
+    MIMRL_REQUIRE(k <= n_keys - n_excluded,
+                  "Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d", k, n_keys - n_excluded);
   return 0;
 }
 
@@ -429,7 +431,7 @@ extern "C" int mimrl_knn_search_rows(const float *keys, int n_keys, int width, i
                                      const float *queries, int n_queries, const int64_t *excluded_sorted,
                                      int n_excluded, int k, int exact_form, int64_t *nbr_orig, double *nbr_dist,
                                      void *workspace, size_t workspace_bytes, void *stream) {
-  if (int rc = knn_check(n_keys, width, n_queries, k, 0)) return rc;
+  if (int rc = knn_check(n_keys, width, n_queries, k, 0, false)) return rc;
   const Plan p = make_plan(n_keys, n_queries, width, k);
   MIMRL_REQUIRE(workspace_bytes >= p.total, "knn_search_rows: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -444,7 +446,7 @@ extern "C" int mimrl_knn_search(const float *keys, int n_keys, int width, const 
                                 int k, float radius, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp,
                                 double *nbr_dist, void *workspace, size_t workspace_bytes, void *stream) {
   (void)radius;  // Model.py:82 passes it to the constructor; kneighbors() never reads it
-  if (int rc = knn_check(n_keys, width, n_queries, k, n_queries)) return rc;
+  if (int rc = knn_check(n_keys, width, n_queries, k, n_queries, true)) return rc;
   const Plan p = make_plan(n_keys, n_queries, width, k);
   MIMRL_REQUIRE(workspace_bytes >= p.total, "knn_search: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;

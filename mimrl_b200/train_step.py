@@ -129,6 +129,12 @@ class GraphedTwoStageStep:
         o_saved = [{id(p): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in o.state.items()}
                    for o in opts]
         rng = np.random.get_state()
+        # module buffers (e.g. BatchNorm running statistics inside `features`) and torch's CUDA RNG (dropout) advance
+        # during warm-up and capture as well: snapshot them so that a recapture leaves no trace
+        mods = [step.heads] + [m for m in (getattr(step.features, "__self__", None), step.features)
+                               if isinstance(m, nn.Module)]
+        b_saved = [(b, b.detach().clone()) for m in mods for b in m.buffers()]
+        cuda_rng = torch.cuda.get_rng_state()
         self.g1 = GraphedCallable(s1, [batch, labels], id_source=HostIdSource())
         self.g2 = GraphedCallable(s2, [batch, labels], id_source=HostIdSource())
         torch.cuda.synchronize()
@@ -140,6 +146,9 @@ class GraphedTwoStageStep:
                     for k, v in st.items():
                         if torch.is_tensor(v):
                             v.copy_(saved[id(p)][k]) if id(p) in saved and k in saved[id(p)] else v.zero_()
+            for b, v in b_saved:
+                b.copy_(v)
+        torch.cuda.set_rng_state(cuda_rng)
         np.random.set_state(rng)
 
     def stage1(self, batch, labels):

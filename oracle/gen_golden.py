@@ -324,6 +324,98 @@ def gen_stage(Model, out):
         out[f"stage_{ci:02d}_{c['bound']}_k{c['k']}"] = rec
 
 
+TINY_BERT = dict(vocab_size=120, hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
+                 max_position_embeddings=64)
+
+
+def tiny_bert_patch():
+    """Model.py:243-244 load bert-base-uncased from the local cache; the goldens use a tiny random-init BERT of the
+    same class instead (d_t = 32), so the fixture stays small.  The BERT encoder itself is out of scope."""
+    import transformers
+    transformers.BertConfig.from_pretrained = staticmethod(
+        lambda *a, **k: transformers.BertConfig(output_hidden_states=True, **TINY_BERT))
+    transformers.BertModel.from_pretrained = staticmethod(lambda *a, config=None, **k: transformers.BertModel(config))
+
+
+MODEL_CASES = [
+    dict(encoders="gru", compose_t="mean", compose_k="mean", bs=6, lt=12, la=15, lv=9),
+    dict(encoders="lstm", compose_t="sum", compose_k="cat", bs=5, lt=20, la=11, lv=20),
+    dict(encoders="conv", compose_t="cat", compose_k="sum", bs=4, lt=7, la=7, lv=7),
+]
+
+
+def model_opts(c):
+    return types.SimpleNamespace(
+        d_common=32, encoders=c["encoders"], features_compose_t=c["compose_t"], features_compose_k=c["compose_k"],
+        num_class=1, activate="gelu", time_len=20, d_hiddens=[[10, 3, 32], [5, 3, 32]], d_outs=[[10, 3, 32], [5, 3, 32]],
+        dropout_mlp=[0.0, 0.0, 0.0], dropout=[0.0, 0.0, 0.0, 0.0], bias=True, ln_first=False, res_project=[True, True],
+        critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2, radius=1.0,
+        cmi_last_acticate="sigmoid")
+
+
+def model_inputs(c, seed):
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(1, TINY_BERT["vocab_size"], size=(c["bs"], c["lt"])).astype(np.int64)
+    a = rng.standard_normal((c["bs"], c["la"], 5)).astype(np.float32)
+    v = rng.standard_normal((c["bs"], c["lv"], 7)).astype(np.float32)
+    if c["encoders"] != "conv":                      # ragged sequences: trailing all-zero frames (Model.py:425-432)
+        for b in range(c["bs"]):
+            a[b, c["la"] - (b % 4):] = 0
+            v[b, c["lv"] - (b % 3):] = 0
+    return ids, a, v
+
+
+def gen_model(Model, out):
+    """Model.forward (Model.py:388-519): encoders (tiny BERT / GRU|LSTM|Conv, stock torch) + feature heads + CubeMLP +
+    composition + classifier.  Stores every non-estimator weight, the five outputs and input/parameter gradients."""
+    tiny_bert_patch()
+    for ci, c in enumerate(MODEL_CASES):
+        seed = 6000 + ci
+        torch.manual_seed(seed)
+        model = Model.Model(model_opts(c), TINY_BERT["hidden_size"], 5, 7)
+        model.train()
+        ids, a, v = model_inputs(c, seed)
+        at, vt = t(a).requires_grad_(True), t(v).requires_grad_(True)
+        mask = torch.ones(ids.shape, dtype=torch.long)
+        outs = model(t(ids), torch.zeros_like(mask), mask, at, vt, return_features=True)
+        w = [t(P.features(seed + 10 + i, int(o.shape[0]), int(np.prod(o.shape[1:]))).reshape(tuple(o.shape)))
+             for i, o in enumerate(outs)]
+        sum((o * wi).sum() for o, wi in zip(outs, w)).backward()
+        rec = dict(seed=seed, ga=at.grad.numpy(), gv=vt.grad.numpy())
+        for name, o in zip(("output", "F_F", "T_F", "A_F", "V_F"), outs):
+            rec["out_" + name] = o.detach().numpy()
+        for name, p_ in model.state_dict().items():
+            if "vmi" not in name and "vcmi" not in name:
+                rec["sd__" + name] = p_.numpy()
+        for name, p_ in model.named_parameters():
+            if p_.grad is not None and "vmi" not in name and "vcmi" not in name:
+                rec["pg__" + name] = p_.grad.numpy()
+        for k_, v_ in c.items():
+            rec["cfg_" + k_] = np.array(v_)
+        out[f"model_{ci:02d}_{c['encoders']}_{c['compose_t']}_{c['compose_k']}"] = rec
+
+
+def gen_mine(VMI, out):
+    """compute_MI / train_MINE / EMA (VMI.py:253-378) on the correlated-Gaussian known answer (VMI.py:389-396)."""
+    for ci, c in enumerate([
+        dict(critic="separate", baseline="constant", bound="infonce", dim=20, rho=0.8, n=1024, epochs=60, bs=128),
+        dict(critic="separate", baseline="constant", bound="mine", dim=20, rho=0.8, n=1024, epochs=60, bs=128),
+        dict(critic="separate", baseline="unnormalized", bound="tuba", dim=20, rho=0.8, n=1024, epochs=60, bs=128),
+        dict(critic="separate", baseline="constant", bound="smile", dim=20, rho=0.8, n=1024, epochs=60, bs=128),
+    ]):
+        seed = 7000 + ci
+        torch.manual_seed(seed)
+        x, y = VMI.sample_correlated_gaussian(rho=c["rho"], dim=c["dim"], num_samples=c["n"])
+        torch.manual_seed(seed + 1)
+        score, hist = VMI.compute_MI(c["critic"], c["baseline"], c["bound"], x, y, c["dim"], c["dim"], hidden_dim=64,
+                                     embed_dim=32, epochs=c["epochs"], batch_size=c["bs"], lr=5e-4, estimation="mean")
+        rec = dict(seed=seed, score=np.array(score), history=np.asarray(hist, dtype=np.float64),
+                   true_mi=np.array(VMI.rho_to_mi(c["dim"], c["rho"])))
+        for k_, v_ in c.items():
+            rec["cfg_" + k_] = np.array(v_)
+        out[f"mine_{ci:02d}_{c['bound']}"] = rec
+
+
 def main():
     VMI, Model, MLPProcess = import_reference()
     torch.manual_seed(0)
@@ -331,7 +423,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     groups = dict(vmi=lambda o: gen_vmi(Model, o), bounds=lambda o: gen_bounds(VMI, o),
                   knn=lambda o: gen_knn(Model, o), vcmi=lambda o: gen_vcmi(Model, o),
-                  cubemlp=lambda o: gen_cubemlp(MLPProcess, o), stage=lambda o: gen_stage(Model, o))
+                  cubemlp=lambda o: gen_cubemlp(MLPProcess, o), stage=lambda o: gen_stage(Model, o),
+                  mine=lambda o: gen_mine(VMI, o), model=lambda o: gen_model(Model, o))
     only = sys.argv[1:]
     for gname, fn in groups.items():
         if only and gname not in only:

@@ -45,3 +45,25 @@ def golden():
             cache[group] = load_golden(group)
         return cache[group]
     return get
+
+
+TINY_BERT = dict(vocab_size=120, hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
+                 max_position_embeddings=64)
+
+
+@pytest.fixture
+def tiny_bert():
+    """``from_pretrained`` -> a tiny random-init BERT (the one oracle/gen_golden.py built the model goldens with); the
+    BERT encoder is out of scope and there are no cached weights offline."""
+    import transformers
+    classes = (transformers.BertConfig, transformers.BertModel)
+    saved = [cls.__dict__.get("from_pretrained") for cls in classes]
+    transformers.BertConfig.from_pretrained = staticmethod(
+        lambda *a, **k: transformers.BertConfig(output_hidden_states=True, **TINY_BERT))
+    transformers.BertModel.from_pretrained = staticmethod(lambda *a, config=None, **k: transformers.BertModel(config))
+    yield TINY_BERT
+    for cls, old in zip(classes, saved):                      # inherited classmethod: remove the override again
+        if old is None:
+            delattr(cls, "from_pretrained")
+        else:
+            setattr(cls, "from_pretrained", old)
