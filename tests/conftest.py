@@ -48,7 +48,7 @@ def golden():
 
 
 TINY_BERT = dict(vocab_size=120, hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
-                 max_position_embeddings=64)
+                 max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
 
 
 @pytest.fixture

@@ -89,7 +89,8 @@ def test_graphed_two_stage_step_matches_eager():
                             torch.optim.Adam(heads.parameters(), 1e-3, capturable=True),
                             clip_params=main + list(heads.parameters()))
         pool = FeaturePool(C=pool_t[0], F=pool_t[1], T=pool_t[2], A=pool_t[3], V=pool_t[4])
-        return step, pool, list(heads.parameters()) + main
+        names = [n for n, _ in heads.named_parameters()] + ["main"] * len(main)
+        return step, pool, list(zip(names, list(heads.parameters()) + main))
 
     step_e, pool_e, params_e = make()
     np.random.seed(3)
@@ -109,6 +110,11 @@ def test_graphed_two_stage_step_matches_eager():
     for (a1, a2, am), (b1, b2, bm) in zip(eager, got):
         assert abs(a1 - b1) <= 1e-4 * max(1.0, abs(a1)) and abs(a2 - b2) <= 1e-4 * max(1.0, abs(a2))
         assert np.allclose(am, bm, rtol=1e-4, atol=1e-5)
-    for pe, pg in zip(params_e, params_g):
-        assert torch.allclose(pe, pg, rtol=1e-4, atol=1e-6)
+    for (name, pe), (_, pg) in zip(params_e, params_g):
+        # InfoNCE is invariant to a per-row shift of the scores, so the exact gradient of the x-side output bias
+        # (S_ij + y_i . b) is zero: Adam normalises pure rounding noise there, and the graph (three-sweep forward) and
+        # eager (fused forward) paths round differently
+        if name.endswith("critic_model.MLP_g.6.bias"):
+            continue
+        assert torch.allclose(pe, pg, rtol=1e-4, atol=1e-6), name
     assert len(pool_g._next["C"]) == 3 and pool_g._next["F"][0].shape == (bs, 128)
