@@ -79,6 +79,74 @@ def test_knn_indices_vs_float64_oracle(N, width, m, k):
     assert np.allclose(dist.cpu().numpy(), wdist, rtol=1e-12, atol=1e-12)
 
 
+_POOL_1M = {}
+
+
+def _pool_1m(width):
+    """BASELINE configs[3] pool: 1,048,576 rows ~N(0,1) (float32), generated once per width."""
+    if width not in _POOL_1M:
+        _POOL_1M[width] = np.random.default_rng(2 + width).standard_normal((1 << 20, width), dtype=np.float32)
+    return _POOL_1M[width]
+
+
+@pytest.mark.parametrize("width,bs,k,dup", [(128, 8192, 2, 0), (128, 8192, 4, 0), (128, 8192, 8, 0), (128, 8192, 16, 0),
+                                            (1, 8192, 2, 0), (1, 8192, 16, 0), (128, 8192, 4, 4096)])
+def test_knn_config4_scale_vs_float64_oracle(width, bs, k, dup):
+    """BASELINE configs[3]: N = 1,048,576 keys, batch 8192 -> m = bs // k queries (4096 ... 512), k in {2,4,8,16}; the
+    width-1 label pool (scikit-learn's kd_tree route) and a pool with exact duplicate rows (tie rule).  The GPU search
+    runs all m queries; the float64 oracle checks a 96-query subset (every neighbour list bit-exact, order included,
+    distances to 1e-12) -- the queries are independent, so a subset checks the same code path at full pool size."""
+    from mimrl_b200.model import knn_search, sklearn_route
+    N = 1 << 20
+    Z = _pool_1m(width)
+    if dup:
+        Z = Z.copy()
+        Z[N - dup:] = Z[:dup]                       # rows N-dup.. are exact copies of rows 0..dup-1
+    m = bs // k
+    ids = np.random.RandomState(0).permutation(N)[:m]
+    if dup:
+        ids[:32] = np.arange(32)                    # 32 queries whose twin (row N-dup+i) stays in the pool at distance 0
+        ids = np.unique(ids)
+        m = len(ids)
+    exc = np.zeros(N, np.uint8)
+    exc[ids] = 1
+    route = sklearn_route(width, k, N - m)
+    assert route == ("brute" if width > 15 else "kd_tree")
+    got, comp, dist = knn_search(T(Z), T(ids), k, return_distance=True)
+    got, comp, dist = got.cpu().numpy(), comp.cpu().numpy(), dist.cpu().numpy()
+    sub = np.r_[0:32, np.linspace(32, m - 1, 64).astype(int)]
+    want, wdist = K.knn(Z, Z[ids[sub]], k, exc, route)
+    if dup:
+        # inside an exact tie scikit-learn guarantees the set (lowest indices), not the order: compare sets and distances
+        assert np.array_equal(np.sort(got[sub], 1), np.sort(want, 1))
+        assert np.array_equal(got[:32, 0] % (N - dup), ids[:32])          # the twin comes first, at distance 0
+        assert np.all(dist[:32, 0] < 1e-5)          # GEMM-form float64 distance of an exact copy: 0 up to rounding
+    else:
+        assert np.array_equal(got[sub], want)
+    assert np.allclose(dist[sub], wdist, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(comp, got - np.searchsorted(np.sort(ids), got))
+    assert not np.isin(got, ids).any() and np.all(np.diff(dist, axis=1) >= 0)
+
+
+def test_knn_shard_with_fewer_than_k_keys():
+    """mimrl_knn_search_rows on a key shard that holds fewer than k keys (other shards fill in): legal, unfilled slots come
+    back as index -1 (the global n_neighbors <= n_samples_fit check belongs to the caller)."""
+    from mimrl_b200 import _lib as L
+    Z = T(P.features(3, 5, 128))
+    q = T(P.features(4, 7, 128))
+    k = 8
+    ws = torch.empty(max(L.lib.mimrl_knn_workspace_bytes(5, 7, 128, k), 16), dtype=torch.uint8, device=dev())
+    nbr = torch.full((7, k), -1, dtype=torch.int64, device=dev())
+    dist = torch.full((7, k), float("inf"), dtype=torch.float64, device=dev())
+    exc = torch.empty(0, dtype=torch.int64, device=dev())
+    L.check(L.lib.mimrl_knn_search_rows(L.ptr(Z), 5, 128, 100, L.ptr(q), 7, L.ptr(exc), 0, k, 1, L.ptr(nbr), L.ptr(dist),
+                                        L.ptr(ws), ws.numel(), L.stream()))
+    nbr = nbr.cpu().numpy()
+    d2 = ((q.double()[:, None, :] - Z.double()[None]) ** 2).sum(-1)
+    want = 100 + torch.argsort(d2, dim=1, stable=True).cpu().numpy()
+    assert np.array_equal(nbr[:, :5], want) and np.all(nbr[:, 5:] == -1)
+
+
 def test_knn_duplicate_keys_lowest_index_wins():
     from mimrl_b200.model import knn_search
     Z = P.features(5, 600, 128)

@@ -59,3 +59,32 @@ def test_too_many_neighbours_raises():
         K.prod_knn_sample(X, X, X, 8, 8)                    # k=8 > N-m=9? no: m=1, fit on 9 rows, k=8 ok
         K.prod_knn_sample(X, X, X, 9, 9)                    # m=1, 9 rows left, k=9 ok
         K.prod_knn_sample(X, X, X, 10, 10)                  # m=1, 9 rows left, k=10 -> error
+
+
+@pytest.mark.parametrize("N,width,m,k,dup", [(120000, 128, 48, 16, 0), (262144, 128, 24, 2, 0), (200000, 1, 64, 4, 0),
+                                             (50000, 8, 64, 3, 0), (60000, 128, 32, 4, 3000)])
+def test_oracle_matches_sklearn_at_scale(N, width, m, k, dup):
+    """The oracle against scikit-learn itself (the un-vendored dependency behind Model.py:82-86) at pool sizes far above
+    the goldens' N <= 1284: both routes (brute for width > 15, kd_tree below), neighbour lists bit-exact, order included
+    (sets inside exact ties)."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    Z = np.random.default_rng(N + width).standard_normal((N, width), dtype=np.float32)
+    if dup:
+        Z[N - dup:] = Z[:dup]
+    ids = np.random.RandomState(1).permutation(N)[:m]
+    if dup:
+        ids[:8] = np.arange(8)
+        ids = np.unique(ids)
+    keep = np.ones(N, bool)
+    keep[ids] = False
+    Z2 = Z[keep]
+    nn_ = sk.NearestNeighbors(n_neighbors=k, radius=1.0, metric="euclidean").fit(Z2)      # Model.py:82-85
+    want = nn_.kneighbors(Z[ids], return_distance=False)                                  # Model.py:86 (compacted ids)
+    route = K.sklearn_route(width, k, N - len(ids))
+    assert nn_._fit_method == route
+    got, _ = K.knn(Z, Z[ids], k, (~keep).astype(np.uint8), route)
+    got_comp = got - np.searchsorted(np.sort(ids), got)
+    if dup:
+        assert np.array_equal(np.sort(got_comp, 1), np.sort(want, 1))
+    else:
+        assert np.array_equal(got_comp, want)
