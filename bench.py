@@ -596,7 +596,7 @@ def run_gpu(args):
     e2e_ms = float(t.item())
 
     # ---- the two sweeps a step launches, each timed alone with CUDA events on its own stream -----
-    # (a) mimrl_sep_fused_forward: statistics + owned-row weighted sum in one sweep (the step's forward)
+    # (a) mimrl_sep_online_forward: statistics + owned-row weighted sum in one sweep (the step's forward)
     # (b) mimrl_sep_weighted_sum, shift indexed by the swept row: the column-side gradient sweep (the step's backward)
     with torch.no_grad():
         xe_, ye_ = est.critic_model.embed(x, y)
@@ -619,9 +619,9 @@ def run_gpu(args):
     out = torch.empty_like(ye_)
     rsum = torch.empty(n_own, device=dev)
 
-    def k_fused():
-        L.check(L.lib.mimrl_sep_fused_forward(L.ptr(ye_), L.ptr(all_x), n_own, n_all, EMBED, rb.offset, 1, L.ptr(ref_pt),
-                                              L.ptr(out), L.ptr(rsum), L.ptr(ws), ws.numel(), st))
+    def k_fused():          # the step's forward: online reference point, statistics and owned-row gradient sum in one sweep
+        L.check(L.lib.mimrl_sep_online_forward(L.ptr(ye_), L.ptr(all_x), n_own, n_all, EMBED, rb.offset, 1, L.ptr(ref_pt),
+                                               L.ptr(out), L.ptr(rsum), None, L.ptr(ws), ws.numel(), st))
 
     def time_kernel(fn, reps=5):
         fn()
@@ -647,15 +647,14 @@ def run_gpu(args):
     ms_wsum_swept = time_kernel(k_wsum_swept)
     ms_wsum = 0.5 * (ms_fused + ms_wsum_swept) if tc_path else ms_wsum_swept
     ms_stats = time_kernel(k_stats)
-    ms_maxonly = time_kernel(lambda: k_stats(L.STAT_MAXONLY)) if tc_path else float("nan")
     pk = peaks()
     flops_wsum = 2.0 * EMBED * n_own * n_all              # algorithmic: one P.X contraction (score recompute not counted)
     achieved = flops_wsum / (ms_wsum * 1e-3) / 1e12
     impl_name = "tcgen05 fp16x3 split (fp32-class)" if tc_path else "fp32 FFMA (CUDA cores)"
     ncu = ncu_record("sep_wsum_tc_kernel") if (world == 1 and B == B_SINGLE) else {}
     roofline = {
-        "kernel": "sep_wsum_tc_kernel (2 launches per step: mimrl_sep_fused_forward = forward statistics + owned-row "
-                  "gradient sum, and mimrl_sep_weighted_sum = swept-side gradient sweep); ms_per_launch is their mean",
+        "kernel": "sep_wsum_tc_kernel (2 launches per step: mimrl_sep_online_forward = online-softmax forward statistics + "
+                  "owned-row gradient sum, and mimrl_sep_weighted_sum = swept-side gradient sweep); ms_per_launch is their mean",
         "bound": "tensor",
         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
         # dram bytes and tensor-pipe activity of one launch come from the committed ncu --set full capture of this
@@ -669,8 +668,8 @@ def run_gpu(args):
                 "ceiling for frac is 1/6 (weighted sum) or 1/3 (row stats)",
         "executed_tflops": 6.0 * achieved, "executed_frac_of_peak": 6.0 * achieved / pk["bf16_tflops"],
         "ms_per_launch_fused_forward": ms_fused, "ms_per_launch_shift_by_swept": ms_wsum_swept,
-        "row_stats_ms_per_launch": ms_stats, "max_prepass_ms_per_launch": ms_maxonly,
-        "sweeps_share_of_step": (ms_fused + ms_wsum_swept + ms_maxonly) / ms if tc_path else None,
+        "row_stats_ms_per_launch": ms_stats,
+        "sweeps_share_of_step": (ms_fused + ms_wsum_swept) / ms if tc_path else None,
         "row_stats_achieved_tflops": 2.0 * EMBED * n_own * n_all / (ms_stats * 1e-3) / 1e12,
         # one ex2 per score in each sweep; MUFU peak = 16 per clock per SM
         "exp_per_s_in_sweep": float(n_own) * n_all / (ms_wsum * 1e-3),

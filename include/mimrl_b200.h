@@ -94,6 +94,17 @@ int mimrl_sep_row_stats(const float *own_emb, const float *all_emb, int n_own, i
 int mimrl_sep_fused_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                             int own_offset, int include_diag, const float *shift, float *wsum, float *row_sum,
                             void *workspace, size_t workspace_bytes, void *stream);
+/* Online-softmax forward sweep (tcgen05 path): mimrl_sep_fused_forward without a supplied reference point.  The sweep
+ * keeps a running reference per row (the row maximum seen so far, lazily updated) and returns it:
+ *   row_ref[i]  = the reference point the sums are referred to (a value near the row maximum; 0 for an empty row)
+ *   row_sum[i]  = sum_{j != i} exp(S_ij - row_ref[i])
+ *   wsum[i,:]   = sum_j exp(S_ij - row_ref[i]) all_emb[j,:]      (j = i included iff include_diag)
+ *   diag[i]     = S_{i, own_offset+i}                             (optional, may be NULL)
+ * This is the whole forward of the exp-family bounds of VMI.py:136-166 in ONE pass over the score tiles (no max
+ * pre-pass): 4 tensor-core units per step instead of 4 1/3. */
+int mimrl_sep_online_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                             int own_offset, int include_diag, float *row_ref, float *wsum, float *row_sum, float *diag,
+                             void *workspace, size_t workspace_bytes, void *stream);
 int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                            int own_offset, int weight_family, int include_diag, const float *shift,
                            int shift_by_swept, const float *coef, const float *dcoef, int impl, float *out,

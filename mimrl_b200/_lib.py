@@ -37,6 +37,7 @@ _SIGS = {
     "mimrl_sep_selected_impl": (c_int, [c_int, c_int, c_int, c_int]),
     "mimrl_sep_row_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_fused_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "mimrl_sep_online_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_weighted_sum": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P,
                                        _P, c_size_t, _P]),
     "mimrl_bound_finalize": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P, _P]),

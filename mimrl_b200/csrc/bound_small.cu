@@ -187,7 +187,9 @@ __global__ void bound_backward_coef_kernel(int bound, const float *__restrict__ 
   const bool global_lse = bound == MIMRL_BOUND_DV || bound == MIMRL_BOUND_MINE || bound == MIMRL_BOUND_TUBA ||
                           bound == MIMRL_BOUND_NWJ;
   const double gmax = result[R_GMAX];
-  const double ref = (global_lse && isfinite(gmax) && isfinite(L)) ? gmax : L;
+  // row_max may be the online forward's reference point, which can sit up to 4.5 below the true row maximum
+  // (kOnlineTau in sep_tc.cu): the margin keeps every weight <= 1 either way
+  const double ref = (global_lse && isfinite(gmax) && isfinite(L)) ? gmax + 4.5 : L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) coef[0] = (float)(global_lse ? c * exp(ref - L) : c);
   if (i >= n) return;

@@ -92,6 +92,9 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
                         int family, int include_diag, const float *shift, int shift_by_swept, const float *coef,
                         const float *dcoef, float *out, void *ws, size_t ws_bytes, cudaStream_t st,
                         float *row_sum = nullptr);
+int sep_online_forward_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
+                          int include_diag, float *row_ref, float *wsum, float *row_sum, void *ws, size_t ws_bytes,
+                          cudaStream_t st);
 size_t sep_tc_workspace_bytes(int n_own, int n_all, int embed);
 bool sep_tc_supported(int n_own, int n_all, int embed);
 

@@ -364,6 +364,24 @@ extern "C" int mimrl_sep_fused_forward(const float *own_emb, const float *all_em
                              /*coef = 1*/ nullptr, nullptr, wsum, workspace, workspace_bytes, st, row_sum);
 }
 
+// Online-softmax forward sweep (tcgen05 path only): like mimrl_sep_fused_forward, but the reference point is found
+// by the sweep itself (running row maximum, lazily rescaled accumulators) and returned in row_ref.  No pre-pass.
+extern "C" int mimrl_sep_online_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                                        int own_offset, int include_diag, float *row_ref, float *wsum, float *row_sum,
+                                        float *diag, void *workspace, size_t workspace_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MIMRL_REQUIRE(n_own > 0 && n_all > 0 && embed > 0 && row_ref && wsum && row_sum, "sep_online_forward: bad arguments");
+  MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "sep_online_forward: row block outside the batch");
+  MIMRL_REQUIRE(sep_tc_supported(n_own, n_all, embed), "sep_online_forward: tcgen05 path needs embed <= 128 (got %d)", embed);
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_sep_workspace_bytes(n_own, n_all, embed), "sep_online_forward: workspace too small");
+  if (diag) {
+    sep_diag_kernel<<<ceil_div(n_own * 32, 256), 256, 0, st>>>(own_emb, all_emb, n_own, n_all, embed, own_offset, diag);
+    if (check_launch("sep_diag")) return 1;
+  }
+  return sep_online_forward_tc(own_emb, all_emb, n_own, n_all, embed, own_offset, include_diag, row_ref, wsum, row_sum,
+                               workspace, workspace_bytes, st);
+}
+
 extern "C" int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                                       int own_offset, int weight_family, int include_diag, const float *shift,
                                       int shift_by_swept, const float *coef, const float *dcoef, int impl,

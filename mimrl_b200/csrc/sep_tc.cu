@@ -88,6 +88,7 @@ constexpr uint32_t kTile16 = 128 * 128;  // 128 rows x 128 B
 constexpr uint32_t kXTile = 64 * 128;    // 64 rows x 128 B
 constexpr uint32_t kAux = 1024;          // barriers, tmem slot, staged shifts
 constexpr uint32_t kRingSmem = kStages * kUnit + kAux + 1024;
+constexpr uint32_t kWsumSmem = kRingSmem + 2048;   // + the online mode's reference / row-sum exchange ([2][2][128] floats)
 // TMEM columns: [0,128) owned block (hi kb0, hi kb1, lo kb0, lo kb1: 32 columns each, one column = two K values)
 constexpr uint32_t kTmemA = 0;
 
@@ -320,9 +321,82 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
 }
 
 // ----------------------------------------------------------- weighted sum ----
-// TMEM: [0,128) owned block, [128,192) S/W buffer 0, [192,256) S/W buffer 1, [256,384) output accumulator.
+// TMEM: [0,128) owned block, [128,192) S/W buffer 0, [192,256) S/W buffer 1, [256,384) output accumulator
+// (ONLINE: [256,384) accumulator of epilogue warpgroup 0's columns, [384,512) of warpgroup 1's).
 // Ring unit = one 64-row tile of the swept operand: [hi kb0 | hi kb1 | lo kb0 | lo kb1] x (64 rows x 128 B).
 // It is read K-major by the score MMAs (rows = N) and MN-major by the W.X MMAs (rows = K).
+//
+// ONLINE (the forward of the exp-family bounds, mimrl_sep_online_forward): no reference point is given.  Every
+// epilogue thread keeps a running reference ref for its row (online softmax): weights are exp(S - ref), and when a
+// tile's maximum exceeds ref by more than kOnlineTau the accumulated sums are rescaled by exp(ref - ref') -- lazily,
+// so that after the first tiles of a sweep almost no tile pays for it.  The two epilogue warpgroups own disjoint
+// column halves of every score tile; giving each its OWN output accumulator (k-steps 0,1 -> accumulator 0, k-steps
+// 2,3 -> accumulator 1) makes their references independent, so no cross-warpgroup exchange happens per tile; the two
+// are merged once at the end.  A rescale of accumulator g must not overlap an MMA that adds into it: the epilogue
+// warp waits for the W.X MMAs of the previous tile (bODone) before it touches the accumulator, and the MMAs of the
+// current tile cannot start before this warp has delivered its weights (bWFull).
+constexpr float kOnlineWExp = 9.f;       // online weights are carried as w * 2^9: w <= 2^kOnlineTau stays below fp16 max
+constexpr float kOnlineTau = 4.5f;       // rescale when a score exceeds the reference by more than this (natural units)
+
+// One thread's 32 scores of a tile -> weights (fp16 hi/lo pairs) + the row-sum statistic.  EDGE = the tile holds the
+// row's diagonal or runs past the batch: invalid entries get weight 0 and the statistic leaves the diagonal out.  It
+// is a separate instantiation so that the common tile carries none of the per-element index tests.
+template <int FAMILY, bool ONLINE, bool EDGE>
+__device__ __forceinline__ void weights_of_tile(const uint32_t (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16],
+                                                float2 (&rs2)[2], float inv, float c2, float wexp, float shift_row,
+                                                const float4 *sh4, bool by_swept, bool want_rsum, int cbase, int gr,
+                                                int n_all, bool include_diag) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float shv[4] = {shift_row, shift_row, shift_row, shift_row};
+    if (!ONLINE && by_swept) {
+      const float4 t4 = sh4[j >> 2];
+      shv[0] = t4.x, shv[1] = t4.y, shv[2] = t4.z, shv[3] = t4.w;
+    }
+    float w[4];
+    if (FAMILY == MIMRL_WEIGHT_EXP) {
+      // two packed FFMA2 per pair: (acc * inv - shift) at score magnitude, then * log2e + wexp
+#pragma unroll
+      for (int u = 0; u < 4; u += 2) {
+        const float2 a2 = make_float2(__uint_as_float(v[j + u]), __uint_as_float(v[j + u + 1]));
+        const float2 t2 = ffma2(a2, make_float2(inv, inv), make_float2(-shv[u], -shv[u + 1]));
+        const float2 e2 = ffma2(t2, make_float2(kLog2e, kLog2e), make_float2(wexp, wexp));
+        // ONLINE: every entry is <= ref + tau by construction, no cap needed
+        w[u] = ex2(ONLINE ? e2.x : fminf(e2.x, 15.9f));
+        w[u + 1] = ex2(ONLINE ? e2.y : fminf(e2.y, 15.9f));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __fdividef(16384.f, 1.f + ex2(-__uint_as_float(v[j + u]) * c2));
+    }
+    float a[4] = {w[0], w[1], w[2], w[3]};
+    if (EDGE) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gc = cbase + j + u;
+        if (!(gc < n_all && (include_diag || gc != gr))) w[u] = 0.f;
+        if (gc == gr || gc >= n_all) a[u] = 0.f;           // the statistic always leaves the diagonal out
+      }
+    }
+    if (want_rsum) {
+      rs2[0] = fadd2(rs2[0], make_float2(a[0], a[1]));
+      rs2[1] = fadd2(rs2[1], make_float2(a[2], a[3]));
+    }
+    // hi = w truncated to 11 significant bits (exactly representable in fp16), lo = w - hi
+    const float2 wh01 = make_float2(__uint_as_float(__float_as_uint(w[0]) & 0xFFFFE000u),
+                                    __uint_as_float(__float_as_uint(w[1]) & 0xFFFFE000u));
+    const float2 wh23 = make_float2(__uint_as_float(__float_as_uint(w[2]) & 0xFFFFE000u),
+                                    __uint_as_float(__float_as_uint(w[3]) & 0xFFFFE000u));
+    const float2 wl01 = fsub2(make_float2(w[0], w[1]), wh01), wl23 = fsub2(make_float2(w[2], w[3]), wh23);
+    const __half2 h0 = __floats2half2_rn(wh01.x, wh01.y), h1 = __floats2half2_rn(wh23.x, wh23.y);
+    const __half2 l0 = __floats2half2_rn(wl01.x, wl01.y), l1 = __floats2half2_rn(wl23.x, wl23.y);
+    hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h0);
+    hi[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&h1);
+    lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l0);
+    lo[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&l1);
+  }
+}
+
 struct WsumParams {
   int n_own, n_all, own_offset, tiles_per_split, include_diag, shift_by_swept;
   const unsigned *absmax;
@@ -330,20 +404,25 @@ struct WsumParams {
   const float *shift;
   float *part;  // [split][n_own][128]
   float *rsum_part;   // nullable: [split * 2 + warpgroup][n_own] sum of the off-diagonal weights of the row
+                      // (ONLINE: [split][n_own], referred to ref_part)
+  float *ref_part;    // ONLINE: [split][n_own] final reference point of the row in this split (-inf: nothing seen)
 };
 
-template <int FAMILY>
+template <int FAMILY, bool ONLINE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                    const WsumParams p) {
+  static_assert(!ONLINE || FAMILY == MIMRL_WEIGHT_EXP, "online mode is for the exp family");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - raw);
   const uint32_t bars = base + kStages * kUnit;
   const uint32_t bXFull = bars, bXEmpty = bars + 64, bSFull = bars + 128, bWFull = bars + 144, bOFull = bars + 160;
+  const uint32_t bODone = bars + 168;                                            // [2], ONLINE only
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kStages * kUnit + 256);
   float *sh_smem = reinterpret_cast<float *>(gen + kStages * kUnit + 512);      // [2][64] staged column shifts
+  float *sh_x = reinterpret_cast<float *>(gen + kStages * kUnit + kAux);        // ONLINE: [2][2][128] ref / rsum exchange
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
@@ -361,6 +440,7 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     for (int i = 0; i < 2; ++i) {
       mbar_init(bSFull + 8 * i, 1);
       mbar_init(bWFull + 8 * i, 8);           // one elected arrive per epilogue warp
+      mbar_init(bODone + 8 * i, 1);
     }
     mbar_init(bOFull, 1);
     fence_barrier_init();
@@ -435,7 +515,8 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         tc_fence_after();
         if (leader) {
           // O += W(i) . x_i : W from the TMEM columns the scores came from (hi | lo per warpgroup half), the x
-          // tile read MN-major (row = K index, 64 contiguous N per 128-byte row, next 64 N one kb block further)
+          // tile read MN-major (row = K index, 64 contiguous N per 128-byte row, next 64 N one kb block further).
+          // k-steps 0,1 are the columns of epilogue warpgroup 0, k-steps 2,3 those of warpgroup 1.
           const uint32_t x0 = base + stage * kUnit;
           const uint32_t w0 = tmem_s + buf * 64;
 #pragma unroll
@@ -443,12 +524,16 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
             const uint32_t w_lo = prod == 2 ? 16 : 0;    // W hi, hi, lo
             const uint32_t x_sel = prod == 1 ? 2 : 0;    // x hi, lo, hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ts(tmem_o, w0 + 32 * (k >> 1) + 8 * (k & 1) + w_lo,
-                          smem_desc_sw128_mn(x0 + x_sel * kXTile + k * 2048, kXTile, 1024), idesc2,
-                          (i > 0 || prod > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t d = ONLINE ? tmem_o + (k >> 1) * 128 : tmem_o;
+              const uint32_t acc = ONLINE ? ((i > 0 || prod > 0 || (k & 1)) ? 1u : 0u)
+                                          : ((i > 0 || prod > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ts(d, w0 + 32 * (k >> 1) + 8 * (k & 1) + w_lo,
+                          smem_desc_sw128_mn(x0 + x_sel * kXTile + k * 2048, kXTile, 1024), idesc2, acc);
+            }
           }
           umma_commit(bXEmpty + 8 * stage);
+          if (ONLINE) umma_commit(bODone + 8 * buf);
         }
         __syncwarp();
         if (i + 2 < T) issue_scores(i + 2);      // overwrites S/W buffer (i & 1): ordered after the MMAs above
@@ -469,11 +554,11 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     const float s_all = scale_from_absmax(p.absmax[1]);
     const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * s_all);
     const float c2 = inv * kLog2e;
-    const bool by_swept = FAMILY == MIMRL_WEIGHT_EXP && p.shift_by_swept;
+    const bool by_swept = !ONLINE && FAMILY == MIMRL_WEIGHT_EXP && p.shift_by_swept;
     // exp family: w * 2^14 = ex2((acc*inv - shift) * log2e + 14); acc*inv is exact (power of two) and the
     // subtraction happens at score magnitude, so the dominant weights keep full fp32 accuracy
     float shift_row = 0.f;
-    if (FAMILY == MIMRL_WEIGHT_EXP && !p.shift_by_swept) shift_row = row_ok ? p.shift[row0 + r] : 0.f;
+    if (!ONLINE && FAMILY == MIMRL_WEIGHT_EXP && !p.shift_by_swept) shift_row = row_ok ? p.shift[row0 + r] : 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     // column shifts of the current tile, staged once per tile (double-buffered) instead of 64 global loads
@@ -483,12 +568,14 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       const int gc = t0 * 64 + et;
       sh_next = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
     }
-    const bool want_rsum = p.rsum_part != nullptr;
+    const bool want_rsum = ONLINE || p.rsum_part != nullptr;
     // weights are carried as w * 2^wexp in fp16 hi/lo.  With an exact shift w <= 1 and 2^14 uses the whole fp16 range;
     // the fused forward's reference point is approximate (w can exceed 1), so it leaves 2^6 of headroom, and the
     // exponent is capped so that even a wildly wrong reference point cannot overflow fp16.
-    const float wexp = (FAMILY == MIMRL_WEIGHT_EXP && want_rsum) ? 10.f : (float)kWExp;
-    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    const float wexp = ONLINE ? kOnlineWExp : ((FAMILY == MIMRL_WEIGHT_EXP && want_rsum) ? 10.f : (float)kWExp);
+    float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float ref = -INFINITY;                    // ONLINE: running reference point of this row (natural score units)
+    const uint32_t tmem_og = tmem_o + (ONLINE ? wg * 128 : 0);
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1;
       const int col0 = (t0 + i) * 64;
@@ -508,50 +595,54 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       uint32_t v[32];
       tmem_ld32(tcol, v);
       tmem_ld_wait();
+      if (ONLINE) {
+        // masked entries (past the batch, or the excluded diagonal) become -inf: weight 0, ignored by the maximum
+        if (!clean) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = col0 + wg * 32 + j;
+            if (!(gc < p.n_all && (p.include_diag || gc != gr))) v[j] = __float_as_uint(-INFINITY);
+          }
+        }
+        float mx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(v[u]);
+#pragma unroll
+        for (int j = 4; j < 32; j += 4)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(v[j + u]));
+        const float cand = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * inv;     // exact: inv is a power of two
+        const bool need = cand > ref + kOnlineTau;            // also the first finite tile (ref = -inf); false for -inf
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2((ref - cand) * kLog2e) : 1.f;                      // ref = -inf -> 0
+          if (i > 0) {
+            // the W.X MMAs of tile i-1 were the last to add into this accumulator; tile i's wait for our weights
+            mbar_wait(bODone + 8 * (buf ^ 1), ((i - 1) >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t o[32];
+              tmem_ld32(tmem_og + lane_off + ch * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+              tmem_st32(tmem_og + lane_off + ch * 32, o);
+            }
+            tmem_st_wait();
+          }
+          rs2[0].x *= f, rs2[0].y *= f, rs2[1].x *= f, rs2[1].y *= f;
+          if (need) ref = cand;
+        }
+      }
+      const float ref_use = ONLINE ? (ref > -INFINITY ? ref : 0.f) : shift_row;
       uint32_t hi[16], lo[16];
       const float4 *sh4 = reinterpret_cast<const float4 *>(sh_smem + buf * 64 + wg * 32);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float shv[4] = {shift_row, shift_row, shift_row, shift_row};
-        if (by_swept) {
-          const float4 t4 = sh4[j >> 2];
-          shv[0] = t4.x, shv[1] = t4.y, shv[2] = t4.z, shv[3] = t4.w;
-        }
-        float w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float a = __uint_as_float(v[j + u]);
-          float wv;
-          if (FAMILY == MIMRL_WEIGHT_EXP) wv = ex2(fminf(fmaf(fmaf(a, inv, -shv[u]), kLog2e, wexp), 15.9f));
-          else wv = __fdividef(16384.f, 1.f + ex2(-a * c2));
-          if (!clean) {
-            const int gc = col0 + wg * 32 + j + u;
-            if (!(gc < p.n_all && (p.include_diag || gc != gr))) wv = 0.f;
-          }
-          w[u] = wv;
-          if (want_rsum) {                      // the statistic always leaves the diagonal out
-            float add = wv;
-            if (!clean_stat) {
-              const int gc = col0 + wg * 32 + j + u;
-              if (gc == gr || gc >= p.n_all) add = 0.f;
-            }
-            rs[u] += add;
-          }
-        }
-        // hi = w truncated to 11 significant bits (exactly representable in fp16), lo = w - hi
-        float wh[4], wl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          wh[u] = __uint_as_float(__float_as_uint(w[u]) & 0xFFFFE000u);
-          wl[u] = w[u] - wh[u];
-        }
-        const __half2 h0 = __floats2half2_rn(wh[0], wh[1]), h1 = __floats2half2_rn(wh[2], wh[3]);
-        const __half2 l0 = __floats2half2_rn(wl[0], wl[1]), l1 = __floats2half2_rn(wl[2], wl[3]);
-        hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h0);
-        hi[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&h1);
-        lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l0);
-        lo[(j >> 1) + 1] = *reinterpret_cast<const uint32_t *>(&l1);
-      }
+      if (clean && clean_stat)
+        weights_of_tile<FAMILY, ONLINE, false>(v, hi, lo, rs2, inv, c2, wexp, ref_use, sh4, by_swept, want_rsum,
+                                               col0 + wg * 32, gr, p.n_all, p.include_diag != 0);
+      else
+        weights_of_tile<FAMILY, ONLINE, true>(v, hi, lo, rs2, inv, c2, wexp, ref_use, sh4, by_swept, want_rsum,
+                                              col0 + wg * 32, gr, p.n_all, p.include_diag != 0);
       tmem_st16(tcol, hi);
       tmem_st16(tcol + 16, lo);
       tmem_st_wait();
@@ -559,33 +650,98 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(bWFull + 8 * buf);
     }
-    if (want_rsum && row_ok)
-      p.rsum_part[(size_t)(split * 2 + wg) * p.n_own + row0 + r] = ((rs[0] + rs[1]) + (rs[2] + rs[3])) * ex2(-wexp);
-    if (T > 0) {
-      mbar_wait(bOFull, 0);
-      tc_fence_after();
-      const float oscale = ex2(-wexp) / s_all;
-#pragma unroll 1
-      for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem_o + lane_off + ch * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + ch * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(v[4 * j]) * oscale, __uint_as_float(v[4 * j + 1]) * oscale,
-                               __uint_as_float(v[4 * j + 2]) * oscale, __uint_as_float(v[4 * j + 3]) * oscale);
-        }
+    const float rs_tot = ((rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y)) * ex2(-wexp);
+    if (ONLINE) {
+      // merge the two warpgroups' references: both scale their sums to R = max(ref_0, ref_1)
+      sh_x[wg * 128 + r] = ref;
+      sh_x[256 + wg * 128 + r] = rs_tot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float ref0 = sh_x[r], ref1 = sh_x[128 + r];
+      const float R = fmaxf(ref0, ref1);
+      const float f0 = ref0 > -INFINITY ? ex2((ref0 - R) * kLog2e) : 0.f;
+      const float f1 = ref1 > -INFINITY ? ex2((ref1 - R) * kLog2e) : 0.f;
+      if (wg == 0 && row_ok) {
+        p.rsum_part[(size_t)split * p.n_own + row0 + r] = sh_x[256 + r] * f0 + sh_x[384 + r] * f1;
+        p.ref_part[(size_t)split * p.n_own + row0 + r] = R;
       }
-    } else if (row_ok) {
-      float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + wg * 64);
-      for (int j = 0; j < 16; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (T > 0) {
+        mbar_wait(bOFull, 0);
+        tc_fence_after();
+        const float os = ex2(-wexp) / s_all;
+        const float g0 = f0 * os, g1 = f1 * os;
+#pragma unroll 1
+        for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tmem_o + lane_off + ch * 32, v0);
+          tmem_ld32(tmem_o + 128 + lane_off + ch * 32, v1);
+          tmem_ld_wait();
+          if (row_ok) {
+            float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(fmaf(__uint_as_float(v0[4 * j]), g0, __uint_as_float(v1[4 * j]) * g1),
+                                 fmaf(__uint_as_float(v0[4 * j + 1]), g0, __uint_as_float(v1[4 * j + 1]) * g1),
+                                 fmaf(__uint_as_float(v0[4 * j + 2]), g0, __uint_as_float(v1[4 * j + 2]) * g1),
+                                 fmaf(__uint_as_float(v0[4 * j + 3]), g0, __uint_as_float(v1[4 * j + 3]) * g1));
+          }
+        }
+      } else if (row_ok) {
+        float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + wg * 64);
+        for (int j = 0; j < 16; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      if (want_rsum && row_ok) p.rsum_part[(size_t)(split * 2 + wg) * p.n_own + row0 + r] = rs_tot;
+      if (T > 0) {
+        mbar_wait(bOFull, 0);
+        tc_fence_after();
+        const float oscale = ex2(-wexp) / s_all;
+#pragma unroll 1
+        for (int ch = wg * 2; ch < wg * 2 + 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem_o + lane_off + ch * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(__uint_as_float(v[4 * j]) * oscale, __uint_as_float(v[4 * j + 1]) * oscale,
+                                 __uint_as_float(v[4 * j + 2]) * oscale, __uint_as_float(v[4 * j + 3]) * oscale);
+          }
+        }
+      } else if (row_ok) {
+        float4 *o = reinterpret_cast<float4 *>(p.part + ((size_t)split * p.n_own + row0 + r) * 128 + wg * 64);
+        for (int j = 0; j < 16; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ONLINE: merge the column splits of a row, each referred to its own reference point:
+// R = max_s ref_s; out = sum_s exp(ref_s - R) part_s; row_sum likewise; row_ref = R (0 when the row saw nothing)
+__global__ void online_reduce_tc_kernel(const float *__restrict__ part, const float *__restrict__ rsum_part,
+                                        const float *__restrict__ ref_part, int n_splits, int n_own, int embed,
+                                        float *__restrict__ out, float *__restrict__ row_sum, float *__restrict__ row_ref) {
+  const size_t total = (size_t)n_own * embed;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / embed), e = (int)(idx - (size_t)r * embed);
+    float R = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) R = fmaxf(R, ref_part[(size_t)s * n_own + r]);
+    float a = 0.f, rs = 0.f;
+    for (int s = 0; s < n_splits; ++s) {
+      const float rf = ref_part[(size_t)s * n_own + r];
+      const float f = rf > -INFINITY ? __expf(rf - R) : 0.f;
+      a = fmaf(f, part[((size_t)s * n_own + r) * 128 + e], a);
+      rs = fmaf(f, rsum_part[(size_t)s * n_own + r], rs);
+    }
+    out[idx] = a;
+    if (e == 0) {
+      row_sum[r] = rs;
+      row_ref[r] = R > -INFINITY ? R : 0.f;
+    }
+  }
 }
 
 __global__ void rsum_reduce_tc_kernel(const float *__restrict__ part, int n_parts, int n_own, float *__restrict__ out) {
@@ -613,7 +769,7 @@ __global__ void wsum_reduce_tc_kernel(const float *__restrict__ part, int n_spli
 
 // ------------------------------------------------------------------ host ----
 struct TcLayout {
-  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_part, off_rsum, total;
+  size_t off_absmax, off_own_hi, off_own_lo, off_all_hi, off_all_lo, off_part, off_rsum, off_ref, total;
 };
 
 
@@ -636,6 +792,8 @@ TcLayout tc_layout(int n_own, int n_all) {
   o += align256((size_t)tc_max_splits() * n_own * 128 * sizeof(float));
   L.off_rsum = o;
   o += align256((size_t)2 * tc_max_splits() * n_own * sizeof(float));
+  L.off_ref = o;
+  o += align256((size_t)tc_max_splits() * n_own * sizeof(float));
   L.total = o;
   return L;
 }
@@ -751,13 +909,15 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   p.part = reinterpret_cast<float *>(ws + L.off_part);
   p.rsum_part = row_sum ? reinterpret_cast<float *>(ws + L.off_rsum) : nullptr;
   dim3 grid(row_tiles, splits);
+  p.ref_part = nullptr;
   if (family == MIMRL_WEIGHT_EXP) {
-    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);
-    sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP><<<grid, kTcThreads, kRingSmem, st>>>(m_x_hi, m_x_lo, p);
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kWsumSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, false><<<grid, kTcThreads, kWsumSmem, st>>>(m_x_hi, m_x_lo, p);
   } else {
-    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kRingSmem);
-    sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID><<<grid, kTcThreads, kRingSmem, st>>>(m_x_hi, m_x_lo, p);
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kWsumSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_SIGMOID, false><<<grid, kTcThreads, kWsumSmem, st>>>(m_x_hi, m_x_lo, p);
   }
   if (check_launch("sep_wsum_tc")) return 1;
   const size_t total = (size_t)n_own * embed;
@@ -770,6 +930,46 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
     return check_launch("rsum_reduce_tc");
   }
   return 0;
+}
+
+// Online-softmax forward (mimrl_sep_online_forward): one sweep, no reference point supplied.
+int sep_online_forward_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
+                          int include_diag, float *row_ref, float *wsum, float *row_sum, void *workspace, size_t ws_bytes,
+                          cudaStream_t st) {
+  const TcLayout L = tc_layout(n_own, n_all);
+  MIMRL_REQUIRE(ws_bytes >= L.total, "sep_online_forward(tcgen05): workspace too small");
+  unsigned char *ws = (unsigned char *)workspace;
+  if (tc_prepass(own, all, n_own, n_all, embed, L, ws, st)) return 1;
+  CUtensorMap m_x_hi, m_x_lo;
+  if (make_map(&m_x_hi, ws + L.off_all_hi, 128, n_all, 128, 64)) return 1;
+  if (make_map(&m_x_lo, ws + L.off_all_lo, 128, n_all, 128, 64)) return 1;
+  const int row_tiles = ceil_div(n_own, 128), col_tiles = ceil_div(n_all, 64);
+  const int splits = tc_pick_splits(row_tiles, col_tiles);
+  WsumParams p;
+  p.n_own = n_own;
+  p.n_all = n_all;
+  p.own_offset = own_offset;
+  p.tiles_per_split = ceil_div(col_tiles, splits);
+  p.include_diag = include_diag;
+  p.shift_by_swept = 0;
+  p.own_hi = reinterpret_cast<const __half *>(ws + L.off_own_hi);
+  p.own_lo = reinterpret_cast<const __half *>(ws + L.off_own_lo);
+  p.absmax = reinterpret_cast<const unsigned *>(ws + L.off_absmax);
+  p.shift = nullptr;
+  p.part = reinterpret_cast<float *>(ws + L.off_part);
+  p.rsum_part = reinterpret_cast<float *>(ws + L.off_rsum);
+  p.ref_part = reinterpret_cast<float *>(ws + L.off_ref);
+  dim3 grid(row_tiles, splits);
+  cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)kWsumSmem);
+  sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, true><<<grid, kTcThreads, kWsumSmem, st>>>(m_x_hi, m_x_lo, p);
+  if (check_launch("sep_wsum_tc(online)")) return 1;
+  const size_t total = (size_t)n_own * embed;
+  int blocks = (int)((total + 255) / 256);
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  online_reduce_tc_kernel<<<blocks, 256, 0, st>>>(p.part, p.rsum_part, p.ref_part, splits, n_own, embed, wsum, row_sum,
+                                                  row_ref);
+  return check_launch("online_reduce_tc");
 }
 
 }  // namespace mimrl

@@ -151,10 +151,10 @@ class _SeparableBoundFused(torch.autograd.Function):
     """Same contract as ``_SeparableBound`` for the exp-family bounds when a gradient is wanted.
 
     The backward of these bounds weights row i's swept embeddings by exp(S_ij - shift_i); up to a per-row factor
-    that is exp(S_ij - ref_i) for ANY reference point ref_i.  So the forward takes an approximate row maximum from a
-    cheap pre-pass (one fp16 product, no exponentials: MIMRL_STAT_MAXONLY) and then ONE sweep (mimrl_sep_fused_forward)
-    returns both the exact row statistic sum_{j != i} exp(S_ij - ref_i) and O_i = sum_j exp(S_ij - ref_i) x_j.  The
-    backward rescales O_i and only has to sweep for the swept side: 1/3 + 2 + 2 tensor-core units instead of 1 + 2 + 2."""
+    that is exp(S_ij - ref_i) for ANY reference point ref_i.  So the forward is ONE sweep (mimrl_sep_online_forward):
+    the kernel keeps a running reference per row (online softmax, accumulators rescaled lazily) and returns the
+    reference, the exact row statistic sum_{j != i} exp(S_ij - ref_i) and O_i = sum_j exp(S_ij - ref_i) x_j.  The
+    backward rescales O_i and only has to sweep for the swept side: 2 + 2 tensor-core units instead of 1 + 2 + 2."""
 
     @staticmethod
     def forward(ctx, x_emb, y_emb, log_baseline, bound_id, impl, rb):
@@ -176,20 +176,15 @@ class _SeparableBoundFused(torch.autograd.Function):
             ymu = y_emb @ mu
         else:
             swept, ymu = all_x, None
-        lift = (2.0 ** -10) * y_emb.norm(dim=1) * swept.norm(dim=1).max()
-        pre = torch.empty(4, n_own, dtype=torch.float32, device=dev)      # approx off-diag max, -, -, diag of y.swept
-        L.check(L.lib.mimrl_sep_row_stats(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, L.STAT_MAXONLY, impl,
-                                          L.ptr(pre[0]), L.ptr(pre[1]), L.ptr(pre[2]), L.ptr(pre[3]), L.ptr(ws), ws.numel(),
-                                          st))
-        ref = torch.maximum(pre[0], pre[3]) if inc else pre[0]
-        # the one-product scores are off by at most 2^-11 |y_i| |x_j| (11-bit operands, Cauchy-Schwarz): lift the
-        # reference point by twice that, so it is a true upper bound of the row and every weight stays <= 1
-        ref = ref + lift
-        ref = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref)).contiguous()
+        # ONE sweep, no reference point supplied: the kernel keeps a running reference per row (online softmax with
+        # lazily rescaled accumulators) and returns it together with the sums referred to it
         wsum = torch.empty(n_own, embed, dtype=torch.float32, device=dev)
         stats = torch.zeros(4, n_own, dtype=torch.float32, device=dev)      # max, sum, softplus, diag (true S units)
-        L.check(L.lib.mimrl_sep_fused_forward(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, inc, L.ptr(ref),
-                                              L.ptr(wsum), L.ptr(stats[1]), L.ptr(ws), ws.numel(), st))
+        ref = torch.empty(n_own, dtype=torch.float32, device=dev)
+        diag = torch.empty(n_own, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_sep_online_forward(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, inc, L.ptr(ref),
+                                               L.ptr(wsum), L.ptr(stats[1]), L.ptr(diag), L.ptr(ws), ws.numel(), st))
+        pre = (None, None, None, diag)
         stats[0] = ref if ymu is None else ref + ymu
         stats[3] = pre[3] if ymu is None else pre[3] + ymu
         base = None
@@ -251,32 +246,9 @@ def separable_bound(x_emb, y_emb, bound_type, log_baseline=None, rowblock=None, 
             and (x_emb.requires_grad or y_emb.requires_grad)):
         n_own = y_emb.shape[0]
         n_all = rowblock.n_all if rowblock is not None else n_own
-        if (L.lib.mimrl_sep_selected_impl(n_own, n_all, y_emb.shape[1], impl) == L.IMPL_TCGEN05
-                and _fused_reference_is_safe(x_emb, y_emb, rowblock)):
+        if L.lib.mimrl_sep_selected_impl(n_own, n_all, y_emb.shape[1], impl) == L.IMPL_TCGEN05:
             return _SeparableBoundFused.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
     return _SeparableBound.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
-
-
-FUSED_MAX_LIFT = 8.0
-
-
-def _fused_reference_is_safe(x_emb, y_emb, rowblock):
-    """The fused forward carries exp(S_ij - ref_i) as w * 2^10 in an fp16 hi/lo pair, with ref_i lifted above the
-    approximate row maximum by up to 2^-10 |y_i| max_j |x_j| (see _SeparableBoundFused).  A row's largest weight is
-    then >= exp(-lift): beyond a lift of ~17 it would be fp16-subnormal and the owned-row gradient would lose its
-    precision while the value still looked right.  Embedding norms that large (|y||x| > 8000) only occur with
-    exploding scores; such a batch takes the exact three-sweep path instead.  The decision needs one scalar on the host
-    (a stream sync); while a CUDA graph is being captured no sync is possible, and the small batches graphs are used
-    for gain nothing from the fused forward, so capture always takes the exact path."""
-    if torch.cuda.is_current_stream_capturing():
-        return False
-    with torch.no_grad():
-        norms = torch.stack([y_emb.detach().norm(dim=1).max(), x_emb.detach().norm(dim=1).max()])
-        if rowblock is not None and rowblock.sharded:          # every rank must take the same path
-            torch.distributed.all_reduce(norms, op=torch.distributed.ReduceOp.MAX, group=rowblock.group)
-        ny, nx = (float(v) for v in norms.cpu())
-        # InfoNCE sweeps the centred embeddings: |x_j - mean| <= 2 max |x_j|
-        return 2.0 * (2.0 ** -10) * ny * nx <= FUSED_MAX_LIFT
 
 
 class _ScoresBound(torch.autograd.Function):

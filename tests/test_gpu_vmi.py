@@ -200,9 +200,9 @@ def test_full_size_properties():
 @pytest.mark.parametrize("bound", ["infonce", "dv", "mine", "tuba", "nwj"])
 @pytest.mark.parametrize("B,scale", [(700, 1.0), (1500, 6.0), (900, 40.0)])
 def test_fused_forward_matches_three_sweep_path(bound, B, scale, monkeypatch):
-    """mimrl_sep_fused_forward (approximate-max pre-pass + one sweep for the statistics and the owned-row gradient
-    sum) against the exact-statistics path it replaces, and both against the float64 oracle.  scale = 6 makes the
-    scores large (|S| ~ 100s), where the one-product row maxima are off by ~0.1 and must not matter."""
+    """The one-sweep forward (mimrl_sep_online_forward: online reference point, statistics and the owned-row gradient
+    sum together) against the exact-statistics path it replaces, and both against the float64 oracle.  scale = 6 makes
+    the scores large (|S| ~ 100s), scale = 40 gives |S| ~ 1e4."""
     import mimrl_b200.vmi as V
     if bound not in ("infonce", "dv") and scale > 10:
         pytest.skip("mine / tuba / nwj exponentiate the scores unshifted (VMI.py:148-159, Model.py:121-124): at |S| ~ 1e4 "
@@ -260,6 +260,53 @@ def test_fused_forward_abi_row_block(n_own, n_all, offset, inc):
     assert rel_err(rsum.cpu().numpy(), Woff.sum(axis=1)) < 5e-5          # fp32 ulp of a score ~ 40 is 4e-6
     want = (W if inc else Woff) @ swept.astype(np.float64)
     assert rel_err(wsum.cpu().numpy(), want) < 5e-5
+
+
+@pytest.mark.parametrize("n_own,n_all,offset,inc,ramp", [(300, 300, 0, 1, 0.0), (200, 517, 130, 0, 0.0), (129, 700, 571, 1, 0.05),
+                                                         (256, 4096, 1024, 1, 0.02), (140, 20000, 7000, 0, 0.004),
+                                                         (1, 1, 0, 0, 0.0), (2, 3, 1, 1, 0.0)])
+def test_online_forward_abi_row_block(n_own, n_all, offset, inc, ramp):
+    """mimrl_sep_online_forward straight through the C ABI against float64: the returned reference point lies within
+    kOnlineTau (4.5) below the true row maximum, the off-diagonal weight sum and the weighted sum (diagonal included
+    iff include_diag) are exact relative to it.  ramp > 0 scales the swept rows up along the batch, so the running
+    maximum keeps growing and the accumulators are rescaled many times during one sweep; the single-pair and
+    empty-off-diagonal corners (n_all = 1) are included."""
+    from mimrl_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    E = 128
+    own = rng.standard_normal((n_own, E)).astype(np.float32)
+    swept = rng.standard_normal((n_all, E)).astype(np.float32)
+    if ramp:
+        swept *= (1.0 + ramp * np.arange(n_all, dtype=np.float32))[:, None] ** 0.5
+    T = lambda a: torch.tensor(a, device=dev())
+    o, a = T(own), T(swept)
+    ws_b = L.lib.mimrl_sep_workspace_bytes(n_own, n_all, E)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device=dev())
+    ref, rsum, diag = (torch.empty(n_own, device=dev()) for _ in range(3))
+    wsum = torch.empty(n_own, E, device=dev())
+    L.check(L.lib.mimrl_sep_online_forward(L.ptr(o), L.ptr(a), n_own, n_all, E, offset, inc, L.ptr(ref), L.ptr(wsum),
+                                           L.ptr(rsum), L.ptr(diag), L.ptr(ws), ws_b, L.stream()))
+    S = own.astype(np.float64) @ swept.astype(np.float64).T
+    rows = np.arange(n_own)
+    seen = S.copy()
+    if not inc:
+        seen[rows, offset + rows] = -np.inf
+    ref = ref.cpu().numpy().astype(np.float64)
+    top = seen.max(axis=1)
+    live = np.isfinite(top)
+    assert np.all(ref[live] <= top[live] + 1e-3 * np.abs(top[live]).clip(1.0)) and np.all(ref[live] >= top[live] - 4.5 - 1e-3)
+    assert np.all(ref[~live] == 0.0)
+    assert np.allclose(diag.cpu().numpy(), S[rows, offset + rows], rtol=1e-5, atol=1e-4)
+    W = np.exp(S - ref[:, None])
+    Woff = W.copy()
+    Woff[rows, offset + rows] = 0.0
+    want_sum = Woff.sum(axis=1)
+    assert np.abs(rsum.cpu().numpy() - want_sum).max() <= 5e-5 * max(want_sum.max(), 1e-30)
+    want = (W if inc else Woff) @ swept.astype(np.float64)
+    if np.abs(want).max() > 0:
+        assert rel_err(wsum.cpu().numpy(), want) < 5e-5
+    else:
+        assert np.all(wsum.cpu().numpy() == 0)
 
 
 def test_fused_forward_one_sided_gradients():
