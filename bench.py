@@ -651,7 +651,13 @@ def run_gpu(args):
     flops_wsum = 2.0 * EMBED * n_own * n_all              # algorithmic: one P.X contraction (score recompute not counted)
     achieved = flops_wsum / (ms_wsum * 1e-3) / 1e12
     impl_name = "tcgen05 fp16x3 split (fp32-class)" if tc_path else "fp32 FFMA (CUDA cores)"
-    ncu = ncu_record("sep_wsum_tc_kernel") if (world == 1 and B == B_SINGLE) else {}
+    # the committed ncu --set full capture of the two instantiations a step launches (online forward, swept-side sweep)
+    ncu = {}
+    if world == 1 and B == B_SINGLE:
+        recs = [ncu_record("sep_wsum_tc_kernel<0, 1>"), ncu_record("sep_wsum_tc_kernel<0, 0>")]
+        if all(r.get("dram_bytes") is not None for r in recs):
+            ncu = {"dram_bytes": sum(r["dram_bytes"] for r in recs) / 2,
+                   "tensor_pipe_active_pct": sum(r["tensor_pipe_active_pct"] for r in recs) / 2, "source": recs[0].get("source")}
     roofline = {
         "kernel": "sep_wsum_tc_kernel (2 launches per step: mimrl_sep_online_forward = online-softmax forward statistics + "
                   "owned-row gradient sum, and mimrl_sep_weighted_sum = swept-side gradient sweep); ms_per_launch is their mean",

@@ -174,6 +174,15 @@ int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, 
 int mimrl_gemm_split_blocked(const void *a_split, const void *b_split, int M, int N, int K, float *C, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* The same three products on the CUDA cores (exact fp32 FFMA), for the layers outside the tensor-core envelope: small
+ * batches (the reference trains at bs = 128, README.md:16-26) and the 1- / 2-wide heads of the unnormalized baseline
+ * (VMI.py:86-89) and the CMI classifier (Model.py:52-57).  Modes, a_mask, bias and relu as mimrl_gemm_f32x3; colsum
+ * (nullable, mode 2 only): colsum[m] += sum_k A'[k, m] of the masked matrix, i.e. the bias gradient. */
+size_t mimrl_linear_small_workspace_bytes(int mode, int M, int N, int K);
+int mimrl_linear_small(int mode, const float *A, const float *a_mask, const float *B, int M, int N, int K,
+                       const float *bias, int relu, float *C, float *colsum, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 /* ------------------------------------------------------------------------
  * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of
  * prod_knn_sample (Model.py:75-106), i.e. sklearn NearestNeighbors.kneighbors.

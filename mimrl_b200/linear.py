@@ -4,14 +4,14 @@ both backward products, with bias + ReLU and the ReLU mask fused in.
 
 ``mlp_apply(seq, x)`` evaluates an ``nn.Sequential`` of ``nn.Linear`` / ``nn.ReLU``
 (the module layout of VMI.py:13-22, kept for state_dict compatibility) through
-these kernels.  Layers outside the kernel's envelope (fewer than 512 rows, or an
-output / input width below 32 such as the 1- and 2-wide heads) are plain library
-GEMMs (``F.linear``)."""
+these kernels.  Layers outside the tensor-core envelope (fewer than 512 rows -- the
+reference trains at batch 128 -- or an output / input width below 32 such as the
+1- and 2-wide heads) run on the CUDA-core kernels of csrc/linear_small.cu
+(``mimrl_linear_small``, exact fp32).  No library GEMM is left on the path."""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib as L
 
@@ -68,6 +68,43 @@ class _LinearTC(torch.autograd.Function):
         dzs = _split(gy, y if relu else None, gb)
         gx = _gemm_split(1, dzs, wsp, M, K, N) if ctx.needs_input_grad[0] else None       # dz [M,N] . W [N,K]
         gw = _gemm_split(2, dzs, xs, N, K, M) if ctx.needs_input_grad[1] else None        # dz^T [N,M] . x [M,K]
+        return gx, gw, gb, None
+
+
+def _small(mode, A, mask, B, M, N, K, bias=None, relu=False, colsum=None):
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    ws = torch.empty(L.lib.mimrl_linear_small_workspace_bytes(mode, M, N, K), dtype=torch.uint8, device=A.device)
+    L.check(L.lib.mimrl_linear_small(mode, L.ptr(A), L.ptr(mask), L.ptr(B), M, N, K, L.ptr(bias), int(relu), L.ptr(C),
+                                     L.ptr(colsum), L.ptr(ws), ws.numel(), L.stream()))
+    return C
+
+
+class _LinearSmall(torch.autograd.Function):
+    """x [M,K], w [N,K] on the CUDA-core kernels (csrc/linear_small.cu): forward with bias + ReLU fused, backward with
+    the ReLU mask applied on load and the bias gradient accumulated by the weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x, w = L.f32(x), L.f32(w)
+        b = L.f32(b) if b is not None else None
+        M, K = x.shape
+        N = w.shape[0]
+        y = _small(0, x, None, w, M, N, K, b, relu)
+        ctx.save_for_backward(x, w, y if relu else x.new_empty(0))
+        ctx.cfg = (relu, b is not None, M, N, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        relu, has_b, M, N, K = ctx.cfg
+        gy = L.f32(gy)
+        mask = y if relu else None
+        gx = _small(1, gy, mask, w, M, K, N) if ctx.needs_input_grad[0] else None         # dz [M,N] . W [N,K]
+        gb = torch.zeros(N, dtype=torch.float32, device=gy.device) if has_b and ctx.needs_input_grad[2] else None
+        gw = None
+        if ctx.needs_input_grad[1] or gb is not None:
+            gw = _small(2, gy, mask, x, N, K, M, colsum=gb)                                # dz^T [N,M] . x [M,K]
         return gx, gw, gb, None
 
 
@@ -141,8 +178,9 @@ def linear(x, weight, bias=None, relu=False):
     if (x.dim() == 2 and x.is_cuda and x.shape[0] >= MIN_ROWS and weight.shape[0] >= MIN_WIDTH
             and weight.shape[1] >= MIN_WIDTH):
         return _LinearTC.apply(x, weight, bias, relu)
-    y = F.linear(x, weight, bias)
-    return F.relu(y) if relu else y
+    if x.dim() != 2:
+        return linear(x.reshape(-1, x.shape[-1]), weight, bias, relu).reshape(*x.shape[:-1], weight.shape[0])
+    return _LinearSmall.apply(x, weight, bias, relu)
 
 
 def mlp_apply(seq: nn.Sequential, x):

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import rowblock as RB
-from .linear import mlp_apply
+from .linear import linear, mlp_apply
 
 _ACTIVATIONS = {  # Utils.py:70-82 get_activation
     "elu": nn.ELU, "gelu": nn.GELU, "hardshrink": nn.Hardshrink, "hardtanh": nn.Hardtanh,
@@ -498,8 +498,8 @@ class CriticModel(nn.Module):
         (W1 [x;y] = W1x x + W1y y) so the B^2 x (dx+dy) pair matrix is never built."""
         first = self.MLP_f[0]
         dx = x_rows.shape[1]
-        u = F.linear(x_rows, first.weight[:, :dx], first.bias)
-        v = F.linear(y, first.weight[:, dx:])
+        u = linear(x_rows, first.weight[:, :dx], first.bias)
+        v = linear(y, first.weight[:, dx:])
         if self._fused_pairs():
             f = self.MLP_f
             return _ConcatPairMLP.apply(u, v, f[2].weight, f[2].bias, f[4].weight, f[4].bias, f[6].weight, f[6].bias)
