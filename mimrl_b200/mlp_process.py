@@ -105,12 +105,17 @@ class _AxisMix(torch.autograd.Function):
                                             L.ptr(s_u), L.ptr(gln[0]), L.ptr(gln[1]), L.stream()))
         x3 = x.view(outer, A, inner)
         u3 = s_u if ln_first else x3
-        # weight gradients: plain contractions over (outer, inner) of tensors already laid out like x
-        gw2 = torch.einsum("oqi,ohi->qh", s_gz, s_h)
-        gw1 = torch.einsum("ohi,oai->ha", s_gpre, u3)
-        gb2 = s_gz.sum(dim=(0, 2)) if b2 is not None else None
-        gb1 = s_gpre.sum(dim=(0, 2)) if b1 is not None else None
-        gwres = torch.einsum("oqi,oai->qa", s_gz, x3) if wres is not None else None
+        # weight gradients: contractions over the fibres (outer, inner) on the CUDA-core product kernel
+        # (csrc/linear_small.cu, mode 2: C[M,N] = A[R,M]^T . B[R,N]); the bias gradients ride along as column sums
+        from .linear import _small
+        rows = lambda t: t.permute(0, 2, 1).reshape(-1, t.shape[1]).contiguous()          # [outer, F, inner] -> [R, F]
+        r_gz, r_h, r_gpre, r_u = rows(s_gz), rows(s_h), rows(s_gpre), rows(u3)
+        R = r_gz.shape[0]
+        gb2 = torch.zeros(A2, device=dev) if b2 is not None else None
+        gb1 = torch.zeros(H, device=dev) if b1 is not None else None
+        gw2 = _small(2, r_gz, None, r_h, A2, H, R, colsum=gb2)
+        gw1 = _small(2, r_gpre, None, r_u, H, A, R, colsum=gb1)
+        gwres = _small(2, r_gz, None, r_u if not ln_first else rows(x3), A2, A, R) if wres is not None else None
         return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
 
 

@@ -128,7 +128,7 @@ class _SeparableBound(torch.autograd.Function):
             # shift): algebraically identical, but the cancellation no longer happens in floating point.
             mu = all_x.mean(dim=0)
             swept = (all_x - mu).contiguous()
-            shift_own = (shift_own - y_emb @ mu).contiguous()
+            shift_own = (shift_own - (y_emb * mu).sum(dim=1)).contiguous()
         dy = torch.empty_like(y_emb)
         L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(y_emb), L.ptr(swept), n_own, n_all, embed, rb.offset, fam, inc,
                                              L.ptr(shift_own), 0, L.ptr(coef), L.ptr(dcoef_own), impl, L.ptr(dy),
@@ -173,7 +173,7 @@ class _SeparableBoundFused(torch.autograd.Function):
         if centred:
             mu = all_x.mean(dim=0)
             swept = (all_x - mu).contiguous()
-            ymu = y_emb @ mu
+            ymu = (y_emb * mu).sum(dim=1)
         else:
             swept, ymu = all_x, None
         # ONE sweep, no reference point supplied: the kernel keeps a running reference per row (online softmax with
@@ -517,7 +517,7 @@ class CriticModel(nn.Module):
     def forward(self, x, y):
         if self.critic_type == 'separate':
             x_, y_ = self.embed(x, y)
-            return torch.matmul(y_, x_.t())
+            return linear(y_, x_)                      # scores = y_ @ x_.T (VMI.py:57) on the repo's product kernels
         if self.critic_type == 'concat':
             if self._fused_pairs():
                 return self._concat_rows(x, y)

@@ -115,3 +115,57 @@ def test_fused_mlp4_vs_float64(M, d_in, d_out):
     assert rel(xt.grad, x64.grad) < 1e-4
     for (n, p), p64 in zip(m.named_parameters(), m64.parameters()):
         assert rel(p.grad, p64.grad) < 1e-4, n
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (128, 1, 256), (96, 2, 256), (1, 1, 1), (130, 70, 33), (3000, 2, 256),
+                                   (65536, 1, 256), (17, 300, 1000)])
+def test_small_linear_modes_against_float64(M, N, K):
+    """csrc/linear_small.cu (CUDA cores, exact fp32): the three products of a Linear layer for small batches and the
+    1- / 2-wide heads, with bias + ReLU, the ReLU mask on load and the fused bias gradient (colsum)."""
+    from mimrl_b200.linear import _small
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bt = torch.randn(N, K, device="cuda", generator=g) * 0.3
+    bias = torch.randn(N, device="cuda", generator=g)
+    want = A.double() @ Bt.double().t() + bias.double()
+    assert rel(_small(0, A, None, Bt, M, N, K, bias, False), want) < 2e-6
+    assert rel(_small(0, A, None, Bt, M, N, K, bias, True), want.clamp_min(0) + 1e-30) < 2e-6
+    Bn = Bt.t().contiguous()                                       # [K, N]
+    mask = torch.randn(M, K, device="cuda", generator=g)
+    want = (A.double() * (mask > 0)) @ Bn.double()
+    assert rel(_small(1, A, mask, Bn, M, N, K), want + 1e-30) < 2e-6
+    At = torch.randn(K, M, device="cuda", generator=g)             # mode 2: contraction over the rows (K may be the batch)
+    maskt = torch.randn(K, M, device="cuda", generator=g)
+    masked = At.double() * (maskt > 0)
+    want = masked.t() @ Bn.double()
+    colsum = torch.full((M,), 0.5, device="cuda")
+    got = _small(2, At, maskt, Bn, M, N, K, colsum=colsum)
+    assert rel(got, want + 1e-30) < 5e-6
+    assert rel(colsum, masked.sum(0) + 0.5) < 5e-6                # accumulated (+=) onto what was there
+
+
+@pytest.mark.parametrize("rows,d_in,d_out", [(128, 128, 128), (96, 128, 1), (2048, 384, 2), (7, 128, 128)])
+def test_small_batch_mlp_stack_matches_torch(rows, d_in, d_out):
+    """The relu MLP stacks at the reference's batch size (128) and with the narrow heads (baseline: 1, CMI classifier: 2)
+    through mlp_apply vs the same modules in float64; no library GEMM is involved."""
+    from mimrl_b200.linear import mlp_apply
+    from mimrl_b200.vmi import mlps
+    torch.manual_seed(1)
+    seq = mlps(d_in, 256, d_out, 2, "relu").cuda()
+    for m in seq:
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.uniform_(m.bias, -0.1, 0.1)
+    x = torch.randn(rows, d_in, device="cuda", requires_grad=True)
+    w = torch.randn(rows, d_out, device="cuda")
+    (mlp_apply(seq, x) * w).sum().backward()
+    got = [x.grad.clone()] + [p.grad.clone() for p in seq.parameters()]
+    import copy
+    seq64 = copy.deepcopy(seq).double()
+    seq64.zero_grad()
+    x64 = x.detach().double().requires_grad_(True)
+    y64 = seq64(x64)
+    (y64 * w.double()).sum().backward()
+    want = [x64.grad] + [p.grad for p in seq64.parameters()]
+    assert rel(mlp_apply(seq, x).detach(), y64.detach()) < 1e-5
+    for a, b in zip(got, want):
+        assert rel(a, b) < 1e-5
