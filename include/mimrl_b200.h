@@ -321,6 +321,24 @@ int mimrl_concat_grad(const float *u, const float *vt, int n_own, int n_all, int
                       float *g_vt, float *g_b2, float *g_b3, float *g_w4, void *op_h1, void *op_h2, void *op_g2,
                       void *op_g3, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- concat critic fused with its bound: neither the score matrix nor dL/dscores exists in memory ----
+ * mimrl_concat_row_stats: the off-diagonal row statistics of mimrl_sep_row_stats (row_max, row_sum, row_sp; flags
+ * MIMRL_STAT_CLAMP | MIMRL_STAT_SOFTPLUS) of scores[i, j] = f([x_i, y_j]) for the owned rows, reduced inside the forward
+ * kernel; the diagonal scores come from the same MLP applied to the n_own diagonal pairs (an ordinary row batch).
+ * mimrl_concat_grad_fused: mimrl_concat_grad with g_ij = coef[0] * w(s_ij) (exp family: exp(s_ij - shift[i]); sigmoid
+ * family: sigmoid(s_ij)) for j != own_offset + i and 0 on the diagonal, formed in the kernel from the recomputed score
+ * (VMI.py:58-65 + VMI.py:136-198 in two passes over the pair tiles); g_b4[0] += sum_ij g_ij. */
+size_t mimrl_concat_stats_workspace_bytes(int hidden, int n_own, int n_all);
+int mimrl_concat_row_stats(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden, int own_offset,
+                           int flags, const float *w2, const float *b2, const float *w3, const float *b3, const float *w4,
+                           const float *b4, float *row_max, float *row_sum, float *row_sp, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int mimrl_concat_grad_fused(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden, int own_offset,
+                            const float *w2, const float *b2, const float *w3, const float *b3, const float *w4,
+                            const float *b4, int family, const float *coef, const float *shift, float *g_u, float *g_vt,
+                            float *g_b2, float *g_b3, float *g_w4, float *g_b4, void *op_h1, void *op_h2, void *op_g2,
+                            void *op_g3, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- feature heads either side of the fusion encoder (reference Model.py:466-475 and 489-507) ----
  * stack: t [bs,len_t,d], a [bs,len_a,d], v [bs,len_v,d] (len_* <= time_len) ->
  *   mean_t/a/v [bs,d] = the unmasked temporal means T_F, A_F, V_F (Model.py:466) and

@@ -86,6 +86,11 @@ _SIGS = {
     "mimrl_concat_pair_rows": (c_int64, [c_int, c_int]),
     "mimrl_concat_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _P, c_size_t, _P]),
+    "mimrl_concat_stats_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mimrl_concat_row_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                       _P, c_size_t, _P]),
+    "mimrl_concat_grad_fused": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_linear_small_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_linear_small": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "mimrl_feature_stack_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

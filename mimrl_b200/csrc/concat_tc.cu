@@ -41,6 +41,11 @@ struct ConcatParams {
   int n_own, n_all, ldv;
   long long n_tiles;
   int n_iq;              // row quads
+  // fused bound (no score matrix): row statistics in the forward, gradient weights formed in the backward
+  float *part;           // STATS: [split][n_own][3] = {max, sum exp(. - max), softplus sum} over the off-diagonal columns
+  int own_offset;        // global row index of local row 0 (the diagonal pair of row i is column own_offset + i)
+  int stat_flags;        // MIMRL_STAT_CLAMP | MIMRL_STAT_SOFTPLUS
+  int n_jb, q_per, jb_per;   // STATS tiling: column blocks, row quads per CTA (grid.x), column blocks per split (grid.y)
 };
 
 // A-operand layout inside a 256-column TMEM region: features [32c, 32c+32) keep their own 32 columns,
@@ -58,6 +63,11 @@ __device__ __forceinline__ void split32h(const float (&v)[32], uint32_t (&hi)[16
   }
 }
 
+// STATS = false: scores[i, j] are written (mimrl_concat_scores, the materialising API).
+// STATS = true:  nothing B x B leaves the SM.  Tiles run row-quad major (a warp keeps its row i over consecutive column
+//                blocks), every lane keeps an online (max, sum exp, softplus sum) of its own columns of the row, and the
+//                32 lanes are merged once per row: the off-diagonal row statistics every bound of VMI.py:136-198 needs.
+template <bool STATS>
 __global__ void __launch_bounds__(kCcThreads, 1)
 concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                   const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo,
@@ -79,9 +89,15 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
   }
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // contiguous tile range per CTA; tiles are ordered column block major so a CTA keeps its v columns hot
+  // scores: contiguous tile range per CTA, tiles ordered column block major so a CTA keeps its v columns hot.
+  // STATS: CTA (x, y) owns row quads [q0, q1) x column blocks [jb0, jb1), row-quad major.
   const long long per = (p.n_tiles + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = per * blockIdx.x, t_end = (t_begin + per < p.n_tiles) ? t_begin + per : p.n_tiles;
+  const long long t_begin = STATS ? 0 : per * blockIdx.x;
+  const int q0 = STATS ? p.q_per * blockIdx.x : 0, q1 = STATS ? min(p.n_iq, q0 + p.q_per) : 0;
+  const int jb0 = STATS ? p.jb_per * blockIdx.y : 0, jb1 = STATS ? min(p.n_jb, jb0 + p.jb_per) : 0;
+  const int njl = STATS ? jb1 - jb0 : 1;
+  const long long t_end = STATS ? (long long)max(q1 - q0, 0) * max(njl, 0)
+                                : ((t_begin + per < p.n_tiles) ? t_begin + per : p.n_tiles);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kCcStages; ++s) {
@@ -161,10 +177,11 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
     const float inv12 = 1.f / (s1 * scale_from_absmax(p.sc_w2[0])), inv23 = 1.f / (s2 * scale_from_absmax(p.sc_w3[0]));
     const float b4 = p.b4 ? p.b4[0] : 0.f;
     uint32_t it = 0;
+    float rm = -INFINITY, rs = 0.f, rsp = 0.f;      // STATS: this lane's running statistics of the current row
     for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
       const uint32_t ph = it & 1;
-      const long long jb = tile / p.n_iq;
-      const int iq = (int)(tile - jb * p.n_iq);
+      const long long jb = STATS ? jb0 + (tile % njl) : tile / p.n_iq;
+      const int iq = STATS ? q0 + (int)(tile / njl) : (int)(tile - jb * p.n_iq);
       const int i = iq * 4 + q, j = (int)jb * 32 + lane;
       const bool ok = i < p.n_own && j < p.n_all;
       const float *ui = p.u + (size_t)(i < p.n_own ? i : 0) * kHid;
@@ -225,10 +242,37 @@ concat_fwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       tc_fence_before();
       if (g > 0) s_part[(g - 1) * 128 + q * 32 + lane] = dot;
       asm volatile("bar.sync 1, %0;" ::"n"(128 * kFwdWG) : "memory");
-      if (g == 0 && ok) {
+      if (g == 0) {
 #pragma unroll
         for (int w = 0; w < kFwdWG - 1; ++w) dot += s_part[w * 128 + q * 32 + lane];
-        p.scores[(size_t)i * p.n_all + j] = dot + b4;
+        const float sc = dot + b4;
+        if (!STATS) {
+          if (ok) p.scores[(size_t)i * p.n_all + j] = sc;
+        } else {
+          if (ok && j != p.own_offset + i) {
+            if (p.stat_flags & MIMRL_STAT_SOFTPLUS) rsp += softplusf(sc);
+            const float z = (p.stat_flags & MIMRL_STAT_CLAMP) ? fminf(fmaxf(sc, -1.f), 1.f) : sc;
+            if (z > rm) {
+              rs = rs * __expf(rm - z) + 1.f;        // rm = -inf: rs = 0 * 0 + 1
+              rm = z;
+            } else {
+              rs += __expf(z - rm);
+            }
+          }
+          if ((tile % njl) == njl - 1) {             // last column block of this row in this CTA: merge the 32 lanes
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const float m2 = __shfl_xor_sync(0xffffffffu, rm, off), s2v = __shfl_xor_sync(0xffffffffu, rs, off);
+              lse_merge(rm, rs, m2, s2v);
+              rsp += __shfl_xor_sync(0xffffffffu, rsp, off);
+            }
+            if (lane == 0 && i < p.n_own) {
+              float *o = p.part + ((size_t)blockIdx.y * p.n_own + i) * 3;
+              o[0] = rm, o[1] = rs, o[2] = rsp;
+            }
+            rm = -INFINITY, rs = 0.f, rsp = 0.f;
+          }
+        }
       }
     }
   }
@@ -254,7 +298,8 @@ constexpr int kBwdWG = 4;                           // epilogue warpgroups of th
 constexpr int kBwdCh = 8 / kBwdWG;
 constexpr int kBwdThreads = 64 + 128 * kBwdWG;
 constexpr uint32_t kCbGvOff = kCcPartOff + 128 * 4;                // g_v accumulator [256 f][32 j] fp32
-constexpr uint32_t kCbSmem = kCbGvOff + kHid * 32 * 4 + 1024;
+constexpr uint32_t kCbDotOff = kCbGvOff + kHid * 32 * 4;           // FUSED: partial score dot products [2][kBwdWG][128]
+constexpr uint32_t kCbSmem = kCbDotOff + 2 * kBwdWG * 128 * 4 + 1024;
 
 struct ConcatBwdParams {
   ConcatParams f;
@@ -263,6 +308,12 @@ struct ConcatBwdParams {
   float *g_vt;               // [256, ldv]     (+=)
   float *g_b2, *g_b3, *g_w4; // [256] each     (+=)
   __half *op[4][2];          // h1, h2, g2, g3 operands: hi / lo, [256, n_tiles * 128]
+  // FUSED (no dL/dscores matrix): g_ij = coef[0] * w(s_ij) off the diagonal, 0 on it, formed from the recomputed score
+  const float *coef;         // [1]
+  const float *shift;        // [n_own] exp family: w = exp(s_ij - shift[i]); sigmoid family: unused
+  const float *b4;           // [1] (nullable) last-layer bias, needed to rebuild s_ij
+  int family;                // MIMRL_WEIGHT_EXP | MIMRL_WEIGHT_SIGMOID
+  float *g_b4;               // [1] (+=) sum of g_ij
 };
 
 // sum over the 32 lanes of v[t] for every t; lane t returns the total of entry t
@@ -297,6 +348,7 @@ __device__ __forceinline__ void store_op32(__half *base_hi, __half *base_lo, siz
   }
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                   const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo,
@@ -314,6 +366,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kCcRing + 160);
   float *s_b2 = reinterpret_cast<float *>(gen + kCcVecOff), *s_b3 = s_b2 + kHid, *s_w4 = s_b2 + 2 * kHid;
   float *s_gv = reinterpret_cast<float *>(gen + kCbGvOff);
+  float *s_dot = reinterpret_cast<float *>(gen + kCbDotOff);
   for (int t = threadIdx.x; t < kHid; t += blockDim.x) {
     s_b2[t] = p.b2 ? p.b2[t] : 0.f;
     s_b3[t] = p.b3 ? p.b3[t] : 0.f;
@@ -412,6 +465,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
     const float sw2 = scale_from_absmax(p.sc_w2[0]), sw3 = scale_from_absmax(p.sc_w3[0]);
     const float inv12 = 1.f / (s1 * sw2), inv23 = 1.f / (s2 * sw3), inv_c = 1.f / (sg3 * sw3), inv_d = 1.f / (sg2 * sw2);
     float acc_b2[kBwdCh] = {}, acc_b3[kBwdCh] = {}, acc_w4[kBwdCh] = {};
+    float acc_gb4 = 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(128 * kBwdWG) : "memory");      // s_gv zeroed (the block-wide barrier above already ordered it; cheap)
     long long cur_jb = -1;
     uint32_t it = 0;
@@ -438,7 +492,7 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       const bool ok = i < p.n_own && j < p.n_all;
       const float *ui = p.u + (size_t)(i < p.n_own ? i : 0) * kHid;
       const float *vj = p.vt + (j < p.n_all ? j : 0);
-      const float gp = ok ? __ldg(bp.g + (size_t)i * p.n_all + j) : 0.f;
+      float gp = (!FUSED && ok) ? __ldg(bp.g + (size_t)i * p.n_all + j) : 0.f;
       const size_t row = (size_t)(tile - 0) * 128 + q * 32 + lane;        // operand row of this pair
       uint32_t mask1[kBwdCh], mask2[kBwdCh];
       // ---- phase 0 operand: h1
@@ -499,6 +553,32 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       // ---- phase 2 operand: g3 = G w4 [pre3 > 0] in place over D3; w4 and b3 gradients
       mbar_wait(bAcc + 8, par);
       tc_fence_after();
+      if (FUSED) {
+        // the pair's gradient weight from its recomputed score: s = w4 . relu(D3 + b3) + b4, every warpgroup sums its
+        // own features, the four partial sums meet in shared memory (double-buffered by tile parity)
+        float dot = 0.f;
+        for (int cc = 0; cc < kBwdCh; ++cc) {
+          const int c = kBwdCh * g + cc;
+          uint32_t d[32];
+          tmem_ld32(tmem_base + lane_off + kR0 + 32 * c, d);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            dot = fmaf(fmaxf(fmaf(__uint_as_float(d[t]), inv23, s_b3[32 * c + t]), 0.f), s_w4[32 * c + t], dot);
+        }
+        float *sd = s_dot + par * (kBwdWG * 128);
+        sd[g * 128 + q * 32 + lane] = dot;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * kBwdWG) : "memory");
+        float sc = bp.b4 ? bp.b4[0] : 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWG; ++w) sc += sd[w * 128 + q * 32 + lane];
+        gp = 0.f;
+        if (ok && j != p.own_offset + i) {
+          const float wgt = bp.family == MIMRL_WEIGHT_EXP ? __expf(sc - __ldg(bp.shift + i)) : sigmoidf(sc);
+          gp = bp.coef[0] * wgt;
+        }
+        if (g == 0) acc_gb4 += gp;
+      }
       for (int cc = 0; cc < kBwdCh; ++cc) {
         const int c = kBwdCh * g + cc;
         uint32_t d[32];
@@ -584,6 +664,11 @@ concat_bwd_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_co
       atomicAdd(bp.g_b3 + f, acc_b3[cc]);
       atomicAdd(bp.g_w4 + f, acc_w4[cc]);
     }
+    if (FUSED && g == 0) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, off);
+      if (lane == 0 && bp.g_b4) atomicAdd(bp.g_b4, acc_gb4);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -621,7 +706,8 @@ __device__ __forceinline__ float pow2_for(float bound) {      // bound * scale i
 //   absmax: [0] u  [1] vt  [2] G  [3] w4
 //   scales: [0] h1 [1] h2 [2..3] the bounds  [4] g3 [5] g2
 __global__ void concat_scales_kernel(const unsigned *absmax, const float *w2, const float *b2, const float *w3,
-                                     float *scales, unsigned *hdr_h1, unsigned *hdr_h2, unsigned *hdr_g2, unsigned *hdr_g3) {
+                                     float *scales, unsigned *hdr_h1, unsigned *hdr_h2, unsigned *hdr_g2, unsigned *hdr_g3,
+                                     const float *g_bound = nullptr) {
   __shared__ float red[256];
   const int n = threadIdx.x;
   auto block_max = [&](float v) {
@@ -643,7 +729,8 @@ __global__ void concat_scales_kernel(const unsigned *absmax, const float *w2, co
   if (n == 0) {
     const float m1 = __uint_as_float(absmax[0]) + __uint_as_float(absmax[1]);
     const float m2 = m1 * row2_max + b2_max;
-    const float mg3 = __uint_as_float(absmax[2]) * __uint_as_float(absmax[3]);
+    // fused bound: |g_ij| = |coef| w_ij <= |coef| (the weights are referred to a shift that keeps them <= 1)
+    const float mg3 = (g_bound ? fabsf(g_bound[0]) : __uint_as_float(absmax[2])) * __uint_as_float(absmax[3]);
     const float mg2 = mg3 * col3_max;
     scales[0] = pow2_for(m1), scales[1] = pow2_for(m2), scales[2] = m1, scales[3] = m2;
     scales[4] = pow2_for(mg3), scales[5] = pow2_for(mg2);
@@ -718,6 +805,7 @@ void concat_fill(ConcatParams &p, const ConcatHost &h, const float *u, const flo
   p.n_own = n_own, p.n_all = n_all, p.ldv = ldv;
   p.n_iq = (n_own + 3) / 4;
   p.n_tiles = (long long)p.n_iq * ((n_all + 31) / 32);
+  p.part = nullptr, p.own_offset = 0, p.stat_flags = 0, p.n_jb = (n_all + 31) / 32, p.q_per = 0, p.jb_per = 0;
 }
 }  // namespace
 
@@ -735,9 +823,9 @@ extern "C" int mimrl_concat_scores(const float *u, const float *vt, int n_own, i
   if (check_launch("concat scales")) return 1;
   ConcatParams p;
   concat_fill(p, h, u, vt, n_own, n_all, ldv, b2, b3, w4, b4, scores);
-  cudaFuncSetAttribute(concat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcSmem);
+  cudaFuncSetAttribute(concat_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcSmem);
   const int blocks = (int)(p.n_tiles < 148 ? p.n_tiles : 148);
-  concat_fwd_kernel<<<blocks, kCcThreads, kCcSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, p);
+  concat_fwd_kernel<false><<<blocks, kCcThreads, kCcSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, p);
   return check_launch("concat_fwd");
 }
 
@@ -770,8 +858,103 @@ extern "C" int mimrl_concat_grad(const float *u, const float *vt, int n_own, int
     bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
     bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + off_lo);
   }
-  cudaFuncSetAttribute(concat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCbSmem);
+  bp.coef = bp.shift = bp.b4 = nullptr, bp.family = 0, bp.g_b4 = nullptr;
+  cudaFuncSetAttribute(concat_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCbSmem);
   const int blocks = (int)(bp.f.n_tiles < 148 ? bp.f.n_tiles : 148);
-  concat_bwd_kernel<<<blocks, kBwdThreads, kCbSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, h.m2h, h.m2l, h.m3h, h.m3l, bp);
+  concat_bwd_kernel<false><<<blocks, kBwdThreads, kCbSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, h.m2h, h.m2l, h.m3h, h.m3l, bp);
   return check_launch("concat_bwd");
+}
+
+// ---- fused bound: no score matrix, no dL/dscores matrix --------------------------------------------------------
+namespace {
+struct StatsGrid {
+  int gx, gy, q_per, jb_per;
+};
+StatsGrid concat_stats_grid(int n_own, int n_all) {
+  const int n_iq = (n_own + 3) / 4, n_jb = (n_all + 31) / 32;
+  StatsGrid g;
+  g.q_per = (n_iq + 147) / 148;
+  g.gx = (n_iq + g.q_per - 1) / g.q_per;
+  int gy = g.gx >= 148 ? 1 : (148 + g.gx - 1) / g.gx;
+  gy = gy > n_jb ? n_jb : (gy > 32 ? 32 : gy);
+  g.jb_per = (n_jb + gy - 1) / gy;
+  g.gy = (n_jb + g.jb_per - 1) / g.jb_per;
+  return g;
+}
+}  // namespace
+
+extern "C" size_t mimrl_concat_stats_workspace_bytes(int hidden, int n_own, int n_all) {
+  if (hidden != kHid || n_own <= 0 || n_all <= 0) return 0;
+  const StatsGrid g = concat_stats_grid(n_own, n_all);
+  return mimrl_concat_workspace_bytes(hidden) + 256 + (size_t)g.gy * n_own * 3 * sizeof(float);
+}
+
+// Off-diagonal row statistics of the all-pairs scores, the scores never leave the SM:
+// row_max[i] = max_{j != o+i} t(s_ij), row_sum[i] = sum exp(t(s_ij) - row_max[i]), row_sp[i] = sum softplus(s_ij)
+extern "C" int mimrl_concat_row_stats(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden,
+                                      int own_offset, int flags, const float *w2, const float *b2, const float *w3,
+                                      const float *b3, const float *w4, const float *b4, float *row_max, float *row_sum,
+                                      float *row_sp, void *workspace, size_t workspace_bytes, void *stream) {
+  MIMRL_REQUIRE(hidden == kHid, "concat_row_stats: hidden width %d not supported (256 only)", hidden);
+  MIMRL_REQUIRE(n_own > 0 && n_all > 0 && ldv >= n_all && u && vt && w2 && w3 && w4 && row_max && row_sum,
+                "concat_row_stats: bad arguments");
+  MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "concat_row_stats: row block outside the batch");
+  MIMRL_REQUIRE(workspace && workspace_bytes >= mimrl_concat_stats_workspace_bytes(hidden, n_own, n_all),
+                "concat_row_stats: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConcatHost h;
+  if (int rc = concat_prepare(h, u, vt, n_own, ldv, w2, w3, nullptr, 0, w4, workspace, false, st)) return rc;
+  concat_scales_kernel<<<1, 256, 0, st>>>(h.absmax, w2, b2, w3, h.scales, nullptr, nullptr, nullptr, nullptr);
+  if (check_launch("concat scales")) return 1;
+  ConcatParams p;
+  concat_fill(p, h, u, vt, n_own, n_all, ldv, b2, b3, w4, b4, nullptr);
+  const StatsGrid g = concat_stats_grid(n_own, n_all);
+  p.part = reinterpret_cast<float *>((unsigned char *)workspace + align256(mimrl_concat_workspace_bytes(hidden)));
+  p.own_offset = own_offset, p.stat_flags = flags, p.n_jb = (n_all + 31) / 32, p.q_per = g.q_per, p.jb_per = g.jb_per;
+  cudaFuncSetAttribute(concat_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcSmem);
+  concat_fwd_kernel<true><<<dim3(g.gx, g.gy), kCcThreads, kCcSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, p);
+  if (check_launch("concat_fwd(stats)")) return 1;
+  return combine_row_stats(p.part, g.gy, n_own, row_max, row_sum, row_sp, st);
+}
+
+// Backward of the fused bound: g_ij = coef[0] * w(s_ij) for j != own_offset + i (exp family: w = exp(s_ij - shift[i]);
+// sigmoid family: w = sigmoid(s_ij)), 0 on the diagonal, formed inside the kernel from the recomputed score.
+// Outputs as mimrl_concat_grad, plus g_b4[0] += sum_ij g_ij.
+extern "C" int mimrl_concat_grad_fused(const float *u, const float *vt, int n_own, int n_all, int ldv, int hidden,
+                                       int own_offset, const float *w2, const float *b2, const float *w3,
+                                       const float *b3, const float *w4, const float *b4, int family, const float *coef,
+                                       const float *shift, float *g_u, float *g_vt, float *g_b2, float *g_b3,
+                                       float *g_w4, float *g_b4, void *op_h1, void *op_h2, void *op_g2, void *op_g3,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+  MIMRL_REQUIRE(hidden == kHid, "concat_grad_fused: hidden width %d not supported (256 only)", hidden);
+  MIMRL_REQUIRE(n_own > 0 && n_all > 0 && ldv >= n_all && u && vt && w2 && w3 && w4 && coef && g_u && g_vt && g_b2 && g_b3 &&
+                    g_w4 && op_h1 && op_h2 && op_g2 && op_g3,
+                "concat_grad_fused: bad arguments");
+  MIMRL_REQUIRE(family == MIMRL_WEIGHT_EXP || family == MIMRL_WEIGHT_SIGMOID, "concat_grad_fused: unknown weight family %d", family);
+  MIMRL_REQUIRE(family != MIMRL_WEIGHT_EXP || shift, "concat_grad_fused: exp family needs a shift vector");
+  MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "concat_grad_fused: row block outside the batch");
+  MIMRL_REQUIRE(workspace && workspace_bytes >= mimrl_concat_workspace_bytes(hidden), "concat_grad_fused: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConcatHost h;
+  // absmax[2..3]: only max |w4| is needed here (the bound of |G| is |coef|)
+  if (int rc = concat_prepare(h, u, vt, n_own, ldv, w2, w3, w4, (size_t)kHid, w4, workspace, true, st)) return rc;
+  concat_scales_kernel<<<1, 256, 0, st>>>(h.absmax, w2, b2, w3, h.scales, (unsigned *)op_h1, (unsigned *)op_h2,
+                                          (unsigned *)op_g2, (unsigned *)op_g3, coef);
+  if (check_launch("concat scales")) return 1;
+  ConcatBwdParams bp;
+  concat_fill(bp.f, h, u, vt, n_own, n_all, ldv, b2, b3, w4, nullptr, nullptr);
+  bp.f.own_offset = own_offset;
+  bp.g = nullptr, bp.g_u = g_u, bp.g_vt = g_vt, bp.g_b2 = g_b2, bp.g_b3 = g_b3, bp.g_w4 = g_w4;
+  bp.coef = coef, bp.shift = shift, bp.b4 = b4, bp.family = family, bp.g_b4 = g_b4;
+  const size_t rows = (size_t)bp.f.n_tiles * 128;
+  const size_t off_lo = 256 + align256((size_t)kHid * rows * 2);
+  void *ops[4] = {op_h1, op_h2, op_g2, op_g3};
+  for (int t = 0; t < 4; ++t) {
+    bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
+    bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + off_lo);
+  }
+  cudaFuncSetAttribute(concat_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCbSmem);
+  const int blocks = (int)(bp.f.n_tiles < 148 ? bp.f.n_tiles : 148);
+  concat_bwd_kernel<true><<<blocks, kBwdThreads, kCbSmem, st>>>(h.k2h, h.k2l, h.k3h, h.k3l, h.m2h, h.m2l, h.m3h, h.m3l, bp);
+  return check_launch("concat_bwd(fused)");
 }

@@ -14,8 +14,10 @@ import torch.nn as nn
 from . import _lib as L
 from . import rowblock as RB
 from .linear import mlp_apply
-from .vmi import (BaselineModel, CriticModel, _scores_bound, gather_rows, get_activation, interp_lower_bound,
-                  separable_bound)
+from .vmi import (BaselineModel, CriticModel, _scores_bound, concat_bound, gather_rows, get_activation,
+                  interp_lower_bound, separable_bound)
+
+FUSED_CONCAT_BOUND = True      # concat critic: bound fused into the all-pairs kernels (no B x B tensor); False = materialise
 
 
 # --------------------------------------------------------------------------
@@ -211,6 +213,10 @@ class VMIEstimator(nn.Module):
             scores = self.critic_model(features_x, features_y)
             mi = interp_lower_bound(scores, self.baseline_model(features_y), alpha_logit)
             return mi, -mi
+        if self.critic_type == 'concat' and self.critic_model._fused_pairs() and FUSED_CONCAT_BOUND:
+            # fused path: neither the B x B score matrix nor its gradient exists
+            base = self.baseline_model(features_y) if needs_base else None
+            return concat_bound(self.critic_model, features_x, features_y, bound, base, self.rowblock)
         # materialised scores: this rank's rows (its x against every rank's y, Model.py global-batch semantics)
         scores = self.critic_model(features_x, gather_rows(features_y, self.rowblock))
         base = self.baseline_model(features_y) if needs_base else None

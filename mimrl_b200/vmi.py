@@ -466,6 +466,114 @@ class _ConcatPairMLP(torch.autograd.Function):
                 g_w4.reshape(1, -1), g.sum().reshape(1))
 
 
+class _ConcatBoundFused(torch.autograd.Function):
+    """(u [n_own,256], v_all [n_all,256], diag [n_own], W2, b2, W3, b3, w4, b4, log_baseline | None) -> (mi, mi_loss) for
+    the concat critic (VMI.py:58-65) under any bound of VMI.py:136-198, with neither the score matrix nor dL/dscores in
+    memory: the forward kernel reduces the off-diagonal row statistics, the backward kernel forms each pair's gradient
+    weight from its recomputed score.  ``diag`` are the scores of the n_own diagonal pairs (i, own_offset + i), computed
+    by the caller with the same MLP as an ordinary row batch; their gradient is returned like any other input's.
+
+    The diagonal weights of a bound are ~n times larger than the off-diagonal ones; keeping them out of the all-pairs
+    sweep lets the sweep's fp16 hi/lo operands be scaled to the off-diagonal magnitude."""
+
+    @staticmethod
+    def forward(ctx, u, v_all, diag, w2, b2, w3, b3, w4, b4, log_baseline, bound_id, rb):
+        u, w2, w3 = L.f32(u), L.f32(w2), L.f32(w3)
+        vt = L.f32(v_all).t().contiguous()
+        w4 = L.f32(w4).reshape(-1)
+        n_own, n_all, hid = u.shape[0], vt.shape[1], u.shape[1]
+        if rb is None:
+            rb = RB.single(n_own)
+        dev = u.device
+        fam, inc, flags = _family(bound_id)
+        st = L.stream()
+        wsb = L.lib.mimrl_concat_stats_workspace_bytes(hid, n_own, n_all)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        stats = torch.zeros(4, n_own, dtype=torch.float32, device=dev)          # max, sum, softplus, diag
+        L.check(L.lib.mimrl_concat_row_stats(L.ptr(u), L.ptr(vt), n_own, n_all, n_all, hid, rb.offset, flags, L.ptr(w2),
+                                             L.ptr(b2), L.ptr(w3), L.ptr(b3), L.ptr(w4), L.ptr(b4), L.ptr(stats[0]),
+                                             L.ptr(stats[1]), L.ptr(stats[2]), L.ptr(ws), wsb, st))
+        stats[3] = L.f32(diag).reshape(-1)
+        base = None
+        if log_baseline is not None:
+            base = RB.all_gather_rows(L.f32(log_baseline).reshape(-1), rb)
+        all_stats = RB.all_gather_rows(stats.t().contiguous(), rb).t().contiguous() if rb.sharded else stats
+        result = torch.zeros(16, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_bound_finalize(bound_id, L.ptr(all_stats[0]), L.ptr(all_stats[1]), L.ptr(all_stats[2]),
+                                           L.ptr(all_stats[3]), L.ptr(base), n_all, L.ptr(result), st))
+        ctx.save_for_backward(u, vt, w2, b2, w3, b3, w4, b4, all_stats, result, base if base is not None else result.new_empty(0))
+        ctx.cfg = (bound_id, fam, inc, base is not None, rb)
+        return result[0].clone(), result[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_mi, g_loss):
+        u, vt, w2, b2, w3, b3, w4, b4, stats, result, base = ctx.saved_tensors
+        bound_id, fam, inc, has_base, rb = ctx.cfg
+        base = base if has_base else None
+        dev = u.device
+        n_own, n_all, hid = u.shape[0], vt.shape[1], u.shape[1]
+        st = L.stream()
+        grad = _grad_pair(g_mi, g_loss, result)
+        coef = torch.empty(1, dtype=torch.float32, device=dev)
+        vec = torch.empty(3, n_all, dtype=torch.float32, device=dev)            # shift, dcoef, dbaseline
+        L.check(L.lib.mimrl_bound_backward_coef(bound_id, L.ptr(result), L.ptr(grad), L.ptr(stats[0]), L.ptr(stats[1]),
+                                                L.ptr(stats[3]), L.ptr(base), n_all, L.ptr(coef), L.ptr(vec[0]),
+                                                L.ptr(vec[1]), L.ptr(vec[2]) if has_base else None, st))
+        own = slice(rb.offset, rb.offset + n_own)
+        shift_own, dcoef_own = vec[0, own].contiguous(), vec[1, own].contiguous()
+        # the diagonal pairs: dcoef, plus the pair weight itself where the bound's sum includes the diagonal (InfoNCE)
+        g_diag = dcoef_own
+        if inc:
+            d_own = stats[3, own]
+            g_diag = g_diag + coef * (torch.exp(d_own - shift_own) if fam == L.WEIGHT_EXP else torch.sigmoid(d_own))
+        g_u = torch.zeros_like(u)
+        g_vt = torch.zeros_like(vt)
+        g_b2, g_b3, g_w4 = (torch.zeros(hid, device=dev) for _ in range(3))
+        g_b4 = torch.zeros(1, device=dev)
+        g_w2, g_w3 = torch.zeros_like(w2), torch.zeros_like(w3)
+        rows = max(4, (CONCAT_GRAD_PAIRS // max(n_all, 1)) // 4 * 4)
+        rows = min(rows, n_own)
+        opb = L.lib.mimrl_split_bytes(hid, L.lib.mimrl_concat_pair_rows(rows, n_all))
+        ops = [torch.empty(opb, dtype=torch.uint8, device=dev) for _ in range(4)]
+        wsb = L.lib.mimrl_concat_workspace_bytes(hid)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        gwb = L.lib.mimrl_gemm_split_workspace_bytes(0, hid, hid, L.lib.mimrl_concat_pair_rows(rows, n_all))
+        gws = torch.empty(gwb, dtype=torch.uint8, device=dev)
+        tmp = torch.empty_like(w2)
+        for r0 in range(0, n_own, rows):
+            r = min(rows, n_own - r0)
+            pr = L.lib.mimrl_concat_pair_rows(r, n_all)
+            L.check(L.lib.mimrl_concat_grad_fused(L.ptr(u[r0:r0 + r]), L.ptr(vt), r, n_all, n_all, hid, rb.offset + r0,
+                                                  L.ptr(w2), L.ptr(b2), L.ptr(w3), L.ptr(b3), L.ptr(w4), L.ptr(b4), fam,
+                                                  L.ptr(coef), L.ptr(shift_own[r0:r0 + r]), L.ptr(g_u[r0:r0 + r]), L.ptr(g_vt),
+                                                  L.ptr(g_b2), L.ptr(g_b3), L.ptr(g_w4), L.ptr(g_b4), L.ptr(ops[0]),
+                                                  L.ptr(ops[1]), L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), wsb, st))
+            for a, b, acc in ((ops[2], ops[0], g_w2), (ops[3], ops[1], g_w3)):
+                L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(a), L.ptr(b), hid, hid, pr, L.ptr(tmp), L.ptr(gws), gwb, st))
+                acc += tmp
+        dbase = vec[2, own].reshape(n_own, 1).clone() if has_base else None
+        return (g_u, g_vt.t(), g_diag, g_w2, g_b2 if b2 is not None else None, g_w3, g_b3 if b3 is not None else None,
+                g_w4.reshape(1, -1), g_b4 if b4 is not None else None, dbase, None, None)
+
+
+def concat_bound(critic, x_own, y_own, bound_type, log_baseline=None, rowblock=None):
+    """Fused ``bound(CriticModel('concat')(x, y))`` (VMI.py:58-65 + VMI.py:136-198) for the reference's default concat
+    critic (ReLU, hidden 256, two hidden layers): returns ``(mi, mi_loss)`` exactly as ``VMIEstimator.forward`` does.
+    Rows of the score matrix index x (VMI.py:65), the rank's own rows; columns index every rank's y."""
+    if bound_type not in L.BOUND_IDS:
+        raise NotImplementedError
+    f = critic.MLP_f
+    first = f[0]
+    dx = x_own.shape[1]
+    u = linear(x_own, first.weight[:, :dx], first.bias)                  # layer 1 factorised: W1 [x; y] = W1x x + W1y y
+    v_own = linear(y_own, first.weight[:, dx:])
+    v_all = gather_rows(v_own, rowblock)
+    # the diagonal pairs (i, own_offset + i) are an ordinary row batch of the same MLP
+    diag = mlp_apply(f[1:], u + v_own).reshape(-1)
+    return _ConcatBoundFused.apply(u, v_all, diag, f[2].weight, f[2].bias, f[4].weight, f[4].bias, f[6].weight, f[6].bias,
+                                   log_baseline, L.BOUND_IDS[bound_type], rowblock)
+
+
 # --------------------------------------------------------------------------
 # modules (VMI.py:25-110)
 # --------------------------------------------------------------------------
