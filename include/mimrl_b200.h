@@ -48,6 +48,9 @@ enum mimrl_bound {
 /* per-pair weight families of the backward sweep */
 #define MIMRL_WEIGHT_EXP 0     /* w_ij = exp(S_ij - shift) */
 #define MIMRL_WEIGHT_SIGMOID 1 /* w_ij = sigmoid(S_ij)     */
+#define MIMRL_WEIGHT_INTERP 2  /* w_ij = p (a1 + a2 / (1 - sg p)), p = exp(S_ij - lse): the row-parameterised part of the
+                                  interpolated bound's gradient (VMI.py:229-250); shift = four vectors [4][n]: lse, a1, a2,
+                                  sg of the score's row, scaled by the caller so that |w| <= 1 (tcgen05 path only) */
 
 /* kernel implementation selector (both are CUDA kernels of this library) */
 #define MIMRL_IMPL_AUTO 0
@@ -105,6 +108,11 @@ int mimrl_sep_fused_forward(const float *own_emb, const float *all_emb, int n_ow
 int mimrl_sep_online_forward(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                              int own_offset, int include_diag, float *row_ref, float *wsum, float *row_sum, float *diag,
                              void *workspace, size_t workspace_bytes, void *stream);
+/* Second forward sweep of the interpolated bound (VMI.py:201-250; tcgen05 path): with p_ij = exp(S_ij - row_lse[i]), over
+ * the off-diagonal columns: row_q[i] = sum_j p_ij / (1 - row_sigma[i] p_ij), row_t[i] = sum_j log(1 - row_sigma[i] p_ij). */
+int mimrl_sep_interp_stats(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed, int own_offset,
+                           const float *row_lse, const float *row_sigma, float *row_q, float *row_t, void *workspace,
+                           size_t workspace_bytes, void *stream);
 int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                            int own_offset, int weight_family, int include_diag, const float *shift,
                            int shift_by_swept, const float *coef, const float *dcoef, int impl, float *out,

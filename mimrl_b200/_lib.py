@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmimrl_b200.so")
 BOUND_IDS = {"dv": 0, "mine": 1, "tuba": 2, "nwj": 3, "infonce": 4, "js_fgan": 5, "js": 6, "smile": 7,
              "interpolate": 8}
 STAT_CLAMP, STAT_SOFTPLUS, STAT_MAXONLY = 1, 2, 4
-WEIGHT_EXP, WEIGHT_SIGMOID = 0, 1
+WEIGHT_EXP, WEIGHT_SIGMOID, WEIGHT_INTERP = 0, 1, 2
 IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05 = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
@@ -38,6 +38,7 @@ _SIGS = {
     "mimrl_sep_row_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_fused_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_online_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mimrl_sep_interp_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_sep_weighted_sum": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P,
                                        _P, c_size_t, _P]),
     "mimrl_bound_finalize": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P, _P]),

@@ -87,7 +87,7 @@ int combine_row_stats(const float *part, int n_splits, int n_own, float *row_max
 // implemented in sep_tc.cu; returns 0 and sets *handled = 1 when it ran
 int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
                      int flags, float *row_max, float *row_sum, float *row_sp, void *ws, size_t ws_bytes,
-                     cudaStream_t st);
+                     cudaStream_t st, const float *row_lse = nullptr, const float *row_sigma = nullptr);
 int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset,
                         int family, int include_diag, const float *shift, int shift_by_swept, const float *coef,
                         const float *dcoef, float *out, void *ws, size_t ws_bytes, cudaStream_t st,

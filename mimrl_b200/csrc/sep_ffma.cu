@@ -382,6 +382,21 @@ extern "C" int mimrl_sep_online_forward(const float *own_emb, const float *all_e
                                workspace, workspace_bytes, st);
 }
 
+// Second forward sweep of the interpolated bound (VMI.py:201-250, tcgen05 path only): with p_ij = exp(S_ij - row_lse[i]),
+// over the off-diagonal columns  row_q[i] = sum_j p_ij / (1 - row_sigma[i] p_ij),  row_t[i] = sum_j log(1 - row_sigma[i] p_ij).
+extern "C" int mimrl_sep_interp_stats(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
+                                      int own_offset, const float *row_lse, const float *row_sigma, float *row_q,
+                                      float *row_t, void *workspace, size_t workspace_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MIMRL_REQUIRE(n_own > 0 && n_all > 0 && embed > 0 && row_lse && row_sigma && row_q && row_t, "sep_interp_stats: bad arguments");
+  MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "sep_interp_stats: row block outside the batch");
+  MIMRL_REQUIRE(sep_tc_supported(n_own, n_all, embed), "sep_interp_stats: tcgen05 path needs embed <= 128 (got %d)", embed);
+  MIMRL_REQUIRE(workspace_bytes >= mimrl_sep_workspace_bytes(n_own, n_all, embed), "sep_interp_stats: workspace too small");
+  // row_q doubles as the (all-zero) row_max output of the shared combine step, which writes row_max before row_sum
+  return sep_row_stats_tc(own_emb, all_emb, n_own, n_all, embed, own_offset, 0, row_q, row_q, row_t, workspace,
+                          workspace_bytes, st, row_lse, row_sigma);
+}
+
 extern "C" int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb, int n_own, int n_all, int embed,
                                       int own_offset, int weight_family, int include_diag, const float *shift,
                                       int shift_by_swept, const float *coef, const float *dcoef, int impl,
@@ -390,9 +405,12 @@ extern "C" int mimrl_sep_weighted_sum(const float *own_emb, const float *all_emb
   MIMRL_REQUIRE(n_own > 0 && n_all > 0 && embed > 0, "sep_weighted_sum: empty input");
   MIMRL_REQUIRE(embed <= 256, "sep_weighted_sum: embed=%d > 256 is not supported", embed);
   MIMRL_REQUIRE(own_offset >= 0 && own_offset + n_own <= n_all, "sep_weighted_sum: row block outside the batch");
-  MIMRL_REQUIRE(weight_family == MIMRL_WEIGHT_EXP || weight_family == MIMRL_WEIGHT_SIGMOID,
+  MIMRL_REQUIRE(weight_family == MIMRL_WEIGHT_EXP || weight_family == MIMRL_WEIGHT_SIGMOID ||
+                    weight_family == MIMRL_WEIGHT_INTERP,
                 "sep_weighted_sum: unknown weight family %d", weight_family);
-  MIMRL_REQUIRE(weight_family != MIMRL_WEIGHT_EXP || shift, "sep_weighted_sum: exp family needs a shift vector");
+  MIMRL_REQUIRE(weight_family == MIMRL_WEIGHT_SIGMOID || shift, "sep_weighted_sum: this family needs its shift / parameter vectors");
+  MIMRL_REQUIRE(weight_family != MIMRL_WEIGHT_INTERP || use_tc(impl, n_own, n_all, embed),
+                "sep_weighted_sum: MIMRL_WEIGHT_INTERP exists on the tcgen05 path only (embed <= 128)");
   MIMRL_REQUIRE(workspace_bytes >= mimrl_sep_workspace_bytes(n_own, n_all, embed), "sep_weighted_sum: workspace too small");
   MIMRL_REQUIRE(impl != MIMRL_IMPL_TCGEN05 || sep_tc_supported(n_own, n_all, embed),
                 "sep_weighted_sum: tcgen05 path needs embed <= 128 (got %d)", embed);

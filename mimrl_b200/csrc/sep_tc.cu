@@ -120,7 +120,20 @@ struct StatsParams {
   const unsigned *absmax;
   const __half *own_hi, *own_lo;
   float *part;
+  const float *row_lse, *row_sigma;   // kStatInterp: per owned row, LSE_i of the whole row and sigma_i (see below)
 };
+
+// FLAGS == kStatInterp: the second forward sweep of the interpolated bound (VMI.py:201-250).  With p_ij =
+// exp(S_ij - LSE_i) and sigma_i from the first sweep, per owned row over the off-diagonal columns:
+//   part[.][1] = Q_i = sum_j p_ij / (1 - sigma_i p_ij),   part[.][2] = T_i = sum_j log(1 - sigma_i p_ij)
+// (part[.][0] = 0, so that the (max, sum) merge of combine_row_stats degenerates to a plain sum).
+constexpr int kStatInterp = 8;
+
+// log(1 - x) for x in [0, 1): series below 2^-6 (the common case, p ~ 1/n), libm above
+__device__ __forceinline__ float log1m(float x) {
+  if (x < 0.015625f) return -x * fmaf(x, fmaf(x, fmaf(x, 0.25f, 0.33333334f), 0.5f), 1.f);
+  return log1pf(-x);
+}
 
 template <int FLAGS>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -256,6 +269,12 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
     float m2 = -INFINITY, s = 0.f, sp = 0.f;
     const int grmin = p.own_offset + row0, grmax = grmin + 127;
     const int buf = wg;
+    constexpr bool kInterp = FLAGS == kStatInterp;
+    float i_lse = 0.f, i_sig = 0.f;
+    if (kInterp) {
+      m2 = 0.f;
+      if (row0 + r < p.n_own) i_lse = p.row_lse[row0 + r], i_sig = p.row_sigma[row0 + r];
+    }
     for (int i = wg; i < T; i += 2) {
       const int col0 = (t0 + i) * 128;
       const bool clean = (FLAGS & 3) == 0 && col0 + 128 <= p.n_all && (col0 + 128 <= grmin || col0 > grmax);
@@ -266,6 +285,22 @@ sep_stats_tc_kernel(const __grid_constant__ CUtensorMap map_all_hi, const __grid
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + buf * 128 + ch * 32, v);
         tmem_ld_wait();
+        if (kInterp) {
+          float qa[2] = {0.f, 0.f}, ta[2] = {0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = col0 + ch * 32 + j;
+            const bool ok = clean || (gc < p.n_all && gc != gr);
+            // exp(S - LSE): the difference is formed at score magnitude, then scaled to log2 units
+            const float pij = ok ? ex2(fmaf(__uint_as_float(v[j]), inv, -i_lse) * kLog2e) : 0.f;
+            const float x = fminf(i_sig * pij, 0.99999994f);
+            qa[j & 1] += __fdividef(pij, 1.f - x);
+            ta[j & 1] += log1m(x);
+          }
+          s += qa[0] + qa[1];
+          sp += ta[0] + ta[1];
+          continue;
+        }
         if (!clean) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -341,11 +376,19 @@ constexpr float kOnlineTau = 4.5f;       // rescale when a score exceeds the ref
 // One thread's 32 scores of a tile -> weights (fp16 hi/lo pairs) + the row-sum statistic.  EDGE = the tile holds the
 // row's diagonal or runs past the batch: invalid entries get weight 0 and the statistic leaves the diagonal out.  It
 // is a separate instantiation so that the common tile carries none of the per-element index tests.
+// MIMRL_WEIGHT_INTERP (backward of the interpolated bound): w = p (a1 + a2 / (1 - sg p)), p = exp(S - lse), with the
+// four parameters of the score's ROW (lse, a1, a2, sg), scaled by the caller so that |w| <= 1.  They belong to the
+// owned row (scalars) or, when the operands are swapped, to the swept row (staged in shared memory as [4][64]).
+struct InterpPar {
+  float lse, a1, a2, sg;
+  const float *sm;          // by_swept: this thread's 32 columns of the staged [4][64] block
+};
+
 template <int FAMILY, bool ONLINE, bool EDGE>
 __device__ __forceinline__ void weights_of_tile(const uint32_t (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16],
                                                 float2 (&rs2)[2], float inv, float c2, float wexp, float shift_row,
                                                 const float4 *sh4, bool by_swept, bool want_rsum, int cbase, int gr,
-                                                int n_all, bool include_diag) {
+                                                int n_all, bool include_diag, const InterpPar &ip) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float shv[4] = {shift_row, shift_row, shift_row, shift_row};
@@ -364,6 +407,14 @@ __device__ __forceinline__ void weights_of_tile(const uint32_t (&v)[32], uint32_
         // ONLINE: every entry is <= ref + tau by construction, no cap needed
         w[u] = ex2(ONLINE ? e2.x : fminf(e2.x, 15.9f));
         w[u + 1] = ex2(ONLINE ? e2.y : fminf(e2.y, 15.9f));
+      }
+    } else if (FAMILY == MIMRL_WEIGHT_INTERP) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float lse = by_swept ? ip.sm[j + u] : ip.lse, a1 = by_swept ? ip.sm[64 + j + u] : ip.a1;
+        const float a2 = by_swept ? ip.sm[128 + j + u] : ip.a2, sg = by_swept ? ip.sm[192 + j + u] : ip.sg;
+        const float pij = ex2(fmaf(__uint_as_float(v[j + u]), inv, -lse) * kLog2e);
+        w[u] = 16384.f * pij * fmaf(a2, __fdividef(1.f, 1.f - fminf(sg * pij, 0.99999994f)), a1);
       }
     } else {
 #pragma unroll
@@ -406,6 +457,7 @@ struct WsumParams {
   float *rsum_part;   // nullable: [split * 2 + warpgroup][n_own] sum of the off-diagonal weights of the row
                       // (ONLINE: [split][n_own], referred to ref_part)
   float *ref_part;    // ONLINE: [split][n_own] final reference point of the row in this split (-inf: nothing seen)
+  int n_par;          // MIMRL_WEIGHT_INTERP: shift holds four vectors [4][n_par] (lse, a1, a2, sg of the score's row)
 };
 
 template <int FAMILY, bool ONLINE>
@@ -554,7 +606,13 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     const float s_all = scale_from_absmax(p.absmax[1]);
     const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * s_all);
     const float c2 = inv * kLog2e;
-    const bool by_swept = !ONLINE && FAMILY == MIMRL_WEIGHT_EXP && p.shift_by_swept;
+    const bool by_swept = !ONLINE && FAMILY != MIMRL_WEIGHT_SIGMOID && p.shift_by_swept;
+    constexpr bool kInterp = FAMILY == MIMRL_WEIGHT_INTERP;
+    InterpPar ip = {0.f, 0.f, 0.f, 0.f, nullptr};
+    if (kInterp && !p.shift_by_swept && row_ok) {
+      const float *q4 = p.shift + row0 + r;
+      ip.lse = q4[0], ip.a1 = q4[p.n_par], ip.a2 = q4[2 * (size_t)p.n_par], ip.sg = q4[3 * (size_t)p.n_par];
+    }
     // exp family: w * 2^14 = ex2((acc*inv - shift) * log2e + 14); acc*inv is exact (power of two) and the
     // subtraction happens at score magnitude, so the dominant weights keep full fp32 accuracy
     float shift_row = 0.f;
@@ -564,16 +622,19 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     // column shifts of the current tile, staged once per tile (double-buffered) instead of 64 global loads
     // per thread: thread et < 64 prefetches shift[col0 + et] one tile ahead
     float sh_next = 0.f;
-    if (by_swept && et < 64 && T > 0) {
-      const int gc = t0 * 64 + et;
-      sh_next = gc < p.n_all ? __ldg(p.shift + gc) : 0.f;
+    if (by_swept && (kInterp || et < 64) && T > 0) {
+      const int gc = t0 * 64 + (et & 63);
+      sh_next = gc < p.n_all ? __ldg(p.shift + (kInterp ? (size_t)(et >> 6) * p.n_par : 0) + gc) : 0.f;
     }
     const bool want_rsum = ONLINE || p.rsum_part != nullptr;
     // weights are carried as w * 2^wexp in fp16 hi/lo.  With an exact shift w <= 1 and 2^14 uses the whole fp16 range;
     // the fused forward's reference point is approximate (w can exceed 1), so it leaves 2^6 of headroom, and the
     // exponent is capped so that even a wildly wrong reference point cannot overflow fp16.
     const float wexp = ONLINE ? kOnlineWExp : ((FAMILY == MIMRL_WEIGHT_EXP && want_rsum) ? 10.f : (float)kWExp);
-    float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    // row-sum statistic: the 32 weights of a tile are summed on their own first and only the tile total joins the
+    // running sum (Kahan-compensated): a row with one dominant weight and tens of thousands of tiny ones would
+    // otherwise lose the tail to the rounding of a large accumulator
+    float rs_run = 0.f, rs_cmp = 0.f;
     float ref = -INFINITY;                    // ONLINE: running reference point of this row (natural score units)
     const uint32_t tmem_og = tmem_o + (ONLINE ? wg * 128 : 0);
     for (int i = 0; i < T; ++i) {
@@ -582,7 +643,11 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       const bool clean = col0 + 64 <= p.n_all && (p.include_diag || col0 + 64 <= grmin || col0 > grmax);
       const bool clean_stat = col0 + 64 <= p.n_all && (col0 + 64 <= grmin || col0 > grmax);
       if (by_swept) {
-        if (et < 64) {
+        if (kInterp) {                        // four parameter vectors of the swept rows: [4][64] per tile, double-buffered
+          sh_x[buf * 256 + et] = sh_next;
+          const int gc = col0 + 64 + (et & 63);
+          sh_next = (i + 1 < T && gc < p.n_all) ? __ldg(p.shift + (size_t)(et >> 6) * p.n_par + gc) : 0.f;
+        } else if (et < 64) {
           sh_smem[buf * 64 + et] = sh_next;
           const int gc = col0 + 64 + et;
           sh_next = (i + 1 < T && gc < p.n_all) ? __ldg(p.shift + gc) : 0.f;
@@ -630,27 +695,35 @@ sep_wsum_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
             }
             tmem_st_wait();
           }
-          rs2[0].x *= f, rs2[0].y *= f, rs2[1].x *= f, rs2[1].y *= f;
+          rs_run *= f, rs_cmp *= f;
           if (need) ref = cand;
         }
       }
       const float ref_use = ONLINE ? (ref > -INFINITY ? ref : 0.f) : shift_row;
       uint32_t hi[16], lo[16];
+      float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       const float4 *sh4 = reinterpret_cast<const float4 *>(sh_smem + buf * 64 + wg * 32);
+      ip.sm = sh_x + buf * 256 + wg * 32;
       if (clean && clean_stat)
         weights_of_tile<FAMILY, ONLINE, false>(v, hi, lo, rs2, inv, c2, wexp, ref_use, sh4, by_swept, want_rsum,
-                                               col0 + wg * 32, gr, p.n_all, p.include_diag != 0);
+                                               col0 + wg * 32, gr, p.n_all, p.include_diag != 0, ip);
       else
         weights_of_tile<FAMILY, ONLINE, true>(v, hi, lo, rs2, inv, c2, wexp, ref_use, sh4, by_swept, want_rsum,
-                                              col0 + wg * 32, gr, p.n_all, p.include_diag != 0);
+                                              col0 + wg * 32, gr, p.n_all, p.include_diag != 0, ip);
       tmem_st16(tcol, hi);
       tmem_st16(tcol + 16, lo);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bWFull + 8 * buf);
+      if (want_rsum) {                        // off the critical path: the MMAs of this tile are already released
+        const float yk = ((rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y)) - rs_cmp;
+        const float tk = rs_run + yk;
+        rs_cmp = (tk - rs_run) - yk;
+        rs_run = tk;
+      }
     }
-    const float rs_tot = ((rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y)) * ex2(-wexp);
+    const float rs_tot = rs_run * ex2(-wexp);
     if (ONLINE) {
       // merge the two warpgroups' references: both scale their sums to R = max(ref_0, ref_1)
       sh_x[wg * 128 + r] = ref;
@@ -845,7 +918,7 @@ size_t sep_tc_workspace_bytes(int n_own, int n_all, int embed) {
 
 int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, int embed, int own_offset, int flags,
                      float *row_max, float *row_sum, float *row_sp, void *workspace, size_t ws_bytes,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float *row_lse, const float *row_sigma) {
   const TcLayout L = tc_layout(n_own, n_all);
   MIMRL_REQUIRE(ws_bytes >= L.total, "sep_row_stats(tcgen05): workspace too small");
   unsigned char *ws = (unsigned char *)workspace;
@@ -864,13 +937,16 @@ int sep_row_stats_tc(const float *own, const float *all, int n_own, int n_all, i
   p.part = reinterpret_cast<float *>(ws + L.off_part);
   p.own_hi = reinterpret_cast<const __half *>(ws + L.off_own_hi);
   p.own_lo = reinterpret_cast<const __half *>(ws + L.off_own_lo);
+  p.row_lse = row_lse, p.row_sigma = row_sigma;
   dim3 grid(row_tiles, splits);
 #define LAUNCH_STATS(F)                                                                                          \
   do {                                                                                                           \
     cudaFuncSetAttribute(sep_stats_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem);    \
     sep_stats_tc_kernel<F><<<grid, kTcThreads, kRingSmem, st>>>(m_all_hi, m_all_lo, p);                           \
   } while (0)
-  switch (flags & 7) {
+  if (row_lse) {
+    LAUNCH_STATS(8);                          // kStatInterp
+  } else switch (flags & 7) {
     case 0: LAUNCH_STATS(0); break;
     case 1: LAUNCH_STATS(1); break;
     case 2: LAUNCH_STATS(2); break;
@@ -910,7 +986,12 @@ int sep_weighted_sum_tc(const float *own, const float *all, int n_own, int n_all
   p.rsum_part = row_sum ? reinterpret_cast<float *>(ws + L.off_rsum) : nullptr;
   dim3 grid(row_tiles, splits);
   p.ref_part = nullptr;
-  if (family == MIMRL_WEIGHT_EXP) {
+  p.n_par = shift_by_swept ? n_all : n_own;
+  if (family == MIMRL_WEIGHT_INTERP) {
+    cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_INTERP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kWsumSmem);
+    sep_wsum_tc_kernel<MIMRL_WEIGHT_INTERP, false><<<grid, kTcThreads, kWsumSmem, st>>>(m_x_hi, m_x_lo, p);
+  } else if (family == MIMRL_WEIGHT_EXP) {
     cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)kWsumSmem);
     sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, false><<<grid, kTcThreads, kWsumSmem, st>>>(m_x_hi, m_x_lo, p);
@@ -959,6 +1040,7 @@ int sep_online_forward_tc(const float *own, const float *all, int n_own, int n_a
   p.part = reinterpret_cast<float *>(ws + L.off_part);
   p.rsum_part = reinterpret_cast<float *>(ws + L.off_rsum);
   p.ref_part = reinterpret_cast<float *>(ws + L.off_ref);
+  p.n_par = 0;
   dim3 grid(row_tiles, splits);
   cudaFuncSetAttribute(sep_wsum_tc_kernel<MIMRL_WEIGHT_EXP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)kWsumSmem);

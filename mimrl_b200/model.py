@@ -15,7 +15,7 @@ from . import _lib as L
 from . import rowblock as RB
 from .linear import mlp_apply
 from .vmi import (BaselineModel, CriticModel, _scores_bound, concat_bound, gather_rows, get_activation,
-                  interp_lower_bound, separable_bound)
+                  interp_lower_bound, separable_bound, separable_interp_bound)
 
 FUSED_CONCAT_BOUND = True      # concat critic: bound fused into the all-pairs kernels (no B x B tensor); False = materialise
 
@@ -207,9 +207,17 @@ class VMIEstimator(nn.Module):
             x_, y_ = self.critic_model.embed(features_x, features_y)
             base = self.baseline_model(features_y) if needs_base else None
             return separable_bound(x_, y_, bound, base, self.rowblock, self.impl)
+        if self.critic_type == 'separate' and bound == 'interpolate' and features_x.is_cuda:
+            x_, y_ = self.critic_model.embed(features_x, features_y)
+            n_own = y_.shape[0]
+            n_all = self.rowblock.n_all if self.rowblock is not None else n_own
+            if L.lib.mimrl_sep_selected_impl(n_own, n_all, y_.shape[1], self.impl) == L.IMPL_TCGEN05:
+                # fused: three statistics sweeps + two weighted-sum sweeps per side over TMEM tiles, row-block shardable
+                return separable_interp_bound(x_, y_, self.baseline_model(features_y), alpha_logit, self.rowblock, self.impl)
         if bound == 'interpolate':
             if self.rowblock is not None and self.rowblock.sharded:
-                raise NotImplementedError("the interpolated bound needs the whole score matrix on one rank")
+                raise NotImplementedError("the interpolated bound over a materialised score matrix (concat critic, or "
+                                          "embed_dim > 128) needs the whole matrix on one rank")
             scores = self.critic_model(features_x, features_y)
             mi = interp_lower_bound(scores, self.baseline_model(features_y), alpha_logit)
             return mi, -mi

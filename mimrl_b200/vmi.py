@@ -251,6 +251,126 @@ def separable_bound(x_emb, y_emb, bound_type, log_baseline=None, rowblock=None, 
     return _SeparableBound.apply(x_emb, y_emb, log_baseline, L.BOUND_IDS[bound_type], impl, rowblock)
 
 
+class _SeparableInterp(torch.autograd.Function):
+    """Interpolated bound (VMI.py:201-250, alpha = sigmoid(alpha_logit)) over the separable critic, fused: the score
+    matrix only exists as TMEM tiles.  With L_i = logsumexp_j S_ij, p_ij = exp(S_ij - L_i), a_i the learnt log-baseline,
+    c_i = logit(alpha) + L_i - log(n-1) - a_i, C_i = exp(c_i), sigma_i = C_i / (1 + C_i) the reference's quantities are
+
+        I_ij  = log(alpha * loo-mean_i,j + (1-alpha) e^{a_i}) = log(1-alpha) + a_i + log(1 + C_i) + log(1 - sigma_i p_ij)
+        joint = sum_{i != j} (S_jj - I_ij) / (n(n-1)),   marg = sum_{i != j} exp(S_ij - I_jj) / (n(n-1)),   mi = 1 + joint - marg
+
+    Forward, three statistics sweeps: rows of S (L_i, diagonal), columns of S (the operands swapped: sum_i e^{S_ij}), and
+    -- once sigma_i and L_i are known -- the row sums T_i = sum_{j != i} log(1 - sigma_i p_ij), Q_i = sum_{j != i}
+    p_ij / (1 - sigma_i p_ij) (mimrl_sep_interp_stats).  Backward, per side two weighted-sum sweeps: the row-parameterised
+    part lambda_i p_ij + sigma_i p_ij / (1 - sigma_i p_ij) (MIMRL_WEIGHT_INTERP) and the column-shifted part
+    -exp(S_ij - I_jj) (MIMRL_WEIGHT_EXP).  Per-row vectors are handled in float64 torch ops (n numbers each).
+    Shardable by row blocks like every other bound: per-row vectors are all-gathered."""
+
+    @staticmethod
+    def forward(ctx, x_emb, y_emb, log_baseline, alpha_logit, impl, rb):
+        x_emb, y_emb = L.f32(x_emb), L.f32(y_emb)
+        n_own, embed = y_emb.shape
+        if rb is None:
+            rb = RB.single(n_own)
+        dev = y_emb.device
+        st = L.stream()
+        all_x = RB.all_gather_rows(x_emb, rb)
+        all_y = RB.all_gather_rows(y_emb, rb)
+        n = all_x.shape[0]
+        ws = torch.empty(max(L.lib.mimrl_sep_workspace_bytes(n_own, n, embed), 16), dtype=torch.uint8, device=dev)
+        own = slice(rb.offset, rb.offset + n_own)
+
+        def stats(own_rows, swept):
+            out = torch.empty(4, n_own, dtype=torch.float32, device=dev)
+            L.check(L.lib.mimrl_sep_row_stats(L.ptr(own_rows), L.ptr(swept), n_own, n, embed, rb.offset, 0, impl,
+                                              L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]), L.ptr(ws),
+                                              ws.numel(), st))
+            return out.double()
+        r = stats(y_emb, all_x)                                   # rows i of S = y_i . x_j
+        c = stats(x_emb, all_y)                                   # columns j of S: own = x_j, swept = y_i
+        d = r[3]
+        lse_off = r[0] + torch.log(r[1])                          # off-diagonal part; -inf when n == 1
+        lse = torch.logaddexp(lse_off, d)
+        a = L.f32(log_baseline).reshape(-1).double()
+        log_alpha = -math.log1p(math.exp(-float(alpha_logit)))
+        log_1m_alpha = -math.log1p(math.exp(float(alpha_logit)))
+        ci = (log_alpha - log_1m_alpha) + lse - math.log(n - 1.0) - a
+        sig = torch.sigmoid(ci)
+        row_par = torch.stack([lse, sig]).float().contiguous()
+        qt = torch.empty(2, n_own, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_sep_interp_stats(L.ptr(y_emb), L.ptr(all_x), n_own, n, embed, rb.offset, L.ptr(row_par[0]),
+                                             L.ptr(row_par[1]), L.ptr(qt[0]), L.ptr(qt[1]), L.ptr(ws), ws.numel(), st))
+        Q, T = qt[0].double(), qt[1].double()
+        p_dd = torch.exp(d - lse)
+        # (VMI.py:219-223 substitutes d = 1 where an entry carries its whole row to fp32 precision, lse - S == 0; the exact
+        # limit log(1 - sigma_i) is evaluated here instead -- DESIGN.md, quirk N9)
+        x_dd = (sig * p_dd).clamp(max=1.0 - 1e-12)
+        base_i = log_1m_alpha + a + F.softplus(ci)                # log(1-alpha) + a_i + log(1 + C_i)
+        I_dd = base_i + torch.log1p(-x_dd)
+        col_log = c[0] + torch.log(c[1])                          # log sum_{i != j} e^{S_ij} for the own columns j
+        Mj = torch.exp(col_log - I_dd)
+        nn_ = n * (n - 1.0)
+        part = torch.stack([((n - 1.0) * d - (n - 1.0) * base_i - T - Mj).sum()])
+        if rb.sharded:
+            torch.distributed.all_reduce(part, group=rb.group)
+        mi = (1.0 + part[0] / nn_).float()
+        ctx.save_for_backward(x_emb, y_emb, all_x, all_y, lse, sig, Q, d, I_dd, Mj, c[0], p_dd)
+        ctx.cfg = (impl, rb, n, ws)
+        return mi, -mi
+
+    @staticmethod
+    def backward(ctx, g_mi, g_loss):
+        x_emb, y_emb, all_x, all_y, lse, sig, Q, d, I_dd, Mj, col_max, p_dd = ctx.saved_tensors
+        impl, rb, n, ws = ctx.cfg
+        n_own, embed = y_emb.shape
+        dev = y_emb.device
+        st = L.stream()
+        g = (g_mi if g_mi is not None else 0.0) - (g_loss if g_loss is not None else 0.0)
+        g = torch.as_tensor(g, dtype=torch.float64, device=dev)
+        nn_ = n * (n - 1.0)
+        r_dd = p_dd / (1.0 - (sig * p_dd).clamp(max=1.0 - 1e-12))        # r_ii = p_ii / (1 - sigma_i p_ii)
+        lam = -(n - 1.0) * sig - sig * sig * Q + Mj * sig * (1.0 + sig * r_dd)           # coefficient of dL_i
+        diag_c = (n - 1.0) + lam * p_dd - Mj * sig * r_dd                                # coefficient of dS_ii
+        da = -(n - 1.0) * (1.0 - sig) - sig * (1.0 - sig) * Q + Mj * (1.0 - sig) * (1.0 + sig * r_dd)
+        # all-gather the per-row vectors both sweeps need
+        def allrows(v):
+            return RB.all_gather_rows(v.float().contiguous(), rb).double() if rb.sharded else v
+        lam_all, sig_all, lse_all, I_all = allrows(lam), allrows(sig), allrows(lse), allrows(I_dd)
+        colmax_all = allrows(col_max)
+        # scale of the row-parameterised weights: |lambda_i p + sigma_i p / (1 - sigma_i p)| <= |lambda_i| + sigma_i / (1 - sigma_i)
+        Lam = (lam_all.abs() + sig_all / (1.0 - sig_all).clamp(min=1e-12)).max().clamp(min=1e-30)
+        par_all = torch.stack([lse_all, lam_all / Lam, sig_all / Lam, sig_all]).float().contiguous()     # [4][n]
+        par_own = par_all[:, rb.offset: rb.offset + n_own].contiguous()
+        # column-shifted exp weights, referred to their global maximum so that they stay <= 1
+        wmax = (colmax_all - I_all).max()
+        shift_all = (I_all + wmax).float().contiguous()
+        shift_own = shift_all[rb.offset: rb.offset + n_own].contiguous()
+        coef_i = (g * Lam / nn_).float().reshape(1)
+        coef_e = (-g * torch.exp(wmax) / nn_).float().reshape(1)
+        dcoef = (g * diag_c / nn_).float().contiguous()
+        zero = torch.zeros(n_own, dtype=torch.float32, device=dev)
+
+        def wsum(own_rows, swept, fam, shift, by_swept, coef, dc):
+            out = torch.empty(n_own, embed, dtype=torch.float32, device=dev)
+            L.check(L.lib.mimrl_sep_weighted_sum(L.ptr(own_rows), L.ptr(swept), n_own, n, embed, rb.offset, fam, 0, L.ptr(shift),
+                                                 by_swept, L.ptr(coef), L.ptr(dc), impl, L.ptr(out), L.ptr(ws), ws.numel(), st))
+            return out
+        dy = dx = None
+        if ctx.needs_input_grad[1]:
+            dy = wsum(y_emb, all_x, L.WEIGHT_INTERP, par_own, 0, coef_i, dcoef) + \
+                wsum(y_emb, all_x, L.WEIGHT_EXP, shift_all, 1, coef_e, zero)
+        if ctx.needs_input_grad[0]:
+            dx = wsum(x_emb, all_y, L.WEIGHT_INTERP, par_all, 1, coef_i, dcoef) + \
+                wsum(x_emb, all_y, L.WEIGHT_EXP, shift_own, 0, coef_e, zero)
+        dbase = (g * da / nn_).float().reshape(n_own, 1) if ctx.needs_input_grad[2] else None
+        return dx, dy, dbase, None, None, None
+
+
+def separable_interp_bound(x_emb, y_emb, log_baseline, alpha_logit, rowblock=None, impl=L.IMPL_AUTO):
+    """Fused ``interp_lower_bound(h(y) @ g(x).T, log_baseline, alpha_logit)`` -> (mi, mi_loss)."""
+    return _SeparableInterp.apply(x_emb, y_emb, log_baseline, alpha_logit, impl, rowblock)
+
+
 class _ScoresBound(torch.autograd.Function):
     """Bound over a materialised score matrix (API parity with VMI.py:136-198).
 

@@ -1,16 +1,17 @@
-"""Where does the 1e-4 of the concat JS gradient at B = 2048 come from?  (a) scores, (b) dL/dS from the bound,
-(c) the pair-MLP backward fed with the float64 dL/dS."""
+"""Concat critic, JS / NWJ at batch B: the fused-bound path and the materialising path against a float64 evaluation of the
+reference's op chain (VMI.py:58-65, 157-182) on the GPU, per tensor."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-import mimrl_b200.vmi as V
+import mimrl_b200.model as M
 from mimrl_b200.model import VMIEstimator
 
 torch.backends.cuda.matmul.allow_tf32 = False
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+bound = sys.argv[2] if len(sys.argv) > 2 else "js"
 torch.manual_seed(11)
-est = VMIEstimator("concat", "constant", "js", 128, 256, 128, 2, "relu", 0, 1).cuda()
+est = VMIEstimator("concat", "constant", bound, 128, 256, 128, 2, "relu", 0, 1).cuda()
 with torch.no_grad():
     for n, p in est.named_parameters():
         if n.endswith("bias"):
@@ -21,47 +22,35 @@ y = 0.6 * x + 0.8 * torch.randn(B, 128, generator=g)
 rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
 
 f = est.critic_model.MLP_f
-W = [m.weight.detach().double() for m in (f[0], f[2], f[4], f[6])]
-bb = [m.bias.detach().double() for m in (f[0], f[2], f[4], f[6])]
+names = [n for n, _ in est.named_parameters()]
+P64 = [p.detach().double().requires_grad_(True) for p in est.parameters()]
+pd = dict(zip(names, P64))
+W = [pd[f"critic_model.MLP_f.{i}.weight"] for i in (0, 2, 4, 6)]
+bb = [pd[f"critic_model.MLP_f.{i}.bias"] for i in (0, 2, 4, 6)]
 xd, yd = x.cuda().double().requires_grad_(True), y.cuda().double().requires_grad_(True)
 u = xd @ W[0][:, :128].t() + bb[0]
 v = yd @ W[0][:, 128:].t()
 h = torch.relu(u[:, None, :] + v[None, :, :])
 h = torch.relu(h @ W[1].t() + bb[1])
 h = torch.relu(h @ W[2].t() + bb[2])
-S64 = (h @ W[3].t() + bb[3]).reshape(B, B)          # rows x, cols y
-S64 = S64.t()                                        # VMI.py:65 returns scores.t(): rows y? keep the module's orientation below
-xs, ys = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
-S = est.critic_model(xs, ys)
-print("scores orientation/equality  rel(S, S64) =", rel(S, S64), " rel(S, S64.t()) =", rel(S, S64.t()))
-Sref = S64 if rel(S, S64) < rel(S, S64.t()) else S64.t()
-# (b) bound gradient
-S_leaf = S.detach().clone().requires_grad_(True)
-mi = V.js_lower_bound(S_leaf)
-(-mi).backward()
-Sd = Sref.detach().clone().requires_grad_(True)
-d = Sd.diag()
-first = -F.softplus(-d).mean()
-second = (F.softplus(Sd).sum() - F.softplus(d).sum()) / (B * (B - 1.0))
-(-(first - second)).backward()
-print("dL/dS: rel =", rel(S_leaf.grad, Sd.grad), " offdiag-only rel =",
-      rel(S_leaf.grad - torch.diag(S_leaf.grad.diag()), Sd.grad - torch.diag(Sd.grad.diag())))
-# (c) pair-MLP backward with the float64 gradient
-G = Sd.grad.float()
-S.backward(G)
-Sref.backward(Sd.grad)
-print("grad x rel =", rel(xs.grad, xd.grad), " grad y rel =", rel(ys.grad, yd.grad))
-# (d) same with the diagonal of G removed / only the diagonal
-for name, Gm in (("offdiag", Sd.grad - torch.diag(Sd.grad.diag())), ("diag", torch.diag(Sd.grad.diag()))):
-    xs2, ys2 = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
-    est.critic_model(xs2, ys2).backward(Gm.float())
-    xd2, yd2 = x.cuda().double().requires_grad_(True), y.cuda().double().requires_grad_(True)
-    u = xd2 @ W[0][:, :128].t() + bb[0]
-    v = yd2 @ W[0][:, 128:].t()
-    h = torch.relu(u[:, None, :] + v[None, :, :])
-    h = torch.relu(h @ W[1].t() + bb[1])
-    h = torch.relu(h @ W[2].t() + bb[2])
-    S2 = (h @ W[3].t() + bb[3]).reshape(B, B)
-    S2 = S2 if rel(S, S64) < rel(S, S64.t()) else S2.t()
-    S2.backward(Gm)
-    print(name, "grad x rel =", rel(xs2.grad, xd2.grad), " grad y rel =", rel(ys2.grad, yd2.grad))
+S = (h @ W[3].t() + bb[3]).reshape(B, B)          # rows x, cols y (VMI.py:65 after the .t())
+d = S.diag()
+n = float(B)
+if bound == "js":
+    val = -F.softplus(-d).mean() - (F.softplus(S).sum() - F.softplus(d).sum()) / (n * (n - 1))
+else:   # nwj
+    Sm = S - 1.0
+    off = ~torch.eye(B, dtype=torch.bool, device="cuda")
+    val = 1 + (Sm.diag()).mean() - torch.exp(torch.logsumexp(Sm[off], 0) - torch.log(torch.tensor(n * (n - 1), dtype=torch.float64)))
+(-val).backward()
+for fused in (True, False):
+    M.FUSED_CONCAT_BOUND = fused
+    est.zero_grad(set_to_none=True)
+    xs, ys = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
+    mi, loss = est(xs, ys)
+    loss.backward()
+    print(f"B={B} {bound} fused={fused}: gx {rel(xs.grad, xd.grad):.2e} gy {rel(ys.grad, yd.grad):.2e}", end="")
+    for nme, p in est.named_parameters():
+        if p.grad is not None:
+            print(f" | {nme.split('MLP_f.')[-1]} {rel(p.grad, pd[nme].grad):.2e}", end="")
+    print()

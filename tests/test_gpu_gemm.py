@@ -15,7 +15,7 @@ def _setup():
 
 
 def rel(a, b):
-    return float((a.double() - b).abs().max() / b.abs().max())
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-3))
 
 
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 128), (128, 128, 64), (777, 130, 100), (4096, 128, 384), (65, 40, 72)])
@@ -129,18 +129,18 @@ def test_small_linear_modes_against_float64(M, N, K):
     bias = torch.randn(N, device="cuda", generator=g)
     want = A.double() @ Bt.double().t() + bias.double()
     assert rel(_small(0, A, None, Bt, M, N, K, bias, False), want) < 2e-6
-    assert rel(_small(0, A, None, Bt, M, N, K, bias, True), want.clamp_min(0) + 1e-30) < 2e-6
+    assert rel(_small(0, A, None, Bt, M, N, K, bias, True), want.clamp_min(0)) < 2e-6
     Bn = Bt.t().contiguous()                                       # [K, N]
     mask = torch.randn(M, K, device="cuda", generator=g)
     want = (A.double() * (mask > 0)) @ Bn.double()
-    assert rel(_small(1, A, mask, Bn, M, N, K), want + 1e-30) < 2e-6
+    assert rel(_small(1, A, mask, Bn, M, N, K), want) < 2e-6
     At = torch.randn(K, M, device="cuda", generator=g)             # mode 2: contraction over the rows (K may be the batch)
     maskt = torch.randn(K, M, device="cuda", generator=g)
     masked = At.double() * (maskt > 0)
     want = masked.t() @ Bn.double()
     colsum = torch.full((M,), 0.5, device="cuda")
     got = _small(2, At, maskt, Bn, M, N, K, colsum=colsum)
-    assert rel(got, want + 1e-30) < 5e-6
+    assert rel(got, want) < 5e-6
     assert rel(colsum, masked.sum(0) + 0.5) < 5e-6                # accumulated (+=) onto what was there
 
 
@@ -155,17 +155,27 @@ def test_small_batch_mlp_stack_matches_torch(rows, d_in, d_out):
     for m in seq:
         if isinstance(m, torch.nn.Linear):
             torch.nn.init.uniform_(m.bias, -0.1, 0.1)
+    import copy
     x = torch.randn(rows, d_in, device="cuda", requires_grad=True)
     w = torch.randn(rows, d_out, device="cuda")
-    (mlp_apply(seq, x) * w).sum().backward()
-    got = [x.grad.clone()] + [p.grad.clone() for p in seq.parameters()]
-    import copy
     seq64 = copy.deepcopy(seq).double()
     seq64.zero_grad()
     x64 = x.detach().double().requires_grad_(True)
-    y64 = seq64(x64)
+    # rows with a hidden pre-activation within 1e-5 of zero get no upstream gradient: there the ReLU mask is decided by
+    # rounding in ANY fp32 implementation
+    h, near = x64, torch.zeros(rows, dtype=torch.bool, device="cuda")
+    for m in seq64:
+        h = m(h)
+        if isinstance(m, torch.nn.Linear) and m is not seq64[-1]:
+            near |= (h.abs() < 1e-5).any(dim=1)
+    assert float(near.double().mean()) < 0.05
+    w = torch.where(near[:, None], torch.zeros_like(w), w)
+    y64 = h
     (y64 * w.double()).sum().backward()
     want = [x64.grad] + [p.grad for p in seq64.parameters()]
-    assert rel(mlp_apply(seq, x).detach(), y64.detach()) < 1e-5
+    y = mlp_apply(seq, x)
+    (y * w).sum().backward()
+    got = [x.grad.clone()] + [p.grad.clone() for p in seq.parameters()]
+    assert rel(y.detach(), y64.detach()) < 1e-5
     for a, b in zip(got, want):
         assert rel(a, b) < 1e-5
