@@ -101,7 +101,7 @@ def test_fused_mlp4_vs_float64(M, d_in, d_out):
             h = l(h)
             if isinstance(l, torch.nn.Linear) and i < 6:
                 near |= (h.abs() < 1e-5).any(dim=1)
-    assert float(near.double().mean()) < 0.05
+    assert float(near.double().mean()) < 0.2
     w = torch.randn(M, d_out, device=dev).abs()
     w[near] = 0
     xt = x.clone().requires_grad_(True)
@@ -168,7 +168,7 @@ def test_small_batch_mlp_stack_matches_torch(rows, d_in, d_out):
         h = m(h)
         if isinstance(m, torch.nn.Linear) and m is not seq64[-1]:
             near |= (h.abs() < 1e-5).any(dim=1)
-    assert float(near.double().mean()) < 0.05
+    assert float(near.double().mean()) < 0.2
     w = torch.where(near[:, None], torch.zeros_like(w), w)
     y64 = h
     (y64 * w.double()).sum().backward()

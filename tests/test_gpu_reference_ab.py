@@ -108,19 +108,21 @@ def test_relu_kink_rows_reference_fp32_misses_float64_too(ref):
 
     def row_err(a, b):                  # per row: max |a - b| over the row / max |b| over the tensor
         return np.abs(a - b).max(axis=1) / np.abs(b).max()
-    report = {}
+    report, worst_ours, worst_ref, ref_missed = {}, 0.0, 0.0, 0
     for name, bad, g_ours, g32, g64 in (("x", bad_x, gx, gx32, gx64), ("y", bad_y, gy, gy32, gy64)):
         e_ours, e_ref32 = row_err(g_ours, g64), row_err(g32, g64)
         assert 0 < bad.sum() < 0.1 * B, bad.sum()
         # away from a kink: both fp32 implementations agree with float64
         assert e_ours[~bad].max() < TOL, (name, e_ours[~bad].max())
         assert e_ref32[~bad].max() < TOL, (name, e_ref32[~bad].max())
-        # at a kink: a row the kernels miss is a row whose mask the rounding decides; the fp32 reference is exposed to
-        # the same rows (it misses some of them itself) and the miss is the size of one flipped unit, not a precision loss
-        missed_ours, missed_ref = bad & (e_ours >= TOL), bad & (e_ref32 >= TOL)
-        report[name] = (int(bad.sum()), int(missed_ours.sum()), int(missed_ref.sum()), float(e_ours[bad].max()),
-                        float(e_ref32[bad].max()))
-        if missed_ours.any():
-            assert missed_ref.any(), (name, report)
-            assert e_ours[bad].max() <= 10 * e_ref32[bad].max(), (name, report)
+        report[name] = (int(bad.sum()), int((bad & (e_ours >= TOL)).sum()), int((bad & (e_ref32 >= TOL)).sum()),
+                        float(e_ours[bad].max()), float(e_ref32[bad].max()))
+        worst_ours, worst_ref = max(worst_ours, float(e_ours[bad].max())), max(worst_ref, float(e_ref32[bad].max()))
+        ref_missed += int((bad & (e_ref32 >= TOL)).sum())
     print("kink rows (n, missed by kernels, missed by fp32 reference, worst kernels, worst reference):", report)
+    # at a kink the mask of a unit is decided by the rounding of its pre-activation, independently in every fp32
+    # implementation: the reference's own fp32 arithmetic misses its float64 evaluation on some of these rows (so the
+    # exclusion is needed to compare ANY fp32 run with float64), and a miss of the kernels is of the same size -- one
+    # flipped unit -- not a loss of precision
+    assert ref_missed > 0 and worst_ref >= TOL, report
+    assert worst_ours <= 10 * worst_ref, report

@@ -301,10 +301,13 @@ def test_online_forward_abi_row_block(n_own, n_all, offset, inc, ramp):
     Woff = W.copy()
     Woff[rows, offset + rows] = 0.0
     want_sum = Woff.sum(axis=1)
-    assert np.abs(rsum.cpu().numpy() - want_sum).max() <= 5e-5 * max(want_sum.max(), 1e-30)
+    # a weight is exp(S - ref): an absolute error of the fp32-class score (a few ulp of |S|: 6e-5 at |S| = 512, where the
+    # ramped cases live) is a relative error of the weight, in ANY fp32 evaluation of the scores
+    tol = 5e-5 + 4 * 2.0 ** -23 * float(np.abs(S).max())
+    assert np.all(np.abs(rsum.cpu().numpy() - want_sum) <= tol * np.maximum(want_sum, 1e-30))
     want = (W if inc else Woff) @ swept.astype(np.float64)
     if np.abs(want).max() > 0:
-        assert rel_err(wsum.cpu().numpy(), want) < 5e-5
+        assert rel_err(wsum.cpu().numpy(), want) < tol
     else:
         assert np.all(wsum.cpu().numpy() == 0)
 
