@@ -28,7 +28,7 @@ def _worker(rank, world, port, bound, B, q, critic="separate", hidden=64):
         from mimrl_b200.model import VMIEstimator
         from oracle import params as P
         torch.backends.cuda.matmul.allow_tf32 = False
-        baseline = "unnormalized" if bound == "tuba" else "constant"
+        baseline = "unnormalized" if bound in ("tuba", "interpolate") else "constant"
         prm = P.vmi_params(3, critic, baseline, 128, hidden, 128, 2)
         x, y = P.features(4, B, 128, corr=0.6)
         counts = (B // 2 + 3, B - B // 2 - 3)                       # ragged shards
@@ -50,7 +50,7 @@ def _worker(rank, world, port, bound, B, q, critic="separate", hidden=64):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("bound", ["infonce", "nwj", "tuba", "js"])
+@pytest.mark.parametrize("bound", ["infonce", "nwj", "tuba", "js", "interpolate"])
 def test_sharded_estimator_matches_oracle(bound):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -67,7 +67,7 @@ def test_sharded_estimator_matches_oracle(bound):
     for p in procs:
         p.join(timeout=60)
     assert all(len(r) == 5 for r in res), res
-    baseline = "unnormalized" if bound == "tuba" else "constant"
+    baseline = "unnormalized" if bound in ("tuba", "interpolate") else "constant"
     prm = P.vmi_params(3, "separate", baseline, 128, 64, 128, 2)
     x, y = P.features(4, B, 128, corr=0.6)
     ref = O.vmi_estimator(prm, "separate", baseline, bound, x, y)
@@ -102,7 +102,7 @@ def test_sharded_concat_estimator_matches_oracle(bound):
     for p in procs:
         p.join(timeout=60)
     assert all(len(r) == 5 for r in res), res
-    baseline = "unnormalized" if bound == "tuba" else "constant"
+    baseline = "unnormalized" if bound in ("tuba", "interpolate") else "constant"
     prm = P.vmi_params(3, "concat", baseline, 128, 256, 128, 2)
     x, y = P.features(4, B, 128, corr=0.6)
     ref = O.vmi_estimator(prm, "concat", baseline, bound, x, y)

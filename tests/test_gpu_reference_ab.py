@@ -64,20 +64,34 @@ def _inputs(B, seed):
 @pytest.mark.parametrize("bound", ["nwj", "js"])
 def test_concat_B2048_against_reference_float64(ref, bound):
     """VMI.py:58-65 (all-pairs concat MLP) + VMI.py:157-182, B = 2048: the reference materialises [B^2, 256] tensors
-    (float64: ~9 GB each), the fused kernels keep them in TMEM."""
+    (float64: ~9 GB each), the fused kernels keep them in TMEM.
+
+    The yardstick is the reference's float64 run.  At this size the input gradient is a small difference of two sums over
+    2048 pairs each (the diagonal term against the mean of the off-diagonal ones), so fp32 arithmetic ITSELF is only good
+    to ~1e-3 here: the reference's own fp32 run (TF32 off) is measured against its float64 run in the same test, and the
+    kernels must be within 1e-4 of float64, or closer to float64 than twice the fp32 reference's own miss."""
     B = 2048
     theirs, ours = _pair(ref, "concat", bound, torch.float64, seed=11)
     x, y = _inputs(B, 12)
     mi_r, gx_r, gy_r, pg_r = _run(theirs, x, y, torch.float64)
+    torch.cuda.empty_cache()
+    mi32, gx32, gy32, pg32 = _run(theirs.to(torch.float32), x, y, torch.float32)
     del theirs
     torch.cuda.empty_cache()
     mi, gx, gy, pg = _run(ours, x, y, torch.float32)
     assert abs(mi - mi_r) <= TOL * max(1.0, abs(mi_r)), (mi, mi_r)
-    assert rel_err(gx, gx_r) < TOL and rel_err(gy, gy_r) < TOL, (rel_err(gx, gx_r), rel_err(gy, gy_r))
+    report = {}
+    for name, got, ref32, want in [("x", gx, gx32, gx_r), ("y", gy, gy32, gy_r)] + [(n, pg[n], pg32[n], pg_r[n]) for n in pg_r]:
+        floor = 1e-7 * max(1.0, float(np.abs(want).max()))
+        e_ours = (np.abs(got - want).max() - floor) / np.abs(want).max()
+        e_ref = np.abs(ref32 - want).max() / np.abs(want).max()
+        report[name] = (float(e_ours), float(e_ref))
+    print("rel. error vs float64 (kernels, reference fp32):", report)
     assert set(pg) == set(pg_r)
-    for n in pg_r:
-        floor = 1e-7 * max(1.0, float(np.abs(pg_r[n]).max()))
-        assert np.abs(pg[n] - pg_r[n]).max() <= TOL * np.abs(pg_r[n]).max() + floor, n
+    for name, (e_ours, e_ref) in report.items():
+        assert e_ours <= max(TOL, 2 * e_ref), (name, report)
+    # the kernels are not riding on that allowance: over all tensors they are at least as close to float64 as fp32 torch
+    assert max(e[0] for e in report.values()) <= max(TOL, max(e[1] for e in report.values())), report
 
 
 def test_relu_kink_rows_reference_fp32_misses_float64_too(ref):
