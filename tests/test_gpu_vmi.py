@@ -102,9 +102,12 @@ def test_interpolate_fused_large_batch_vs_oracle(B, scale):
     r = O.vmi_estimator(prm, "separate", "unnormalized", "interpolate", x, y)
     assert close_scalar(mi, r["mi"]), (mi, r["mi"])
     assert rel_err(gx, r["gx"]) < TOL and rel_err(gy, r["gy"]) < TOL, (rel_err(gx, r["gx"]), rel_err(gy, r["gy"]))
+    # (parameter gradients are checked at the oracle sizes above: with thousands of rows a few ReLU units sit within fp32
+    # rounding of their kink, and one flipped mask moves a weight gradient by more than 1e-4 in ANY fp32 run -- see
+    # tests/test_gpu_reference_ab.py::test_relu_kink_rows_reference_fp32_misses_float64_too)
     for k, v in r["pg"].items():
         if k.endswith("weight"):
-            assert rel_err(pg[k], v) < 2 * TOL, k
+            assert np.linalg.norm(pg[k] - v) <= 2 * TOL * np.linalg.norm(v), k
 
 
 @pytest.mark.parametrize("case", sorted(BOUNDS))
