@@ -40,6 +40,35 @@ __device__ __forceinline__ float softplusf(float z) {
 }
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + __expf(-z)); }
 
+// Gaussian cdf and pdf of z for the exact-erf GELU (Utils.py:88: GELU(z) = z Phi(z), GELU'(z) = Phi(z) + z phi(z)).
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 absolute, i.e. fp32 rounding level) instead of libm's erff: a
+// dozen instructions and two MUFU ops against ~60 -- the CubeMLP epilogues evaluate 7e7 of these per forward pass and
+// are bound by instruction issue.  The tail is formed without cancellation (Phi(z) = q for z < 0, 1 - q otherwise), and
+// the exponential exp(-z^2 / 2) is shared with the pdf.
+__device__ __forceinline__ void gauss_cdf_pdf(float z, float &cdf, float &pdf) {
+  const float ax = fabsf(z) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float q = 0.5f * t * poly * e;
+  cdf = z < 0.f ? q : 1.f - q;
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_fwd(float z) {
+  float cdf, pdf;
+  gauss_cdf_pdf(z, cdf, pdf);
+  return z * cdf;
+}
+__device__ __forceinline__ float gelu_bwd(float z) {
+  float cdf, pdf;
+  gauss_cdf_pdf(z, cdf, pdf);
+  return fmaf(z, pdf, cdf);
+}
+
 // merge two (max, sum-of-exp) pairs; (-inf, 0) is the identity
 __device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2) {
   float mn = fmaxf(m, m2);

@@ -29,16 +29,12 @@ constexpr int kThreads = 256;   // 8 row groups x 32 columns
 constexpr int kRB = 16;         // output rows per thread and chunk (chunk = 128 rows)
 
 __device__ __forceinline__ float act_fwd(int act, float z) {
-  if (act == 0) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));      // exact-erf GELU (Utils.py:88)
+  if (act == 0) return gelu_fwd(z);                                             // exact-erf GELU (Utils.py:88)
   if (act == 1) return fmaxf(z, 0.f);
   return tanhf(z);
 }
 __device__ __forceinline__ float act_bwd(int act, float z) {
-  if (act == 0) {
-    const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-    return cdf + z * pdf;
-  }
+  if (act == 0) return gelu_bwd(z);
   if (act == 1) return z > 0.f ? 1.f : 0.f;
   const float t = tanhf(z);
   return 1.f - t * t;

@@ -41,7 +41,7 @@ struct CubeTcParams {
 };
 
 __device__ __forceinline__ float cube_act(int act, float z) {
-  if (act == 0) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  if (act == 0) return gelu_fwd(z);
   if (act == 1) return fmaxf(z, 0.f);
   return tanhf(z);
 }
@@ -385,7 +385,7 @@ struct CubeBwdParams {
 };
 
 __device__ __forceinline__ float cube_dact(int act, float z) {
-  if (act == 0) return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+  if (act == 0) return gelu_bwd(z);
   if (act == 1) return z > 0.f ? 1.f : 0.f;
   const float t = tanhf(z);
   return 1.f - t * t;
