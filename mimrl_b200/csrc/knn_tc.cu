@@ -261,37 +261,24 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
       mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
-      // all four 32-column chunks of the row are requested before the single wait (one TMEM round trip per tile instead
-      // of four), and the accumulator is handed back to the MMA warp as soon as the values sit in registers
-      uint32_t v0[32], v1[32], v2[32], v3[32];
-      {
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + buf * 128;
-        tmem_ld32(tbase, v0);
-        tmem_ld32(tbase + 32, v1);
-        tmem_ld32(tbase + 64, v2);
-        tmem_ld32(tbase + 96, v3);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + buf * 128 + ch * 32, v);
         tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
-      // d = |q|^2 + |z|^2 - 2 q.z with packed FADD2 / FFMA2; no clamp at 0: the filter only orders candidates, the
-      // float64 re-rank recomputes the survivors' distances
-      auto chunk = [&](uint32_t (&v)[32], int ch) {
         const float4 *k4 = reinterpret_cast<const float4 *>(kn_s + ch * 32);
-        float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        float dmin = INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 kk = k4[j >> 2];
-          const float2 s01 = fadd2(make_float2(kk.x, kk.y), make_float2(qn, qn));
-          const float2 s23 = fadd2(make_float2(kk.z, kk.w), make_float2(qn, qn));
-          const float2 d01 = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(m2inv, m2inv), s01);
-          const float2 d23 = ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(m2inv, m2inv), s23);
-          v[j] = __float_as_uint(d01.x), v[j + 1] = __float_as_uint(d01.y), v[j + 2] = __float_as_uint(d23.x),
-          v[j + 3] = __float_as_uint(d23.y);
-          m4[0] = fminf(m4[0], d01.x), m4[1] = fminf(m4[1], d01.y), m4[2] = fminf(m4[2], d23.x), m4[3] = fminf(m4[3], d23.y);
+          const float d0 = fmaxf(fmaf(__uint_as_float(v[j]), m2inv, qn + kk.x), 0.f);
+          const float d1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), m2inv, qn + kk.y), 0.f);
+          const float d2 = fmaxf(fmaf(__uint_as_float(v[j + 2]), m2inv, qn + kk.z), 0.f);
+          const float d3 = fmaxf(fmaf(__uint_as_float(v[j + 3]), m2inv, qn + kk.w), 0.f);
+          v[j] = __float_as_uint(d0), v[j + 1] = __float_as_uint(d1), v[j + 2] = __float_as_uint(d2),
+          v[j + 3] = __float_as_uint(d3);
+          dmin = fminf(dmin, fminf(fminf(d0, d1), fminf(d2, d3)));
         }
-        const float dmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         if (row_ok && dmin <= tau_d) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -302,11 +289,10 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
             }
           }
         }
-      };
-      chunk(v0, 0);
-      chunk(v1, 1);
-      chunk(v2, 2);
-      chunk(v3, 3);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * buf);
       if (row_ok) {
         const int it = i >> 1;               // tiles this warpgroup has finished
         // refresh points: tiles 1, 2, 4, 8 of this warpgroup while the lists warm up, then every 16th

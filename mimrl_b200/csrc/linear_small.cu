@@ -128,7 +128,9 @@ __global__ void linear_small_colsum_kernel(const float *__restrict__ part, int s
 
 int pick_k_splits(int M, int N, int K) {
   const int tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
-  if (tiles >= 148 || K <= 4 * kBK) return 1;
+  // a short contraction is not worth a second (reduce) launch: at the reference's batch of 128 every layer is
+  // launch-latency bound, and one launch per product is what counts
+  if (tiles >= 148 || K < 2048) return 1;
   int s = ceil_div(2 * 148, tiles);
   const int max_s = ceil_div(K, 4 * kBK);
   s = s > max_s ? max_s : s;
