@@ -10,16 +10,17 @@
 // backward with the saved layer output as mask); colsum (nullable, mode 2 only): colsum[m] += sum_k A'[k, m], the bias
 // gradient of the same masked matrix, accumulated by the CTAs of the first column tile.
 //
-// One kernel, generic element strides: C[i,j] = sum_p A(i,p) B(p,j).  64 x 64 output tile, 16-deep k slices staged in
-// shared memory, 256 threads x (4 x 4) outputs.  The contraction is split over blockIdx.z when the output alone cannot
-// fill the SMs (weight gradients: N x K outputs, contraction over the batch); partial tiles are summed in a fixed order
-// by a second kernel, so results are deterministic.
+// One kernel, generic element strides: C[i,j] = sum_p A(i,p) B(p,j).  16 x 32 output tile, 32-deep k slices staged in
+// shared memory with the next slice prefetched into registers, 128 threads x (1 x 4) outputs.  Long contractions (weight
+// gradients over a large batch) are split over blockIdx.z; partial tiles are summed in a fixed order by a second kernel,
+// so results are deterministic.
 #include "common.cuh"
 
 namespace mimrl {
 namespace {
 
-constexpr int kBM = 64, kBN = 64, kBK = 16, kThreads = 256;
+constexpr int kBM = 16, kBN = 32, kBK = 32, kThreads = 128;      // small tiles: 64+ CTAs already at 128 x 256 outputs
+constexpr int kLA = kBM * kBK / kThreads, kLB = kBN * kBK / kThreads;   // elements of a k-slice each thread loads
 
 struct SmallParams {
   const float *A, *mask, *B, *bias;
@@ -29,81 +30,88 @@ struct SmallParams {
   int relu, k_per_split, splits;
 };
 
+// One k-slice ahead in registers (global -> registers while the previous slice is multiplied out of shared memory): at
+// these sizes a launch is a single wave of a few dozen CTAs and its duration is the serial latency of the k loop.
 __global__ void __launch_bounds__(kThreads) linear_small_kernel(const SmallParams p) {
-  __shared__ float As[kBK][kBM + 4];
+  __shared__ float As[kBK][kBM + 1];
   __shared__ float Bs[kBK][kBN + 4];
-  const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
+  const int i0 = blockIdx.x * kBM, j0 = blockIdx.y * kBN;          // row tiles on x: no 65535 limit on the batch
   const int k_lo = blockIdx.z * p.k_per_split, k_hi = min(p.K, k_lo + p.k_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // outputs (ty*4 .. +3, tx*4 .. +3)
-  float acc[4][4] = {};
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;          // outputs (row ty, columns tx*4 .. +3)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float csum = 0.f;                                                // column sum of A' for row (of C) i0 + threadIdx.x
   // loader mapping: which index runs fastest in memory decides which one the lanes walk
   const bool a_i_fast = p.sa_i == 1, b_j_fast = p.sb_j == 1;
-  for (int k0 = k_lo; k0 < k_hi; k0 += kBK) {
+  float ra[kLA], rb[kLB];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int t = 0; t < (kBM * kBK) / kThreads; ++t) {
+    for (int t = 0; t < kLA; ++t) {
       const int e = t * kThreads + threadIdx.x;
       const int ii = a_i_fast ? (e % kBM) : (e / kBK), pp = a_i_fast ? (e / kBM) : (e % kBK);
       const int gi = i0 + ii, gp = k0 + pp;
       float v = 0.f;
       if (gi < p.M && gp < k_hi) {
         const long long off = gi * p.sa_i + gp * p.sa_p;
-        v = p.A[off];
-        if (p.mask && !(p.mask[off] > 0.f)) v = 0.f;
+        v = __ldg(p.A + off);
+        if (p.mask && !(__ldg(p.mask + off) > 0.f)) v = 0.f;
       }
-      As[pp][ii] = v;
+      ra[t] = v;
     }
 #pragma unroll
-    for (int t = 0; t < (kBN * kBK) / kThreads; ++t) {
+    for (int t = 0; t < kLB; ++t) {
       const int e = t * kThreads + threadIdx.x;
       const int jj = b_j_fast ? (e % kBN) : (e / kBK), pp = b_j_fast ? (e / kBN) : (e % kBK);
       const int gj = j0 + jj, gp = k0 + pp;
-      Bs[pp][jj] = (gj < p.N && gp < k_hi) ? p.B[gp * p.sb_p + gj * p.sb_j] : 0.f;
+      rb[t] = (gj < p.N && gp < k_hi) ? __ldg(p.B + gp * p.sb_p + gj * p.sb_j) : 0.f;
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int t = 0; t < kLA; ++t) {
+      const int e = t * kThreads + threadIdx.x;
+      const int ii = a_i_fast ? (e % kBM) : (e / kBK), pp = a_i_fast ? (e / kBM) : (e % kBK);
+      As[pp][ii] = ra[t];
+    }
+#pragma unroll
+    for (int t = 0; t < kLB; ++t) {
+      const int e = t * kThreads + threadIdx.x;
+      const int jj = b_j_fast ? (e % kBN) : (e / kBK), pp = b_j_fast ? (e / kBN) : (e % kBK);
+      Bs[pp][jj] = rb[t];
+    }
+  };
+  if (k_lo < k_hi) fetch(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += kBK) {
+    stage();
     __syncthreads();
+    if (k0 + kBK < k_hi) fetch(k0 + kBK);                          // in flight while this slice is multiplied
 #pragma unroll
     for (int pp = 0; pp < kBK; ++pp) {
-      const float4 a = *reinterpret_cast<const float4 *>(&As[pp][ty * 4]);
+      const float a = As[pp][ty];
       const float4 b = *reinterpret_cast<const float4 *>(&Bs[pp][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(av[u], bv[w], acc[u][w]);
+      acc[0] = fmaf(a, b.x, acc[0]), acc[1] = fmaf(a, b.y, acc[1]), acc[2] = fmaf(a, b.z, acc[2]), acc[3] = fmaf(a, b.w, acc[3]);
     }
-    if (p.colsum && blockIdx.x == 0 && threadIdx.x < kBM) {
+    if (p.colsum && blockIdx.y == 0 && threadIdx.x < kBM) {
 #pragma unroll
       for (int pp = 0; pp < kBK; ++pp) csum += As[pp][threadIdx.x];
     }
     __syncthreads();
   }
-  if (p.splits == 1) {
+  const int gi = i0 + ty;
+  if (gi < p.M) {
+    float *dst = p.splits == 1 ? p.C : p.C + (size_t)blockIdx.z * p.M * p.N;      // split mode: C is the partial buffer
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int gi = i0 + ty * 4 + u;
-      if (gi >= p.M) continue;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int gj = j0 + tx * 4 + w;
-        if (gj >= p.N) continue;
-        float v = acc[u][w] + (p.bias ? p.bias[gj] : 0.f);
-        p.C[(size_t)gi * p.N + gj] = p.relu ? fmaxf(v, 0.f) : v;
+    for (int w = 0; w < 4; ++w) {
+      const int gj = j0 + tx * 4 + w;
+      if (gj >= p.N) continue;
+      float v = acc[w];
+      if (p.splits == 1) {
+        v += p.bias ? p.bias[gj] : 0.f;
+        if (p.relu) v = fmaxf(v, 0.f);
       }
-    }
-  } else {
-    float *part = p.C + (size_t)blockIdx.z * p.M * p.N;            // C points at the partial buffer here
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int gi = i0 + ty * 4 + u;
-      if (gi >= p.M) continue;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int gj = j0 + tx * 4 + w;
-        if (gj < p.N) part[(size_t)gi * p.N + gj] = acc[u][w];
-      }
+      dst[(size_t)gi * p.N + gj] = v;
     }
   }
-  if (p.colsum && blockIdx.x == 0 && threadIdx.x < kBM && i0 + threadIdx.x < p.M) {
+  if (p.colsum && blockIdx.y == 0 && threadIdx.x < kBM && i0 + threadIdx.x < p.M) {
     if (p.splits == 1) p.colsum[i0 + threadIdx.x] += csum;
     else p.colsum[(size_t)(1 + blockIdx.z) * p.M + i0 + threadIdx.x] = csum;     // partials behind the output vector
   }
@@ -165,7 +173,7 @@ extern "C" int mimrl_linear_small(int mode, const float *A, const float *a_mask,
   const int splits = pick_k_splits(M, N, K);
   p.splits = splits;
   p.k_per_split = ceil_div(ceil_div(K, splits), kBK) * kBK;
-  dim3 grid(ceil_div(N, kBN), ceil_div(M, kBM), splits);
+  dim3 grid(ceil_div(M, kBM), ceil_div(N, kBN), splits);
   if (splits == 1) {
     linear_small_kernel<<<grid, kThreads, 0, st>>>(p);
     return check_launch("linear_small");
