@@ -693,6 +693,197 @@ cubemlp_small_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const Mi
   }
 }
 
+// ---------------------------------------------------------------------------
+// The modality mix of the reference model exactly (A = H = A' = 3, LayerNorm last, inner % 4 == 0: x [outer, 3, inner]
+// with inner = 128 channels).  A thread owns FOUR neighbouring fibres: its three inputs are three 16-byte loads, every
+// output is a 16-byte store, there is no index division (outer = blockIdx-strided, inner = lane * 4), the activation is
+// a template parameter and the four fibres are independent instruction streams that hide each other's latencies.
+// Purely bandwidth-bound when it works: 3 loads + 3 stores (+ 2 for the saved statistics) per four fibres.
+struct K3Params {
+  float w1[9], w2[9], wr[9], b1[3], b2[3], lw[3], lb[3];
+};
+
+template <int ACT>
+__device__ __forceinline__ float k3_act(float z) {
+  if (ACT == 0) return gelu_fwd(z);
+  if (ACT == 1) return fmaxf(z, 0.f);
+  return tanhf(z);
+}
+template <int ACT>
+__device__ __forceinline__ float k3_dact(float z) {
+  if (ACT == 0) return gelu_bwd(z);
+  if (ACT == 1) return z > 0.f ? 1.f : 0.f;
+  const float t = tanhf(z);
+  return 1.f - t * t;
+}
+
+__device__ __forceinline__ void k3_load_params(K3Params &sp, const MixArgs &m) {
+  for (int t = threadIdx.x; t < 9; t += blockDim.x) {
+    sp.w1[t] = m.w1[t];
+    sp.w2[t] = m.w2[t];
+    sp.wr[t] = m.wres ? m.wres[t] : ((t / 3) == (t % 3) ? 1.f : 0.f);
+  }
+  for (int t = threadIdx.x; t < 3; t += blockDim.x) {
+    sp.b1[t] = m.b1 ? m.b1[t] : 0.f;
+    sp.b2[t] = m.b2 ? m.b2[t] : 0.f;
+    sp.lw[t] = m.ln_w[t];
+    sp.lb[t] = m.ln_b[t];
+  }
+}
+
+// forward of one fibre (x[3] -> pre[3], h[3], z[3], mean, rstd)
+template <int ACT>
+__device__ __forceinline__ void k3_forward(const K3Params &sp, const float (&x)[3], float (&pre)[3], float (&h)[3],
+                                           float (&z)[3], float &mean, float &rstd) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    pre[r] = fmaf(sp.w1[3 * r + 2], x[2], fmaf(sp.w1[3 * r + 1], x[1], fmaf(sp.w1[3 * r], x[0], sp.b1[r])));
+    h[r] = k3_act<ACT>(pre[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = fmaf(sp.w2[3 * r + 2], h[2], fmaf(sp.w2[3 * r + 1], h[1], fmaf(sp.w2[3 * r], h[0], sp.b2[r])));
+    z[r] = fmaf(sp.wr[3 * r + 2], x[2], fmaf(sp.wr[3 * r + 1], x[1], fmaf(sp.wr[3 * r], x[0], acc)));
+  }
+  mean = (z[0] + z[1] + z[2]) * (1.f / 3.f);
+  const float d0 = z[0] - mean, d1 = z[1] - mean, d2 = z[2] - mean;
+  rstd = rsqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) * (1.f / 3.f) + 1e-6f);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256)
+cubemlp_k3_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict__ saved) {
+  __shared__ K3Params sp;
+  k3_load_params(sp, m);
+  __syncthreads();
+  const int inner = m.d.inner, q4 = inner >> 2;                 // float4 groups per row
+  const long long n_units = (long long)m.d.outer * q4;           // one unit = four fibres
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_units; u += (long long)gridDim.x * blockDim.x) {
+    const long long o = u / q4;
+    const int i4 = (int)(u - o * q4);
+    const float4 *xp = reinterpret_cast<const float4 *>(m.x + (size_t)o * 3 * inner) + i4;
+    const float4 a0 = __ldg(xp), a1 = __ldg(xp + q4), a2 = __ldg(xp + 2 * q4);
+    const float xs[4][3] = {{a0.x, a1.x, a2.x}, {a0.y, a1.y, a2.y}, {a0.z, a1.z, a2.z}, {a0.w, a1.w, a2.w}};
+    float yo[3][4], st[8];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      float pre[3], h[3], z[3], mean, rstd;
+      k3_forward<ACT>(sp, xs[f], pre, h, z, mean, rstd);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) yo[r][f] = fmaf((z[r] - mean) * rstd, sp.lw[r], sp.lb[r]);
+      st[2 * f] = mean, st[2 * f + 1] = rstd;
+    }
+    float4 *yp = reinterpret_cast<float4 *>(y + (size_t)o * 3 * inner) + i4;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) yp[r * q4] = make_float4(yo[r][0], yo[r][1], yo[r][2], yo[r][3]);
+    float4 *sv = reinterpret_cast<float4 *>(saved + 2 * ((size_t)o * inner + 4 * (size_t)i4));
+    sv[0] = make_float4(st[0], st[1], st[2], st[3]);
+    sv[1] = make_float4(st[4], st[5], st[6], st[7]);
+  }
+}
+
+// Backward with the weight, bias and LayerNorm-parameter gradients accumulated in registers over the thread's units,
+// then warp shuffles -> shared memory -> one global atomic per block and entry.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+cubemlp_k3_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBwdOut o) {
+  __shared__ K3Params sp;
+  __shared__ float s_acc[39];               // gw1[9] gw2[9] gwr[9] gb1[3] gb2[3] glw[3] glb[3]
+  k3_load_params(sp, m);
+  if (threadIdx.x < 39) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[39];
+#pragma unroll
+  for (int t = 0; t < 39; ++t) acc[t] = 0.f;
+  const int inner = m.d.inner, q4 = inner >> 2;
+  const long long n_units = (long long)m.d.outer * q4;
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_units; u += (long long)gridDim.x * blockDim.x) {
+    const long long oo = u / q4;
+    const int i4 = (int)(u - oo * q4);
+    const size_t base = (size_t)oo * 3 * inner;
+    const float4 *xp = reinterpret_cast<const float4 *>(m.x + base) + i4;
+    const float4 *gp = reinterpret_cast<const float4 *>(gy + base) + i4;
+    const float4 a0 = __ldg(xp), a1 = __ldg(xp + q4), a2 = __ldg(xp + 2 * q4);
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + q4), g2 = __ldg(gp + 2 * q4);
+    const float xs[4][3] = {{a0.x, a1.x, a2.x}, {a0.y, a1.y, a2.y}, {a0.z, a1.z, a2.z}, {a0.w, a1.w, a2.w}};
+    const float gs[4][3] = {{g0.x, g1.x, g2.x}, {g0.y, g1.y, g2.y}, {g0.z, g1.z, g2.z}, {g0.w, g1.w, g2.w}};
+    float gxo[3][4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      float pre[3], h[3], z[3], mean, rstd;
+      k3_forward<ACT>(sp, xs[f], pre, h, z, mean, rstd);
+      // LayerNorm backward
+      float zh[3], gw[3], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        zh[r] = (z[r] - mean) * rstd;
+        gw[r] = gs[f][r] * sp.lw[r];
+        t1 += gw[r];
+        t2 = fmaf(gw[r], zh[r], t2);
+        acc[33 + r] = fmaf(gs[f][r], zh[r], acc[33 + r]);
+        acc[36 + r] += gs[f][r];
+      }
+      t1 *= (1.f / 3.f), t2 *= (1.f / 3.f);
+      float gz[3], gpre[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) gz[r] = (gw[r] - t1 - zh[r] * t2) * rstd;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        gpre[c] = fmaf(sp.w2[6 + c], gz[2], fmaf(sp.w2[3 + c], gz[1], sp.w2[c] * gz[0])) * k3_dact<ACT>(pre[c]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float gu = fmaf(sp.w1[6 + a], gpre[2], fmaf(sp.w1[3 + a], gpre[1], sp.w1[a] * gpre[0]));
+        gxo[a][f] = fmaf(sp.wr[6 + a], gz[2], fmaf(sp.wr[3 + a], gz[1], fmaf(sp.wr[a], gz[0], gu)));
+      }
+      // gW1[h, a] += gpre[h] x[a];  gW2[q, h] += gz[q] h[h];  gWres[q, a] += gz[q] x[a]
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          acc[3 * r + c] = fmaf(gpre[r], xs[f][c], acc[3 * r + c]);
+          acc[9 + 3 * r + c] = fmaf(gz[r], h[c], acc[9 + 3 * r + c]);
+          acc[18 + 3 * r + c] = fmaf(gz[r], xs[f][c], acc[18 + 3 * r + c]);
+        }
+        acc[27 + r] += gpre[r];
+        acc[30 + r] += gz[r];
+      }
+    }
+    float4 *op = reinterpret_cast<float4 *>(o.gx + base) + i4;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) op[a * q4] = make_float4(gxo[a][0], gxo[a][1], gxo[a][2], gxo[a][3]);
+  }
+#pragma unroll
+  for (int t = 0; t < 39; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[t], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    atomicAdd(o.gw1 + threadIdx.x, s_acc[threadIdx.x]);
+    atomicAdd(o.gw2 + threadIdx.x, s_acc[9 + threadIdx.x]);
+    if (o.gwr) atomicAdd(o.gwr + threadIdx.x, s_acc[18 + threadIdx.x]);
+  }
+  if (threadIdx.x < 3) {
+    if (o.gb1) atomicAdd(o.gb1 + threadIdx.x, s_acc[27 + threadIdx.x]);
+    if (o.gb2) atomicAdd(o.gb2 + threadIdx.x, s_acc[30 + threadIdx.x]);
+    atomicAdd(o.gln_w + threadIdx.x, s_acc[33 + threadIdx.x]);
+    atomicAdd(o.gln_b + threadIdx.x, s_acc[36 + threadIdx.x]);
+  }
+}
+
+// the exact shape of the reference's modality mix
+bool is_k3(const MixArgs &m, const void *p0, const void *p1) {
+  return m.d.A == 3 && m.d.H == 3 && m.d.A2 == 3 && !m.ln_first && (m.d.inner & 3) == 0 && m.act >= 0 && m.act <= 2 &&
+         ((reinterpret_cast<uintptr_t>(m.x) | reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+}
+int k3_grid(const MixArgs &m) {
+  const long long units = (long long)m.d.outer * (m.d.inner >> 2);
+  const long long nb = (units + 255) / 256;
+  return (int)(nb < 148 * 16 ? nb : 148 * 16);
+}
+
 bool is_small(const MixDims &d) { return d.A <= kSmallMax && d.H <= kSmallMax && d.A2 <= kSmallMax; }
 
 size_t fwd_smem(const MixDims &d, int ln_first) {
@@ -735,6 +926,13 @@ extern "C" int mimrl_cubemlp_mix_fwd(const float *x, int outer, int a_in, int in
                                      float *saved, void *stream) {
   MixArgs m;
   if (int rc = fill_args(m, x, outer, a_in, inner, w1, b1, a_hid, w2, b2, a_out, wres, ln_w, ln_b, ln_first, act)) return rc;
+  if (is_k3(m, y, saved)) {
+    const int grid = k3_grid(m);
+    if (act == 0) cubemlp_k3_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(m, y, saved);
+    else if (act == 1) cubemlp_k3_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, y, saved);
+    else cubemlp_k3_fwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(m, y, saved);
+    return check_launch("cubemlp_k3_fwd");
+  }
   if (is_small(m.d)) {
     const long long nb = (m.d.n_cols + 255) / 256;
     cubemlp_small_fwd_kernel<<<(int)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, (cudaStream_t)stream>>>(m, y, saved);
@@ -791,6 +989,13 @@ extern "C" int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int oute
   MIMRL_REQUIRE(gx && gw1 && gw2 && gln_w && gln_b && (!wres || gwres), "cubemlp_small_bwd: missing outputs");
   MixBwdOut so{gx, nullptr, nullptr, nullptr, nullptr, gln_w, gln_b};
   so.gw1 = gw1, so.gw2 = gw2, so.gwr = wres ? gwres : nullptr, so.gb1 = gb1, so.gb2 = gb2;
+  if (is_k3(m, gy, gx)) {
+    const int grid = k3_grid(m) > 148 * 4 ? 148 * 4 : k3_grid(m);
+    if (act == 0) cubemlp_k3_bwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+    else if (act == 1) cubemlp_k3_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+    else cubemlp_k3_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
+    return check_launch("cubemlp_k3_bwd");
+  }
   const long long nb = (m.d.n_cols + 255) / 256;
   cubemlp_small_bwd_kernel<4><<<(int)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, (cudaStream_t)stream>>>(m, gy, so);
   return check_launch("cubemlp_small_bwd (with weight gradients)");

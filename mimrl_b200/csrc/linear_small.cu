@@ -10,7 +10,7 @@
 // backward with the saved layer output as mask); colsum (nullable, mode 2 only): colsum[m] += sum_k A'[k, m], the bias
 // gradient of the same masked matrix, accumulated by the CTAs of the first column tile.
 //
-// One kernel, generic element strides: C[i,j] = sum_p A(i,p) B(p,j).  16 x 32 output tile, 32-deep k slices staged in
+// One kernel, generic element strides: C[i,j] = sum_p A(i,p) B(p,j).  16 x 32 output tile, 64-deep k slices staged in
 // shared memory with the next slice prefetched into registers, 128 threads x (1 x 4) outputs.  Long contractions (weight
 // gradients over a large batch) are split over blockIdx.z; partial tiles are summed in a fixed order by a second kernel,
 // so results are deterministic.
@@ -19,7 +19,7 @@
 namespace mimrl {
 namespace {
 
-constexpr int kBM = 16, kBN = 32, kBK = 32, kThreads = 128;      // small tiles: 64+ CTAs already at 128 x 256 outputs
+constexpr int kBM = 16, kBN = 32, kBK = 64, kThreads = 128;      // small tiles: 64+ CTAs already at 128 x 256 outputs
 constexpr int kLA = kBM * kBK / kThreads, kLB = kBN * kBK / kThreads;   // elements of a k-slice each thread loads
 
 struct SmallParams {
