@@ -191,6 +191,20 @@ int mimrl_linear_small(int mode, const float *A, const float *a_mask, const floa
                        const float *bias, int relu, float *C, float *colsum, void *workspace, size_t workspace_bytes,
                        void *stream);
 
+/* The whole relu MLP of VMI.py:13-22 / Model.py:52-57 (Linear+ReLU x3, Linear; hidden 256) for SMALL batches in three
+ * launches: forward of all four layers (h1..h3 [M,256] saved), data gradients of all four layers (dz1..dz3 [M,256],
+ * dz4 [M,d_out]: caller-allocated scratch; gx nullable), and one grouped launch for the weight gradients
+ * gw_l = dz_l^T input_l and bias gradients gb_l (written, not accumulated; any of them nullable).  d_in <= 384,
+ * d_out <= 256, fp32 FFMA. */
+int mimrl_mlp4_small_supported(int d_in, int hidden, int d_out);
+int mimrl_mlp4_small_fwd(const float *x, int M, int d_in, const float *w1, const float *b1, const float *w2, const float *b2,
+                         const float *w3, const float *b3, const float *w4, const float *b4, int d_out, float *h1, float *h2,
+                         float *h3, float *y, void *stream);
+int mimrl_mlp4_small_bwd(const float *gy, const float *x, int M, int d_in, int d_out, const float *w1, const float *w2,
+                         const float *w3, const float *w4, const float *h1, const float *h2, const float *h3, float *dz1,
+                         float *dz2, float *dz3, float *dz4, float *gx, float *gw1, float *gb1, float *gw2, float *gb2,
+                         float *gw3, float *gb3, float *gw4, float *gb4, void *stream);
+
 /* ------------------------------------------------------------------------
  * k-NN conditional-MI sampler.  Replaces the neighbour search and gathers of
  * prod_knn_sample (Model.py:75-106), i.e. sklearn NearestNeighbors.kneighbors.

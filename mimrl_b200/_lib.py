@@ -94,6 +94,10 @@ _SIGS = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_linear_small_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_linear_small": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "mimrl_mlp4_small_supported": (c_int, [c_int, c_int, c_int]),
+    "mimrl_mlp4_small_fwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "mimrl_mlp4_small_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                     _P, _P, _P, _P, _P, _P]),
     "mimrl_feature_stack_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "mimrl_feature_stack_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mimrl_feature_reduce_fwd": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),

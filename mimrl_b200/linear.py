@@ -161,6 +161,62 @@ class _MLP4TC(torch.autograd.Function):
         return (gx, gws[0], gbs[0], gws[1], gbs[1], gws[2], gbs[2], gws[3], gbs[3])
 
 
+class _MLP4Small(torch.autograd.Function):
+    """The same four-layer stack for SMALL batches (< 512 rows: the reference trains at 128) on the CUDA cores, three
+    launches per forward + backward instead of sixteen: mimrl_mlp4_small_fwd (all layers, a row group's activations in
+    shared memory) and mimrl_mlp4_small_bwd (data gradients of all layers, then one grouped launch for the four weight and
+    bias gradients).  Inputs up to 384 wide (the CMI classifier), outputs 1 ... 256 wide (baseline head, classifier head)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
+        x = L.f32(x)
+        ws = [L.f32(w) for w in (w1, w2, w3, w4)]
+        bs = [L.f32(b) if b is not None else None for b in (b1, b2, b3, b4)]
+        M, d_in = x.shape
+        d_out = ws[3].shape[0]
+        dev = x.device
+        hs = torch.empty(3, M, 256, dtype=torch.float32, device=dev)
+        y = torch.empty(M, d_out, dtype=torch.float32, device=dev)
+        L.check(L.lib.mimrl_mlp4_small_fwd(L.ptr(x), M, d_in, L.ptr(ws[0]), L.ptr(bs[0]), L.ptr(ws[1]), L.ptr(bs[1]),
+                                           L.ptr(ws[2]), L.ptr(bs[2]), L.ptr(ws[3]), L.ptr(bs[3]), d_out, L.ptr(hs[0]),
+                                           L.ptr(hs[1]), L.ptr(hs[2]), L.ptr(y), L.stream()))
+        ctx.save_for_backward(x, hs, *ws)
+        ctx.cfg = (M, d_in, d_out, [b is not None for b in bs])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, hs, w1, w2, w3, w4 = ctx.saved_tensors
+        M, d_in, d_out, has_b = ctx.cfg
+        gy = L.f32(gy)
+        dev = gy.device
+        need = ctx.needs_input_grad
+        dz = torch.empty(3, M, 256, dtype=torch.float32, device=dev)
+        dz4 = torch.empty(M, d_out, dtype=torch.float32, device=dev)
+        gx = torch.empty(M, d_in, dtype=torch.float32, device=dev) if need[0] else None
+        dims = [(256, d_in), (256, 256), (256, 256), (d_out, 256)]
+        gws = [torch.empty(n, k, dtype=torch.float32, device=dev) if (need[1 + 2 * l] or (has_b[l] and need[2 + 2 * l])) else None
+               for l, (n, k) in enumerate(dims)]
+        gbs = [torch.empty(n, dtype=torch.float32, device=dev) if (has_b[l] and need[2 + 2 * l]) else None
+               for l, (n, _) in enumerate(dims)]
+        L.check(L.lib.mimrl_mlp4_small_bwd(L.ptr(gy), L.ptr(x), M, d_in, d_out, L.ptr(w1), L.ptr(w2), L.ptr(w3), L.ptr(w4),
+                                           L.ptr(hs[0]), L.ptr(hs[1]), L.ptr(hs[2]), L.ptr(dz[0]), L.ptr(dz[1]), L.ptr(dz[2]),
+                                           L.ptr(dz4), L.ptr(gx), L.ptr(gws[0]), L.ptr(gbs[0]), L.ptr(gws[1]), L.ptr(gbs[1]),
+                                           L.ptr(gws[2]), L.ptr(gbs[2]), L.ptr(gws[3]), L.ptr(gbs[3]), L.stream()))
+        return (gx, gws[0], gbs[0], gws[1], gbs[1], gws[2], gbs[2], gws[3], gbs[3])
+
+
+def _is_mlp4_small(mods, x):
+    if not (USE_FUSED_MLP and len(mods) == 7 and x.dim() == 2 and x.is_cuda and x.shape[0] < MIN_ROWS):
+        return False
+    if not all(isinstance(mods[i], nn.Linear) for i in (0, 2, 4, 6)) or not all(isinstance(mods[i], nn.ReLU) for i in (1, 3, 5)):
+        return False
+    l1, l2, l3, l4 = mods[0], mods[2], mods[4], mods[6]
+    return (l1.out_features == 256 and l2.in_features == 256 and l2.out_features == 256 and l3.in_features == 256
+            and l3.out_features == 256 and l4.in_features == 256 and l1.in_features == x.shape[1]
+            and bool(L.lib.mimrl_mlp4_small_supported(l1.in_features, 256, l4.out_features)))
+
+
 def _is_mlp4(mods, x):
     if not (USE_FUSED_MLP and len(mods) == 7 and x.dim() == 2 and x.is_cuda and x.shape[0] >= MIN_ROWS):
         return False
@@ -186,6 +242,9 @@ def linear(x, weight, bias=None, relu=False):
 def mlp_apply(seq: nn.Sequential, x):
     """Evaluate a Linear/activation stack; Linear+ReLU pairs run as one fused call."""
     mods = list(seq)
+    if _is_mlp4_small(mods, x):
+        l1, l2, l3, l4 = mods[0], mods[2], mods[4], mods[6]
+        return _MLP4Small.apply(x, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias, l4.weight, l4.bias)
     if _is_mlp4(mods, x):
         l1, l2, l3, l4 = mods[0], mods[2], mods[4], mods[6]
         return _MLP4TC.apply(x, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias, l4.weight, l4.bias)

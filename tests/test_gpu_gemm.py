@@ -144,7 +144,8 @@ def test_small_linear_modes_against_float64(M, N, K):
     assert rel(colsum, masked.sum(0) + 0.5) < 5e-6                # accumulated (+=) onto what was there
 
 
-@pytest.mark.parametrize("rows,d_in,d_out", [(128, 128, 128), (96, 128, 1), (2048, 384, 2), (7, 128, 128)])
+@pytest.mark.parametrize("rows,d_in,d_out", [(128, 128, 128), (96, 128, 1), (2048, 384, 2), (7, 128, 128), (256, 384, 2),
+                                            (130, 127, 5)])
 def test_small_batch_mlp_stack_matches_torch(rows, d_in, d_out):
     """The relu MLP stacks at the reference's batch size (128) and with the narrow heads (baseline: 1, CMI classifier: 2)
     through mlp_apply vs the same modules in float64; no library GEMM is involved."""
