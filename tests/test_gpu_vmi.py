@@ -107,7 +107,7 @@ def test_interpolate_fused_large_batch_vs_oracle(B, scale):
     # tests/test_gpu_reference_ab.py::test_relu_kink_rows_reference_fp32_misses_float64_too)
     for k, v in r["pg"].items():
         if k.endswith("weight"):
-            assert np.linalg.norm(pg[k] - v) <= 2 * TOL * np.linalg.norm(v), k
+            assert np.linalg.norm(pg[k] - v) <= 1e-3 * np.linalg.norm(v), k       # one flipped unit of 4096 x 192 ~ 3e-4
 
 
 @pytest.mark.parametrize("case", sorted(BOUNDS))
