@@ -279,11 +279,26 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
           v[j + 3] = __float_as_uint(d3);
           dmin = fminf(dmin, fminf(fminf(d0, d1), fminf(d2, d3)));
         }
-        if (row_ok && dmin <= tau_d) {
+        // Survivors.  A chunk that holds one for ANY of the warp's 32 rows sends the whole warp down this path, so its
+        // cost is what matters early in a sweep (the chance of a survivor decays like K'/keys seen).  Every lane first
+        // builds the bit mask of its own survivors without divergence and parks its 32 distances in local memory; the
+        // lanes then walk their masks together, so the serialised insertions are max-per-lane (typically one), not one
+        // per distinct column position in the warp.
+        if (__any_sync(0xffffffffu, row_ok && dmin <= tau_d)) {
+          uint32_t mask = 0;
+          float loc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float dj = __uint_as_float(v[j]);
-            if (dj <= tau_d && dj < INFINITY) {
+            loc[j] = dj;
+            mask |= (dj <= tau_d && dj < INFINITY) ? (1u << j) : 0u;
+          }
+          if (!row_ok) mask = 0;
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float dj = loc[j];
+            if (dj <= tau_d) {
               knn_insert(lst, len, p.list_len, tau_local, tau_i, worst, dj, col0 + ch * 32 + j);
               tau_d = fminf(tau_local, tau_shared);
             }
