@@ -376,13 +376,16 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   KnnTcPlan p;
   p.list_len = list_len;
   const int q_tiles = ceil_div(n_queries, 128), k_tiles = ceil_div(n_keys, 128);
-  // key splits: as few idle waves over the 148 SMs as possible (one CTA per SM); every split pays a warm-up of a few
-  // tiles while its candidate lists fill.  n_lists = 2 * splits <= 128 (one merge thread per list in the re-rank).
+  // key splits: as few idle waves over the 148 SMs as possible (one CTA per SM).  Every split pays a warm-up while its
+  // candidate lists fill and its threshold is loose (survivor path taken by every chunk); measured on the B200 (A/B of
+  // the constant at 4096 x 1M x 128: 6 -> 5.15 ms, 30 / 100 -> 3.9 ms, 300 -> 3.53 ms) that warm-up is worth ~200-300
+  // steady-state tiles, so few long splits beat many short ones.  n_lists = 2 * splits <= 128 (one merge thread per
+  // list in the re-rank).
   int splits = 1;
   double best = 1e300;
   for (int s = 1; s <= 64 && s <= k_tiles; ++s) {
     const int per = ceil_div(k_tiles, s), eff = ceil_div(k_tiles, per);
-    const double cost = (double)ceil_div(q_tiles * eff, 148) * (per + 6.0);
+    const double cost = (double)ceil_div(q_tiles * eff, 148) * (per + 300.0);
     if (cost < best - 1e-9) best = cost, splits = eff;
   }
   p.tiles_per_split = ceil_div(k_tiles, splits);
