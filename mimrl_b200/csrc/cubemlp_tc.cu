@@ -17,6 +17,7 @@
 // (hi.hi + hi.lo + lo.hi) per contraction keep fp32-class accuracy.
 // No permute copies, no intermediate tensors: one read and one write of x / y.
 #include "tc_common.cuh"
+#include "cubemlp_tc.cuh"
 
 namespace mimrl {
 namespace {
@@ -30,42 +31,6 @@ constexpr uint32_t kWMat = 4 * kW16;                   // hi kb0, hi kb1, lo kb0
 constexpr uint32_t kCubeSmem = 3 * kWMat + 256 + 4 * 128 * 4 + kCubeWG * 128 * 4 + 1024;    // weights, barriers, b1/b2/ln_w/ln_b, LN partials, alignment
 // TMEM columns
 constexpr uint32_t kTX = 0, kTD1 = 128, kTH = 256, kTD2 = 384;
-
-struct CubeTcParams {
-  const float *x, *b1, *b2, *ln_w, *ln_b;
-  float *y, *saved;
-  const unsigned *sc_w1, *sc_w2, *sc_wr;               // absmax headers of the split weights
-  const float *scales;                                 // forward: [0] scale of x, [1] scale of h (powers of two)
-  int outer, A, H, A2, inner, act, has_res;
-  long long n_cols;
-};
-
-__device__ __forceinline__ float cube_act(int act, float z) {
-  if (act == 0) return gelu_fwd(z);
-  if (act == 1) return fmaxf(z, 0.f);
-  return tanhf(z);
-}
-
-__device__ __forceinline__ float pow2_scale(float amax) {      // amax * scale in [2^13, 2^14)
-  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
-  int e;
-  frexpf(amax, &e);
-  int sh = 14 - e;
-  sh = sh < -60 ? -60 : (sh > 60 ? 60 : sh);
-  return ldexpf(1.f, sh);
-}
-
-// split 32 scaled values into fp16 hi / lo pairs (column c = values 2c, 2c+1)
-__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const __half2 h = __floats2half2_rn(v[j], v[j + 1]);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v[j] - hf.x, v[j + 1] - hf.y);
-    hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
-    lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l);
-  }
-}
 
 // 32 consecutive features [a0, a0 + 32) of one fibre (element a at base[a * stride]); entries past n are 0.  When the
 // mixed axis is the innermost one (stride 1, the D mix) the fibre is a contiguous row: 16-byte accesses.
@@ -229,6 +194,7 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
     const float s3 = p.has_res ? 1.f / (sx * scale_from_absmax(p.sc_wr[0])) : 0.f;
     const bool vec_in = p.inner == 1 && (p.A & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
     const bool vec_out = p.inner == 1 && (p.A2 & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
+    float rstd_max = 0.f;
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -342,9 +308,14 @@ cubemlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
         if (g == 0) {
           p.saved[2 * c] = mean;
           p.saved[2 * c + 1] = rstd;
+          rstd_max = fmaxf(rstd_max, rstd);
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * kCubeWG) : "memory");             // partial-sum slots are free for the next tile
+    }
+    if (g == 0) {                     // the backward scales its operands with the largest rstd: no extra pass over `saved`
+      for (int o = 16; o; o >>= 1) rstd_max = fmaxf(rstd_max, __shfl_xor_sync(0xffffffffu, rstd_max, o));
+      if (lane == 0) atomicMax(p.absmax + 2, __float_as_uint(rstd_max));
     }
   }
   tc_fence_before();
@@ -375,36 +346,8 @@ constexpr uint32_t kCbVec = 3 * kWMat + 256;                   // b1 | b2 | ln_w
 constexpr uint32_t kCbPart = kCbVec + 3 * 128 * 4;             // [warpgroups][128 fibres][2] partial LN sums
 constexpr uint32_t kCubeBwdSmem = kCbPart + kCubeBwdWG * 128 * 2 * 4 + 1024;
 
-struct CubeBwdParams {
-  CubeTcParams f;
-  const float *gy;
-  float *gx, *g_b1, *g_b2, *g_lnw, *g_lnb;
-  __half *op[4][2];          // x, h, gz, gpre: hi / lo, [features][ld]
-  size_t ld;
-  const float *scales;       // [0] x [1] h [2] gz [3] gpre
-};
 
-__device__ __forceinline__ float cube_dact(int act, float z) {
-  if (act == 0) return gelu_bwd(z);
-  if (act == 1) return z > 0.f ? 1.f : 0.f;
-  const float t = tanhf(z);
-  return 1.f - t * t;
-}
 
-// sum over the 32 lanes of v[t] for every t; lane t returns the total of entry t
-__device__ __forceinline__ float cube_lane_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
-    const bool upper = lane & s;
-#pragma unroll
-    for (int k = 0; k < n / 2; ++k) {
-      const float keep = upper ? v[k + n / 2] : v[k];
-      const float send = upper ? v[k] : v[k + n / 2];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
 
 // features [f0, f0 + 32) of one fibre -> feature-major operand in the blocked-K layout of make_map_blocked (tiles of
 // 64 consecutive fibres, each [n_feat][64] contiguous); features past n_feat do not exist
@@ -798,70 +741,144 @@ cubemlp_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __gri
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ---- scales of the backward operands ------------------------------------------------------------------------
-// absmax: [0] x  [1] gy  [2] rstd (saved[2c+1])
-__global__ void cube_absmax_kernel(const float *x, size_t nx, const float *gy, size_t ngy, const float *saved, size_t n_cols,
-                                   unsigned *out) {
-  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
-  auto amax4 = [&](const float *p, size_t n, float m) {          // 16-byte loads where the pointer allows it
-    size_t head = 0;
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-      const float4 *p4 = reinterpret_cast<const float4 *>(p);
-      for (size_t t = t0; t < n / 4; t += st) {
-        const float4 v = __ldg(p4 + t);
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-      }
-      head = (n / 4) * 4;
-    }
-    for (size_t t = head + t0; t < n; t += st) m = fmaxf(m, fabsf(p[t]));
-    return m;
-  };
-  m0 = amax4(x, nx, m0);
-  m1 = amax4(gy, ngy, m1);
-  for (size_t t = t0; t < n_cols; t += st) m2 = fmaxf(m2, fabsf(saved[2 * t + 1]));
-  for (int o = 16; o; o >>= 1) {
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMax(out, __float_as_uint(m0));
-    atomicMax(out + 1, __float_as_uint(m1));
-    atomicMax(out + 2, __float_as_uint(m2));
-  }
-}
+// ---- one preparation launch per mix --------------------------------------------------------------------------
+// Blocks [0, n_abs): absmax of x, gy and of the saved rstd column (grid-stride, one atomicMax per warp).
+// Blocks n_abs + {0, 1, 2}: fp16 hi/lo split of W1 / W2 / Wres in the mimrl_split_f32 layout (absmax header, zero
+// padded rows of ld halves); the matrices are <= 128 x 128, one block each.  The LAST block to finish (atomic ticket)
+// derives the power-of-two operand scales from those maxima and from L1 norms of the weights:
+//   |h| <= |pre| <= max|x| max_h sum_a |W1[h,a]| + max|b1|          (|act(z)| <= |z| for gelu, relu, tanh)
+//   |gz| <= rstd (2 + sqrt(A')) max|gy ln_w|,     |gpre| <= 1.2 |gz| max_h sum_q |W2[q,h]|   (|gelu'| < 1.13)
+// and, with a residual projection, ties the scales of gz and gpre together so that gpre W1 and gz Wres can share one
+// accumulator (s_gpre s_W1 == s_gz s_Wres; both are powers of two and the bounds are loose, so nothing is lost).
+// tail: [0] max|x|  [1] max|gy|  [2] max rstd  [3] ticket; scales at tail + 16 (floats).
+struct CubePrepArgs {
+  const float *x, *gy, *saved;
+  size_t nx, ngy, n_cols;
+  const float *w[3];                 // W1 [H, A], W2 [A2, H], Wres [A2, A] (nullable)
+  unsigned char *split[3];           // split buffers; nullptr = already split (backward after forward)
+  const unsigned char *hdr[3];       // where the absmax headers of the splits live (always valid)
+  const float *b1, *ln_w;
+  int A, H, A2, n_abs, backward;
+  unsigned *tail;
+  unsigned *hdr_op[4];               // backward: absmax headers of the weight-gradient operands x, h, gz, gpre
+};
 
-// one block of 128 threads
-__global__ void cube_scales_kernel(const unsigned *absmax, const float *w1, const float *b1, const float *w2, const float *ln_w,
-                                   int A, int H, int A2, float *scales, unsigned *hdr_x, unsigned *hdr_h, unsigned *hdr_gz,
-                                   unsigned *hdr_gp) {
-  __shared__ float red[128];
-  const int n = threadIdx.x;
+__global__ void __launch_bounds__(256) cube_prep_kernel(const CubePrepArgs a) {
+  __shared__ float red[256];
+  __shared__ unsigned s_last;
+  const int t = threadIdx.x;
+  if ((int)blockIdx.x < a.n_abs) {
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + t, st = (size_t)a.n_abs * blockDim.x;
+    auto amax4 = [&](const float *p, size_t n, float m) {          // 16-byte loads where the pointer allows it
+      if (!p) return m;
+      size_t head = 0;
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        for (size_t i = t0; i < n / 4; i += st) {
+          const float4 v = __ldg(p4 + i);
+          m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        head = (n / 4) * 4;
+      }
+      for (size_t i = head + t0; i < n; i += st) m = fmaxf(m, fabsf(p[i]));
+      return m;
+    };
+    m0 = amax4(a.x, a.nx, m0);
+    m1 = amax4(a.gy, a.ngy, m1);
+    if (a.saved)
+      for (size_t i = t0; i < a.n_cols; i += st) m2 = fmaxf(m2, fabsf(a.saved[2 * i + 1]));
+    for (int o = 16; o; o >>= 1) {
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if ((t & 31) == 0) {
+      if (a.x) atomicMax(a.tail, __float_as_uint(m0));
+      if (a.gy) atomicMax(a.tail + 1, __float_as_uint(m1));
+      if (a.saved) atomicMax(a.tail + 2, __float_as_uint(m2));
+    }
+  } else {
+    const int m = blockIdx.x - a.n_abs;
+    const float *w = a.w[m];
+    unsigned char *out = a.split[m];
+    if (w && out) {
+      const int rows = m == 0 ? a.H : a.A2, cols = m == 1 ? a.H : a.A;
+      const int ld = (cols + 63) & ~63;
+      float mx = 0.f;
+      for (int i = t; i < rows * cols; i += 256) mx = fmaxf(mx, fabsf(w[i]));
+      red[t] = mx;
+      __syncthreads();
+      for (int o = 128; o; o >>= 1) {
+        if (t < o) red[t] = fmaxf(red[t], red[t + o]);
+        __syncthreads();
+      }
+      const unsigned bits = __float_as_uint(red[0]);
+      if (t == 0) *reinterpret_cast<unsigned *>(out) = bits;
+      const float sc = scale_from_absmax(bits);
+      __half *hi = reinterpret_cast<__half *>(out + 256);
+      __half *lo = reinterpret_cast<__half *>(out + 256 + align256((size_t)rows * ld * 2));
+      const int half_ld = ld >> 1;
+      for (int i = t; i < rows * half_ld; i += 256) {
+        const int r = i / half_ld, c = (i - r * half_ld) * 2;
+        const float v0 = c < cols ? w[r * cols + c] * sc : 0.f, v1 = c + 1 < cols ? w[r * cols + c + 1] * sc : 0.f;
+        const __half2 h = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(h);
+        *reinterpret_cast<__half2 *>(hi + r * ld + c) = h;
+        *reinterpret_cast<__half2 *>(lo + r * ld + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      }
+    }
+  }
+  // ---- ticket: the last block computes the scales
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(a.tail + 3, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   auto block_max = [&](float v) {
     __syncthreads();
-    red[n] = v;
+    red[t] = v;
     __syncthreads();
-    for (int o = 64; o; o >>= 1) {
-      if (n < o) red[n] = fmaxf(red[n], red[n + o]);
+    for (int o = 128; o; o >>= 1) {
+      if (t < o) red[t] = fmaxf(red[t], red[t + o]);
       __syncthreads();
     }
     return red[0];
   };
+  const int A = a.A, H = a.H, A2 = a.A2;
   float row1 = 0.f, col2 = 0.f;
-  if (n < H) {
-    for (int a = 0; a < A; ++a) row1 += fabsf(w1[(size_t)n * A + a]);          // sum_a |W1[h, a]|
-    for (int q = 0; q < A2; ++q) col2 += fabsf(w2[(size_t)q * H + n]);         // sum_q |W2[q, h]|
+  if (t < H) {
+    for (int k = 0; k < A; ++k) row1 += fabsf(a.w[0][(size_t)t * A + k]);          // sum_a |W1[h, a]|
+    for (int q = 0; q < A2; ++q) col2 += fabsf(a.w[1][(size_t)q * H + t]);         // sum_q |W2[q, h]|
   }
   const float row1_max = block_max(row1), col2_max = block_max(col2);
-  const float b1_max = block_max((b1 && n < H) ? fabsf(b1[n]) : 0.f), lw_max = block_max(n < A2 ? fabsf(ln_w[n]) : 0.f);
-  if (n == 0) {
-    const float m_x = __uint_as_float(absmax[0]), m_gy = __uint_as_float(absmax[1]), m_rstd = __uint_as_float(absmax[2]);
-    const float m_h = m_x * row1_max + b1_max;                                 // |act(z)| <= |z| for gelu, relu, tanh
-    const float m_gz = m_rstd * (2.f + sqrtf((float)A2)) * m_gy * lw_max;
-    const float m_gp = 1.2f * m_gz * col2_max;                                 // |gelu'| < 1.13
-    scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h), scales[2] = pow2_scale(m_gz), scales[3] = pow2_scale(m_gp);
-    if (hdr_x) *hdr_x = __float_as_uint(m_x), *hdr_h = __float_as_uint(m_h), *hdr_gz = __float_as_uint(m_gz), *hdr_gp = __float_as_uint(m_gp);
+  const float b1_max = block_max((a.b1 && t < H) ? fabsf(a.b1[t]) : 0.f), lw_max = block_max(t < A2 ? fabsf(a.ln_w[t]) : 0.f);
+  if (t == 0) {
+    volatile unsigned *tl = a.tail;
+    const float m_x = __uint_as_float(tl[0]), m_gy = __uint_as_float(tl[1]), m_rstd = __uint_as_float(tl[2]);
+    float *scales = reinterpret_cast<float *>(a.tail + 4);
+    const float m_h = m_x * row1_max + b1_max;
+    scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h);
+    if (a.backward) {
+      const float m_gz = m_rstd * (2.f + sqrtf((float)A2)) * m_gy * lw_max;
+      const float m_gp = 1.2f * m_gz * col2_max;
+      float s_gz = pow2_scale(m_gz), s_gp = pow2_scale(m_gp);
+      if (a.w[2]) {                  // s_gp s_w1 == s_gz s_wr, neither operand above 2^14
+        const float sw1 = scale_from_absmax(*reinterpret_cast<const volatile unsigned *>(a.hdr[0]));
+        const float swr = scale_from_absmax(*reinterpret_cast<const volatile unsigned *>(a.hdr[2]));
+        const float rho = swr / sw1;                       // required s_gp / s_gz
+        if (s_gz * rho <= s_gp) s_gp = s_gz * rho;         // gpre gets the smaller scale
+        else s_gz = s_gp / rho;                            // gz gets the smaller scale
+      }
+      scales[2] = s_gz, scales[3] = s_gp;
+      if (a.hdr_op[0]) {
+        *a.hdr_op[0] = __float_as_uint(m_x), *a.hdr_op[1] = __float_as_uint(m_h);
+        // the operand headers carry the absmax the GEMM derives its scale from: invert pow2_scale (2^13.5 / scale)
+        *a.hdr_op[2] = __float_as_uint(11585.2375f / s_gz), *a.hdr_op[3] = __float_as_uint(11585.2375f / s_gp);
+      }
+    }
+    tl[3] = 0;                        // ticket ready for the next launch on this workspace
   }
 }
 
@@ -871,8 +888,6 @@ __global__ void cube_scales_kernel(const unsigned *absmax, const float *w1, cons
 using namespace mimrl;
 
 extern "C" size_t mimrl_split_bytes(int rows, int cols);
-extern "C" int mimrl_split_f32(const float *src, const float *mask, int rows, int cols, void *out, float *colsum,
-                               void *stream);
 
 extern "C" int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln_first, int act) {
   const bool small = a_in <= 4 && a_hid <= 4 && a_out <= 4;      // the register-resident kernel of cubemlp.cu
@@ -882,6 +897,41 @@ extern "C" int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln
 extern "C" size_t mimrl_cubemlp_tc_workspace_bytes(int a_in, int a_hid, int a_out) {
   return mimrl_split_bytes(a_hid, a_in) + mimrl_split_bytes(a_out, a_hid) + mimrl_split_bytes(a_out, a_in) + 256;
 }
+
+namespace {
+
+struct CubeWs {
+  unsigned char *s[3];
+  unsigned *tail;
+};
+CubeWs cube_ws(void *workspace, int a_in, int a_hid, int a_out) {
+  CubeWs w;
+  w.s[0] = (unsigned char *)workspace;
+  w.s[1] = w.s[0] + mimrl_split_bytes(a_hid, a_in);
+  w.s[2] = w.s[1] + mimrl_split_bytes(a_out, a_hid);
+  w.tail = reinterpret_cast<unsigned *>(w.s[2] + mimrl_split_bytes(a_out, a_in));           // the 256 spare bytes
+  return w;
+}
+
+// maps[0..5] = W1 hi, lo | W2 hi, lo | Wres hi, lo with the given box heights
+int cube_weight_maps(const CubeWs &w, int a_in, int a_hid, int a_out, bool has_res, int r1, int r2, int rr, CUtensorMap *maps) {
+  auto two = [&](unsigned char *s, int rows, int cols, int box_rows, CUtensorMap *hi, CUtensorMap *lo) {
+    const int ld = (cols + 63) & ~63;
+    const size_t off_lo = 256 + align256((size_t)rows * ld * 2);
+    if (make_map(hi, s + 256, cols, rows, ld, box_rows)) return 1;
+    return make_map(lo, s + off_lo, cols, rows, ld, box_rows);
+  };
+  if (two(w.s[0], a_hid, a_in, r1, &maps[0], &maps[1])) return 1;
+  if (two(w.s[1], a_out, a_hid, r2, &maps[2], &maps[3])) return 1;
+  if (has_res) {
+    if (two(w.s[2], a_out, a_in, rr, &maps[4], &maps[5])) return 1;
+  } else {
+    maps[4] = maps[0], maps[5] = maps[1];
+  }
+  return 0;
+}
+
+}  // namespace
 
 extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
                                         int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
@@ -893,45 +943,42 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   MIMRL_REQUIRE(wres || a_in == a_out, "cubemlp_mix: without res_project d_in must equal d_out (MLPProcess.py:46-48)");
   MIMRL_REQUIRE(workspace_bytes >= mimrl_cubemlp_tc_workspace_bytes(a_in, a_hid, a_out), "cubemlp_mix_fwd_tc: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned char *ws = (unsigned char *)workspace;
-  unsigned char *s1 = ws, *s2 = s1 + mimrl_split_bytes(a_hid, a_in), *s3 = s2 + mimrl_split_bytes(a_out, a_hid);
-  if (int rc = mimrl_split_f32(w1, nullptr, a_hid, a_in, s1, nullptr, stream)) return rc;
-  if (int rc = mimrl_split_f32(w2, nullptr, a_out, a_hid, s2, nullptr, stream)) return rc;
-  if (wres)
-    if (int rc = mimrl_split_f32(wres, nullptr, a_out, a_in, s3, nullptr, stream)) return rc;
-  auto maps = [&](unsigned char *s, int rows, int cols, CUtensorMap *hi, CUtensorMap *lo) {
-    const int ld = (cols + 63) & ~63;
-    const size_t off_lo = 256 + align256((size_t)rows * ld * 2);
-    if (make_map(hi, s + 256, cols, rows, ld, 128)) return 1;
-    return make_map(lo, s + off_lo, cols, rows, ld, 128);
-  };
-  CUtensorMap m1h, m1l, m2h, m2l, mrh, mrl;
-  if (maps(s1, a_hid, a_in, &m1h, &m1l)) return 1;
-  if (maps(s2, a_out, a_hid, &m2h, &m2l)) return 1;
-  if (wres) {
-    if (maps(s3, a_out, a_in, &mrh, &mrl)) return 1;
-  } else {
-    mrh = m1h, mrl = m1l;
+  const CubeWs w = cube_ws(workspace, a_in, a_hid, a_out);
+  const long long n_cols = (long long)outer * inner;
+  cudaMemsetAsync(w.tail, 0, 16, st);
+  CubePrepArgs pa{};
+  pa.x = x, pa.nx = (size_t)n_cols * a_in;
+  pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
+  for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
+  pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;
+  {
+    const size_t want = (pa.nx + 8191) / 8192;
+    pa.n_abs = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
   }
-  unsigned *x_absmax = reinterpret_cast<unsigned *>(s3 + mimrl_split_bytes(a_out, a_in));      // the 256 spare bytes
-  float *scales = reinterpret_cast<float *>(x_absmax + 16);
-  cudaMemsetAsync(x_absmax, 0, 16, st);
-  cube_absmax_kernel<<<148 * 8, 256, 0, st>>>(x, (size_t)outer * inner * a_in, nullptr, 0, nullptr, 0, x_absmax);
-  if (check_launch("cubemlp absmax")) return 1;
-  cube_scales_kernel<<<1, 128, 0, st>>>(x_absmax, w1, b1, w2, ln_w, a_in, a_hid, a_out, scales, nullptr, nullptr, nullptr, nullptr);
-  if (check_launch("cubemlp scales")) return 1;
+  cube_prep_kernel<<<pa.n_abs + 3, 256, 0, st>>>(pa);
+  if (check_launch("cubemlp prep")) return 1;
   CubeTcParams p;
-  p.scales = scales;
+  p.scales = reinterpret_cast<const float *>(w.tail + 4);
+  p.absmax = w.tail;
   p.x = x, p.b1 = b1, p.b2 = b2, p.ln_w = ln_w, p.ln_b = ln_b, p.y = y, p.saved = saved;
-  p.sc_w1 = reinterpret_cast<const unsigned *>(s1), p.sc_w2 = reinterpret_cast<const unsigned *>(s2);
-  p.sc_wr = reinterpret_cast<const unsigned *>(s3);
+  p.sc_w1 = reinterpret_cast<const unsigned *>(w.s[0]), p.sc_w2 = reinterpret_cast<const unsigned *>(w.s[1]);
+  p.sc_wr = reinterpret_cast<const unsigned *>(w.s[2]);
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
-  p.n_cols = (long long)outer * inner;
+  p.n_cols = n_cols;
+  CUtensorMap maps[6];
+  if (cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res)) {
+    int r1, r2, rr, handled = 0;
+    cube2_box_rows(a_in, a_hid, a_out, &r1, &r2, &rr);
+    if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, r1, r2, rr, maps)) return 1;
+    if (int rc = cube2_fwd(maps, p, st, &handled)) return rc;
+    if (handled) return 0;
+  }
+  if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
   const long long n_tiles = (p.n_cols + 127) / 128;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeSmem);
-    kern<<<blocks, kCubeThreads, kCubeSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, p);
+    kern<<<blocks, kCubeThreads, kCubeSmem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   };
   if (act == 0) launch(cubemlp_tc_fwd_kernel<0>);
   else if (act == 1) launch(cubemlp_tc_fwd_kernel<1>);
@@ -948,13 +995,14 @@ extern "C" long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner) {
 // Backward of mimrl_cubemlp_mix_fwd_tc.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
 // writes op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R] (R = mimrl_cubemlp_tc_fibre_rows,
 // mimrl_split_f32 sizes, blocked-K order): gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T via
-// mimrl_gemm_split_blocked.
+// mimrl_gemm_split_blocked.  ws_from_forward != 0: `workspace` is the buffer the forward of the same mix filled
+// (same x and weights), so the weight split, max|x| and the rstd maximum are taken from it instead of recomputed.
 extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
                                         const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
                                         const float *wres, const float *ln_w, const float *ln_b, int act,
                                         const float *saved, float *gx, float *g_b1, float *g_b2, float *gln_w, float *gln_b,
                                         void *op_x, void *op_h, void *op_gz, void *op_gpre, void *workspace,
-                                        size_t workspace_bytes, void *stream) {
+                                        size_t workspace_bytes, int ws_from_forward, void *stream) {
   MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in, a_hid, a_out, 0, act), "cubemlp_mix_bwd_tc: sizes %d/%d/%d act %d not supported",
                 a_in, a_hid, a_out, act);
   MIMRL_REQUIRE(outer > 0 && inner > 0 && x && gy && saved && gx && w1 && w2 && ln_w && gln_w && gln_b && op_x && op_h && op_gz &&
@@ -964,46 +1012,37 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   MIMRL_REQUIRE(workspace_bytes >= mimrl_cubemlp_tc_workspace_bytes(a_in, a_hid, a_out), "cubemlp_mix_bwd_tc: workspace too small");
   (void)ln_b;
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned char *ws = (unsigned char *)workspace;
-  unsigned char *s1 = ws, *s2 = s1 + mimrl_split_bytes(a_hid, a_in), *s3 = s2 + mimrl_split_bytes(a_out, a_hid);
-  unsigned char *tail = s3 + mimrl_split_bytes(a_out, a_in);           // 256 spare bytes: absmax[3] | scales[4]
-  unsigned *absmax = reinterpret_cast<unsigned *>(tail);
-  float *scales = reinterpret_cast<float *>(tail + 64);
-  if (int rc = mimrl_split_f32(w1, nullptr, a_hid, a_in, s1, nullptr, stream)) return rc;
-  if (int rc = mimrl_split_f32(w2, nullptr, a_out, a_hid, s2, nullptr, stream)) return rc;
-  if (wres)
-    if (int rc = mimrl_split_f32(wres, nullptr, a_out, a_in, s3, nullptr, stream)) return rc;
+  const CubeWs w = cube_ws(workspace, a_in, a_hid, a_out);
   const long long n_cols = (long long)outer * inner;
-  cudaMemsetAsync(absmax, 0, 16, st);
-  cube_absmax_kernel<<<148 * 8, 256, 0, st>>>(x, (size_t)n_cols * a_in, gy, (size_t)n_cols * a_out, saved, (size_t)n_cols, absmax);
-  if (check_launch("cubemlp absmax")) return 1;
-  cube_scales_kernel<<<1, 128, 0, st>>>(absmax, w1, b1, w2, ln_w, a_in, a_hid, a_out, scales, (unsigned *)op_x, (unsigned *)op_h,
-                                        (unsigned *)op_gz, (unsigned *)op_gpre);
-  if (check_launch("cubemlp scales")) return 1;
-  auto maps = [&](unsigned char *s, int rows, int cols, CUtensorMap *hi, CUtensorMap *lo) {
-    const int ld = (cols + 63) & ~63;
-    const size_t off_lo = 256 + align256((size_t)rows * ld * 2);
-    if (make_map(hi, s + 256, cols, rows, ld, 128)) return 1;
-    return make_map(lo, s + off_lo, cols, rows, ld, 128);
-  };
-  CUtensorMap m1h, m1l, m2h, m2l, mrh, mrl;
-  if (maps(s1, a_hid, a_in, &m1h, &m1l)) return 1;
-  if (maps(s2, a_out, a_hid, &m2h, &m2l)) return 1;
-  if (wres) {
-    if (maps(s3, a_out, a_in, &mrh, &mrl)) return 1;
+  CubePrepArgs pa{};
+  if (ws_from_forward) {
+    cudaMemsetAsync(w.tail + 1, 0, 4, st);                      // max|gy| only; x, rstd and the ticket stay
   } else {
-    mrh = m1h, mrl = m1l;
+    cudaMemsetAsync(w.tail, 0, 16, st);
+    pa.x = x, pa.nx = (size_t)n_cols * a_in, pa.saved = saved, pa.n_cols = (size_t)n_cols;
   }
+  pa.gy = gy, pa.ngy = (size_t)n_cols * a_out;
+  pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
+  for (int m = 0; m < 3; ++m) pa.split[m] = ws_from_forward ? nullptr : w.s[m], pa.hdr[m] = w.s[m];
+  pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 1, pa.tail = w.tail;
+  pa.hdr_op[0] = (unsigned *)op_x, pa.hdr_op[1] = (unsigned *)op_h, pa.hdr_op[2] = (unsigned *)op_gz, pa.hdr_op[3] = (unsigned *)op_gpre;
+  {
+    const size_t want = ((ws_from_forward ? 0 : pa.nx) + pa.ngy + 8191) / 8192;
+    pa.n_abs = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+  }
+  cube_prep_kernel<<<pa.n_abs + 3, 256, 0, st>>>(pa);
+  if (check_launch("cubemlp prep")) return 1;
   CubeBwdParams bp;
   CubeTcParams &p = bp.f;
-  p.scales = scales;
+  p.scales = reinterpret_cast<const float *>(w.tail + 4);
+  p.absmax = w.tail;
   p.x = x, p.b1 = b1, p.b2 = b2, p.ln_w = ln_w, p.ln_b = ln_b, p.y = nullptr, p.saved = const_cast<float *>(saved);
-  p.sc_w1 = reinterpret_cast<const unsigned *>(s1), p.sc_w2 = reinterpret_cast<const unsigned *>(s2);
-  p.sc_wr = reinterpret_cast<const unsigned *>(s3);
+  p.sc_w1 = reinterpret_cast<const unsigned *>(w.s[0]), p.sc_w2 = reinterpret_cast<const unsigned *>(w.s[1]);
+  p.sc_wr = reinterpret_cast<const unsigned *>(w.s[2]);
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
   p.n_cols = n_cols;
   bp.gy = gy, bp.gx = gx, bp.g_b1 = g_b1, bp.g_b2 = g_b2, bp.g_lnw = gln_w, bp.g_lnb = gln_b;
-  bp.scales = scales;
+  bp.scales = p.scales;
   const long long n_tiles = (n_cols + 127) / 128;
   bp.ld = (size_t)n_tiles * 128;
   void *ops[4] = {op_x, op_h, op_gz, op_gpre};
@@ -1012,10 +1051,19 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
     bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
     bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256 + align256((size_t)feats[t] * bp.ld * 2));
   }
+  CUtensorMap maps[6];
+  if (cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res)) {
+    int r1, r2, rr, handled = 0;
+    cube2_box_rows(a_in, a_hid, a_out, &r1, &r2, &rr);
+    if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, r1, r2, rr, maps)) return 1;
+    if (int rc = cube2_bwd(maps, bp, st, &handled)) return rc;
+    if (handled) return 0;
+  }
+  if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);
-    kern<<<blocks, kCubeBwdThreads, kCubeBwdSmem, st>>>(m1h, m1l, m2h, m2l, mrh, mrl, bp);
+    kern<<<blocks, kCubeBwdThreads, kCubeBwdSmem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], bp);
   };
   if (act == 0) launch(cubemlp_tc_bwd_kernel<0>);
   else if (act == 1) launch(cubemlp_tc_bwd_kernel<1>);

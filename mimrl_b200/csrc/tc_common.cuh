@@ -230,7 +230,7 @@ __device__ __forceinline__ float scale_from_absmax(unsigned bits) {
 }
 
 // ------------------------------------------------------------------ host ----
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -53,6 +53,7 @@ class _AxisMix(torch.autograd.Function):
         oshape = shape[:axis] + [A2] + shape[axis + 1:]
         y = torch.empty(oshape, dtype=torch.float32, device=x.device)
         saved = torch.empty(2 * outer * inner, dtype=torch.float32, device=x.device)
+        ws = None
         if (USE_TC and outer * inner >= 1024
                 and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id)):
             ws = torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=x.device)
@@ -67,8 +68,8 @@ class _AxisMix(torch.autograd.Function):
                                                 L.stream()))
         ctx.save_for_backward(x, saved, *[p if p is not None else x.new_empty(0) for p in prm])
         ctx.cfg = (outer, A, inner, H, A2, int(ln_first), act_id, [p is not None for p in prm])
-        ctx.use_tc = bool(USE_TC and outer * inner >= 1024
-                          and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id))
+        ctx.use_tc = ws is not None
+        ctx.ws = ws          # split weights, max|x| and max rstd of this call: the backward reuses them
         return y
 
     @staticmethod
@@ -81,7 +82,7 @@ class _AxisMix(torch.autograd.Function):
         dev = x.device
         gx = torch.empty_like(x)
         if ctx.use_tc:
-            return _AxisMix._backward_tc(x, gy, saved, prm, ctx.cfg, gx)
+            return _AxisMix._backward_tc(x, gy, saved, prm, ctx.cfg, gx, ctx.ws)
         if L.lib.mimrl_cubemlp_small_supported(A, H, A2):
             # the modality mix: data, weight, bias and LayerNorm gradients from one register-resident kernel
             gw1, gw2 = torch.zeros_like(w1), torch.zeros_like(w2)
@@ -119,7 +120,7 @@ class _AxisMix(torch.autograd.Function):
         return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
 
 
-def _backward_tc(x, gy, saved, prm, cfg, gx):
+def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
     """Tensor-core backward: one fused data-gradient kernel, then three split-K GEMMs over the feature-major
     fp16 hi/lo operands it leaves behind (csrc/cubemlp_tc.cu)."""
     outer, A, inner, H, A2, ln_first, act_id, present = cfg
@@ -128,14 +129,15 @@ def _backward_tc(x, gy, saved, prm, cfg, gx):
     st = L.stream()
     R = L.lib.mimrl_cubemlp_tc_fibre_rows(outer, inner)
     ops = [torch.empty(L.lib.mimrl_split_bytes(n, R), dtype=torch.uint8, device=dev) for n in (A, H, A2, H)]
-    ws = torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=dev)
+    ws = ws_fwd if ws_fwd is not None else torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8,
+                                                       device=dev)
     gb1 = torch.zeros(H, device=dev) if b1 is not None else None
     gb2 = torch.zeros(A2, device=dev) if b2 is not None else None
     gln = torch.zeros(2, A2, device=dev)
     L.check(L.lib.mimrl_cubemlp_mix_bwd_tc(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2), L.ptr(b2),
                                            A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), act_id, L.ptr(saved), L.ptr(gx),
                                            L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(ops[0]), L.ptr(ops[1]),
-                                           L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), ws.numel(), st))
+                                           L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), ws.numel(), int(ws_fwd is not None), st))
 
     def wgrad(a, b, m, n):
         out = torch.empty(m, n, device=dev)
