@@ -974,6 +974,11 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
     if (handled) return 0;
   }
   if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
+  if (cube3_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    int handled = 0;
+    if (int rc = cube3_fwd(maps, p, st, &handled)) return rc;
+    if (handled) return 0;
+  }
   const long long n_tiles = (p.n_cols + 127) / 128;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   auto launch = [&](auto kern) {
@@ -1060,6 +1065,12 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
     if (handled) return 0;
   }
   if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
+  if (cube3_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx)) & 15) == 0) {
+    int handled = 0;
+    if (int rc = cube3_bwd(maps, bp, st, &handled)) return rc;
+    if (handled) return 0;
+  }
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);

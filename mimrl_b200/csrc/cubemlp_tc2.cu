@@ -24,67 +24,6 @@
 namespace mimrl {
 namespace {
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
-               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-// 16 scaled values -> 8 + 8 packed fp16 hi / lo words (word c = values 2c, 2c+1)
-__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-#pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    const __half2 h = __floats2half2_rn(v[j], v[j + 1]);
-    const float2 hf = __half22float2(h);
-    const float2 d = fsub2(make_float2(v[j], v[j + 1]), hf);
-    const __half2 l = __floats2half2_rn(d.x, d.y);
-    hi[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
-    lo[j >> 1] = *reinterpret_cast<const uint32_t *>(&l);
-  }
-}
-
-// exact-erf GELU of two values (Abramowitz-Stegun 7.1.26 as in common.cuh::gauss_cdf_pdf) in packed fp32x2 arithmetic.
-// With q = Phi(-|z|): gelu(z) = max(z, 0) - |z| q, which needs no select on the sign of z.
-__device__ __forceinline__ float2 gelu2(float2 z) {
-  const float2 ax = make_float2(fabsf(z.x) * 0.70710678118654752f, fabsf(z.y) * 0.70710678118654752f);
-  const float2 den = ffma2(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.f, 1.f));
-  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
-  const float2 arg = fmul2(fmul2(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  const float2 e = make_float2(ex2(arg.x), ex2(arg.y));
-  float2 poly = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
-  poly = ffma2(t, poly, make_float2(1.421413741f, 1.421413741f));
-  poly = ffma2(t, poly, make_float2(-0.284496736f, -0.284496736f));
-  poly = ffma2(t, poly, make_float2(0.254829592f, 0.254829592f));
-  const float2 q = fmul2(fmul2(t, poly), fmul2(e, make_float2(0.5f, 0.5f)));
-  return make_float2(fmaf(-fabsf(z.x), q.x, fmaxf(z.x, 0.f)), fmaf(-fabsf(z.y), q.y, fmaxf(z.y, 0.f)));
-}
-
-// column sums over the 32 lanes of a warp for N (16 or 32) values per lane: lane t (and t + 16 for N = 16) returns
-// the total of entry t % N
-template <int N>
-__device__ __forceinline__ float lane_sum(float (&v)[N], int lane) {
-#pragma unroll
-  for (int s = N / 2, n = N; s >= 1; s >>= 1, n >>= 1) {
-    const bool upper = lane & s;
-#pragma unroll
-    for (int k = 0; k < n / 2; ++k) {
-      const float keep = upper ? v[k + n / 2] : v[k];
-      const float send = upper ? v[k] : v[k + n / 2];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-  return v[0];
-}
-
 template <int A_, int H_, int Q_, int INNER_>
 struct C2 {
   static constexpr int A = A_, H = H_, Q = Q_, INNER = INNER_;
@@ -112,30 +51,6 @@ struct C2 {
 };
 
 constexpr int kC2Threads = 160;      // warps 0-3: compute (thread = fibre = TMEM lane), warp 4: TMA + MMA issue
-
-// D (+)= A . W^T, W [rows x K] K-major as loaded (three products: hi.hi + hi.lo + lo.hi); a_lo = column offset of the
-// lo half of the TMEM operand, w_half = byte offset of the lo half of the weight, rows = box height of the weight
-__device__ __forceinline__ void c2_mma_k(uint32_t d, uint32_t a, uint32_t a_lo, uint32_t sw, uint32_t w_half, uint32_t rows,
-                                         int ksteps, uint32_t idesc, uint32_t acc) {
-  for (int prod = 0; prod < 3; ++prod) {
-    const uint32_t a_off = prod == 2 ? a_lo : 0, b_off = prod == 1 ? w_half : 0;
-    for (int k = 0; k < ksteps; ++k) {
-      umma_f16_ts(d, a + a_off + k * 8, smem_desc_sw128(sw + b_off + (k >> 2) * rows * 128 + (k & 3) * 32), idesc, acc);
-      acc = 1;
-    }
-  }
-}
-// D (+)= A . W, the contraction running over the ROWS of the same tile (MN-major view)
-__device__ __forceinline__ void c2_mma_mn(uint32_t d, uint32_t a, uint32_t a_lo, uint32_t sw, uint32_t w_half, uint32_t rows,
-                                          int ksteps, uint32_t idesc, uint32_t acc) {
-  for (int prod = 0; prod < 3; ++prod) {
-    const uint32_t a_off = prod == 2 ? a_lo : 0, b_off = prod == 1 ? w_half : 0;
-    for (int k = 0; k < ksteps; ++k) {
-      umma_f16_ts(d, a + a_off + k * 8, smem_desc_sw128_mn(sw + b_off + k * 2048, rows * 128, 1024), idesc, acc);
-      acc = 1;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------- forward
 template <class C>
@@ -317,27 +232,6 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
 }
 
 // --------------------------------------------------------------------------------------------------------- backward
-// features [f0, f0 + 16) of fibre `row` -> feature-major weight-gradient operand (blocked-K layout of
-// make_map_blocked: tiles of 64 consecutive fibres, each [NF][64] contiguous)
-template <int NF>
-__device__ __forceinline__ void c2_store_op(__half *hi_base, __half *lo_base, size_t row, int f0, const uint32_t (&hi)[8],
-                                            const uint32_t (&lo)[8]) {
-  const size_t off = ((row >> 6) * NF) * 64 + (row & 63);
-  unsigned short *h = reinterpret_cast<unsigned short *>(hi_base) + off, *l = reinterpret_cast<unsigned short *>(lo_base) + off;
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int f = f0 + 2 * t;
-    if (f < NF) {
-      h[f * 64] = (unsigned short)(hi[t] & 0xffffu);
-      l[f * 64] = (unsigned short)(lo[t] & 0xffffu);
-    }
-    if (f + 1 < NF) {
-      h[(f + 1) * 64] = (unsigned short)(hi[t] >> 16);
-      l[(f + 1) * 64] = (unsigned short)(lo[t] >> 16);
-    }
-  }
-}
-
 template <class C>
 __global__ void __launch_bounds__(kC2Threads, C::BWD_CTAS)
 cube2_bwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
