@@ -32,6 +32,20 @@ __global__ void knn_absmax_kernel(const float *__restrict__ a, size_t na, const 
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(m));
 }
 
+// Scale of the key operand without a pass over the keys: |z_e| <= |z| for every element, so the square root of the
+// largest finite row norm (the norms exist already, 4 bytes per key) bounds the absmax from above by at most
+// sqrt(width) -- 3.5 binades of the 15 the fp16 hi/lo pair has to spare.  Excluded rows carry +inf and are skipped.
+__global__ void knn_norm_max_kernel(const float *__restrict__ kn, size_t n, unsigned *__restrict__ out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(kn + i);
+    if (v < INFINITY) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(sqrtf(m)));
+}
+
 // [n, width] fp32 -> hi, lo [n, 128] fp16 (K zero-padded), scaled by 2^k
 __global__ void knn_split_kernel(const float *__restrict__ src, size_t n, int width, const unsigned *__restrict__ absmax,
                                  int which, __half *__restrict__ hi, __half *__restrict__ lo) {
@@ -331,16 +345,37 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
           }
         }
         if (refresh) {
-          // n_lists is even; 8 independent L2 loads in flight per round trip
+          // n_lists is even; 8 independent L2 loads in flight per round trip.
+          // Fewer parts than K' (jth > 1): t = max over parts of their jth-smallest.  At least K' parts (jth == 1):
+          // the parts are taken in K' groups and t = max over groups of (min over the group's parts) --
+          // the K' group minima are K' distinct keys within t, so the K'-th best of the union is <= t.  With 74 parts
+          // and K' = 20 that bound sits at the ~0.9/n quantile of the distances seen instead of ~4.7/n for the plain
+          // maximum (n = keys seen per part), i.e. five times fewer survivors.
           float t = 0.f;
           int pp = 0;
-          for (; pp + 8 <= p.n_lists; pp += 8) {
-            const float a0 = __ldcg(pub_row + pp), a1 = __ldcg(pub_row + pp + 1), a2 = __ldcg(pub_row + pp + 2),
-                        a3 = __ldcg(pub_row + pp + 3), a4 = __ldcg(pub_row + pp + 4), a5 = __ldcg(pub_row + pp + 5),
-                        a6 = __ldcg(pub_row + pp + 6), a7 = __ldcg(pub_row + pp + 7);
-            t = fmaxf(t, fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7))));
+          if (p.jth == 1 && p.n_lists > p.list_len) {
+            // group g = parts g, g + K', g + 2 K', ...: interleaved, so that the few splits of a query tile that run in
+            // the same wave already populate every group (consecutive groups would stay empty until the last wave)
+            const int G = p.list_len;
+            for (int g0 = 0; g0 < G; g0 += 2) {
+              float m0 = INFINITY, m1 = INFINITY;
+              const bool two = g0 + 1 < G;
+#pragma unroll 4
+              for (int e = g0; e < p.n_lists; e += G) {
+                m0 = fminf(m0, __ldcg(pub_row + e));
+                if (two && e + 1 < p.n_lists) m1 = fminf(m1, __ldcg(pub_row + e + 1));
+              }
+              t = fmaxf(t, two ? fmaxf(m0, m1) : m0);
+            }
+          } else {
+            for (; pp + 8 <= p.n_lists; pp += 8) {
+              const float a0 = __ldcg(pub_row + pp), a1 = __ldcg(pub_row + pp + 1), a2 = __ldcg(pub_row + pp + 2),
+                          a3 = __ldcg(pub_row + pp + 3), a4 = __ldcg(pub_row + pp + 4), a5 = __ldcg(pub_row + pp + 5),
+                          a6 = __ldcg(pub_row + pp + 6), a7 = __ldcg(pub_row + pp + 7);
+              t = fmaxf(t, fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7))));
+            }
+            for (; pp < p.n_lists; pp += 2) t = fmaxf(t, fmaxf(__ldcg(pub_row + pp), __ldcg(pub_row + pp + 1)));
           }
-          for (; pp < p.n_lists; pp += 2) t = fmaxf(t, fmaxf(__ldcg(pub_row + pp), __ldcg(pub_row + pp + 1)));
           tau_shared = fminf(tau_shared, t);
           tau_d = fminf(tau_local, tau_shared);
         }
@@ -377,15 +412,16 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   p.list_len = list_len;
   const int q_tiles = ceil_div(n_queries, 128), k_tiles = ceil_div(n_keys, 128);
   // key splits: as few idle waves over the 148 SMs as possible (one CTA per SM).  Every split pays a warm-up while its
-  // candidate lists fill and its threshold is loose (survivor path taken by every chunk); measured on the B200 (A/B of
-  // the constant at 4096 x 1M x 128: 6 -> 5.15 ms, 30 / 100 -> 3.9 ms, 300 -> 3.53 ms) that warm-up is worth ~200-300
-  // steady-state tiles, so few long splits beat many short ones.  n_lists = 2 * splits <= 128 (one merge thread per
-  // list in the re-rank).
+  // candidate lists fill and its threshold is loose (survivor path taken by every chunk).  Measured on the B200 at
+  // 4096 x 1M x 128 (A/B of the constant): with the grouped shared bound of the filter 6 -> 3.71 ms, 30 -> 3.30 ms,
+  // 100 -> 3.35 ms, 300 -> 3.38 ms (before it: 5.15 / 3.9 / 3.9 / 3.53 ms).  n_lists = 2 * splits <= 128 (one merge
+  // thread per list in the re-rank).
   int splits = 1;
   double best = 1e300;
   for (int s = 1; s <= 64 && s <= k_tiles; ++s) {
     const int per = ceil_div(k_tiles, s), eff = ceil_div(k_tiles, per);
-    const double cost = (double)ceil_div(q_tiles * eff, 148) * (per + 300.0);
+    static const double warm = getenv("MIMRL_KNN_WARM") ? atof(getenv("MIMRL_KNN_WARM")) : 30.0;
+    const double cost = (double)ceil_div(q_tiles * eff, 148) * (per + warm);
     if (cost < best - 1e-9) best = cost, splits = eff;
   }
   p.tiles_per_split = ceil_div(k_tiles, splits);
@@ -411,10 +447,14 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
   cudaMemsetAsync(absmax, 0, 8, st);
   const size_t nq = (size_t)n_queries * width, nk = (size_t)n_keys * width;
-  int blocks = (int)((nk + 2047) / 2048);
+  int blocks = (int)((nq + 2047) / 2048);
   blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
-  knn_absmax_kernel<<<dim3(blocks, 2), 256, 0, st>>>(queries, nq, keys, nk, absmax);
+  knn_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(queries, nq, keys, nk, absmax);
   if (check_launch("knn absmax")) return 1;
+  blocks = (n_keys + 2047) / 2048;
+  blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
+  knn_norm_max_kernel<<<blocks, 256, 0, st>>>(key_norms, (size_t)n_keys, absmax + 1);
+  if (check_launch("knn key scale")) return 1;
   knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
   if (check_launch("knn split q")) return 1;
   blocks = (int)(((size_t)n_keys * 64 + 255) / 256);

@@ -41,8 +41,11 @@ if "cubemlp" in which:  # config 5: [1024, 100, 3, 128] -> 50-3-128 -> 10-3-128
         x = torch.randn(bs, 100, 3, 128, device=dev, requires_grad=True)
         with torch.no_grad():
             fwd = timeit(lambda: enc(x))
+        params = list(enc.parameters())
         def fb():
             x.grad = None
+            for q in params:           # optimizer.zero_grad(set_to_none=True), as a training step does
+                q.grad = None
             enc(x).sum().backward()
         both = timeit(fb)
         out(component="cubemlp", bs=bs, fwd_ms=fwd, fwd_bwd_ms=both, fwd_gbs=(bs * 100 * 384 * 4 * 1.0 + bs * 50 * 384 * 4 * 2 + bs * 10 * 384 * 4) / fwd / 1e6)
