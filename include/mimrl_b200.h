@@ -181,6 +181,10 @@ int mimrl_gemm_split(int mode, const void *a_split, const void *b_split, int M, 
  * weight gradients over pairs / fibres).  Workspace: mimrl_gemm_split_workspace_bytes(0, M, N, K). */
 int mimrl_gemm_split_blocked(const void *a_split, const void *b_split, int M, int N, int K, float *C, void *workspace,
                              size_t workspace_bytes, void *stream);
+/* Same contraction ADDED into C[M,N] (zero-filled by the caller or holding a running sum): every split-K work item
+ * adds its partial sum with red.global.add.f32 -- no partial buffer, no reduction launch.  The order of the additions
+ * is not fixed (last-bit differences from run to run); used for the CubeMLP weight gradients. */
+int mimrl_gemm_split_blocked_acc(const void *a_split, const void *b_split, int M, int N, int K, float *C, void *stream);
 
 /* The same three products on the CUDA cores (exact fp32 FFMA), for the layers outside the tensor-core envelope: small
  * batches (the reference trains at bs = 128, README.md:16-26) and the 1- / 2-wide heads of the unnormalized baseline

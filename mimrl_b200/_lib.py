@@ -59,6 +59,7 @@ _SIGS = {
     "mimrl_mlp4_bwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P, _P]),
     "mimrl_gemm_split_blocked": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "mimrl_gemm_split_blocked_acc": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "mimrl_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_knn_search": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "mimrl_knn_search_rows": (c_int, [_P, c_int, c_int, c_int64, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P,

@@ -108,9 +108,11 @@ __global__ void gemm_split_kernel(const float *__restrict__ src, const float *__
 
 struct GemmParams {
   int M, N, K, kblocks_per_split, relu, splits;
-  const unsigned *absmax;
+  const unsigned *absmax;     // [0] A, [1] B -- or, when absmax_b is set, absmax[0] = A and absmax_b[0] = B
+  const unsigned *absmax_b;
   const float *bias;
   float *C;       // [M, N] when splits == 1, else partials [splits][M][N]
+  int atomic_out; // split-K partial sums are ADDED into C [M, N] with red.global (no partial buffer, no reduce pass)
 };
 
 // A_MN / B_MN: operand stored with the contraction index as the SLOW one (read MN-major)
@@ -243,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
+    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax_b ? p.absmax_b[0] : p.absmax[1]));
     const bool partial = p.splits > 1;
     uint32_t j = 0;
     for (long long it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
@@ -251,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       item_of(it, m0, n0, split, kb0, T);
       const uint32_t acc = j & 1;
       const int row = m0 + r;
-      float *out = p.C + ((size_t)split * p.M + row) * p.N;
+      float *out = p.C + ((size_t)(p.atomic_out ? 0 : split) * p.M + row) * p.N;
       mbar_wait(bAccFull + 8 * acc, (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -267,7 +269,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (row >= p.M) continue;
         const int c0 = n0 + ch * 32;
         if (c0 >= p.N) continue;
-        if (c0 + 32 <= p.N && (p.N & 3) == 0) {
+        if (p.atomic_out) {
+          if (T > 0) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (c0 + jj < p.N) atomicAdd(out + c0 + jj, __uint_as_float(v[jj]) * inv);
+          }
+        } else if (c0 + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
           for (int jj = 0; jj < 32; jj += 4) {
             float o[4];
@@ -480,6 +488,7 @@ extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_spl
   p.splits = g.splits;
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
+  p.absmax_b = nullptr, p.atomic_out = 0;
   p.bias = g.splits > 1 ? nullptr : bias;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
@@ -524,6 +533,7 @@ extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split
   p.splits = g.splits;
   p.relu = 0;
   p.absmax = absmax;
+  p.absmax_b = nullptr, p.atomic_out = 0;
   p.bias = nullptr;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
@@ -536,6 +546,36 @@ extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split
     return check_launch("gemm reduce");
   }
   return 0;
+}
+
+// Same contraction, ADDED into C [M, N] (the caller zero-fills or passes a running sum): every split-K work item adds
+// its partial sum with red.global.add.f32 -- no partial buffer, no reduction launch, no header copies (the kernel reads
+// the two absmax headers in place).  The order of the additions is not fixed, so the last bits can differ from run to
+// run; the CubeMLP weight gradients use it, the critic MLPs keep the deterministic two-stage sum.
+extern "C" int mimrl_gemm_split_blocked_acc(const void *a_split, const void *b_split, int M, int N, int K, float *C,
+                                            void *stream) {
+  MIMRL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 64) == 0 && a_split && b_split && C, "gemm_split_blocked_acc: bad arguments");
+  const GemmLayout g = gemm_layout(0, M, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const SplitLayout la = split_layout(M, K), lb = split_layout(N, K);
+  const unsigned char *pa = (const unsigned char *)a_split, *pb = (const unsigned char *)b_split;
+  CUtensorMap ah, al, bh, bl;
+  const uint64_t kt = (uint64_t)K / 64;
+  if (make_map_blocked(&ah, pa + la.off_hi, M, kt, 128) || make_map_blocked(&al, pa + la.off_lo, M, kt, 128) ||
+      make_map_blocked(&bh, pb + lb.off_hi, N, kt, 128) || make_map_blocked(&bl, pb + lb.off_lo, N, kt, 128))
+    return 1;
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K;
+  p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
+  p.splits = g.splits;
+  p.relu = 0;
+  p.absmax = reinterpret_cast<const unsigned *>(pa);
+  p.absmax_b = reinterpret_cast<const unsigned *>(pb);
+  p.atomic_out = 1;
+  p.bias = nullptr;
+  p.C = C;
+  dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
+  return launch_gemm<false, false, true>(ah, al, bh, bl, p, grid, st);
 }
 
 extern "C" size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K) {
@@ -583,6 +623,7 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   p.splits = g.splits;
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
+  p.absmax_b = nullptr, p.atomic_out = 0;
   p.bias = g.splits > 1 ? nullptr : bias;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(ws + g.off_part) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);

@@ -347,7 +347,7 @@ Plan make_plan(int n_keys, int n_queries, int width, int k) {
   }
   size_t o = 0;
   p.off_kn = o;
-  o += ((size_t)n_keys * sizeof(float) + 255) & ~(size_t)255;
+  o += ((((size_t)n_keys + 127) & ~(size_t)127) * sizeof(float) + 255) & ~(size_t)255;      // whole 128-key tiles (16-byte reads)
   p.off_q = o;
   o += ((size_t)n_queries * width * sizeof(float) + 255) & ~(size_t)255;
   p.off_cand = o;

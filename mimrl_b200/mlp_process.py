@@ -85,11 +85,13 @@ class _AxisMix(torch.autograd.Function):
             return _AxisMix._backward_tc(x, gy, saved, prm, ctx.cfg, gx, ctx.ws)
         if L.lib.mimrl_cubemlp_small_supported(A, H, A2):
             # the modality mix: data, weight, bias and LayerNorm gradients from one register-resident kernel
-            gw1, gw2 = torch.zeros_like(w1), torch.zeros_like(w2)
-            gb1 = torch.zeros_like(b1) if b1 is not None else None
-            gb2 = torch.zeros_like(b2) if b2 is not None else None
-            gwres = torch.zeros_like(wres) if wres is not None else None
-            gln = torch.zeros(2, ln_w.numel(), device=dev)
+            sizes = [w1.numel(), w2.numel(), H, A2, wres.numel() if wres is not None else 0, A2, A2]
+            parts = torch.split(torch.zeros(sum(sizes), device=dev), sizes)       # one fill launch for all of them
+            gw1, gw2 = parts[0].view_as(w1), parts[1].view_as(w2)
+            gb1 = parts[2] if b1 is not None else None
+            gb2 = parts[3] if b2 is not None else None
+            gwres = parts[4].view_as(wres) if wres is not None else None
+            gln = (parts[5], parts[6])
             L.check(L.lib.mimrl_cubemlp_small_bwd(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2),
                                                   L.ptr(b2), A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), ln_first, act_id,
                                                   L.ptr(gx), L.ptr(gw1), L.ptr(gb1), L.ptr(gw2), L.ptr(gb2), L.ptr(gwres),
@@ -131,24 +133,26 @@ def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
     ops = [torch.empty(L.lib.mimrl_split_bytes(n, R), dtype=torch.uint8, device=dev) for n in (A, H, A2, H)]
     ws = ws_fwd if ws_fwd is not None else torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8,
                                                        device=dev)
-    gb1 = torch.zeros(H, device=dev) if b1 is not None else None
-    gb2 = torch.zeros(A2, device=dev) if b2 is not None else None
-    gln = torch.zeros(2, A2, device=dev)
+    # every accumulated output of this mix lives in ONE zero-filled buffer (one fill launch instead of seven)
+    sizes = [H, A2, A2, A2, H * A, A2 * H, A2 * A if wres is not None else 0]
+    zbuf = torch.zeros(sum(sizes), device=dev)
+    parts = torch.split(zbuf, sizes)
+    gb1 = parts[0] if b1 is not None else None
+    gb2 = parts[1] if b2 is not None else None
+    gln = (parts[2], parts[3])
     L.check(L.lib.mimrl_cubemlp_mix_bwd_tc(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2), L.ptr(b2),
                                            A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), act_id, L.ptr(saved), L.ptr(gx),
                                            L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(ops[0]), L.ptr(ops[1]),
                                            L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), ws.numel(), int(ws_fwd is not None), st))
 
-    def wgrad(a, b, m, n):
-        out = torch.empty(m, n, device=dev)
-        gwb = L.lib.mimrl_gemm_split_workspace_bytes(0, m, n, R)
-        gws = torch.empty(gwb, dtype=torch.uint8, device=dev)
-        L.check(L.lib.mimrl_gemm_split_blocked(L.ptr(a), L.ptr(b), m, n, R, L.ptr(out), L.ptr(gws), gwb, st))
+    def wgrad(a, b, m, n, out):                      # split-K partial sums are added in place (no reduce launch)
+        out = out.view(m, n)
+        L.check(L.lib.mimrl_gemm_split_blocked_acc(L.ptr(a), L.ptr(b), m, n, R, L.ptr(out), st))
         return out
 
-    gw1 = wgrad(ops[3], ops[0], H, A)
-    gw2 = wgrad(ops[2], ops[1], A2, H)
-    gwres = wgrad(ops[2], ops[0], A2, A) if wres is not None else None
+    gw1 = wgrad(ops[3], ops[0], H, A, parts[4])
+    gw2 = wgrad(ops[2], ops[1], A2, H, parts[5])
+    gwres = wgrad(ops[2], ops[0], A2, A, parts[6]) if wres is not None else None
     return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
 
 

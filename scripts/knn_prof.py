@@ -1,0 +1,13 @@
+"""One k-NN search at BASELINE config-4 scale for ncu (usage: knn_prof.py [queries] [k])."""
+import sys, torch
+sys.path.insert(0, ".")
+from mimrl_b200.model import knn_search
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+N = 1 << 20
+g = torch.Generator(device="cuda").manual_seed(2)
+Z = torch.randn(N, 128, device="cuda", generator=g)
+ids = torch.randperm(N, device="cuda", generator=g)[:m]
+for _ in range(2):
+    knn_search(Z, ids, k)
+torch.cuda.synchronize()
