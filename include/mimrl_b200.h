@@ -290,13 +290,16 @@ int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int outer, int a_in
 
 /* Tensor-core forward of the same mix (ln_first = 0, axis sizes <= 128, not the tiny-axis case): fibres in TMEM
  * lanes, W1 / W2 / Wres resident in shared memory, LayerNorm thread-local in the epilogue.  Writes the same
- * `saved` statistics, so mimrl_cubemlp_mix_bwd applies unchanged. */
+ * `saved` statistics, so mimrl_cubemlp_mix_bwd applies unchanged.  prev_ln_w / prev_ln_b [prev_n] (nullable): x is the
+ * unmodified output of a LayerNorm with these parameters over prev_n features (the previous mix of the block); its
+ * operand scale then comes from the bound max|ln_w| sqrt(prev_n - 1) + max|ln_b| instead of a pass over x. */
 int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln_first, int act);
 size_t mimrl_cubemlp_tc_workspace_bytes(int a_in, int a_hid, int a_out);
 int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
                              int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
                              const float *ln_w, const float *ln_b, int act, float *y, float *saved, void *workspace,
-                             size_t workspace_bytes, void *stream);
+                             size_t workspace_bytes, const float *prev_ln_w, const float *prev_ln_b, int prev_n,
+                             void *stream);
 
 /* Tensor-core backward of the same mix.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
  * writes the weight-gradient operands op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R]

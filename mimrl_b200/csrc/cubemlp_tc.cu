@@ -758,6 +758,8 @@ struct CubePrepArgs {
   unsigned char *split[3];           // split buffers; nullptr = already split (backward after forward)
   const unsigned char *hdr[3];       // where the absmax headers of the splits live (always valid)
   const float *b1, *ln_w;
+  const float *prev_ln_w, *prev_ln_b;      // LayerNorm parameters of the mix that produced x (nullable), prev_n of them
+  int prev_n;
   int A, H, A2, n_abs, backward;
   unsigned *tail;
   unsigned *hdr_op[4];               // backward: absmax headers of the weight-gradient operands x, h, gz, gpre
@@ -854,9 +856,19 @@ __global__ void __launch_bounds__(256) cube_prep_kernel(const CubePrepArgs a) {
   }
   const float row1_max = block_max(row1), col2_max = block_max(col2);
   const float b1_max = block_max((a.b1 && t < H) ? fabsf(a.b1[t]) : 0.f), lw_max = block_max(t < A2 ? fabsf(a.ln_w[t]) : 0.f);
+  // x is the output of a LayerNorm over prev_n features: |x| <= max|ln_w| sqrt(prev_n - 1) + max|ln_b| (a z-score of n
+  // values is at most sqrt(n - 1)); loose by a few binades, which the fp16 hi/lo pair has to spare -- no pass over x
+  float prev_bound = 0.f;
+  if (a.prev_ln_w) {
+    const float pw = block_max(t < a.prev_n ? fabsf(a.prev_ln_w[t]) : 0.f);
+    const float pb = block_max((a.prev_ln_b && t < a.prev_n) ? fabsf(a.prev_ln_b[t]) : 0.f);
+    prev_bound = pw * sqrtf((float)(a.prev_n > 1 ? a.prev_n - 1 : 1)) * 1.0001f + pb;
+  }
   if (t == 0) {
     volatile unsigned *tl = a.tail;
-    const float m_x = __uint_as_float(tl[0]), m_gy = __uint_as_float(tl[1]), m_rstd = __uint_as_float(tl[2]);
+    float m_x = __uint_as_float(tl[0]);
+    const float m_gy = __uint_as_float(tl[1]), m_rstd = __uint_as_float(tl[2]);
+    if (prev_bound > 0.f) m_x = prev_bound, tl[0] = __float_as_uint(prev_bound);
     float *scales = reinterpret_cast<float *>(a.tail + 4);
     const float m_h = m_x * row1_max + b1_max;
     scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h);
@@ -936,7 +948,8 @@ int cube_weight_maps(const CubeWs &w, int a_in, int a_hid, int a_out, bool has_r
 extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
                                         int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
                                         const float *ln_w, const float *ln_b, int act, float *y, float *saved,
-                                        void *workspace, size_t workspace_bytes, void *stream) {
+                                        void *workspace, size_t workspace_bytes, const float *prev_ln_w,
+                                        const float *prev_ln_b, int prev_n, void *stream) {
   MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in, a_hid, a_out, 0, act), "cubemlp_mix_fwd_tc: sizes %d/%d/%d act %d not supported",
                 a_in, a_hid, a_out, act);
   MIMRL_REQUIRE(outer > 0 && inner > 0 && x && y && saved && w1 && w2 && ln_w && ln_b, "cubemlp_mix_fwd_tc: bad arguments");
@@ -947,7 +960,9 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   const long long n_cols = (long long)outer * inner;
   cudaMemsetAsync(w.tail, 0, 16, st);
   CubePrepArgs pa{};
-  pa.x = x, pa.nx = (size_t)n_cols * a_in;
+  const bool bounded = prev_ln_w != nullptr && prev_n > 0 && prev_n <= 256;
+  pa.x = bounded ? nullptr : x, pa.nx = bounded ? 0 : (size_t)n_cols * a_in;
+  pa.prev_ln_w = bounded ? prev_ln_w : nullptr, pa.prev_ln_b = bounded ? prev_ln_b : nullptr, pa.prev_n = bounded ? prev_n : 0;
   pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
   for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
   pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;

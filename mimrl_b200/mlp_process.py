@@ -38,7 +38,7 @@ class _AxisMix(torch.autograd.Function):
     """y = mix along `axis` of x [bs, L, K, D]; parameters in nn.Linear layout."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, wres, ln_w, ln_b, axis, ln_first, act_id):
+    def forward(ctx, x, w1, b1, w2, b2, wres, ln_w, ln_b, axis, ln_first, act_id, prev_w=None, prev_b=None):
         x = L.f32(x)
         shape = list(x.shape)
         A = shape[axis]
@@ -60,7 +60,9 @@ class _AxisMix(torch.autograd.Function):
             L.check(L.lib.mimrl_cubemlp_mix_fwd_tc(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
                                                    L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
                                                    L.ptr(prm[6]), act_id, L.ptr(y), L.ptr(saved), L.ptr(ws), ws.numel(),
-                                                   L.stream()))
+                                                   L.ptr(L.f32(prev_w.detach())) if prev_w is not None else None,
+                                                   L.ptr(L.f32(prev_b.detach())) if prev_b is not None else None,
+                                                   prev_w.numel() if prev_w is not None else 0, L.stream()))
         else:
             L.check(L.lib.mimrl_cubemlp_mix_fwd(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
                                                 L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
@@ -96,7 +98,7 @@ class _AxisMix(torch.autograd.Function):
                                                   L.ptr(b2), A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), ln_first, act_id,
                                                   L.ptr(gx), L.ptr(gw1), L.ptr(gb1), L.ptr(gw2), L.ptr(gb2), L.ptr(gwres),
                                                   L.ptr(gln[0]), L.ptr(gln[1]), L.stream()))
-            return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+            return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
         s_gz = torch.empty(outer, A2, inner, device=dev)
         s_h = torch.empty(outer, H, inner, device=dev)
         s_gpre = torch.empty(outer, H, inner, device=dev)
@@ -119,7 +121,7 @@ class _AxisMix(torch.autograd.Function):
         gw2 = _small(2, r_gz, None, r_h, A2, H, R, colsum=gb2)
         gw1 = _small(2, r_gpre, None, r_u, H, A, R, colsum=gb1)
         gwres = _small(2, r_gz, None, r_u if not ln_first else rows(x3), A2, A, R) if wres is not None else None
-        return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+        return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
 
 
 def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
@@ -153,7 +155,7 @@ def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
     gw1 = wgrad(ops[3], ops[0], H, A, parts[4])
     gw2 = wgrad(ops[2], ops[1], A2, H, parts[5])
     gwres = wgrad(ops[2], ops[0], A2, A, parts[6]) if wres is not None else None
-    return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None
+    return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
 
 
 _AxisMix._backward_tc = staticmethod(_backward_tc)
@@ -205,19 +207,25 @@ class MLPsBlock(nn.Module):
         drop = self.training and any(d.p > 0 for d in (self.dropout_l, self.dropout_k, self.dropout_d))
         return mask is None and not drop and self.activate in _ACT_IDS
 
-    def _mix(self, x, axis, ax):
+    def _mix(self, x, axis, ax, prev_ln=None):
+        """prev_ln: the LayerNorm whose unmodified output x is (ln_last order); the kernels then bound |x| from its
+        parameters instead of reading x once more."""
         mlp, ln = getattr(self, "mlp_" + ax), getattr(self, "ln_" + ax)
         wres = getattr(self, "res_projection_" + ax).weight if self.res_project else None
+        pw = pb = None
+        if prev_ln is not None and not self.ln_fist and prev_ln.weight is not None:
+            pw, pb = prev_ln.weight, prev_ln.bias
         return _AxisMix.apply(x, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, wres, ln.weight, ln.bias,
-                              axis, self.ln_fist, _ACT_IDS[self.activate])
+                              axis, self.ln_fist, _ACT_IDS[self.activate], pw, pb)
 
-    def forward(self, x, mask=None):
+    def forward(self, x, mask=None, _prev_ln=None):
+        """_prev_ln (internal, set by MLPEncoder): x is the unmodified output of that LayerNorm."""
         if mask is not None:
             print("Warning from MLPsBlock: If using mask, d_in should be equal to d_out.")   # MLPProcess.py:56-57
         if self._fusable(mask):
-            x = self._mix(x, 1, "l")
+            x = self._mix(x, 1, "l", _prev_ln)
             x = self._mix(x, 2, "k")
-            return self._mix(x, 3, "d")
+            return self._mix(x, 3, "d", self.ln_k)
         if not self._warned:
             warnings.warn("MLPsBlock: dropout>0 in training / mask / this activation are outside the fused CubeMLP "
                           "kernels; running the reference op order with torch ops")
@@ -255,6 +263,9 @@ class MLPEncoder(nn.Module):
             for i in range(len(d_hiddens))])
 
     def forward(self, x, mask=None):
+        prev = None
         for enc_layer in self.layers_stack:
-            x = enc_layer(x, mask)
+            fused = enc_layer._fusable(mask) and not enc_layer.ln_fist
+            x = enc_layer(x, mask, _prev_ln=prev) if fused else enc_layer(x, mask)
+            prev = enc_layer.ln_d if fused else None          # the block's output is ln_d's output (MLPProcess.py:120)
         return x

@@ -48,7 +48,27 @@ if "cubemlp" in which:  # config 5: [1024, 100, 3, 128] -> 50-3-128 -> 10-3-128
                 q.grad = None
             enc(x).sum().backward()
         both = timeit(fb)
-        out(component="cubemlp", bs=bs, fwd_ms=fwd, fwd_bwd_ms=both, fwd_gbs=(bs * 100 * 384 * 4 * 1.0 + bs * 50 * 384 * 4 * 2 + bs * 10 * 384 * 4) / fwd / 1e6)
+        alg_bytes = bs * 100 * 384 * 4 * 1.0 + bs * 50 * 384 * 4 * 2 + bs * 10 * 384 * 4          # 330 MB at bs = 1024
+        out(component="cubemlp", bs=bs, fwd_ms=fwd, fwd_bwd_ms=both, fwd_gbs=alg_bytes / fwd / 1e6)
+        # the same two calls as CUDA graphs (a forward is ~20 launches, fwd+bwd ~70: at these sizes the eager numbers
+        # above include host launch time)
+        from mimrl_b200.graphs import GraphedCallable
+        def fwd_only(xx):
+            with torch.no_grad():
+                return enc(xx)
+        gf = GraphedCallable(fwd_only, [x.detach()])
+        fwd_g = timeit(lambda: gf(x.detach()))
+        xs = x.detach().clone().requires_grad_(True)
+        def fwd_bwd(xx):
+            xs.grad = None
+            for q in params:
+                q.grad = None
+            enc(xs).sum().backward()
+            return xs.grad
+        gb = GraphedCallable(fwd_bwd, [xs.detach()])
+        both_g = timeit(lambda: gb(xs.detach()))
+        out(component="cubemlp_cuda_graph", bs=bs, fwd_ms=fwd_g, fwd_bwd_ms=both_g, fwd_gbs=alg_bytes / fwd_g / 1e6,
+            fwd_frac_of_hbm_peak=alg_bytes / fwd_g / 1e6 / 6546.6)
 
 if "vcmi" in which:
     est = VCMIEstimator(128, 256, 2, "relu", 2, 1.0, "hardtanh").to(dev)
