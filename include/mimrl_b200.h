@@ -301,21 +301,25 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
                              size_t workspace_bytes, const float *prev_ln_w, const float *prev_ln_b, int prev_n,
                              void *stream);
 
-/* Tensor-core backward of the same mix.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
- * writes the weight-gradient operands op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R]
- * (R = mimrl_cubemlp_tc_fibre_rows(outer, inner), mimrl_split_f32 sizes, feature-major in blocked-K order):
- * gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T through mimrl_gemm_split_blocked.
+/* Tensor-core backward of the same mix.  Writes gx; accumulates (+=, caller zero-fills) g_b1 [a_hid], g_b2 [a_out],
+ * gln_w, gln_b [a_out] and the weight gradients gw1 [a_hid, a_in], gw2 [a_out, a_hid], gwres [a_out, a_in] (NULL
+ * without res_projection).  op_x, op_h, op_gz, op_gpre: scratch for the fp16 hi/lo weight-gradient operands the data
+ * pass leaves behind (a_in / a_hid / a_out / a_hid features over R = mimrl_cubemlp_tc_fibre_rows(outer, inner) fibre
+ * rows; mimrl_cubemlp_tc_op_bytes(features, R) bytes each).  The three contractions over the fibres
+ * (gW1 = gpre^T x, gW2 = gz^T h, gWres = gz^T x) are launched by this call: split over K, partial sums added in place.
  * ws_from_forward != 0: `workspace` is the buffer mimrl_cubemlp_mix_fwd_tc filled for the same x and weights; the
  * weight split, max|x| and the largest rstd are then taken from it instead of being recomputed.
  * Both directions take ONE preparation launch (operand maxima, weight split, operand scales) and one main kernel;
- * the strided mixes of the reference configuration (100->50->50 and 50->10->10 over inner = 384, gelu, residual
- * projection) run on compile-time specialised kernels with 2-4 CTAs per SM (csrc/cubemlp_tc2.cu). */
+ * the mixes of the reference configuration (sequence mix 100->50->50 and 50->10->10 over inner = 384, channel mix
+ * 128->128->128; gelu, residual projection) run on compile-time specialised kernels (csrc/cubemlp_tc2.cu, _tc3.cu). */
 long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner);
+size_t mimrl_cubemlp_tc_op_bytes(int features, long long R);
 int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
                              const float *b1, int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
                              const float *ln_w, const float *ln_b, int act, const float *saved, float *gx, float *g_b1,
-                             float *g_b2, float *gln_w, float *gln_b, void *op_x, void *op_h, void *op_gz, void *op_gpre,
-                             void *workspace, size_t workspace_bytes, int ws_from_forward, void *stream);
+                             float *g_b2, float *gln_w, float *gln_b, float *gw1, float *gw2, float *gwres, void *op_x,
+                             void *op_h, void *op_gz, void *op_gpre, void *workspace, size_t workspace_bytes,
+                             int ws_from_forward, void *stream);
 
 /* ---- the critic MLP in one forward kernel (reference VMI.py:13-22 `mlps(dim, 256, out, layers=2, 'relu')`) ----
  * y = W4 relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3) + b4 for x [M, d_in], d_in <= 128, hidden 256, d_out <= 128:

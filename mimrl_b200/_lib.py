@@ -81,7 +81,8 @@ _SIGS = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mimrl_cubemlp_tc_fibre_rows": (c_int64, [c_int, c_int]),
     "mimrl_cubemlp_mix_bwd_tc": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P,
-                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
+                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
+    "mimrl_cubemlp_tc_op_bytes": (c_size_t, [c_int, c_int64]),
     "mimrl_concat_tc_supported": (c_int, [c_int, c_int]),
     "mimrl_concat_workspace_bytes": (c_size_t, [c_int]),
     "mimrl_concat_scores": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -1006,6 +1006,12 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   return check_launch("cubemlp_tc_fwd");
 }
 
+// bytes of one weight-gradient operand buffer with `features` features over R fibre rows (either layout fits)
+extern "C" size_t mimrl_cubemlp_tc_op_bytes(int features, long long R) {
+  if (features <= 0 || R <= 0) return 0;
+  return mimrl_split_bytes(features, (int)R);
+}
+
 // rows (fibres, whole tiles) of the feature-major weight-gradient operands
 extern "C" long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner) {
   if (outer <= 0 || inner <= 0) return 0;
@@ -1015,18 +1021,20 @@ extern "C" long long mimrl_cubemlp_tc_fibre_rows(int outer, int inner) {
 // Backward of mimrl_cubemlp_mix_fwd_tc.  Writes gx; accumulates (+=) g_b1 [a_hid], g_b2 [a_out], gln_w, gln_b [a_out];
 // writes op_x [a_in, R], op_h [a_hid, R], op_gz [a_out, R], op_gpre [a_hid, R] (R = mimrl_cubemlp_tc_fibre_rows,
 // mimrl_split_f32 sizes, blocked-K order): gW1 = op_gpre op_x^T, gW2 = op_gz op_h^T, gWres = op_gz op_x^T via
-// mimrl_gemm_split_blocked.  ws_from_forward != 0: `workspace` is the buffer the forward of the same mix filled
+// mimrl_gemm_split_blocked -- launched here: gw1 [a_hid, a_in], gw2 [a_out, a_hid], gwres [a_out, a_in] are ACCUMULATED
+// (+=, caller zero-fills).  Operand buffers: mimrl_cubemlp_tc_op_bytes each.  ws_from_forward != 0: `workspace` is the buffer the forward of the same mix filled
 // (same x and weights), so the weight split, max|x| and the rstd maximum are taken from it instead of recomputed.
 extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int outer, int a_in, int inner, const float *w1,
                                         const float *b1, int a_hid, const float *w2, const float *b2, int a_out,
                                         const float *wres, const float *ln_w, const float *ln_b, int act,
                                         const float *saved, float *gx, float *g_b1, float *g_b2, float *gln_w, float *gln_b,
-                                        void *op_x, void *op_h, void *op_gz, void *op_gpre, void *workspace,
-                                        size_t workspace_bytes, int ws_from_forward, void *stream) {
+                                        float *gw1, float *gw2, float *gwres, void *op_x, void *op_h, void *op_gz,
+                                        void *op_gpre, void *workspace, size_t workspace_bytes, int ws_from_forward,
+                                        void *stream) {
   MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in, a_hid, a_out, 0, act), "cubemlp_mix_bwd_tc: sizes %d/%d/%d act %d not supported",
                 a_in, a_hid, a_out, act);
   MIMRL_REQUIRE(outer > 0 && inner > 0 && x && gy && saved && gx && w1 && w2 && ln_w && gln_w && gln_b && op_x && op_h && op_gz &&
-                    op_gpre,
+                    op_gpre && gw1 && gw2 && (gwres || !wres),
                 "cubemlp_mix_bwd_tc: bad arguments");
   MIMRL_REQUIRE(wres || a_in == a_out, "cubemlp_mix: without res_project d_in must equal d_out (MLPProcess.py:46-48)");
   MIMRL_REQUIRE(workspace_bytes >= mimrl_cubemlp_tc_workspace_bytes(a_in, a_hid, a_out), "cubemlp_mix_bwd_tc: workspace too small");
@@ -1067,25 +1075,39 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   bp.ld = (size_t)n_tiles * 128;
   void *ops[4] = {op_x, op_h, op_gz, op_gpre};
   const int feats[4] = {a_in, a_hid, a_out, a_hid};
+  const long long R = n_tiles * 128;
+  CUtensorMap maps[6];
+  const bool c2 = cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res);
+  const bool c3 = !c2 && cube3_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res) &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx)) & 15) == 0;
+  // weight-gradient operands: feature-major fp16 hi/lo planes in blocked-K order (tiles of 64 fibres, each
+  // [features][64] contiguous): a warp's 2-byte stores of one feature are one 64-byte run
   for (int t = 0; t < 4; ++t) {
     bp.op[t][0] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256);
     bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256 + align256((size_t)feats[t] * bp.ld * 2));
   }
-  CUtensorMap maps[6];
-  if (cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res)) {
-    int r1, r2, rr, handled = 0;
-    cube2_box_rows(a_in, a_hid, a_out, &r1, &r2, &rr);
-    if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, r1, r2, rr, maps)) return 1;
-    if (int rc = cube2_bwd(maps, bp, st, &handled)) return rc;
-    if (handled) return 0;
-  }
-  if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
-  if (cube3_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res) &&
-      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx)) & 15) == 0) {
+  auto wgrads = [&]() -> int {
+    if (int rc = mimrl_gemm_split_blocked_acc(op_gpre, op_x, a_hid, a_in, (int)R, gw1, stream)) return rc;
+    if (int rc = mimrl_gemm_split_blocked_acc(op_gz, op_h, a_out, a_hid, (int)R, gw2, stream)) return rc;
+    if (wres)
+      if (int rc = mimrl_gemm_split_blocked_acc(op_gz, op_x, a_out, a_in, (int)R, gwres, stream)) return rc;
+    return 0;
+  };
+  if (c2 || c3) {
     int handled = 0;
-    if (int rc = cube3_bwd(maps, bp, st, &handled)) return rc;
-    if (handled) return 0;
+    if (c2) {
+      int r1, r2, rr;
+      cube2_box_rows(a_in, a_hid, a_out, &r1, &r2, &rr);
+      if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, r1, r2, rr, maps)) return 1;
+      if (int rc = cube2_bwd(maps, bp, st, &handled)) return rc;
+    } else {
+      if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
+      if (int rc = cube3_bwd(maps, bp, st, &handled)) return rc;
+    }
+    return wgrads();
   }
+  // general kernel
+  if (cube_weight_maps(w, a_in, a_hid, a_out, wres != nullptr, 128, 128, 128, maps)) return 1;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCubeBwdSmem);
@@ -1094,5 +1116,6 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   if (act == 0) launch(cubemlp_tc_bwd_kernel<0>);
   else if (act == 1) launch(cubemlp_tc_bwd_kernel<1>);
   else launch(cubemlp_tc_bwd_kernel<2>);
-  return check_launch("cubemlp_tc_bwd");
+  if (check_launch("cubemlp_tc_bwd")) return 1;
+  return wgrads();
 }

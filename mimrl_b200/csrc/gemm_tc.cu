@@ -113,6 +113,10 @@ struct GemmParams {
   const float *bias;
   float *C;       // [M, N] when splits == 1, else partials [splits][M][N]
   int atomic_out; // split-K partial sums are ADDED into C [M, N] with red.global (no partial buffer, no reduce pass)
+  // narrow operands (weight gradients of the CubeMLP mixes): MMA N (multiple of 16), how many 64-wide boxes of each
+  // MN-major operand exist (the second one is not loaded when the operand has <= 64 features), output transposed
+  int n_mma, a_boxes, b_boxes, trans_out, ldc;
+  int b_rows;     // blocked-K layout: box height of the B operand (its rows rounded up to 16)
 };
 
 // A_MN / B_MN: operand stored with the contraction index as the SLOW one (read MN-major)
@@ -179,13 +183,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int stage = n % kGStages, k0 = (kb0 + i) * 64;
           mbar_wait(bEmpty + 8 * stage, ((n / kGStages) & 1) ^ 1);
           const uint32_t fb = bFull + 8 * stage;
-          mbar_expect_tx(fb, kGStage);
+          mbar_expect_tx(fb, (A_MN && B_MN) ? (uint32_t)(p.a_boxes + p.b_boxes) * 2u * 8192u
+                                 : BLK ? 2u * kOp16 + 2u * (uint32_t)p.b_rows * 128u : kGStage);
           const uint32_t dst = base + stage * kGStage;
           if (A_MN) {   // rows = contraction index, 64 per box; two boxes cover 128 M
             tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, m0, k0);
-            tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
             tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
-            tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
+            if (!B_MN || p.a_boxes == 2) {
+              tma_load_2d(dst + 0 * kOp16 + 8192, &map_a_hi, fb, m0 + 64, k0);
+              tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
+            }
           } else if (BLK) {
             tma_load_3d(dst + 0 * kOp16, &map_a_hi, fb, 0, m0, kb0 + i);
             tma_load_3d(dst + 1 * kOp16, &map_a_lo, fb, 0, m0, kb0 + i);
@@ -195,9 +202,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           if (B_MN) {
             tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, n0, k0);
-            tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
             tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, n0, k0);
-            tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
+            if (!A_MN || p.b_boxes == 2) {
+              tma_load_2d(dst + 2 * kOp16 + 8192, &map_b_hi, fb, n0 + 64, k0);
+              tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
+            }
           } else if (BLK) {
             tma_load_3d(dst + 2 * kOp16, &map_b_hi, fb, 0, n0, kb0 + i);
             tma_load_3d(dst + 3 * kOp16, &map_b_lo, fb, 0, n0, kb0 + i);
@@ -210,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
-    constexpr uint32_t idesc = instr_desc_f16(128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+    const uint32_t idesc = instr_desc_f16(128, p.n_mma) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
     uint32_t n = 0, j = 0;
     for (long long it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
       int m0, n0, split, kb0, T;
@@ -253,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       item_of(it, m0, n0, split, kb0, T);
       const uint32_t acc = j & 1;
       const int row = m0 + r;
-      float *out = p.C + ((size_t)(p.atomic_out ? 0 : split) * p.M + row) * p.N;
+      float *out = p.C + ((size_t)(p.atomic_out ? 0 : split) * p.M + row) * (p.atomic_out ? p.ldc : p.N);
       mbar_wait(bAccFull + 8 * acc, (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -271,9 +280,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (c0 >= p.N) continue;
         if (p.atomic_out) {
           if (T > 0) {
+            if (p.trans_out) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (c0 + jj < p.N) atomicAdd(out + c0 + jj, __uint_as_float(v[jj]) * inv);
+              for (int jj = 0; jj < 32; ++jj)
+                if (c0 + jj < p.N) atomicAdd(p.C + (size_t)(c0 + jj) * p.ldc + row, __uint_as_float(v[jj]) * inv);
+            } else if (c0 + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 4)          // one 16-byte reduction per four outputs
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + jj),
+                             "f"(__uint_as_float(v[jj]) * inv), "f"(__uint_as_float(v[jj + 1]) * inv),
+                             "f"(__uint_as_float(v[jj + 2]) * inv), "f"(__uint_as_float(v[jj + 3]) * inv)
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj)
+                if (c0 + jj < p.N) atomicAdd(out + c0 + jj, __uint_as_float(v[jj]) * inv);
+            }
           }
         } else if (c0 + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
@@ -489,6 +511,7 @@ extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_spl
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
   p.absmax_b = nullptr, p.atomic_out = 0;
+  p.n_mma = 128, p.a_boxes = 2, p.b_boxes = 2, p.trans_out = 0, p.ldc = N, p.b_rows = 128;
   p.bias = g.splits > 1 ? nullptr : bias;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
@@ -534,6 +557,7 @@ extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split
   p.relu = 0;
   p.absmax = absmax;
   p.absmax_b = nullptr, p.atomic_out = 0;
+  p.n_mma = 128, p.a_boxes = 2, p.b_boxes = 2, p.trans_out = 0, p.ldc = N, p.b_rows = 128;
   p.bias = nullptr;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(workspace) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
@@ -554,28 +578,39 @@ extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split
 // run; the CubeMLP weight gradients use it, the critic MLPs keep the deterministic two-stage sum.
 extern "C" int mimrl_gemm_split_blocked_acc(const void *a_split, const void *b_split, int M, int N, int K, float *C,
                                             void *stream) {
-  MIMRL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 64) == 0 && a_split && b_split && C, "gemm_split_blocked_acc: bad arguments");
-  const GemmLayout g = gemm_layout(0, M, N, K);
+  MIMRL_REQUIRE(M > 0 && N > 0 && M <= 128 && N <= 128 && K > 0 && (K % 64) == 0 && a_split && b_split && C,
+                "gemm_split_blocked_acc: bad arguments (M, N <= 128, K %% 64 == 0)");
   cudaStream_t st = (cudaStream_t)stream;
-  const SplitLayout la = split_layout(M, K), lb = split_layout(N, K);
-  const unsigned char *pa = (const unsigned char *)a_split, *pb = (const unsigned char *)b_split;
-  CUtensorMap ah, al, bh, bl;
+  // the wider operand takes the 128 MMA rows, the narrower one the MMA columns rounded up to 16 (a 10 x 50 gradient
+  // is a 128 x 16 MMA, not 128 x 128) and a TMA box of that height; the output is written transposed when swapped
+  const bool swap = N > M;
+  const unsigned char *pm = (const unsigned char *)(swap ? b_split : a_split), *pn = (const unsigned char *)(swap ? a_split : b_split);
+  const int Mm = swap ? N : M, Nn = swap ? M : N;
+  const int n_pad = (Nn + 15) & ~15;
+  const SplitLayout lm = split_layout(Mm, K), ln = split_layout(Nn, K);
+  CUtensorMap mh, ml, nh, nl;
   const uint64_t kt = (uint64_t)K / 64;
-  if (make_map_blocked(&ah, pa + la.off_hi, M, kt, 128) || make_map_blocked(&al, pa + la.off_lo, M, kt, 128) ||
-      make_map_blocked(&bh, pb + lb.off_hi, N, kt, 128) || make_map_blocked(&bl, pb + lb.off_lo, N, kt, 128))
+  if (make_map_blocked(&mh, pm + lm.off_hi, Mm, kt, 128) || make_map_blocked(&ml, pm + lm.off_lo, Mm, kt, 128) ||
+      make_map_blocked(&nh, pn + ln.off_hi, Nn, kt, n_pad) || make_map_blocked(&nl, pn + ln.off_lo, Nn, kt, n_pad))
     return 1;
+  // enough pieces of the contraction for every SM, at most 32 k-blocks per accumulator (tensor-core adds truncate)
+  const int n_kb = K / 64;
+  const int want = ceil_div(n_kb, 32);
+  int splits = want <= 148 ? 148 : 148 * ceil_div(want, 148);
+  if (splits > n_kb) splits = n_kb;
   GemmParams p;
-  p.M = M, p.N = N, p.K = K;
-  p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
-  p.splits = g.splits;
+  p.M = Mm, p.N = Nn, p.K = K;
+  p.kblocks_per_split = ceil_div(n_kb, splits);
+  p.splits = ceil_div(n_kb, p.kblocks_per_split);
   p.relu = 0;
-  p.absmax = reinterpret_cast<const unsigned *>(pa);
-  p.absmax_b = reinterpret_cast<const unsigned *>(pb);
+  p.absmax = reinterpret_cast<const unsigned *>(pm);
+  p.absmax_b = reinterpret_cast<const unsigned *>(pn);
   p.atomic_out = 1;
+  p.n_mma = n_pad, p.a_boxes = 2, p.b_boxes = 2, p.trans_out = swap ? 1 : 0, p.ldc = N, p.b_rows = n_pad;
   p.bias = nullptr;
   p.C = C;
-  dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
-  return launch_gemm<false, false, true>(ah, al, bh, bl, p, grid, st);
+  dim3 grid(1, 1, p.splits);
+  return launch_gemm<false, false, true>(mh, ml, nh, nl, p, grid, st);
 }
 
 extern "C" size_t mimrl_gemm_workspace_bytes(int mode, int M, int N, int K) {
@@ -624,6 +659,7 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   p.relu = g.splits > 1 ? 0 : relu;          // split-K: bias and ReLU are applied by the reduction
   p.absmax = absmax;
   p.absmax_b = nullptr, p.atomic_out = 0;
+  p.n_mma = 128, p.a_boxes = 2, p.b_boxes = 2, p.trans_out = 0, p.ldc = N, p.b_rows = 128;
   p.bias = g.splits > 1 ? nullptr : bias;
   p.C = g.splits > 1 ? reinterpret_cast<float *>(ws + g.off_part) : C;
   dim3 grid(ceil_div(M, 128), ceil_div(N, 128), g.splits);
@@ -641,3 +677,4 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   }
   return 0;
 }
+

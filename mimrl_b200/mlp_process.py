@@ -132,7 +132,7 @@ def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
     dev = x.device
     st = L.stream()
     R = L.lib.mimrl_cubemlp_tc_fibre_rows(outer, inner)
-    ops = [torch.empty(L.lib.mimrl_split_bytes(n, R), dtype=torch.uint8, device=dev) for n in (A, H, A2, H)]
+    ops = [torch.empty(L.lib.mimrl_cubemlp_tc_op_bytes(n, R), dtype=torch.uint8, device=dev) for n in (A, H, A2, H)]
     ws = ws_fwd if ws_fwd is not None else torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8,
                                                        device=dev)
     # every accumulated output of this mix lives in ONE zero-filled buffer (one fill launch instead of seven)
@@ -142,19 +142,14 @@ def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
     gb1 = parts[0] if b1 is not None else None
     gb2 = parts[1] if b2 is not None else None
     gln = (parts[2], parts[3])
+    gw1, gw2 = parts[4].view(H, A), parts[5].view(A2, H)
+    gwres = parts[6].view(A2, A) if wres is not None else None
+    # one call: the fused data-gradient kernel, then the three weight-gradient contractions over the operands it leaves
     L.check(L.lib.mimrl_cubemlp_mix_bwd_tc(L.ptr(x), L.ptr(gy), outer, A, inner, L.ptr(w1), L.ptr(b1), H, L.ptr(w2), L.ptr(b2),
                                            A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), act_id, L.ptr(saved), L.ptr(gx),
-                                           L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(ops[0]), L.ptr(ops[1]),
-                                           L.ptr(ops[2]), L.ptr(ops[3]), L.ptr(ws), ws.numel(), int(ws_fwd is not None), st))
-
-    def wgrad(a, b, m, n, out):                      # split-K partial sums are added in place (no reduce launch)
-        out = out.view(m, n)
-        L.check(L.lib.mimrl_gemm_split_blocked_acc(L.ptr(a), L.ptr(b), m, n, R, L.ptr(out), st))
-        return out
-
-    gw1 = wgrad(ops[3], ops[0], H, A, parts[4])
-    gw2 = wgrad(ops[2], ops[1], A2, H, parts[5])
-    gwres = wgrad(ops[2], ops[0], A2, A, parts[6]) if wres is not None else None
+                                           L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(gw1), L.ptr(gw2),
+                                           L.ptr(gwres), L.ptr(ops[0]), L.ptr(ops[1]), L.ptr(ops[2]), L.ptr(ops[3]),
+                                           L.ptr(ws), ws.numel(), int(ws_fwd is not None), st))
     return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
 
 
