@@ -517,8 +517,10 @@ cubemlp_small_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restri
 #pragma unroll
     for (int r = 0; r < kSmallMax; ++r)
       if (r < d.A2) y[bo + (size_t)r * d.inner] = yo[r];
-    saved[2 * c] = mean;
-    saved[2 * c + 1] = rstd;
+    if (saved) {
+      saved[2 * c] = mean;
+      saved[2 * c + 1] = rstd;
+    }
   }
 }
 
@@ -776,9 +778,11 @@ cubemlp_k3_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict_
     float4 *yp = reinterpret_cast<float4 *>(y + (size_t)o * 3 * inner) + i4;
 #pragma unroll
     for (int r = 0; r < 3; ++r) yp[r * q4] = make_float4(yo[r][0], yo[r][1], yo[r][2], yo[r][3]);
-    float4 *sv = reinterpret_cast<float4 *>(saved + 2 * ((size_t)o * inner + 4 * (size_t)i4));
-    sv[0] = make_float4(st[0], st[1], st[2], st[3]);
-    sv[1] = make_float4(st[4], st[5], st[6], st[7]);
+    if (saved) {                  // the tiny-axis backward recomputes the statistics: callers pass NULL and save the write
+      float4 *sv = reinterpret_cast<float4 *>(saved + 2 * ((size_t)o * inner + 4 * (size_t)i4));
+      sv[0] = make_float4(st[0], st[1], st[2], st[3]);
+      sv[1] = make_float4(st[4], st[5], st[6], st[7]);
+    }
   }
 }
 

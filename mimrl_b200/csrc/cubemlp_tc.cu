@@ -765,10 +765,21 @@ struct CubePrepArgs {
   unsigned *hdr_op[4];               // backward: absmax headers of the weight-gradient operands x, h, gz, gpre
 };
 
-__global__ void __launch_bounds__(256) cube_prep_kernel(const CubePrepArgs a) {
-  __shared__ float red[256];
+constexpr int kPrepThreads = 1024;
+__global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepArgs a) {
+  __shared__ float red[kPrepThreads];
   __shared__ unsigned s_last;
   const int t = threadIdx.x;
+  auto block_max = [&](float v) {
+    __syncthreads();
+    red[t] = v;
+    __syncthreads();
+    for (int o = kPrepThreads / 2; o; o >>= 1) {
+      if (t < o) red[t] = fmaxf(red[t], red[t + o]);
+      __syncthreads();
+    }
+    return red[0];
+  };
   if ((int)blockIdx.x < a.n_abs) {
     float m0 = 0.f, m1 = 0.f, m2 = 0.f;
     const size_t t0 = (size_t)blockIdx.x * blockDim.x + t, st = (size_t)a.n_abs * blockDim.x;
@@ -804,30 +815,52 @@ __global__ void __launch_bounds__(256) cube_prep_kernel(const CubePrepArgs a) {
     const int m = blockIdx.x - a.n_abs;
     const float *w = a.w[m];
     unsigned char *out = a.split[m];
-    if (w && out) {
+    if (w && out) {                                            // block-uniform
       const int rows = m == 0 ? a.H : a.A2, cols = m == 1 ? a.H : a.A;
       const int ld = (cols + 63) & ~63;
       float mx = 0.f;
-      for (int i = t; i < rows * cols; i += 256) mx = fmaxf(mx, fabsf(w[i]));
-      red[t] = mx;
-      __syncthreads();
-      for (int o = 128; o; o >>= 1) {
-        if (t < o) red[t] = fmaxf(red[t], red[t + o]);
-        __syncthreads();
-      }
-      const unsigned bits = __float_as_uint(red[0]);
+      for (int i = t; i < rows * cols; i += kPrepThreads) mx = fmaxf(mx, fabsf(w[i]));
+      const unsigned bits = __float_as_uint(block_max(mx));
       if (t == 0) *reinterpret_cast<unsigned *>(out) = bits;
       const float sc = scale_from_absmax(bits);
       __half *hi = reinterpret_cast<__half *>(out + 256);
       __half *lo = reinterpret_cast<__half *>(out + 256 + align256((size_t)rows * ld * 2));
       const int half_ld = ld >> 1;
-      for (int i = t; i < rows * half_ld; i += 256) {
+      for (int i = t; i < rows * half_ld; i += kPrepThreads) {
         const int r = i / half_ld, c = (i - r * half_ld) * 2;
         const float v0 = c < cols ? w[r * cols + c] * sc : 0.f, v1 = c + 1 < cols ? w[r * cols + c + 1] * sc : 0.f;
         const __half2 h = __floats2half2_rn(v0, v1);
         const float2 hf = __half22float2(h);
         *reinterpret_cast<__half2 *>(hi + r * ld + c) = h;
         *reinterpret_cast<__half2 *>(lo + r * ld + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      }
+      // L1 norms the scale bounds need, while this block has the matrix in cache (tail[12]: max_h sum_a |W1[h,a]|,
+      // tail[13]: max_h sum_q |W2[q,h]|); they stay in the workspace for a backward that reuses it
+      if (m < 2) {
+        float part = 0.f;
+        if (m == 0) {                                   // row sums: eight threads per row
+          const int r = t >> 3;
+          if (r < rows)
+            for (int c = t & 7; c < cols; c += 8) part += fabsf(w[r * cols + c]);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+        } else {                                        // column sums: eight threads per column (coalesced rows)
+          const int c = t & 127;
+          if (c < cols)
+            for (int r = t >> 7; r < rows; r += 8) part += fabsf(w[r * cols + c]);
+          __syncthreads();
+          red[t] = part;
+          __syncthreads();
+          if (t < 128) {
+            part = 0.f;
+            for (int k = 0; k < 8; ++k) part += red[t + 128 * k];
+          } else {
+            part = 0.f;
+          }
+        }
+        const float nm = block_max(part);
+        if (t == 0) a.tail[12 + m] = __float_as_uint(nm);
       }
     }
   }
@@ -838,23 +871,9 @@ __global__ void __launch_bounds__(256) cube_prep_kernel(const CubePrepArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  auto block_max = [&](float v) {
-    __syncthreads();
-    red[t] = v;
-    __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-      if (t < o) red[t] = fmaxf(red[t], red[t + o]);
-      __syncthreads();
-    }
-    return red[0];
-  };
   const int A = a.A, H = a.H, A2 = a.A2;
-  float row1 = 0.f, col2 = 0.f;
-  if (t < H) {
-    for (int k = 0; k < A; ++k) row1 += fabsf(a.w[0][(size_t)t * A + k]);          // sum_a |W1[h, a]|
-    for (int q = 0; q < A2; ++q) col2 += fabsf(a.w[1][(size_t)q * H + t]);         // sum_q |W2[q, h]|
-  }
-  const float row1_max = block_max(row1), col2_max = block_max(col2);
+  const float row1_max = __uint_as_float(reinterpret_cast<volatile unsigned *>(a.tail)[12]);
+  const float col2_max = __uint_as_float(reinterpret_cast<volatile unsigned *>(a.tail)[13]);
   const float b1_max = block_max((a.b1 && t < H) ? fabsf(a.b1[t]) : 0.f), lw_max = block_max(t < A2 ? fabsf(a.ln_w[t]) : 0.f);
   // x is the output of a LayerNorm over prev_n features: |x| <= max|ln_w| sqrt(prev_n - 1) + max|ln_b| (a z-score of n
   // values is at most sqrt(n - 1)); loose by a few binades, which the fp16 hi/lo pair has to spare -- no pass over x
@@ -967,10 +986,10 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
   pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;
   {
-    const size_t want = (pa.nx + 8191) / 8192;
-    pa.n_abs = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+    const size_t want = (pa.nx + 32767) / 32768;
+    pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
   }
-  cube_prep_kernel<<<pa.n_abs + 3, 256, 0, st>>>(pa);
+  cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
   if (check_launch("cubemlp prep")) return 1;
   CubeTcParams p;
   p.scales = reinterpret_cast<const float *>(w.tail + 4);
@@ -1055,10 +1074,10 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 1, pa.tail = w.tail;
   pa.hdr_op[0] = (unsigned *)op_x, pa.hdr_op[1] = (unsigned *)op_h, pa.hdr_op[2] = (unsigned *)op_gz, pa.hdr_op[3] = (unsigned *)op_gpre;
   {
-    const size_t want = ((ws_from_forward ? 0 : pa.nx) + pa.ngy + 8191) / 8192;
-    pa.n_abs = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+    const size_t want = ((ws_from_forward ? 0 : pa.nx) + pa.ngy + 32767) / 32768;
+    pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
   }
-  cube_prep_kernel<<<pa.n_abs + 3, 256, 0, st>>>(pa);
+  cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
   if (check_launch("cubemlp prep")) return 1;
   CubeBwdParams bp;
   CubeTcParams &p = bp.f;

@@ -22,21 +22,25 @@
 namespace mimrl {
 namespace {
 
-constexpr int kC3Threads = 288;                        // warps 0-3 / 4-7: the two feature halves; warp 8: TMA + MMA issue
+// G warpgroups share a row: thread = (row, feature slice of 128 / G); warp 4 G: TMA + MMA issue
+template <int G> struct C3 {
+  static constexpr int FT = 128 / G, NU = FT / 16, NC = FT / 32, THREADS = 128 * G + 32;
+  static_assert(G == 2 || G == 4, "two or four warpgroups");
+};
 constexpr uint32_t kC3Blk = 128 * 128;                 // one 64-wide K block of a weight: 128 rows x 128 B
 constexpr uint32_t kC3Half = 2 * kC3Blk;               // hi or lo
 constexpr uint32_t kC3W = 2 * kC3Half;                 // one weight
 constexpr uint32_t kC3Bars = 3 * kC3W;
 constexpr uint32_t kC3Vec = kC3Bars + 256;             // b1 | b2 | ln_w | ln_b (4 x 128 floats)
-constexpr uint32_t kC3Part = kC3Vec + 4 * 128 * 4;     // [2 rounds][2 halves][128 rows] float2
-constexpr uint32_t kC3Red = kC3Part + 2 * 2 * 128 * 8; // [8 warps][8][32] floats
-constexpr uint32_t kC3Smem = kC3Red + 8 * 8 * 32 * 4 + 1024;
+constexpr uint32_t kC3Part = kC3Vec + 4 * 128 * 4;     // [2 rounds][G slices][128 rows] float2
+constexpr uint32_t kC3Red = kC3Part + 2 * 4 * 128 * 8; // [4 G warps][8][32] floats
+constexpr uint32_t kC3Smem = kC3Red + 16 * 8 * 32 * 4 + 1024;
 constexpr uint32_t kTX3 = 0, kTH3 = 128, kTPre3 = 256, kTR3 = 384;      // o, gh, gx reuse kTX3; GZ kTH3; GPRE kTR3
 
 // barrier indices
 enum { B_W = 0, B_X, B_D1A, B_D1B, B_HA, B_HB, B_D2, B_GZA, B_GZB, B_D3, B_GP, B_D4, B_COUNT };
 
-template <bool BWD>
+template <int G>
 __device__ __forceinline__ uint32_t c3_setup(uint8_t *gen, uint32_t base, const CubeTcParams &p, int warp) {
   const uint32_t bars = base + kC3Bars;
   float *vec = reinterpret_cast<float *>(gen + kC3Vec);
@@ -46,17 +50,17 @@ __device__ __forceinline__ uint32_t c3_setup(uint8_t *gen, uint32_t base, const 
   }
   if (threadIdx.x == 0) {
     mbar_init(bars + 8 * B_W, 1);
-    mbar_init(bars + 8 * B_X, 8);
+    mbar_init(bars + 8 * B_X, 4 * G);
     mbar_init(bars + 8 * B_D1A, 1), mbar_init(bars + 8 * B_D1B, 1);
-    mbar_init(bars + 8 * B_HA, 4), mbar_init(bars + 8 * B_HB, 4);
+    mbar_init(bars + 8 * B_HA, 2 * G), mbar_init(bars + 8 * B_HB, 2 * G);
     mbar_init(bars + 8 * B_D2, 1);
-    mbar_init(bars + 8 * B_GZA, 4), mbar_init(bars + 8 * B_GZB, 4);
+    mbar_init(bars + 8 * B_GZA, 2 * G), mbar_init(bars + 8 * B_GZB, 2 * G);
     mbar_init(bars + 8 * B_D3, 1);
-    mbar_init(bars + 8 * B_GP, 8);
+    mbar_init(bars + 8 * B_GP, 4 * G);
     mbar_init(bars + 8 * B_D4, 1);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 4 * G) {
     tmem_alloc(smem_u32(gen + kC3Bars + 128), 512);
     tmem_relinquish();
   }
@@ -109,27 +113,28 @@ __device__ __forceinline__ void c3_load16(const float *src, bool ok, float (&v)[
 }
 
 // gelu(pre + b1) of one 16-feature unit, scaled and split, into the H operand
-__device__ __forceinline__ void c3_hidden_unit(uint32_t tb, int g, int u, const float *s_b1, float i_pre, float sh, uint32_t (&hi)[8],
+__device__ __forceinline__ void c3_hidden_unit(uint32_t tb, int fb, int u, const float *s_b1, float i_pre, float sh, uint32_t (&hi)[8],
                                                uint32_t (&lo)[8]) {
   uint32_t d[16];
-  tmem_ld16(tb + kTPre3 + 64 * g + u * 16, d);
+  tmem_ld16(tb + kTPre3 + fb + u * 16, d);
   tmem_ld_wait();
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
-    const int h = 64 * g + u * 16 + j;
+    const int h = fb + u * 16 + j;
     const float2 pre = ffma2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])), make_float2(i_pre, i_pre),
                              make_float2(s_b1[h], s_b1[h + 1]));
     const float2 gl = fmul2(gelu2(pre), make_float2(sh, sh));
     v[j] = gl.x, v[j + 1] = gl.y;
   }
   split16(v, hi, lo);
-  tmem_st8(tb + kTH3 + 32 * g + u * 8, hi);
-  tmem_st8(tb + kTH3 + 64 + 32 * g + u * 8, lo);
+  tmem_st8(tb + kTH3 + fb / 2 + u * 8, hi);
+  tmem_st8(tb + kTH3 + 64 + fb / 2 + u * 8, lo);
 }
 
 // ---------------------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kC3Threads, 1)
+template <int G>
+__global__ void __launch_bounds__(C3<G>::THREADS, 1)
 cube3_fwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant__ CUtensorMap w1l,
                  const __grid_constant__ CUtensorMap w2h, const __grid_constant__ CUtensorMap w2l,
                  const __grid_constant__ CUtensorMap wrh, const __grid_constant__ CUtensorMap wrl, const CubeTcParams p) {
@@ -142,10 +147,11 @@ cube3_fwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
   const float *s_b1 = reinterpret_cast<const float *>(gen + kC3Vec), *s_b2 = s_b1 + 128, *s_lw = s_b1 + 256, *s_lb = s_b1 + 384;
   float *s_part = reinterpret_cast<float *>(gen + kC3Part);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const uint32_t tmem_base = c3_setup<false>(gen, base, p, warp);
+  constexpr int FT = C3<G>::FT, NU = C3<G>::NU;
+  const uint32_t tmem_base = c3_setup<G>(gen, base, p, warp);
   const long long n_tiles = (p.n_cols + 127) / 128;
 
-  if (warp == 8) {
+  if (warp == 4 * G) {
     const uint32_t leader = elect_one();
     if (leader) c3_load_weights(base, bars + 8 * B_W, &w1h, &w1l, &w2h, &w2l, &wrh, &wrl);
     mbar_wait(bars + 8 * B_W, 0);
@@ -177,6 +183,7 @@ cube3_fwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
     }
   } else {
     const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const int fb = FT * g, hf = (2 * g) / G;            // first feature of this thread's slice; its half of the row
     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sx = p.scales[0], sh = p.scales[1];
     const float i_pre = 1.f / (sx * scale_from_absmax(p.sc_w1[0])), i_o = 1.f / (sh * scale_from_absmax(p.sc_w2[0]));
@@ -187,74 +194,80 @@ cube3_fwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
       const uint32_t ph = it & 1;
       const long long c = tile * 128 + r;
       const bool ok = c < p.n_cols;
-      const float *xr = p.x + (size_t)(ok ? c : 0) * 128 + 64 * g;
+      const float *xr = p.x + (size_t)(ok ? c : 0) * 128 + fb;
       // ---- 1. my half of the row -> X operand
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         float v[16];
         c3_load16(xr + u * 16, ok, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] *= sx;
         uint32_t hi[8], lo[8];
         split16(v, hi, lo);
-        tmem_st8(tb + kTX3 + 32 * g + u * 8, hi);
-        tmem_st8(tb + kTX3 + 64 + 32 * g + u * 8, lo);
+        tmem_st8(tb + kTX3 + fb / 2 + u * 8, hi);
+        tmem_st8(tb + kTX3 + 64 + fb / 2 + u * 8, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * B_X);
       // ---- 2. h = gelu(pre + b1), my half, as soon as its product is done
-      mbar_wait(bars + 8 * (g ? B_D1B : B_D1A), ph);
+      mbar_wait(bars + 8 * (hf ? B_D1B : B_D1A), ph);
       tc_fence_after();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t hi[8], lo[8];
-        c3_hidden_unit(tb, g, u, s_b1, i_pre, sh, hi, lo);
+        c3_hidden_unit(tb, fb, u, s_b1, i_pre, sh, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (g ? B_HB : B_HA));
+      if (lane == 0) mbar_arrive(bars + 8 * (hf ? B_HB : B_HA));
       // ---- 3. z = o + r + b2; LayerNorm over the 128 features (two halves meet in shared memory)
       mbar_wait(bars + 8 * B_D2, ph);
       tc_fence_after();
-      float z[64];
+      float z[FT];
       float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t d[16], w[16];
-        tmem_ld16(tb + kTX3 + 64 * g + u * 16, d);
-        tmem_ld16(tb + kTR3 + 64 * g + u * 16, w);
+        tmem_ld16(tb + kTX3 + fb + u * 16, d);
+        tmem_ld16(tb + kTR3 + fb + u * 16, w);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float t = fmaf(__uint_as_float(w[j]), i_r, fmaf(__uint_as_float(d[j]), i_o, s_b2[64 * g + u * 16 + j]));
+          const float t = fmaf(__uint_as_float(w[j]), i_r, fmaf(__uint_as_float(d[j]), i_o, s_b2[fb + u * 16 + j]));
           z[u * 16 + j] = t;
           sum += t;
         }
       }
       tc_fence_before();
       s_part[g * 128 + r] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mean = (s_part[r] + s_part[128 + r]) * (1.f / 128.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < G; ++w) tot += s_part[w * 128 + r];
+      const float mean = tot * (1.f / 128.f);
       float var = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
+      for (int j = 0; j < FT; ++j) {
         const float dlt = z[j] - mean;
         var = fmaf(dlt, dlt, var);
       }
-      s_part[256 + g * 128 + r] = var;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float rstd = rsqrtf((s_part[256 + r] + s_part[384 + r]) * (1.f / 128.f) + 1e-6f);
-      if (ok) {
-        float4 *yr = reinterpret_cast<float4 *>(p.y + (size_t)c * 128 + 64 * g);
+      s_part[512 + g * 128 + r] = var;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");
+      float vtot = 0.f;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+      for (int w = 0; w < G; ++w) vtot += s_part[512 + w * 128 + r];
+      const float rstd = rsqrtf(vtot * (1.f / 128.f) + 1e-6f);
+      if (ok) {
+        float4 *yr = reinterpret_cast<float4 *>(p.y + (size_t)c * 128 + fb);
+#pragma unroll
+        for (int t = 0; t < FT / 4; ++t) {
           float o4[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int f = 64 * g + 4 * t + e;
+            const int f = fb + 4 * t + e;
             const float gg = rstd * s_lw[f];
             o4[e] = fmaf(z[4 * t + e], gg, fmaf(-mean, gg, s_lb[f]));
           }
@@ -273,11 +286,12 @@ cube3_fwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == 4 * G) tmem_dealloc(tmem_base, 512);
 }
 
 // --------------------------------------------------------------------------------------------------------- backward
-__global__ void __launch_bounds__(kC3Threads, 1)
+template <int G>
+__global__ void __launch_bounds__(C3<G>::THREADS, 1)
 cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant__ CUtensorMap w1l,
                  const __grid_constant__ CUtensorMap w2h, const __grid_constant__ CUtensorMap w2l,
                  const __grid_constant__ CUtensorMap wrh, const __grid_constant__ CUtensorMap wrl, const CubeBwdParams bp) {
@@ -292,10 +306,11 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
   float2 *s_part = reinterpret_cast<float2 *>(gen + kC3Part);
   float *s_red = reinterpret_cast<float *>(gen + kC3Red);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const uint32_t tmem_base = c3_setup<true>(gen, base, p, warp);
+  constexpr int FT = C3<G>::FT, NU = C3<G>::NU, NC = C3<G>::NC;
+  const uint32_t tmem_base = c3_setup<G>(gen, base, p, warp);
   const long long n_tiles = (p.n_cols + 127) / 128;
 
-  if (warp == 8) {
+  if (warp == 4 * G) {
     const uint32_t leader = elect_one();
     if (leader) c3_load_weights(base, bars + 8 * B_W, &w1h, &w1l, &w2h, &w2l, &wrh, &wrl);
     mbar_wait(bars + 8 * B_W, 0);
@@ -346,40 +361,41 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
     }
   } else {
     const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const int fb = FT * g, hf = (2 * g) / G;            // first feature of this thread's slice; its half of the row
     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sx = bp.scales[0], sh = bp.scales[1], sgz = bp.scales[2], sgp = bp.scales[3];
     const float sw1 = scale_from_absmax(p.sc_w1[0]), sw2 = scale_from_absmax(p.sc_w2[0]), swr = scale_from_absmax(p.sc_wr[0]);
     const float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr), i_gh = 1.f / (sgz * sw2),
                 i_gx = 1.f / (sgp * sw1);            // == 1 / (sgz * swr)
-    float acc_lnw[2] = {}, acc_lnb[2] = {}, acc_b2[2] = {}, acc_b1[2] = {};
+    float acc_lnw[NC] = {}, acc_lnb[NC] = {}, acc_b2[NC] = {}, acc_b1[NC] = {};
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const long long c = tile * 128 + r;
       const bool ok = c < p.n_cols;
       const size_t row = (size_t)c;
-      const float *xr = p.x + (size_t)(ok ? c : 0) * 128 + 64 * g;
-      const float *gyr = bp.gy + (size_t)(ok ? c : 0) * 128 + 64 * g;
+      const float *xr = p.x + (size_t)(ok ? c : 0) * 128 + fb;
+      const float *gyr = bp.gy + (size_t)(ok ? c : 0) * 128 + fb;
       // ---- 1. x -> X operand (+ weight-gradient operand)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         float v[16];
         c3_load16(xr + u * 16, ok, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] *= sx;
         uint32_t hi[8], lo[8];
         split16(v, hi, lo);
-        tmem_st8(tb + kTX3 + 32 * g + u * 8, hi);
-        tmem_st8(tb + kTX3 + 64 + 32 * g + u * 8, lo);
-        c2_store_op<128>(bp.op[0][0], bp.op[0][1], row, 64 * g + u * 16, hi, lo);
+        tmem_st8(tb + kTX3 + fb / 2 + u * 8, hi);
+        tmem_st8(tb + kTX3 + 64 + fb / 2 + u * 8, lo);
+        c2_store_op<128>(bp.op[0][0], bp.op[0][1], row, fb + u * 16, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * B_X);
-      float gyv[64];
+      float gyv[FT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         float v[16];
         c3_load16(gyr + u * 16, ok, v);
 #pragma unroll
@@ -388,32 +404,32 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
       const float2 ms = ok ? __ldg(reinterpret_cast<const float2 *>(p.saved) + c) : make_float2(0.f, 0.f);
       const float mean = ms.x, rstd = ms.y;
       // ---- 2. h
-      mbar_wait(bars + 8 * (g ? B_D1B : B_D1A), ph);
+      mbar_wait(bars + 8 * (hf ? B_D1B : B_D1A), ph);
       tc_fence_after();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t hi[8], lo[8];
-        c3_hidden_unit(tb, g, u, s_b1, i_pre, sh, hi, lo);
-        c2_store_op<128>(bp.op[1][0], bp.op[1][1], row, 64 * g + u * 16, hi, lo);
+        c3_hidden_unit(tb, fb, u, s_b1, i_pre, sh, hi, lo);
+        c2_store_op<128>(bp.op[1][0], bp.op[1][1], row, fb + u * 16, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (g ? B_HB : B_HA));
+      if (lane == 0) mbar_arrive(bars + 8 * (hf ? B_HB : B_HA));
       // ---- 3. LayerNorm backward -> gz
       mbar_wait(bars + 8 * B_D2, ph);
       tc_fence_after();
-      float zh[64];
+      float zh[FT];
       float sum_g = 0.f, sum_gz = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t d[16], w[16];
-        tmem_ld16(tb + kTX3 + 64 * g + u * 16, d);
-        tmem_ld16(tb + kTR3 + 64 * g + u * 16, w);
+        tmem_ld16(tb + kTX3 + fb + u * 16, d);
+        tmem_ld16(tb + kTR3 + fb + u * 16, w);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int f = 64 * g + u * 16 + j;
+          const int f = fb + u * 16 + j;
           const float z = fmaf(__uint_as_float(w[j]), i_r, fmaf(__uint_as_float(d[j]), i_o, s_b2[f]));
           const float t = (z - mean) * rstd;
           const float gw = gyv[u * 16 + j] * s_lw[f];
@@ -424,11 +440,13 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
       }
       tc_fence_before();
       s_part[g * 128 + r] = make_float2(sum_g, sum_gz);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float2 pa = s_part[r], pb = s_part[128 + r];
-      const float m1 = (pa.x + pb.x) * (1.f / 128.f), m2 = (pa.y + pb.y) * (1.f / 128.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");
+      float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+      for (int w = 0; w < G; ++w) m1 += s_part[w * 128 + r].x, m2 += s_part[w * 128 + r].y;
+      m1 *= (1.f / 128.f), m2 *= (1.f / 128.f);
+#pragma unroll
+      for (int c2 = 0; c2 < NC; ++c2) {
         float t1[32], t2[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) t1[j] = gyv[c2 * 32 + j] * zh[c2 * 32 + j], t2[j] = gyv[c2 * 32 + j];
@@ -436,54 +454,54 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
         acc_lnb[c2] += lane_sum<32>(t2, lane);
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) zh[j] = rstd * (fmaf(gyv[j], s_lw[64 * g + j], -m1) - zh[j] * m2);         // gz
+      for (int j = 0; j < FT; ++j) zh[j] = rstd * (fmaf(gyv[j], s_lw[fb + j], -m1) - zh[j] * m2);         // gz
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+      for (int c2 = 0; c2 < NC; ++c2) {
         float t1[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) t1[j] = zh[c2 * 32 + j];
         acc_b2[c2] += lane_sum<32>(t1, lane);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = zh[u * 16 + j] * sgz;
         uint32_t hi[8], lo[8];
         split16(v, hi, lo);
-        tmem_st8(tb + kTH3 + 32 * g + u * 8, hi);
-        tmem_st8(tb + kTH3 + 64 + 32 * g + u * 8, lo);
-        c2_store_op<128>(bp.op[2][0], bp.op[2][1], row, 64 * g + u * 16, hi, lo);
+        tmem_st8(tb + kTH3 + fb / 2 + u * 8, hi);
+        tmem_st8(tb + kTH3 + 64 + fb / 2 + u * 8, lo);
+        c2_store_op<128>(bp.op[2][0], bp.op[2][1], row, fb + u * 16, hi, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (g ? B_GZB : B_GZA));
+      if (lane == 0) mbar_arrive(bars + 8 * (hf ? B_GZB : B_GZA));
       // ---- 4. gpre = gh gelu'(pre)
       mbar_wait(bars + 8 * B_D3, ph);
       tc_fence_after();
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+      for (int c2 = 0; c2 < NC; ++c2) {
         float gp[32];
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
           const int u = c2 * 2 + uu;
           uint32_t d[16], w[16];
-          tmem_ld16(tb + kTX3 + 64 * g + u * 16, d);
-          tmem_ld16(tb + kTPre3 + 64 * g + u * 16, w);
+          tmem_ld16(tb + kTX3 + fb + u * 16, d);
+          tmem_ld16(tb + kTPre3 + fb + u * 16, w);
           tmem_ld_wait();
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float gpv = __uint_as_float(d[j]) * i_gh * gelu_bwd(fmaf(__uint_as_float(w[j]), i_pre, s_b1[64 * g + u * 16 + j]));
+            const float gpv = __uint_as_float(d[j]) * i_gh * gelu_bwd(fmaf(__uint_as_float(w[j]), i_pre, s_b1[fb + u * 16 + j]));
             gp[uu * 16 + j] = gpv;
             v[j] = gpv * sgp;
           }
           uint32_t hi[8], lo[8];
           split16(v, hi, lo);
-          tmem_st8(tb + kTR3 + 32 * g + u * 8, hi);
-          tmem_st8(tb + kTR3 + 64 + 32 * g + u * 8, lo);
-          c2_store_op<128>(bp.op[3][0], bp.op[3][1], row, 64 * g + u * 16, hi, lo);
+          tmem_st8(tb + kTR3 + fb / 2 + u * 8, hi);
+          tmem_st8(tb + kTR3 + 64 + fb / 2 + u * 8, lo);
+          c2_store_op<128>(bp.op[3][0], bp.op[3][1], row, fb + u * 16, hi, lo);
         }
         acc_b1[c2] += lane_sum<32>(gp, lane);
       }
@@ -494,11 +512,11 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
       // ---- 5. gx
       mbar_wait(bars + 8 * B_D4, ph);
       tc_fence_after();
-      float4 *gxr = reinterpret_cast<float4 *>(bp.gx + (size_t)(ok ? c : 0) * 128 + 64 * g);
+      float4 *gxr = reinterpret_cast<float4 *>(bp.gx + (size_t)(ok ? c : 0) * 128 + fb);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t d[16];
-        tmem_ld16(tb + kTX3 + 64 * g + u * 16, d);
+        tmem_ld16(tb + kTX3 + fb + u * 16, d);
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
@@ -508,36 +526,41 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // the other half has read its gx columns: X of the next tile may land
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");      // the other half has read its gx columns: X of the next tile may land
     }
     // parameter-gradient sums: lane t of a warp holds feature 64 g + 32 c + t
     float *mine = s_red + warp * 8 * 32;
 #pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
+    for (int c2 = 0; c2 < NC; ++c2) {
       mine[(0 + c2) * 32 + lane] = acc_lnw[c2];
       mine[(2 + c2) * 32 + lane] = acc_lnb[c2];
       mine[(4 + c2) * 32 + lane] = acc_b2[c2];
       mine[(6 + c2) * 32 + lane] = acc_b1[c2];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");
     {
       const int quant = q;                                             // one quantity per warp of the half
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+      for (int c2 = 0; c2 < NC; ++c2) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) s += s_red[(g * 4 + w) * 8 * 32 + (quant * 2 + c2) * 32 + lane];
         float *dst = quant == 0 ? bp.g_lnw : quant == 1 ? bp.g_lnb : quant == 2 ? bp.g_b2 : bp.g_b1;
-        if (dst) atomicAdd(dst + 64 * g + 32 * c2 + lane, s);
+        if (dst) atomicAdd(dst + fb + 32 * c2 + lane, s);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == 4 * G) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
+
+static int c3_groups() {
+  static const int g = getenv("MIMRL_CUBE3_G") ? atoi(getenv("MIMRL_CUBE3_G")) : 4;
+  return g == 2 ? 2 : 4;
+}
 
 bool cube3_supported(int a_in, int a_hid, int a_out, int inner, long long n_cols, int act, int has_res) {
   if (getenv("MIMRL_CUBE3_OFF")) return false;
@@ -548,8 +571,13 @@ int cube3_fwd(const CUtensorMap *m, const CubeTcParams &p, cudaStream_t st, int 
   *handled = 1;
   const long long n_tiles = (p.n_cols + 127) / 128;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
-  cudaFuncSetAttribute(cube3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
-  cube3_fwd_kernel<<<blocks, kC3Threads, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  if (c3_groups() == 4) {
+    cudaFuncSetAttribute(cube3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+    cube3_fwd_kernel<4><<<blocks, C3<4>::THREADS, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  } else {
+    cudaFuncSetAttribute(cube3_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+    cube3_fwd_kernel<2><<<blocks, C3<2>::THREADS, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  }
   return check_launch("cube3_fwd");
 }
 
@@ -557,8 +585,13 @@ int cube3_bwd(const CUtensorMap *m, const CubeBwdParams &bp, cudaStream_t st, in
   *handled = 1;
   const long long n_tiles = (bp.f.n_cols + 127) / 128;
   const int blocks = (int)(n_tiles < 148 ? n_tiles : 148);
-  cudaFuncSetAttribute(cube3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
-  cube3_bwd_kernel<<<blocks, kC3Threads, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], bp);
+  if (c3_groups() == 4) {
+    cudaFuncSetAttribute(cube3_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+    cube3_bwd_kernel<4><<<blocks, C3<4>::THREADS, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], bp);
+  } else {
+    cudaFuncSetAttribute(cube3_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+    cube3_bwd_kernel<2><<<blocks, C3<2>::THREADS, kC3Smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], bp);
+  }
   return check_launch("cube3_bwd");
 }
 

@@ -52,7 +52,9 @@ class _AxisMix(torch.autograd.Function):
         prm = [None if t is None else L.f32(t.detach()) for t in (w1, b1, w2, b2, wres, ln_w, ln_b)]
         oshape = shape[:axis] + [A2] + shape[axis + 1:]
         y = torch.empty(oshape, dtype=torch.float32, device=x.device)
-        saved = torch.empty(2 * outer * inner, dtype=torch.float32, device=x.device)
+        small = bool(L.lib.mimrl_cubemlp_small_supported(A, H, A2))
+        # LayerNorm statistics for the backward; the tiny-axis backward (modality mix) recomputes them instead
+        saved = None if small else torch.empty(2 * outer * inner, dtype=torch.float32, device=x.device)
         ws = None
         if (USE_TC and outer * inner >= 1024
                 and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id)):
@@ -68,7 +70,7 @@ class _AxisMix(torch.autograd.Function):
                                                 L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
                                                 L.ptr(prm[6]), int(ln_first), act_id, L.ptr(y), L.ptr(saved),
                                                 L.stream()))
-        ctx.save_for_backward(x, saved, *[p if p is not None else x.new_empty(0) for p in prm])
+        ctx.save_for_backward(x, saved if saved is not None else x.new_empty(0), *[p if p is not None else x.new_empty(0) for p in prm])
         ctx.cfg = (outer, A, inner, H, A2, int(ln_first), act_id, [p is not None for p in prm])
         ctx.use_tc = ws is not None
         ctx.ws = ws          # split weights, max|x| and max rstd of this call: the backward reuses them
