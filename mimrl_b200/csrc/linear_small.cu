@@ -234,8 +234,21 @@ __global__ void __launch_bounds__(kHidW) mlp4_small_fwd_kernel(const Mlp4SmallPa
       for (int r = 0; r < kTR; ++r) acc[r] = bias;
       const float *wrow = p.w[l] + (size_t)t * K;
       if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(wrow) & 15) == 0) {
-#pragma unroll 4
-        for (int k = 0; k < K; k += 4) {
+        int k = 0;
+        for (; k + 32 <= K; k += 32) {                     // eight 16-byte weight loads in flight
+          float4 w4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w4[j] = __ldg(reinterpret_cast<const float4 *>(wrow + k + 4 * j));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int r = 0; r < kTR; ++r) {
+              const float4 a = *reinterpret_cast<const float4 *>(&act[cur][r][k + 4 * j]);
+              acc[r] = fmaf(w4[j].w, a.w, fmaf(w4[j].z, a.z, fmaf(w4[j].y, a.y, fmaf(w4[j].x, a.x, acc[r]))));
+            }
+          }
+        }
+        for (; k < K; k += 4) {
           const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wrow + k));
 #pragma unroll
           for (int r = 0; r < kTR; ++r) {
@@ -291,8 +304,23 @@ __global__ void __launch_bounds__(kHidW) mlp4_small_bwd_kernel(const Mlp4SmallBw
 #pragma unroll
       for (int r = 0; r < kTR; ++r) acc[r] = 0.f;
       const float *wcol = p.w[l] + k;
-#pragma unroll 4
-      for (int o = 0; o < N; ++o) {
+      // sixteen weight loads in flight per thread: the kernel is a chain of L2 round trips otherwise (32 CTAs, every one
+      // streams the whole matrix)
+      int o = 0;
+      for (; o + 16 <= N; o += 16) {
+        float wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = __ldg(wcol + (size_t)(o + j) * K);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+#pragma unroll
+          for (int r = 0; r < kTR; ++r) {
+            const float4 gv = *reinterpret_cast<const float4 *>(&g[cur][r][o + j]);
+            acc[r] = fmaf(wv[j + 3], gv.w, fmaf(wv[j + 2], gv.z, fmaf(wv[j + 1], gv.y, fmaf(wv[j], gv.x, acc[r]))));
+          }
+        }
+      }
+      for (; o < N; ++o) {
         const float wv = __ldg(wcol + (size_t)o * K);
 #pragma unroll
         for (int r = 0; r < kTR; ++r) acc[r] = fmaf(wv, g[cur][r][o], acc[r]);
