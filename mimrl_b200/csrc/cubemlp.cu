@@ -733,14 +733,23 @@ __device__ __forceinline__ void k3_load_params(K3Params &sp, const MixArgs &m) {
   }
 }
 
-// forward of one fibre (x[3] -> pre[3], h[3], z[3], mean, rstd)
-template <int ACT>
+// forward of one fibre (x[3] -> pre[3], h[3], z[3], mean, rstd); da (backward only): act'(pre), for gelu from the SAME
+// erf / exp evaluation as h (gelu = z Phi, gelu' = Phi + z phi)
+template <int ACT, bool WITH_D = false>
 __device__ __forceinline__ void k3_forward(const K3Params &sp, const float (&x)[3], float (&pre)[3], float (&h)[3],
-                                           float (&z)[3], float &mean, float &rstd) {
+                                           float (&z)[3], float &mean, float &rstd, float *da = nullptr) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     pre[r] = fmaf(sp.w1[3 * r + 2], x[2], fmaf(sp.w1[3 * r + 1], x[1], fmaf(sp.w1[3 * r], x[0], sp.b1[r])));
-    h[r] = k3_act<ACT>(pre[r]);
+    if (WITH_D && ACT == 0) {
+      float cdf, pdf;
+      gauss_cdf_pdf(pre[r], cdf, pdf);
+      h[r] = pre[r] * cdf;
+      da[r] = fmaf(pre[r], pdf, cdf);
+    } else {
+      h[r] = k3_act<ACT>(pre[r]);
+      if (WITH_D) da[r] = k3_dact<ACT>(pre[r]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -814,8 +823,8 @@ cubemlp_k3_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBw
     float gxo[3][4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      float pre[3], h[3], z[3], mean, rstd;
-      k3_forward<ACT>(sp, xs[f], pre, h, z, mean, rstd);
+      float pre[3], h[3], z[3], da[3], mean, rstd;
+      k3_forward<ACT, true>(sp, xs[f], pre, h, z, mean, rstd, da);
       // LayerNorm backward
       float zh[3], gw[3], t1 = 0.f, t2 = 0.f;
 #pragma unroll
@@ -833,7 +842,7 @@ cubemlp_k3_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBw
       for (int r = 0; r < 3; ++r) gz[r] = (gw[r] - t1 - zh[r] * t2) * rstd;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        gpre[c] = fmaf(sp.w2[6 + c], gz[2], fmaf(sp.w2[3 + c], gz[1], sp.w2[c] * gz[0])) * k3_dact<ACT>(pre[c]);
+        gpre[c] = fmaf(sp.w2[6 + c], gz[2], fmaf(sp.w2[3 + c], gz[1], sp.w2[c] * gz[0])) * da[c];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float gu = fmaf(sp.w1[6 + a], gpre[2], fmaf(sp.w1[3 + a], gpre[1], sp.w1[a] * gpre[0]));

@@ -111,3 +111,37 @@ def test_tensor_core_forward_vs_oracle(bs, d_in, d_h, d_out, act, res):
     assert rel_err(xt.grad.cpu().numpy(), gxo) < 2 * TOL
     for n, p in enc.named_parameters():
         assert np.abs(p.grad.cpu().numpy() - pgo[n]).max() <= 2 * TOL * np.abs(pgo[n]).max() + 2e-6, n
+
+
+@pytest.mark.parametrize("bs", [24, 131])
+def test_specialised_kernels_agree_with_the_general_kernel(bs, monkeypatch):
+    """README configuration (two blocks) at batches with whole and ragged channel-mix tiles: the compile-time specialised
+    sequence- / channel-mix kernels (cubemlp_tc2.cu, cubemlp_tc3.cu) against the general tensor-core kernel
+    (cubemlp_tc.cu), outputs and every gradient."""
+    d_in, d_h, d_out = [100, 3, 128], [[50, 3, 128], [10, 3, 128]], [[50, 3, 128], [10, 3, 128]]
+    c = dict(act="gelu", d_in=d_in, d_hiddens=d_h, d_outs=d_out, bias=True, ln_first=False, res=[True, True])
+    blocks = P.cubemlp_params(123, d_in, d_h, d_out, True, False, [True, True])
+    enc = build(c, blocks)
+    g = torch.Generator(device="cuda").manual_seed(bs)
+    x = torch.randn(bs, *d_in, device="cuda", generator=g)
+    w = torch.randn(bs, *d_out[-1], device="cuda", generator=g)
+
+    def run():
+        for p_ in enc.parameters():
+            p_.grad = None
+        xt = x.clone().requires_grad_(True)
+        y = enc(xt)
+        (y * w).sum().backward()
+        return y.detach(), xt.grad, {n: p_.grad.clone() for n, p_ in enc.named_parameters()}
+
+    y1, gx1, pg1 = run()
+    monkeypatch.setenv("MIMRL_CUBE2_OFF", "1")
+    monkeypatch.setenv("MIMRL_CUBE3_OFF", "1")
+    y0, gx0, pg0 = run()
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-5
+    assert rel_err(gx1.cpu().numpy(), gx0.cpu().numpy()) < 2 * TOL       # each is ~1e-4 from float64 at this depth (scripts/cube_ab.py)
+    for n in pg0:
+        a, b = pg1[n].cpu().numpy(), pg0[n].cpu().numpy()
+        # (parameter gradients are sums over 1e5-1e6 fibres; each family is within 2 TOL of float64 -- the bound of the
+        # oracle tests above, measured in scripts/cube_ab.py -- so the two may differ by twice that)
+        assert np.abs(a - b).max() <= 4 * TOL * np.abs(b).max() + 2e-6, n

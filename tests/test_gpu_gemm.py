@@ -180,3 +180,40 @@ def test_small_batch_mlp_stack_matches_torch(rows, d_in, d_out):
     assert rel(y.detach(), y64.detach()) < 1e-5
     for a, b in zip(got, want):
         assert rel(a, b) < 1e-5
+
+
+def _blocked_operand(mat):
+    """[rows, K] fp32 -> the blocked-K fp16 hi/lo operand buffer of mimrl_gemm_split_blocked (header, hi, lo)."""
+    import math
+    from mimrl_b200 import _lib as L
+    rows, K = mat.shape
+    amax = float(mat.abs().max())
+    _, e = math.frexp(amax)
+    v = mat.double() * 2.0 ** (14 - e)
+    hi = v.to(torch.float16)
+    lo = (v - hi.double()).to(torch.float16)
+    blk = lambda t: t.view(rows, K // 64, 64).permute(1, 0, 2).contiguous().view(-1).view(torch.uint8)
+    buf = torch.zeros(L.lib.mimrl_split_bytes(rows, K), dtype=torch.uint8, device=mat.device)
+    buf[:4] = torch.tensor([amax], dtype=torch.float32, device=mat.device).view(torch.uint8)
+    plane = (rows * K * 2 + 255) // 256 * 256
+    buf[256:256 + rows * K * 2] = blk(hi)
+    buf[256 + plane:256 + plane + rows * K * 2] = blk(lo)
+    return buf
+
+
+@pytest.mark.parametrize("M,N,K", [(10, 50, 64 * 96), (50, 100, 64 * 200), (50, 50, 64 * 7), (128, 128, 64 * 480),
+                                   (100, 10, 64 * 33), (3, 128, 64)])
+def test_blocked_accumulating_gemm(M, N, K):
+    """mimrl_gemm_split_blocked_acc (the CubeMLP weight gradients): narrow operand on the MMA columns, transposed
+    output when swapped, one piece of K per SM, partial sums added in place -- against float64, on top of a running sum."""
+    from mimrl_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    C = C0.clone()
+    op_a, op_b = _blocked_operand(A), _blocked_operand(B)          # (keep both alive across the call)
+    L.check(L.lib.mimrl_gemm_split_blocked_acc(L.ptr(op_a), L.ptr(op_b), M, N, K, L.ptr(C), L.stream()))
+    torch.cuda.synchronize()
+    want = C0.double() + A.double() @ B.double().t()
+    assert rel(C, want) < 2e-5
