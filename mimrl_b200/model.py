@@ -323,26 +323,67 @@ _CMI_PLAN = (  # (estimator, X, Y, Z) with C = labels; Z is the searched pool  (
     ("tv_c", "T", "V", "C"), ("tc_a", "T", "C", "A"), ("tc_v", "T", "C", "V"))
 
 
+_BRANCH_STREAMS = {}
+
+
+def _branch_streams(device, n):
+    pool = _BRANCH_STREAMS.setdefault(device, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def run_branches(jobs, parallel):
+    """``jobs``: list of (key, thunk) of INDEPENDENT pieces of work -> {key: result}.  ``parallel``: every thunk is
+    enqueued on its own side stream (forked from and joined back into the current stream), so that the small-batch
+    regime -- a stage is eleven estimators of a few latency-bound launches each -- overlaps on the GPU instead of
+    running as one chain.  The thunks still RUN on the host in list order (numpy RNG consumption order of the samplers is
+    the reference's); autograd replays every branch's backward on the stream of its forward.  Works under CUDA-graph
+    capture (the side streams fork from the capturing stream and rejoin it)."""
+    if not parallel or len(jobs) < 2 or not torch.cuda.is_available():
+        return {k: f() for k, f in jobs}
+    main = torch.cuda.current_stream()
+    streams = _branch_streams(main.device, min(len(jobs), 6))
+    capturing = torch.cuda.is_current_stream_capturing()
+    out = {}
+    for i, (k, f) in enumerate(jobs):
+        s = streams[i % len(streams)]
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+            r = f()
+        if not capturing:             # results are consumed on the main stream after the join
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+        out[k] = r
+    for s in streams:
+        main.wait_stream(s)
+    return out
+
+
 class MIStageMixin:
     """compute_vmi_loss_stage1 / stage2 with the reference's call order (and
     therefore its numpy RNG consumption order)."""
 
+    parallel_branches = False        # opt-in: the independent estimators of a stage on side streams (run_branches)
+
     def _mi_terms(self, F_F, T_F, A_F, V_F):
-        out = {}
+        jobs = []
         for name, (a, b) in (("f_t", (F_F, T_F)), ("f_a", (F_F, A_F)), ("f_v", (F_F, V_F)),
                              ("t_a", (T_F, A_F)), ("t_v", (T_F, V_F))):
-            out[name] = getattr(self, "vmi_estimator_" + name)(a, b)
-        return out
+            jobs.append((name, (lambda n=name, a=a, b=b: getattr(self, "vmi_estimator_" + n)(a, b))))
+        return run_branches(jobs, self.parallel_branches)
 
     def _cmi_terms(self, labels, T_F, A_F, V_F, C_F_all, T_F_all, A_F_all, V_F_all):
         feats = {"T": T_F, "A": A_F, "V": V_F, "C": labels}
         pools = {"T": T_F_all, "A": A_F_all, "V": V_F_all, "C": C_F_all}
         bs = labels.shape[0]
-        out = {}
-        for name, x, y, z in _CMI_PLAN:
+
+        def one(name, x, y, z):
             kx, ky, kz = prod_knn_sample(pools[x], pools[y], pools[z], bs, self.k_neighbor, self.radius)
-            out[name] = getattr(self, "vcmi_estimator_" + name)(feats[x], feats[y], feats[z], kx, ky, kz)
-        return out
+            return getattr(self, "vcmi_estimator_" + name)(feats[x], feats[y], feats[z], kx, ky, kz)
+        jobs = [(name, (lambda n=name, x=x, y=y, z=z: one(n, x, y, z))) for name, x, y, z in _CMI_PLAN]
+        return run_branches(jobs, self.parallel_branches)
 
     def compute_vmi_loss_stage1(self, predictions, labels, F_F, T_F, A_F, V_F, C_F_all, F_F_all, T_F_all, A_F_all,
                                 V_F_all):

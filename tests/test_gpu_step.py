@@ -118,3 +118,48 @@ def test_graphed_two_stage_step_matches_eager():
             continue
         assert torch.allclose(pe, pg, rtol=1e-4, atol=1e-6), name
     assert len(pool_g._next["C"]) == 3 and pool_g._next["F"][0].shape == (bs, 128)
+
+
+def test_stage_branches_on_side_streams_match_the_sequential_run():
+    """MIStageMixin.parallel_branches: the eleven estimators of a stage enqueued on side streams give the values,
+    feature gradients, estimator gradients and numpy RNG state of the sequential run."""
+    import __graft_entry__ as g
+    g.build()
+    from mimrl_b200.model import MIHeads
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    opt = SimpleNamespace(critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2, radius=1.0,
+                          cmi_last_acticate="hardtanh", d_common=128)
+    heads = MIHeads(opt).to(dev)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    bs, N = 128, 1284
+    feats = [torch.randn(bs, 128, device=dev, generator=gen) for _ in range(4)]
+    labels = torch.randn(bs, device=dev, generator=gen)
+    pools = [torch.randn(N, 1, device=dev, generator=gen)] + [torch.randn(N, 128, device=dev, generator=gen) for _ in range(4)]
+
+    def run(parallel, stage):
+        heads.parallel_branches = parallel
+        for p in heads.parameters():
+            p.grad = None
+        fs = [f.clone().requires_grad_(True) for f in feats]
+        np.random.seed(11)
+        fn = heads.compute_vmi_loss_stage1 if stage == 1 else heads.compute_vmi_loss_stage2
+        mis, losses = fn(None, labels, *fs, *pools)
+        torch.stack([l.reshape(()) for l in losses]).sum().backward()
+        torch.cuda.synchronize()
+        return (torch.stack([m.detach().reshape(()) for m in mis]), [f.grad.clone() for f in fs],
+                [p.grad.clone() if p.grad is not None else None for p in heads.parameters()], np.random.get_state()[1].copy())
+
+    for stage in (1, 2):
+        m0, g0, p0, r0 = run(False, stage)
+        for _ in range(3):                       # a race would not show every time
+            m1, g1, p1, r1 = run(True, stage)
+            assert np.array_equal(r0, r1)
+            assert torch.allclose(m0, m1, rtol=1e-6, atol=1e-7)
+            for a, b in zip(g0, g1):
+                assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+            for a, b in zip(p0, p1):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+    heads.parallel_branches = False
