@@ -100,11 +100,15 @@ struct KnnCand {
 };
 struct KnnTcPlan {
   int splits, tiles_per_split, n_lists, list_len;
-  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, off_pub, bytes;
+  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, off_pub, off_tscale, bytes;
 };
 bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len);
 KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len);
 // per query and list: list_len candidates sorted by (d, idx), padded with (+inf, -1); lists = splits * 2
+// one pass over the keys: squared row norms -> key_norms, fp16 hi / lo split with a scale per 128-key tile -> ws
+int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcPlan &plan, unsigned char *ws, float *key_norms,
+                        cudaStream_t st);
+// after knn_tc_prepare_keys (and after excluded rows got +inf norms)
 int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st);
 

@@ -366,8 +366,12 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
              const Plan &p, unsigned char *ws, cudaStream_t st) {
   float *kn = reinterpret_cast<float *>(ws + p.off_kn);
   Cand *cand = reinterpret_cast<Cand *>(ws + p.off_cand);
-  key_norms_kernel<<<ceil_div(n_keys * 32, 256), 256, 0, st>>>(keys, n_keys, width, kn);
-  if (check_launch("knn key_norms")) return 1;
+  if (p.use_tc) {          // norms, fp16 hi / lo split and per-tile scales in one pass over the keys
+    if (knn_tc_prepare_keys(keys, n_keys, width, p.tc, ws + p.off_tc, kn, st)) return 1;
+  } else {
+    key_norms_kernel<<<ceil_div(n_keys * 32, 256), 256, 0, st>>>(keys, n_keys, width, kn);
+    if (check_launch("knn key_norms")) return 1;
+  }
   if (n_excluded > 0) {
     mark_excluded_kernel<<<ceil_div(n_excluded, 256), 256, 0, st>>>(excluded, n_excluded, key_offset, n_keys, kn);
     if (check_launch("knn mark_excluded")) return 1;

@@ -32,18 +32,62 @@ __global__ void knn_absmax_kernel(const float *__restrict__ a, size_t na, const 
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(m));
 }
 
-// Scale of the key operand without a pass over the keys: |z_e| <= |z| for every element, so the square root of the
-// largest finite row norm (the norms exist already, 4 bytes per key) bounds the absmax from above by at most
-// sqrt(width) -- 3.5 binades of the 15 the fp16 hi/lo pair has to spare.  Excluded rows carry +inf and are skipped.
-__global__ void knn_norm_max_kernel(const float *__restrict__ kn, size_t n, unsigned *__restrict__ out) {
-  float m = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = __ldg(kn + i);
-    if (v < INFINITY) m = fmaxf(m, v);
+// Keys: ONE pass.  A CTA takes a tile of 128 keys (the tile the filter later streams as one TMA box): squared row
+// norms, the tile's absmax -> a power-of-two scale of ITS OWN (the filter folds 1 / scale into the per-tile factor of
+// the distance, so nothing is paid per element), fp16 hi / lo split.  Replaces a norms pass, an absmax pass and a split pass over the keys.
+__global__ void __launch_bounds__(256) knn_prep_keys_kernel(const float *__restrict__ keys, int n_keys, int width,
+                                                            float *__restrict__ kn, float *__restrict__ tile_inv_scale,
+                                                            __half *__restrict__ hi, __half *__restrict__ lo) {
+  __shared__ float s_max[8];
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  // warp w owns rows w, w + 8, ... of the tile; a lane owns columns 4 lane .. 4 lane + 3 of each (one 512-byte row per
+  // warp-wide 16-byte load, one 256-byte run per plane and store)
+  float4 v[16];
+  const bool vec = width == 128 && (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  float mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const size_t row = (size_t)blockIdx.x * 128 + w + 8 * j;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < (size_t)n_keys) {
+      if (vec) {
+        q = __ldg(reinterpret_cast<const float4 *>(keys + row * 128) + lane);
+      } else {
+        const float *src = keys + row * width;
+        const int c = 4 * lane;
+        q.x = c < width ? __ldg(src + c) : 0.f, q.y = c + 1 < width ? __ldg(src + c + 1) : 0.f;
+        q.z = c + 2 < width ? __ldg(src + c + 2) : 0.f, q.w = c + 3 < width ? __ldg(src + c + 3) : 0.f;
+      }
+    }
+    v[j] = q;
+    float nrm = fmaf(q.w, q.w, fmaf(q.z, q.z, fmaf(q.y, q.y, q.x * q.x)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0 && row < (size_t)n_keys) kn[row] = nrm;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
   }
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(sqrtf(m)));
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_max[w] = mx;
+  __syncthreads();
+  mx = s_max[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, s_max[k]);
+  const float sc = scale_from_absmax(__float_as_uint(mx));
+  if (t == 0) tile_inv_scale[blockIdx.x] = 1.f / sc;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const size_t row = (size_t)blockIdx.x * 128 + w + 8 * j;
+    if (row >= (size_t)n_keys) continue;                  // rows past the end are zero-filled by the TMA box
+    const float a0 = v[j].x * sc, a1 = v[j].y * sc, a2 = v[j].z * sc, a3 = v[j].w * sc;
+    const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
+    reinterpret_cast<uint2 *>(hi + row * 128)[lane] =
+        make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+    reinterpret_cast<uint2 *>(lo + row * 128)[lane] =
+        make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+  }
 }
 
 // [n, width] fp32 -> hi, lo [n, 128] fp16 (K zero-padded), scaled by 2^k
@@ -78,7 +122,8 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
 struct KnnTcParams {
   int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group;
   float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
-  const unsigned *absmax;          // [0] queries, [1] keys
+  const unsigned *absmax;          // [0] queries
+  const float *tile_inv_scale;     // 1 / (power-of-two scale) of every 128-key tile (knn_prep_keys_kernel)
   const __half *q_hi, *q_lo;
   const float *qn, *kn;
   KnnCand *cand;
@@ -243,8 +288,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const bool row_ok = row0 + r < p.n_queries;
-    const float inv = 1.f / (scale_from_absmax(p.absmax[0]) * scale_from_absmax(p.absmax[1]));
-    const float m2inv = -2.f * inv;
+    const float m2q = -2.f / scale_from_absmax(p.absmax[0]);        // times 1 / (scale of the key tile), per tile
     const float qn = row_ok ? p.qn[row0 + r] : 0.f;
     KnnCand *lst = lists + (size_t)(wg * 128 + r) * kListMax;
     float *kn_s = knbuf + wg * 128;
@@ -273,6 +317,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
         kn_next = gk < p.n_keys ? __ldg(p.kn + gk) : INFINITY;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+      const float m2inv = m2q * __ldg(p.tile_inv_scale + t0 + i);
       mbar_wait(bTFull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -435,32 +480,34 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   p.off_k_hi = o, o += align256((size_t)n_keys * 128 * 2);
   p.off_k_lo = o, o += align256((size_t)n_keys * 128 * 2);
   p.off_pub = o, o += align256((size_t)n_queries * p.n_lists * 4);
+  p.off_tscale = o, o += align256((size_t)k_tiles * 4);
   p.bytes = o;
   return p;
 }
 
+int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcPlan &plan, unsigned char *ws, float *key_norms,
+                        cudaStream_t st) {
+  __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
+  knn_prep_keys_kernel<<<ceil_div(n_keys, 128), 256, 0, st>>>(keys, n_keys, width, key_norms,
+                                                             reinterpret_cast<float *>(ws + plan.off_tscale), k_hi, k_lo);
+  return check_launch("knn prepare keys");
+}
+
 int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st) {
+  (void)keys;
   unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
   float *qn = reinterpret_cast<float *>(ws + plan.off_qn);
   __half *q_hi = reinterpret_cast<__half *>(ws + plan.off_q_hi), *q_lo = reinterpret_cast<__half *>(ws + plan.off_q_lo);
   __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
   cudaMemsetAsync(absmax, 0, 8, st);
-  const size_t nq = (size_t)n_queries * width, nk = (size_t)n_keys * width;
+  const size_t nq = (size_t)n_queries * width;
   int blocks = (int)((nq + 2047) / 2048);
   blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
-  knn_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(queries, nq, keys, nk, absmax);
+  knn_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(queries, nq, nullptr, 0, absmax);
   if (check_launch("knn absmax")) return 1;
-  blocks = (n_keys + 2047) / 2048;
-  blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
-  knn_norm_max_kernel<<<blocks, 256, 0, st>>>(key_norms, (size_t)n_keys, absmax + 1);
-  if (check_launch("knn key scale")) return 1;
   knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
   if (check_launch("knn split q")) return 1;
-  blocks = (int)(((size_t)n_keys * 64 + 255) / 256);
-  blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
-  knn_split_kernel<<<blocks, 256, 0, st>>>(keys, n_keys, width, absmax, 1, k_hi, k_lo);
-  if (check_launch("knn split k")) return 1;
   knn_row_norms_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(queries, n_queries, width, qn);
   if (check_launch("knn query norms")) return 1;
   CUtensorMap mh, ml;
@@ -473,6 +520,7 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   p.pub = reinterpret_cast<float *>(ws + plan.off_pub);
   cudaMemsetAsync(p.pub, 0x7f, (size_t)n_queries * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
+  p.tile_inv_scale = reinterpret_cast<const float *>(ws + plan.off_tscale);
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
   p.splits = plan.splits;
   p.q_tiles = ceil_div(n_queries, 128);
