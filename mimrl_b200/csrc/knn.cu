@@ -303,21 +303,18 @@ knn_rerank_kernel(const float *__restrict__ keys, int n_keys, int width, int64_t
   }
 }
 
-// nbr_comp = nbr_orig - #(excluded ids < nbr_orig)
+// nbr_comp = nbr_orig - #(excluded ids < nbr_orig); one warp per output, the ids split over its lanes
 __global__ void compact_index_kernel(const int64_t *__restrict__ nbr_orig, size_t n_out,
                                      const int64_t *__restrict__ ids, int n_ids, int64_t *__restrict__ nbr_comp) {
-  __shared__ int64_t sid[1024];
-  const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const int64_t v = o < n_out ? nbr_orig[o] : 0;
+  const size_t o = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= n_out) return;
+  const int64_t v = nbr_orig[o];
   int below = 0;
-  for (int base = 0; base < n_ids; base += 1024) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 1024 && base + i < n_ids; i += blockDim.x) sid[i] = ids[base + i];
-    __syncthreads();
-    const int lim = min(1024, n_ids - base);
-    for (int i = 0; i < lim; ++i) below += sid[i] < v ? 1 : 0;
-  }
-  if (o < n_out) nbr_comp[o] = v - below;
+  for (int i = lane; i < n_ids; i += 32) below += __ldg(ids + i) < v ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
+  if (lane == 0) nbr_comp[o] = v - below;
 }
 
 struct Plan {
@@ -462,7 +459,7 @@ extern "C" int mimrl_knn_search(const float *keys, int n_keys, int width, const 
     return rc;
   if (nbr_comp) {
     const size_t n_out = (size_t)n_queries * k;
-    compact_index_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(nbr_orig, n_out, query_ids, n_queries, nbr_comp);
+    compact_index_kernel<<<(int)((n_out * 32 + 255) / 256), 256, 0, st>>>(nbr_orig, n_out, query_ids, n_queries, nbr_comp);
     return check_launch("knn compact_index");
   }
   return 0;
