@@ -448,6 +448,45 @@ def extra_configs(args, world, rank, dev, flush):
     except Exception as e:
         out["config4_knn_1Mx128"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- CubeMLP fusion encoder alone (the third kernel family of the north star), config-5 shape, per GPU ----
+    try:
+        from mimrl_b200.graphs import GraphedCallable
+        from mimrl_b200.mlp_process import MLPEncoder
+        torch.manual_seed(0)
+        bs = 1024
+        enc = MLPEncoder("gelu", [100, 3, 128], [[50, 3, 128], [10, 3, 128]], [[50, 3, 128], [10, 3, 128]], [0.0] * 3, True,
+                         False, [True, True]).to(dev)
+        xe = torch.randn(bs, 100, 3, 128, device=dev)
+        prm = list(enc.parameters())
+
+        def fwd_only(xx):
+            with torch.no_grad():
+                return enc(xx)
+        xs = xe.clone().requires_grad_(True)
+
+        def fwd_bwd(xx):
+            xs.grad = None
+            for q in prm:
+                q.grad = None
+            enc(xs).sum().backward()
+            return xs.grad
+        gf, gb = GraphedCallable(fwd_only, [xe]), GraphedCallable(fwd_bwd, [xs.detach()])
+        ms_f = timed(lambda: gf(gf.static_in[0]), warm=2, reps=5)
+        ms_b = timed(lambda: gb(gb.static_in[0]), warm=2, reps=5)
+        ms_fe = timed(lambda: fwd_only(xe), warm=2, reps=5)
+        ms_be = timed(lambda: fwd_bwd(None), warm=2, reps=5)
+        alg = bs * 384 * 4.0 * (100 + 2 * 50 + 10)            # one read + one write per block, 330 MB
+        peak = peaks()["hbm_gbs"]
+        out["cubemlp_encoder"] = {
+            "shape": [bs, 100, 3, 128], "blocks": "50-3-128=10-3-128", "fwd_ms_cuda_graph": ms_f, "fwd_bwd_ms_cuda_graph": ms_b,
+            "fwd_ms_eager": ms_fe, "fwd_bwd_ms_eager": ms_be, "algorithmic_bytes_fwd": alg,
+            "fwd_gbs": alg / ms_f * 1e-6, "hbm_peak_gbs": peak, "fwd_frac_of_hbm_peak": alg / ms_f * 1e-6 / peak,
+            "what": "MLPEncoder forward / forward+backward per GPU, CUDA events; graph = the same calls replayed as one CUDA graph"}
+        del enc, xe, xs, gf, gb
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["cubemlp_encoder"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- config 5 ----
     try:
         from mimrl_b200.full_model import bench_config5

@@ -392,8 +392,22 @@ def bench_config5(world, rank, dev, timed, bs=1024):
             model.zero_grad(set_to_none=True)
             loss.backward()
     ms_hot = timed(hot, warm=1, reps=2)
+    # the same hot path as ONE CUDA graph with the estimators of a stage as parallel branches (single GPU: the sharded
+    # estimators all-gather through NCCL, which this capture leaves alone)
+    ms_graph = None
+    if world == 1:
+        try:
+            from .graphs import GraphedCallable, HostIdSource
+            model.parallel_branches = True
+            graphed = GraphedCallable(lambda: (hot(), t.grad)[1], [], warmup=2, id_source=HostIdSource())
+            ms_graph = timed(lambda: graphed(), warm=1, reps=3)
+        except Exception as e:       # reported, never fatal for the bench line
+            ms_graph = f"{type(e).__name__}: {e}"[:200]
+        finally:
+            model.parallel_branches = False
     return {"bs_per_gpu": bs, "global_batch": bs * world, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
             "samples_per_s": bs * world * 1e3 / ms, "hot_path_ms": ms_hot, "hot_path_share": ms_hot / ms,
+            "hot_path_cuda_graph_ms": ms_graph,
             "what": "stage-1 + stage-2 step (Solver.py:204-236): random-init bert-base + 2-layer bidirectional GRUs "
                     "(stock torch, fp32, TF32 off) + feature heads + CubeMLP 50-3-128=10-3-128 + 5 VMI (separate/infonce, "
                     "global batch) + 6 k-NN samplers (pool 16326) + 6 VCMI, Adam on both optimisers, gradient all-reduce; "
