@@ -152,7 +152,7 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
         out(component="two_stage_step_mi_cmi", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
             note="5 VMI + 6 k-NN samplers + 6 VCMI per stage, Adam on both optimisers; encoders replaced by one Linear")
         from mimrl_b200.train_step import GraphedTwoStageStep
-        graphed = GraphedTwoStageStep(step, batch, labels, pool)
+        graphed = GraphedTwoStageStep(step, batch, labels, pool, parallel_branches=False)
         def one_g():
             graphed.stage1(batch, labels); graphed.stage2(batch, labels)
         ms = timeit(one_g, reps=5, warm=2)
@@ -200,7 +200,7 @@ if "step5" in which or "step" in which:   # config 5 shape: the same two-stage s
     ms = timeit(one, reps=5, warm=2)
     out(component="two_stage_step_cubemlp_mi_cmi", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
         note="config 5 without BERT/GRU: CubeMLP 50-3-128=10-3-128 on [bs,100,3,128] + 5 VMI + 6 k-NN + 6 VCMI per stage, Adam x2")
-    graphed = GraphedTwoStageStep(step, batch, labels, pool)
+    graphed = GraphedTwoStageStep(step, batch, labels, pool, parallel_branches=False)
     def one_g():
         graphed.stage1(batch, labels); graphed.stage2(batch, labels)
     ms = timeit(one_g, reps=5, warm=2)

@@ -14,23 +14,18 @@ print({k.split("stalled_")[1]: v for k, v in sorted(st.items(), key=lambda kv: -
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 secs = [i for i, r in enumerate(rows) if r and r[0] == "File Path"] + [len(rows)]
-# sections repeat per launch: group by launch using the function-name row order
-per = {}
-launch = -1; seen = set()
-for s in range(len(secs) - 1):
-    a, b = secs[s], secs[s + 1]
+# the sections of one launch are consecutive (one per source file); a new launch starts when the function name changes
+# or a (function, file) pair repeats
+launches, cur, seen = [], [], set()
+for s_ in range(len(secs) - 1):
+    a, b = secs[s_], secs[s_ + 1]
     f = rows[a][1]
-    if f in seen: launch += 0
-    key = (rows[a + 1][1] if len(rows[a + 1]) > 1 else "", f)
-    per.setdefault(rows[a + 1][1], []).append((a, b, f))
-names = list(per)
-files_per_launch = {}
-# launches of the same kernel are concatenated: split evenly
-allsecs = [(a, b, f) for k in names for (a, b, f) in per[k]]
-firstfile = allsecs[0][2]
-starts = [i for i, (a, b, f) in enumerate(allsecs) if f == firstfile]
-starts.append(len(allsecs))
-sel = allsecs[starts[which]:starts[which + 1]]
+    fn = rows[a + 1][1] if len(rows[a + 1]) > 1 else ""
+    if cur and ((fn, f) in seen or fn != cur_fn):
+        launches.append(cur); cur, seen = [], set()
+    cur.append((a, b, f)); seen.add((fn, f)); cur_fn = fn
+if cur: launches.append(cur)
+sel = launches[which]
 agg = []; tot = 0; toti = 0
 for a, b, f in sel:
     h = rows[a + 2]
