@@ -338,8 +338,10 @@ def run_branches(jobs, parallel):
     enqueued on its own side stream (forked from and joined back into the current stream), so that the small-batch
     regime -- a stage is eleven estimators of a few latency-bound launches each -- overlaps on the GPU instead of
     running as one chain.  The thunks still RUN on the host in list order (numpy RNG consumption order of the samplers is
-    the reference's); autograd replays every branch's backward on the stream of its forward.  Works under CUDA-graph
-    capture (the side streams fork from the capturing stream and rejoin it)."""
+    the reference's); autograd replays every branch's backward on the stream of its forward.  Meant for CUDA-graph
+    capture (the side streams fork from the capturing stream and rejoin it; GraphedTwoStageStep turns it on).  Eager use is
+    correct but not useful: the step is host-bound there, and PyTorch's allocator caches every side stream's workspaces
+    separately (at bs = 1024 the main stream then runs into cudaMalloc / cudaFree cycles)."""
     if not parallel or len(jobs) < 2 or not torch.cuda.is_available():
         return {k: f() for k, f in jobs}
     main = torch.cuda.current_stream()

@@ -158,15 +158,12 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
         ms = timeit(one_g, reps=5, warm=2)
         out(component="two_stage_step_mi_cmi_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
             note="same step, one CUDA graph per stage; k-NN ids drawn on the host before each replay")
-        heads.parallel_branches = True          # the eleven estimators of a stage on side streams (model.run_branches)
-        ms = timeit(one, reps=5, warm=2)
-        out(component="two_stage_step_mi_cmi_branches", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
-            note="eager, estimators of a stage enqueued on side streams")
+        # the eleven estimators of a stage as parallel branches (model.run_branches); eager side streams are not timed:
+        # the step is host-bound there (22 ms at bs = 128) and record_stream leaves the allocator fragmented for what follows
         graphed = GraphedTwoStageStep(step, batch, labels, pool)
         ms = timeit(one_g, reps=5, warm=2)
         out(component="two_stage_step_mi_cmi_branches_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
             note="one CUDA graph per stage with the estimators as parallel branches")
-        heads.parallel_branches = False
 
 if "step5" in which or "step" in which:   # config 5 shape: the same two-stage step with the CubeMLP fusion encoder in the loop
     from types import SimpleNamespace
@@ -206,9 +203,7 @@ if "step5" in which or "step" in which:   # config 5 shape: the same two-stage s
     ms = timeit(one_g, reps=5, warm=2)
     out(component="two_stage_step_cubemlp_mi_cmi_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
         note="same, one CUDA graph per stage")
-    heads.parallel_branches = True
     graphed = GraphedTwoStageStep(step, batch, labels, pool)
     ms = timeit(one_g, reps=5, warm=2)
     out(component="two_stage_step_cubemlp_mi_cmi_branches_cuda_graph", bs=bs, pool=N, ms=ms, steps_per_s=1e3 / ms,
         note="same, the estimators of a stage as parallel branches of the graph")
-    heads.parallel_branches = False
