@@ -309,7 +309,9 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
     // keys within t, so nothing beyond t can be among the K' best: the splits tighten each other's thresholds as
     // if they were one sweep, and the (warp-divergent) insertion path stays rare.
     const int part = split * 2 + wg;
-    float *pub_row = p.pub + (size_t)(row0 + r) * p.n_lists;
+    // pub[part][query]: the 32 rows of a warp read / write one 128-byte line per part
+    float *pub_q = p.pub + (row0 + r);
+    const size_t pub_ld = (size_t)p.q_tiles * 128;
     const int buf = wg;
     float kn_next = INFINITY;
     if (wg < T) {
@@ -395,7 +397,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
           }
           if (mine < published) {
             published = mine;
-            __stcg(pub_row + part, mine);
+            __stcg(pub_q + part * pub_ld, mine);
           }
         }
         if (refresh) {
@@ -416,19 +418,19 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
               const bool two = g0 + 1 < G;
 #pragma unroll 4
               for (int e = g0; e < p.n_lists; e += G) {
-                m0 = fminf(m0, __ldcg(pub_row + e));
-                if (two && e + 1 < p.n_lists) m1 = fminf(m1, __ldcg(pub_row + e + 1));
+                m0 = fminf(m0, __ldcg(pub_q + e * pub_ld));
+                if (two && e + 1 < p.n_lists) m1 = fminf(m1, __ldcg(pub_q + (e + 1) * pub_ld));
               }
               t = fmaxf(t, two ? fmaxf(m0, m1) : m0);
             }
           } else {
             for (; pp + 8 <= p.n_lists; pp += 8) {
-              const float a0 = __ldcg(pub_row + pp), a1 = __ldcg(pub_row + pp + 1), a2 = __ldcg(pub_row + pp + 2),
-                          a3 = __ldcg(pub_row + pp + 3), a4 = __ldcg(pub_row + pp + 4), a5 = __ldcg(pub_row + pp + 5),
-                          a6 = __ldcg(pub_row + pp + 6), a7 = __ldcg(pub_row + pp + 7);
+              const float a0 = __ldcg(pub_q + pp * pub_ld), a1 = __ldcg(pub_q + (pp + 1) * pub_ld), a2 = __ldcg(pub_q + (pp + 2) * pub_ld),
+                          a3 = __ldcg(pub_q + (pp + 3) * pub_ld), a4 = __ldcg(pub_q + (pp + 4) * pub_ld), a5 = __ldcg(pub_q + (pp + 5) * pub_ld),
+                          a6 = __ldcg(pub_q + (pp + 6) * pub_ld), a7 = __ldcg(pub_q + (pp + 7) * pub_ld);
               t = fmaxf(t, fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7))));
             }
-            for (; pp < p.n_lists; pp += 2) t = fmaxf(t, fmaxf(__ldcg(pub_row + pp), __ldcg(pub_row + pp + 1)));
+            for (; pp < p.n_lists; pp += 2) t = fmaxf(t, fmaxf(__ldcg(pub_q + pp * pub_ld), __ldcg(pub_q + (pp + 1) * pub_ld)));
           }
           tau_shared = fminf(tau_shared, t);
           tau_d = fminf(tau_local, tau_shared);
@@ -436,14 +438,24 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       }
     }
     if (row_ok) {
-      for (int u = 1; u < len; ++u) {            // sort ascending by (d, idx): the re-rank merges sorted lists
-        const KnnCand x = lst[u];
-        int v = u;
-        while (v > 0 && knn_less(x.d, x.idx, lst[v - 1].d, lst[v - 1].idx)) {
-          lst[v] = lst[v - 1];
-          --v;
+      // sort ascending by (d, idx): the re-rank merges sorted lists.  A full list is a max-heap: pop the root to the
+      // end, K' - 1 times (heapsort); a list that never filled is a short plain array: insertion sort.
+      if (len == p.list_len) {
+        for (int u = len - 1; u > 0; --u) {
+          const KnnCand top = lst[0], last = lst[u];
+          lst[u] = top;
+          knn_sift_down(lst, u, 0, last);
         }
-        lst[v] = x;
+      } else {
+        for (int u = 1; u < len; ++u) {
+          const KnnCand x = lst[u];
+          int v = u;
+          while (v > 0 && knn_less(x.d, x.idx, lst[v - 1].d, lst[v - 1].idx)) {
+            lst[v] = lst[v - 1];
+            --v;
+          }
+          lst[v] = x;
+        }
       }
       KnnCand *o = p.cand + ((size_t)(row0 + r) * p.n_lists + (split * 2 + wg)) * p.list_len;
       for (int u = 0; u < p.list_len; ++u) o[u] = u < len ? lst[u] : KnnCand{INFINITY, -1};
@@ -488,7 +500,7 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   p.off_q_lo = o, o += align256((size_t)n_queries * 128 * 2);
   p.off_k_hi = o, o += align256((size_t)n_keys * 128 * 2);
   p.off_k_lo = o, o += align256((size_t)n_keys * 128 * 2);
-  p.off_pub = o, o += align256((size_t)n_queries * p.n_lists * 4);
+  p.off_pub = o, o += align256((size_t)q_tiles * 128 * p.n_lists * 4);
   p.off_tscale = o, o += align256((size_t)k_tiles * 4);
   p.bytes = o;
   return p;
@@ -527,7 +539,7 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   p.n_lists = plan.n_lists;
   p.jth = ceil_div(plan.list_len, plan.n_lists);
   p.pub = reinterpret_cast<float *>(ws + plan.off_pub);
-  cudaMemsetAsync(p.pub, 0x7f, (size_t)n_queries * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
+  cudaMemsetAsync(p.pub, 0x7f, (size_t)ceil_div(n_queries, 128) * 128 * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
   p.tile_inv_scale = reinterpret_cast<const float *>(ws + plan.off_tscale);
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
