@@ -120,7 +120,7 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
 }
 
 struct KnnTcParams {
-  int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group;
+  int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group, refresh_mask;
   float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
   const unsigned *absmax;          // [0] queries
   const float *tile_inv_scale;     // 1 / (power-of-two scale) of every 128-key tile (knn_prep_keys_kernel)
@@ -381,7 +381,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
       if (row_ok) {
         const int it = i >> 1;               // tiles this warpgroup has finished
         // refresh points: tiles 1, 2, 4, 8 of this warpgroup while the lists warm up, then every 16th
-        const bool refresh = it == 0 || it == 1 || it == 3 || it == 7 || (it & 15) == 15;
+        const bool refresh = it == 0 || it == 1 || it == 3 || (it & p.refresh_mask) == p.refresh_mask;
         if (refresh && len >= p.jth) {
           // jth-smallest distance of this part (jth is 1 or 2 in practice): partial selection over the unsorted list
           float lo_d = -1.f, mine = INFINITY;
@@ -545,6 +545,7 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
   p.splits = plan.splits;
   p.q_tiles = ceil_div(n_queries, 128);
+  p.refresh_mask = getenv("MIMRL_KNN_REFRESH") ? atoi(getenv("MIMRL_KNN_REFRESH")) : 15;
   p.q_group = getenv("MIMRL_KNN_QGROUP") ? atoi(getenv("MIMRL_KNN_QGROUP")) : 32;
   if (p.q_group < 1) p.q_group = 1;
   const int groups = ceil_div(p.q_tiles, p.q_group);
