@@ -798,7 +798,7 @@ cubemlp_k3_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict_
 // Backward with the weight, bias and LayerNorm-parameter gradients accumulated in registers over the thread's units,
 // then warp shuffles -> shared memory -> one global atomic per block and entry.
 template <int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 cubemlp_k3_bwd_kernel(const MixArgs m, const float *__restrict__ gy, const MixBwdOut o) {
   __shared__ K3Params sp;
   __shared__ float s_acc[39];               // gw1[9] gw2[9] gwr[9] gb1[3] gb2[3] glw[3] glb[3]
@@ -1003,7 +1003,10 @@ extern "C" int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int oute
   MixBwdOut so{gx, nullptr, nullptr, nullptr, nullptr, gln_w, gln_b};
   so.gw1 = gw1, so.gw2 = gw2, so.gwr = wres ? gwres : nullptr, so.gb1 = gb1, so.gb2 = gb2;
   if (is_k3(m, gy, gx)) {
-    const int grid = k3_grid(m) > 148 * 4 ? 148 * 4 : k3_grid(m);
+    // two 256-thread blocks of 128 registers are resident per SM: one persistent wave (A/B: 296 blocks 72 us, 592 blocks
+    // 78 us, 1184 blocks 90 us at [1024,50,3,128]; 110 us before the register cap, with one resident block)
+    static const int cap = getenv("MIMRL_K3_GRID") ? atoi(getenv("MIMRL_K3_GRID")) : 148 * 2;
+    const int grid = k3_grid(m) > cap ? cap : k3_grid(m);
     if (act == 0) cubemlp_k3_bwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
     else if (act == 1) cubemlp_k3_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
     else cubemlp_k3_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(m, gy, so);
