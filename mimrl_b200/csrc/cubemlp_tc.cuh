@@ -124,6 +124,22 @@ __device__ __forceinline__ float2 gelu2(float2 z) {
   return make_float2(fmaf(-fabsf(z.x), q.x, fmaxf(z.x, 0.f)), fmaf(-fabsf(z.y), q.y, fmaxf(z.y, 0.f)));
 }
 
+// gelu'(z) = Phi(z) + z phi(z) of two values, same packed evaluation
+__device__ __forceinline__ float2 gelu_bwd2(float2 z) {
+  const float2 ax = make_float2(fabsf(z.x) * 0.70710678118654752f, fabsf(z.y) * 0.70710678118654752f);
+  const float2 den = ffma2(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.f, 1.f));
+  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
+  const float2 arg = fmul2(fmul2(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(ex2(arg.x), ex2(arg.y));
+  float2 poly = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  poly = ffma2(t, poly, make_float2(1.421413741f, 1.421413741f));
+  poly = ffma2(t, poly, make_float2(-0.284496736f, -0.284496736f));
+  poly = ffma2(t, poly, make_float2(0.254829592f, 0.254829592f));
+  const float2 q = fmul2(fmul2(t, poly), fmul2(e, make_float2(0.5f, 0.5f)));
+  const float2 zp = fmul2(z, fmul2(e, make_float2(0.3989422804014327f, 0.3989422804014327f)));
+  return make_float2(zp.x + (z.x < 0.f ? q.x : 1.f - q.x), zp.y + (z.y < 0.f ? q.y : 1.f - q.y));
+}
+
 // column sums over the 32 lanes of a warp for N (16 or 32) values per lane: lane t (and t + 16 for N = 16) returns
 // the total of entry t % N
 template <int N>

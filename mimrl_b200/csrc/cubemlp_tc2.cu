@@ -470,9 +470,16 @@ cube2_bwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
         tmem_ld_wait();
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; j += 2) {
           const int h = u * 16 + j;
-          v[j] = h < H ? __uint_as_float(d[j]) * i_gh * gelu_bwd(fmaf(__uint_as_float(w[j]), i_pre, s_b1[h < H ? h : 0])) : 0.f;
+          float2 g = make_float2(0.f, 0.f);
+          if (h < H) {
+            const float2 pre = ffma2(make_float2(__uint_as_float(w[j]), __uint_as_float(w[j + 1])), make_float2(i_pre, i_pre),
+                                     make_float2(s_b1[h], s_b1[h + 1]));
+            g = fmul2(fmul2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])), make_float2(i_gh, i_gh)), gelu_bwd2(pre));
+            if (h + 1 >= H) g.y = 0.f;
+          }
+          v[j] = g.x, v[j + 1] = g.y;
         }
         {                                         // bias gradient of the first layer
           constexpr int W = 16;

@@ -492,10 +492,13 @@ cube3_bwd_kernel(const __grid_constant__ CUtensorMap w1h, const __grid_constant_
           tmem_ld_wait();
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float gpv = __uint_as_float(d[j]) * i_gh * gelu_bwd(fmaf(__uint_as_float(w[j]), i_pre, s_b1[fb + u * 16 + j]));
-            gp[uu * 16 + j] = gpv;
-            v[j] = gpv * sgp;
+          for (int j = 0; j < 16; j += 2) {
+            const float2 pre = ffma2(make_float2(__uint_as_float(w[j]), __uint_as_float(w[j + 1])), make_float2(i_pre, i_pre),
+                                     make_float2(s_b1[fb + u * 16 + j], s_b1[fb + u * 16 + j + 1]));
+            const float2 gpv = fmul2(fmul2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])), make_float2(i_gh, i_gh)),
+                                     gelu_bwd2(pre));
+            gp[uu * 16 + j] = gpv.x, gp[uu * 16 + j + 1] = gpv.y;
+            v[j] = gpv.x * sgp, v[j + 1] = gpv.y * sgp;
           }
           uint32_t hi[8], lo[8];
           split16(v, hi, lo);
