@@ -299,7 +299,15 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
                              int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
                              const float *ln_w, const float *ln_b, int act, float *y, float *saved, void *workspace,
                              size_t workspace_bytes, const float *prev_ln_w, const float *prev_ln_b, int prev_n,
-                             void *stream);
+                             int prepared, void *stream);
+/* The preparation (weight split, operand scales) of n <= 8 mixes of an encoder forward in ONE launch.  Every array has n
+ * entries, in execution order; workspace[m] must be ZERO-FILLED (mimrl_cubemlp_tc_workspace_bytes each).  Mix m > 0 must
+ * carry prev_ln_w / prev_ln_b / prev_n (its input is the previous mix's LayerNorm output); x and n_cols[0] describe the
+ * input of mix 0.  Afterwards mimrl_cubemlp_mix_fwd_tc is called with prepared = 1 on the same workspaces. */
+int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n_cols, const int *a_in, const int *a_hid,
+                            const int *a_out, const float *const *w1, const float *const *b1, const float *const *w2,
+                            const float *const *wres, const float *const *ln_w, const float *const *prev_ln_w,
+                            const float *const *prev_ln_b, const int *prev_n, void *const *workspace, void *stream);
 
 /* Tensor-core backward of the same mix.  Writes gx; accumulates (+=, caller zero-fills) g_b1 [a_hid], g_b2 [a_out],
  * gln_w, gln_b [a_out] and the weight gradients gw1 [a_hid, a_in], gw2 [a_out, a_hid], gwres [a_out, a_in] (NULL

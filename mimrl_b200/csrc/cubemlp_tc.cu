@@ -766,7 +766,7 @@ struct CubePrepArgs {
 };
 
 constexpr int kPrepThreads = 1024;
-__global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepArgs a) {
+__device__ __forceinline__ void cube_prep_body(const CubePrepArgs &a, const int block, const int n_blocks) {
   __shared__ float red[kPrepThreads];
   __shared__ unsigned s_last;
   const int t = threadIdx.x;
@@ -780,9 +780,9 @@ __global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepA
     }
     return red[0];
   };
-  if ((int)blockIdx.x < a.n_abs) {
+  if (block < a.n_abs) {
     float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-    const size_t t0 = (size_t)blockIdx.x * blockDim.x + t, st = (size_t)a.n_abs * blockDim.x;
+    const size_t t0 = (size_t)block * blockDim.x + t, st = (size_t)a.n_abs * blockDim.x;
     auto amax4 = [&](const float *p, size_t n, float m) {          // 16-byte loads where the pointer allows it
       if (!p) return m;
       size_t head = 0;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepA
       if (a.saved) atomicMax(a.tail + 2, __float_as_uint(m2));
     }
   } else {
-    const int m = blockIdx.x - a.n_abs;
+    const int m = block - a.n_abs;
     const float *w = a.w[m];
     unsigned char *out = a.split[m];
     if (w && out) {                                            // block-uniform
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepA
   // ---- ticket: the last block computes the scales
   __threadfence();
   __syncthreads();
-  if (t == 0) s_last = atomicAdd(a.tail + 3, 1u) == gridDim.x - 1;
+  if (t == 0) s_last = atomicAdd(a.tail + 3, 1u) == (unsigned)(n_blocks - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -910,7 +910,24 @@ __global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepA
       }
     }
     tl[3] = 0;                        // ticket ready for the next launch on this workspace
+    if (!a.backward) tl[2] = 0;       // the forward kernel collects its largest rstd here
   }
+}
+
+__global__ void __launch_bounds__(kPrepThreads) cube_prep_kernel(const CubePrepArgs a) { cube_prep_body(a, blockIdx.x, gridDim.x); }
+
+// the preparation of SEVERAL mixes in one launch (a whole encoder forward: every mix but the first is independent of the
+// activations -- weights and the LayerNorm bound of its input only); mix m owns blocks [first[m], first[m + 1])
+constexpr int kPrepMany = 8;
+struct CubePrepBatch {
+  CubePrepArgs a[kPrepMany];
+  int first[kPrepMany + 1];
+  int n;
+};
+__global__ void __launch_bounds__(kPrepThreads) cube_prep_many_kernel(const __grid_constant__ CubePrepBatch b) {
+  int m = 0;
+  while (m + 1 < b.n && (int)blockIdx.x >= b.first[m + 1]) ++m;
+  cube_prep_body(b.a[m], blockIdx.x - b.first[m], b.first[m + 1] - b.first[m]);
 }
 
 }  // namespace
@@ -964,11 +981,58 @@ int cube_weight_maps(const CubeWs &w, int a_in, int a_hid, int a_out, bool has_r
 
 }  // namespace
 
+namespace {
+CubePrepArgs cube_fwd_prep_args(const CubeWs &w, const float *x, long long n_cols, int a_in, int a_hid, int a_out, const float *w1,
+                                const float *b1, const float *w2, const float *wres, const float *ln_w, const float *prev_ln_w,
+                                const float *prev_ln_b, int prev_n) {
+  CubePrepArgs pa{};
+  const bool bounded = prev_ln_w != nullptr && prev_n > 0 && prev_n <= 256;
+  pa.x = bounded ? nullptr : x, pa.nx = bounded ? 0 : (size_t)n_cols * a_in;
+  pa.prev_ln_w = bounded ? prev_ln_w : nullptr, pa.prev_ln_b = bounded ? prev_ln_b : nullptr, pa.prev_n = bounded ? prev_n : 0;
+  pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
+  for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
+  pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;
+  const size_t want = (pa.nx + 32767) / 32768;
+  pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
+  return pa;
+}
+}  // namespace
+
+// The preparation (weight split, operand scales) of n <= 8 mixes of an encoder forward in ONE launch.  Every argument is
+// an array of n entries, in execution order; workspace[m] must be ZERO-FILLED (mimrl_cubemlp_tc_workspace_bytes each).
+// Mix m > 0 must carry prev_ln_w / prev_ln_b / prev_n (its input is the previous mix's LayerNorm output); x / n_cols
+// describe the input of mix 0 (ignored when mix 0 has prev_ln_w).  Afterwards call mimrl_cubemlp_mix_fwd_tc with
+// prepared = 1 on the same workspaces.
+extern "C" int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n_cols, const int *a_in, const int *a_hid,
+                                       const int *a_out, const float *const *w1, const float *const *b1,
+                                       const float *const *w2, const float *const *wres, const float *const *ln_w,
+                                       const float *const *prev_ln_w, const float *const *prev_ln_b, const int *prev_n,
+                                       void *const *workspace, void *stream) {
+  MIMRL_REQUIRE(n >= 1 && n <= kPrepMany, "cubemlp_prep_many: 1..%d mixes", kPrepMany);
+  CubePrepBatch b{};
+  b.n = n;
+  int first = 0;
+  for (int m = 0; m < n; ++m) {
+    MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in[m], a_hid[m], a_out[m], 0, 0) && w1[m] && w2[m] && ln_w[m] && workspace[m],
+                  "cubemlp_prep_many: mix %d is outside the tensor-core kernels", m);
+    MIMRL_REQUIRE(m == 0 || (prev_ln_w[m] && prev_n[m] > 0 && prev_n[m] <= 256), "cubemlp_prep_many: mix %d needs the LayerNorm bound of its input", m);
+    const CubeWs w = cube_ws(workspace[m], a_in[m], a_hid[m], a_out[m]);
+    b.a[m] = cube_fwd_prep_args(w, m == 0 ? x : nullptr, n_cols[m], a_in[m], a_hid[m], a_out[m], w1[m], b1[m], w2[m], wres[m], ln_w[m],
+                                prev_ln_w[m], prev_ln_b[m], prev_n[m]);
+    MIMRL_REQUIRE(m != 0 || b.a[0].prev_ln_w || x, "cubemlp_prep_many: mix 0 needs x or a LayerNorm bound");
+    b.first[m] = first;
+    first += b.a[m].n_abs + 3;
+  }
+  b.first[n] = first;
+  cube_prep_many_kernel<<<first, kPrepThreads, 0, (cudaStream_t)stream>>>(b);
+  return check_launch("cubemlp prep (encoder)");
+}
+
 extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
                                         int a_hid, const float *w2, const float *b2, int a_out, const float *wres,
                                         const float *ln_w, const float *ln_b, int act, float *y, float *saved,
                                         void *workspace, size_t workspace_bytes, const float *prev_ln_w,
-                                        const float *prev_ln_b, int prev_n, void *stream) {
+                                        const float *prev_ln_b, int prev_n, int prepared, void *stream) {
   MIMRL_REQUIRE(mimrl_cubemlp_tc_supported(a_in, a_hid, a_out, 0, act), "cubemlp_mix_fwd_tc: sizes %d/%d/%d act %d not supported",
                 a_in, a_hid, a_out, act);
   MIMRL_REQUIRE(outer > 0 && inner > 0 && x && y && saved && w1 && w2 && ln_w && ln_b, "cubemlp_mix_fwd_tc: bad arguments");
@@ -977,20 +1041,12 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   cudaStream_t st = (cudaStream_t)stream;
   const CubeWs w = cube_ws(workspace, a_in, a_hid, a_out);
   const long long n_cols = (long long)outer * inner;
-  cudaMemsetAsync(w.tail, 0, 16, st);
-  CubePrepArgs pa{};
-  const bool bounded = prev_ln_w != nullptr && prev_n > 0 && prev_n <= 256;
-  pa.x = bounded ? nullptr : x, pa.nx = bounded ? 0 : (size_t)n_cols * a_in;
-  pa.prev_ln_w = bounded ? prev_ln_w : nullptr, pa.prev_ln_b = bounded ? prev_ln_b : nullptr, pa.prev_n = bounded ? prev_n : 0;
-  pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
-  for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
-  pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;
-  {
-    const size_t want = (pa.nx + 32767) / 32768;
-    pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
+  if (!prepared) {
+    cudaMemsetAsync(w.tail, 0, 16, st);
+    const CubePrepArgs pa = cube_fwd_prep_args(w, x, n_cols, a_in, a_hid, a_out, w1, b1, w2, wres, ln_w, prev_ln_w, prev_ln_b, prev_n);
+    cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
+    if (check_launch("cubemlp prep")) return 1;
   }
-  cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
-  if (check_launch("cubemlp prep")) return 1;
   CubeTcParams p;
   p.scales = reinterpret_cast<const float *>(w.tail + 4);
   p.absmax = w.tail;

@@ -38,7 +38,7 @@ class _AxisMix(torch.autograd.Function):
     """y = mix along `axis` of x [bs, L, K, D]; parameters in nn.Linear layout."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, wres, ln_w, ln_b, axis, ln_first, act_id, prev_w=None, prev_b=None):
+    def forward(ctx, x, w1, b1, w2, b2, wres, ln_w, ln_b, axis, ln_first, act_id, prev_w=None, prev_b=None, ws_prepared=None):
         x = L.f32(x)
         shape = list(x.shape)
         A = shape[axis]
@@ -58,13 +58,16 @@ class _AxisMix(torch.autograd.Function):
         ws = None
         if (USE_TC and outer * inner >= 1024
                 and L.lib.mimrl_cubemlp_tc_supported(A, H, A2, int(ln_first), act_id)):
-            ws = torch.empty(L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=x.device)
+            # ws_prepared: this mix's slice of the encoder-wide workspace, already filled by mimrl_cubemlp_prep_many
+            ws = ws_prepared if ws_prepared is not None else torch.empty(
+                L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2), dtype=torch.uint8, device=x.device)
             L.check(L.lib.mimrl_cubemlp_mix_fwd_tc(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
                                                    L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
                                                    L.ptr(prm[6]), act_id, L.ptr(y), L.ptr(saved), L.ptr(ws), ws.numel(),
                                                    L.ptr(L.f32(prev_w.detach())) if prev_w is not None else None,
                                                    L.ptr(L.f32(prev_b.detach())) if prev_b is not None else None,
-                                                   prev_w.numel() if prev_w is not None else 0, L.stream()))
+                                                   prev_w.numel() if prev_w is not None else 0,
+                                                   int(ws_prepared is not None), L.stream()))
         else:
             L.check(L.lib.mimrl_cubemlp_mix_fwd(L.ptr(x), outer, A, inner, L.ptr(prm[0]), L.ptr(prm[1]), H,
                                                 L.ptr(prm[2]), L.ptr(prm[3]), A2, L.ptr(prm[4]), L.ptr(prm[5]),
@@ -100,7 +103,7 @@ class _AxisMix(torch.autograd.Function):
                                                   L.ptr(b2), A2, L.ptr(wres), L.ptr(ln_w), L.ptr(ln_b), ln_first, act_id,
                                                   L.ptr(gx), L.ptr(gw1), L.ptr(gb1), L.ptr(gw2), L.ptr(gb2), L.ptr(gwres),
                                                   L.ptr(gln[0]), L.ptr(gln[1]), L.stream()))
-            return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
+            return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None, None
         s_gz = torch.empty(outer, A2, inner, device=dev)
         s_h = torch.empty(outer, H, inner, device=dev)
         s_gpre = torch.empty(outer, H, inner, device=dev)
@@ -123,7 +126,7 @@ class _AxisMix(torch.autograd.Function):
         gw2 = _small(2, r_gz, None, r_h, A2, H, R, colsum=gb2)
         gw1 = _small(2, r_gpre, None, r_u, H, A, R, colsum=gb1)
         gwres = _small(2, r_gz, None, r_u if not ln_first else rows(x3), A2, A, R) if wres is not None else None
-        return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
+        return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None, None
 
 
 def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
@@ -152,7 +155,7 @@ def _backward_tc(x, gy, saved, prm, cfg, gx, ws_fwd=None):
                                            L.ptr(gb1), L.ptr(gb2), L.ptr(gln[0]), L.ptr(gln[1]), L.ptr(gw1), L.ptr(gw2),
                                            L.ptr(gwres), L.ptr(ops[0]), L.ptr(ops[1]), L.ptr(ops[2]), L.ptr(ops[3]),
                                            L.ptr(ws), ws.numel(), int(ws_fwd is not None), st))
-    return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None
+    return gx, gw1, gb1, gw2, gb2, gwres, gln[0], gln[1], None, None, None, None, None, None
 
 
 _AxisMix._backward_tc = staticmethod(_backward_tc)
@@ -204,7 +207,7 @@ class MLPsBlock(nn.Module):
         drop = self.training and any(d.p > 0 for d in (self.dropout_l, self.dropout_k, self.dropout_d))
         return mask is None and not drop and self.activate in _ACT_IDS
 
-    def _mix(self, x, axis, ax, prev_ln=None):
+    def _mix(self, x, axis, ax, prev_ln=None, ws=None):
         """prev_ln: the LayerNorm whose unmodified output x is (ln_last order); the kernels then bound |x| from its
         parameters instead of reading x once more."""
         mlp, ln = getattr(self, "mlp_" + ax), getattr(self, "ln_" + ax)
@@ -213,16 +216,17 @@ class MLPsBlock(nn.Module):
         if prev_ln is not None and not self.ln_fist and prev_ln.weight is not None:
             pw, pb = prev_ln.weight, prev_ln.bias
         return _AxisMix.apply(x, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, wres, ln.weight, ln.bias,
-                              axis, self.ln_fist, _ACT_IDS[self.activate], pw, pb)
+                              axis, self.ln_fist, _ACT_IDS[self.activate], pw, pb, ws)
 
-    def forward(self, x, mask=None, _prev_ln=None):
-        """_prev_ln (internal, set by MLPEncoder): x is the unmodified output of that LayerNorm."""
+    def forward(self, x, mask=None, _prev_ln=None, _ws=None):
+        """_prev_ln (internal, set by MLPEncoder): x is the unmodified output of that LayerNorm.  _ws (internal): the
+        prepared workspaces of this block's sequence and channel mix."""
         if mask is not None:
             print("Warning from MLPsBlock: If using mask, d_in should be equal to d_out.")   # MLPProcess.py:56-57
         if self._fusable(mask):
-            x = self._mix(x, 1, "l", _prev_ln)
+            x = self._mix(x, 1, "l", _prev_ln, _ws[0] if _ws else None)
             x = self._mix(x, 2, "k")
-            return self._mix(x, 3, "d", self.ln_k)
+            return self._mix(x, 3, "d", self.ln_k, _ws[1] if _ws else None)
         if not self._warned:
             warnings.warn("MLPsBlock: dropout>0 in training / mask / this activation are outside the fused CubeMLP "
                           "kernels; running the reference op order with torch ops")
@@ -260,9 +264,59 @@ class MLPEncoder(nn.Module):
             for i in range(len(d_hiddens))])
 
     def forward(self, x, mask=None):
+        ws = self._prepare(x, mask)
         prev = None
-        for enc_layer in self.layers_stack:
+        for i, enc_layer in enumerate(self.layers_stack):
             fused = enc_layer._fusable(mask) and not enc_layer.ln_fist
-            x = enc_layer(x, mask, _prev_ln=prev) if fused else enc_layer(x, mask)
+            x = enc_layer(x, mask, _prev_ln=prev, _ws=ws[i] if ws else None) if fused else enc_layer(x, mask)
             prev = enc_layer.ln_d if fused else None          # the block's output is ln_d's output (MLPProcess.py:120)
         return x
+
+    def _prepare(self, x, mask):
+        """Weight split and operand scales of EVERY tensor-core mix of the encoder in one launch (every mix but the first
+        depends on weights and on the LayerNorm bound of its input only): one zero-fill and one kernel instead of a memset
+        and a preparation launch per mix.  Returns [(ws_l, ws_d)] per block, or None when the plan does not apply."""
+        if not (USE_TC and x.is_cuda and x.dim() == 4 and len(self.layers_stack) * 2 <= 8):
+            return None
+        bs, Ld, Kd, Dd = x.shape
+        plan = []          # (A, H, A2, n_cols, mlp, wres, ln, prev_ln)
+        prev = None
+        for blk in self.layers_stack:
+            if not blk._fusable(mask) or blk.ln_fist:
+                return None
+            for ax in "lkd":
+                mlp, ln = getattr(blk, "mlp_" + ax), getattr(blk, "ln_" + ax)
+                A, H, A2 = mlp.fc1.in_features, mlp.fc1.out_features, mlp.fc2.out_features
+                n_cols = bs * Ld * Kd * Dd // A
+                if ax != "k":
+                    if n_cols < 1024 or not L.lib.mimrl_cubemlp_tc_supported(A, H, A2, 0, _ACT_IDS[blk.activate]):
+                        return None
+                    wres = getattr(blk, "res_projection_" + ax).weight if blk.res_project else None
+                    plan.append((A, H, A2, n_cols, mlp, wres, ln, prev if ax == "l" else blk.ln_k))
+                if ax == "l":
+                    Ld = A2
+                elif ax == "k":
+                    Kd = A2
+                else:
+                    Dd = A2
+            prev = blk.ln_d
+        import ctypes
+        n = len(plan)
+        sizes = [-(-L.lib.mimrl_cubemlp_tc_workspace_bytes(A, H, A2) // 256) * 256 for A, H, A2, *_ in plan]
+        ws_all = torch.zeros(sum(sizes), dtype=torch.uint8, device=x.device)
+        slices = list(torch.split(ws_all, sizes))
+        f = lambda t: None if t is None else L.ptr(L.f32(t.detach()))
+        arr_p = lambda vals: (ctypes.c_void_p * n)(*vals)
+        arr_i = lambda vals: (ctypes.c_int * n)(*vals)
+        x32 = L.f32(x)
+        L.check(L.lib.mimrl_cubemlp_prep_many(
+            n, L.ptr(x32), (ctypes.c_longlong * n)(*[p_[3] for p_ in plan]), arr_i([p_[0] for p_ in plan]),
+            arr_i([p_[1] for p_ in plan]), arr_i([p_[2] for p_ in plan]),
+            arr_p([f(p_[4].fc1.weight) for p_ in plan]), arr_p([f(p_[4].fc1.bias) for p_ in plan]),
+            arr_p([f(p_[4].fc2.weight) for p_ in plan]), arr_p([f(p_[5]) for p_ in plan]),
+            arr_p([f(p_[6].weight) for p_ in plan]),
+            arr_p([f(p_[7].weight) if p_[7] is not None else None for p_ in plan]),
+            arr_p([f(p_[7].bias) if p_[7] is not None else None for p_ in plan]),
+            arr_i([p_[7].weight.numel() if p_[7] is not None else 0 for p_ in plan]),
+            arr_p([L.ptr(s_) for s_ in slices]), L.stream()))
+        return [(slices[2 * i], slices[2 * i + 1]) for i in range(len(self.layers_stack))]
