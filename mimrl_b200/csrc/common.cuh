@@ -112,6 +112,13 @@ int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcPla
 int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st);
 
+// width-1 pools on the kd_tree route (knn_1d.cu): sort + per-query two-sided walk
+bool knn1d_supported(int width, int exact_form);
+size_t knn1d_workspace_bytes(int n_keys);
+int knn1d_search(const float *keys, int n_keys, int64_t key_offset, const float *queries, int n_queries,
+                 const int64_t *excluded, int n_excluded, int k, int64_t *nbr_orig, double *nbr_dist, unsigned char *ws,
+                 cudaStream_t st);
+
 // Partial-statistics layout shared by every score sweep (FFMA and tcgen05):
 // part[(split * n_own + row) * 3 + {0,1,2}] = {max, sum, softplus-sum}
 int combine_row_stats(const float *part, int n_splits, int n_own, float *row_max, float *row_sum, float *row_sp,

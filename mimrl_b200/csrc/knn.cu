@@ -321,7 +321,7 @@ struct Plan {
   int list_len, splits, tiles_per_split, n_lists;
   bool use_tc;
   KnnTcPlan tc;
-  size_t off_kn, off_q, off_cand, off_tc, total;
+  size_t off_kn, off_q, off_cand, off_tc, off_1d, total;
 };
 
 Plan make_plan(int n_keys, int n_queries, int width, int k) {
@@ -351,6 +351,8 @@ Plan make_plan(int n_keys, int n_queries, int width, int k) {
   o += ((size_t)n_queries * p.n_lists * p.list_len * sizeof(Cand) + 255) & ~(size_t)255;
   p.off_tc = o;
   o += p.use_tc ? p.tc.bytes : 0;
+  p.off_1d = o;
+  o += width == 1 ? knn1d_workspace_bytes(n_keys) : 0;          // sorted pool of the width-1 route (knn_1d.cu)
   p.total = o;
   return p;
 }
@@ -361,6 +363,9 @@ constexpr size_t kFilterSmem = (size_t)(kWC * kQS + kWC * kKS + 2 * kQT) * 4 + (
 int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const float *queries, int n_queries,
              const int64_t *excluded, int n_excluded, int k, int exact_form, int64_t *nbr_orig, double *nbr_dist,
              const Plan &p, unsigned char *ws, cudaStream_t st) {
+  if (knn1d_supported(width, exact_form))          // label pools: sort once, walk per query
+    return knn1d_search(keys, n_keys, key_offset, queries, n_queries, excluded, n_excluded, k, nbr_orig, nbr_dist,
+                        ws + p.off_1d, st);
   float *kn = reinterpret_cast<float *>(ws + p.off_kn);
   Cand *cand = reinterpret_cast<Cand *>(ws + p.off_cand);
   if (p.use_tc) {          // norms, fp16 hi / lo split and per-tile scales in one pass over the keys

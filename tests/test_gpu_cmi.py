@@ -128,6 +128,64 @@ def test_knn_config4_scale_vs_float64_oracle(width, bs, k, dup):
     assert not np.isin(got, ids).any() and np.all(np.diff(dist, axis=1) >= 0)
 
 
+@pytest.mark.parametrize("kind,N,m,k", [("labels", 200000, 512, 2), ("labels", 200000, 300, 16), ("signed_zero", 5000, 64, 8),
+                                       ("colliding", 60000, 100, 12), ("few_keys", 60, 30, 7), ("few_keys", 50, 36, 6), ("constant", 30000, 200, 5)])
+def test_knn_width1_sorted_route_ties(kind, N, m, k):
+    """Width-1 pools (the label pools, knn_1d.cu: sort + two-sided walk) where ties decide the answer: label-like
+    pools with a handful of distinct values (runs of thousands of equal distances, symmetric ties q - a / q + a),
+    +0.0 / -0.0 mixed, distinct values whose float64 distances collide (large q, tiny distinct keys), fewer valid keys
+    than 2k, one constant value.  Indices bit-exact and in the oracle's (distance, row) order, distances bit-equal;
+    then the same queries through mimrl_knn_search_rows on a key shard with an index offset."""
+    import mimrl_b200._lib as L
+    from mimrl_b200.model import knn_search, sklearn_route
+    rng = np.random.default_rng(N + k)
+    if kind == "labels":
+        Z = rng.integers(-3, 4, N).astype(np.float32) + rng.integers(0, 3, N).astype(np.float32) * 0.2
+    elif kind == "signed_zero":
+        Z = rng.choice(np.array([0.0, -0.0, 1.0, -1.0, 2.5], np.float32), N)
+    elif kind == "colliding":
+        Z = (rng.integers(1, 2000, N) * 1e-9).astype(np.float32)
+        Z[rng.permutation(N)[: N // 50]] = 3.0          # queries drawn below include rows at 3.0: 3 - 1e-9 rounds in float64
+    elif kind == "constant":
+        Z = np.full(N, 0.7, np.float32)
+    else:
+        Z = rng.integers(0, 4, N).astype(np.float32)
+    Z = Z.reshape(N, 1)
+    ids = rng.permutation(N)[:m]
+    if kind == "colliding":
+        ids[:20] = np.flatnonzero(Z[:, 0] == 3.0)[:20]
+        ids = np.unique(ids)
+        m = len(ids)
+    exc = np.zeros(N, np.uint8)
+    exc[ids] = 1
+    route = sklearn_route(1, k, N - m)
+    if route != "kd_tree":
+        pytest.skip("brute route")
+    want, wdist = K.knn(Z, Z[ids], k, exc, route)
+    got, comp, dist = knn_search(T(Z), T(ids), k, return_distance=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(dist.cpu().numpy(), wdist)
+    assert np.array_equal(comp.cpu().numpy(), want - np.searchsorted(np.sort(ids), want))
+    # key shard [lo, hi) with global row numbers, explicit queries, excluded ids as a global list
+    lo, hi = N // 3, N - N // 5
+    Zs = np.ascontiguousarray(Z[lo:hi])
+    e2 = np.zeros(hi - lo, np.uint8)
+    inside = ids[(ids >= lo) & (ids < hi)]
+    e2[inside - lo] = 1
+    kk = min(k, int((e2 == 0).sum()))
+    want2, wd2 = K.knn(Zs, Z[ids], kk, e2, "kd_tree")
+    ws = torch.empty(max(L.lib.mimrl_knn_workspace_bytes(hi - lo, m, 1, k), 16), dtype=torch.uint8, device=dev())
+    nbr = torch.full((m, k), -1, dtype=torch.int64, device=dev())
+    d2 = torch.full((m, k), float("inf"), dtype=torch.float64, device=dev())
+    keys_t, q_t, exc_t = T(Zs), T(Z[ids]), T(np.sort(ids))          # (kept alive until the kernels have run)
+    L.check(L.lib.mimrl_knn_search_rows(L.ptr(keys_t), hi - lo, 1, lo, L.ptr(q_t), m, L.ptr(exc_t), m, k, 0,
+                                        L.ptr(nbr), L.ptr(d2), L.ptr(ws), ws.numel(), L.stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(nbr.cpu().numpy()[:, :kk], want2 + lo)
+    assert np.array_equal(d2.cpu().numpy()[:, :kk], wd2)
+    assert (nbr.cpu().numpy()[:, kk:] == -1).all()
+
+
 def test_knn_shard_with_fewer_than_k_keys():
     """mimrl_knn_search_rows on a key shard that holds fewer than k keys (other shards fill in): legal, unfilled slots come
     back as index -1 (the global n_neighbors <= n_samples_fit check belongs to the caller)."""
