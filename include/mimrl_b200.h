@@ -230,6 +230,20 @@ size_t mimrl_knn_workspace_bytes(int n_keys, int n_queries, int width, int k);
 int mimrl_knn_search(const float *keys, int n_keys, int width, const int64_t *query_ids, int n_queries, int k,
                      float radius, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist,
                      void *workspace, size_t workspace_bytes, void *stream);
+/* Fitted pool: the part of a search that depends on the keys alone (squared norms, fp16 hi / lo planes with one scale per
+ * 128-key tile), computed once per pool instead of once per search.  The reference refits on every call
+ * (Model.py:82-85, NearestNeighbors(...).fit(Z2) on the pool minus the drawn rows); here the drawn rows are masked per
+ * search, so one fit of the WHOLE pool serves every search until the pool's contents change (Model.py:323,329 search
+ * T_F_all twice per step; the *_F_all pools are constant over an epoch).  mimrl_knn_fit_bytes returns 0 for pools the
+ * search does not prepare (width <= 15: direct-difference / sorted routes; fewer than 2048 keys): search those with
+ * mimrl_knn_search.  mimrl_knn_search_fitted: `fitted` filled by mimrl_knn_fit for the same keys; everything else as
+ * mimrl_knn_search, results bit-identical to it. */
+size_t mimrl_knn_fit_bytes(int n_keys, int width);
+int mimrl_knn_fit(const float *keys, int n_keys, int width, void *fitted, size_t fitted_bytes, void *stream);
+int mimrl_knn_search_fitted(const float *keys, int n_keys, int width, const void *fitted, size_t fitted_bytes,
+                            const int64_t *query_ids, int n_queries, int k, float radius, int exact_form,
+                            int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist, void *workspace,
+                            size_t workspace_bytes, void *stream);
 /* Same search with explicit query rows (multi-GPU: queries live on another rank).
  * excluded_sorted: ascending global ids to skip, may be NULL. */
 int mimrl_knn_search_rows(const float *keys, int n_keys, int width, int64_t key_index_offset,

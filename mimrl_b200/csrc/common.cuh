@@ -104,12 +104,17 @@ struct KnnTcPlan {
 };
 bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len);
 KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len);
+// prepared keys of the tensor-core filter: fp16 hi / lo planes [n_keys, 128] and 1 / scale per 128-key tile
+struct KnnTcKeys {
+  void *hi, *lo;
+  float *tile_inv_scale;
+};
+KnnTcKeys knn_tc_keys_in_workspace(const KnnTcPlan &plan, unsigned char *ws);
 // per query and list: list_len candidates sorted by (d, idx), padded with (+inf, -1); lists = splits * 2
-// one pass over the keys: squared row norms -> key_norms, fp16 hi / lo split with a scale per 128-key tile -> ws
-int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcPlan &plan, unsigned char *ws, float *key_norms,
-                        cudaStream_t st);
+// one pass over the keys: squared row norms -> key_norms, fp16 hi / lo split with a scale per 128-key tile -> out
+int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKeys &out, float *key_norms, cudaStream_t st);
 // after knn_tc_prepare_keys (and after excluded rows got +inf norms)
-int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
+int knn_filter_tc(const KnnTcKeys &keys, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st);
 
 // width-1 pools on the kd_tree route (knn_1d.cu): sort + per-query two-sided walk

@@ -360,16 +360,45 @@ Plan make_plan(int n_keys, int n_queries, int width, int k) {
 constexpr size_t kFilterSmem = (size_t)(kWC * kQS + kWC * kKS + 2 * kQT) * 4 + (size_t)(3 * kQT + 4) * 4 +
                                (size_t)kQT * kMaxList * sizeof(Cand) + (size_t)kQT * kKT * sizeof(Cand);
 
+// Fitted pool (mimrl_knn_fit): what a search computes from the keys alone -- clean squared norms, per-tile scales, fp16
+// hi / lo planes -- so that repeated searches of one pool (Model.py:323,329 search T_F_all twice per step, and the pools
+// are constant over an epoch) skip the preparation pass.
+struct FitLayout {
+  size_t off_kn, off_tscale, off_hi, off_lo, total;
+};
+FitLayout fit_layout(int n_keys) {
+  FitLayout f;
+  size_t o = 0;
+  f.off_kn = o, o += ((((size_t)n_keys + 127) & ~(size_t)127) * sizeof(float) + 255) & ~(size_t)255;
+  f.off_tscale = o, o += ((size_t)ceil_div(n_keys, 128) * 4 + 255) & ~(size_t)255;
+  f.off_hi = o, o += ((size_t)n_keys * 128 * 2 + 255) & ~(size_t)255;
+  f.off_lo = o, o += ((size_t)n_keys * 128 * 2 + 255) & ~(size_t)255;
+  f.total = o;
+  return f;
+}
+bool fit_applies(int n_keys, int width) { return width > 15 && knn_tc_supported(n_keys, 1, width, 1) && !getenv("MIMRL_KNN_FFMA"); }
+KnnTcKeys fitted_keys(const FitLayout &f, unsigned char *fitted) {
+  KnnTcKeys k;
+  k.hi = fitted + f.off_hi, k.lo = fitted + f.off_lo, k.tile_inv_scale = reinterpret_cast<float *>(fitted + f.off_tscale);
+  return k;
+}
+
 int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const float *queries, int n_queries,
              const int64_t *excluded, int n_excluded, int k, int exact_form, int64_t *nbr_orig, double *nbr_dist,
-             const Plan &p, unsigned char *ws, cudaStream_t st) {
+             const Plan &p, unsigned char *ws, cudaStream_t st, const unsigned char *fitted = nullptr) {
   if (knn1d_supported(width, exact_form))          // label pools: sort once, walk per query
     return knn1d_search(keys, n_keys, key_offset, queries, n_queries, excluded, n_excluded, k, nbr_orig, nbr_dist,
                         ws + p.off_1d, st);
   float *kn = reinterpret_cast<float *>(ws + p.off_kn);
   Cand *cand = reinterpret_cast<Cand *>(ws + p.off_cand);
-  if (p.use_tc) {          // norms, fp16 hi / lo split and per-tile scales in one pass over the keys
-    if (knn_tc_prepare_keys(keys, n_keys, width, p.tc, ws + p.off_tc, kn, st)) return 1;
+  KnnTcKeys tck{};
+  if (p.use_tc && fitted) {          // fitted pool: only the norms are copied (excluded rows are marked in the copy)
+    const FitLayout f = fit_layout(n_keys);
+    tck = fitted_keys(f, const_cast<unsigned char *>(fitted));
+    cudaMemcpyAsync(kn, fitted + f.off_kn, (size_t)n_keys * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  } else if (p.use_tc) {          // norms, fp16 hi / lo split and per-tile scales in one pass over the keys
+    tck = knn_tc_keys_in_workspace(p.tc, ws + p.off_tc);
+    if (knn_tc_prepare_keys(keys, n_keys, width, tck, kn, st)) return 1;
   } else {
     key_norms_kernel<<<ceil_div(n_keys * 32, 256), 256, 0, st>>>(keys, n_keys, width, kn);
     if (check_launch("knn key_norms")) return 1;
@@ -379,7 +408,7 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
     if (check_launch("knn mark_excluded")) return 1;
   }
   if (p.use_tc) {
-    if (knn_filter_tc(keys, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st)) return 1;
+    if (knn_filter_tc(tck, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st)) return 1;
   } else {
     dim3 grid(ceil_div(n_queries, kQT), p.splits);
     if (width <= 15) {
@@ -448,10 +477,47 @@ extern "C" int mimrl_knn_search_rows(const float *keys, int n_keys, int width, i
                   nbr_orig, nbr_dist, p, (unsigned char *)workspace, st);
 }
 
+extern "C" size_t mimrl_knn_fit_bytes(int n_keys, int width) {
+  if (n_keys <= 0 || width <= 0 || !fit_applies(n_keys, width)) return 0;
+  return fit_layout(n_keys).total;
+}
+
+extern "C" int mimrl_knn_fit(const float *keys, int n_keys, int width, void *fitted, size_t fitted_bytes, void *stream) {
+  MIMRL_REQUIRE(keys && n_keys > 0 && width > 0 && fit_applies(n_keys, width),
+                "knn_fit: nothing to fit for a %d x %d pool (mimrl_knn_fit_bytes returns 0)", n_keys, width);
+  const FitLayout f = fit_layout(n_keys);
+  MIMRL_REQUIRE(fitted && fitted_bytes >= f.total, "knn_fit: buffer too small");
+  unsigned char *fb = static_cast<unsigned char *>(fitted);
+  return knn_tc_prepare_keys(keys, n_keys, width, fitted_keys(f, fb), reinterpret_cast<float *>(fb + f.off_kn),
+                             (cudaStream_t)stream);
+}
+
+static int knn_search_impl(const float *keys, int n_keys, int width, const unsigned char *fitted, const int64_t *query_ids,
+                           int n_queries, int k, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+extern "C" int mimrl_knn_search_fitted(const float *keys, int n_keys, int width, const void *fitted, size_t fitted_bytes,
+                                       const int64_t *query_ids, int n_queries, int k, float radius, int exact_form,
+                                       int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+  (void)radius;
+  MIMRL_REQUIRE(fitted && n_keys > 0 && width > 0 && fit_applies(n_keys, width) && fitted_bytes >= fit_layout(n_keys).total,
+                "knn_search_fitted: not a buffer filled by mimrl_knn_fit for a %d x %d pool", n_keys, width);
+  return knn_search_impl(keys, n_keys, width, static_cast<const unsigned char *>(fitted), query_ids, n_queries, k, exact_form,
+                         nbr_orig, nbr_comp, nbr_dist, workspace, workspace_bytes, stream);
+}
+
 extern "C" int mimrl_knn_search(const float *keys, int n_keys, int width, const int64_t *query_ids, int n_queries,
                                 int k, float radius, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp,
                                 double *nbr_dist, void *workspace, size_t workspace_bytes, void *stream) {
   (void)radius;  // Model.py:82 passes it to the constructor; kneighbors() never reads it
+  return knn_search_impl(keys, n_keys, width, nullptr, query_ids, n_queries, k, exact_form, nbr_orig, nbr_comp, nbr_dist,
+                         workspace, workspace_bytes, stream);
+}
+
+static int knn_search_impl(const float *keys, int n_keys, int width, const unsigned char *fitted, const int64_t *query_ids,
+                           int n_queries, int k, int exact_form, int64_t *nbr_orig, int64_t *nbr_comp, double *nbr_dist,
+                           void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = knn_check(n_keys, width, n_queries, k, n_queries, true)) return rc;
   const Plan p = make_plan(n_keys, n_queries, width, k);
   MIMRL_REQUIRE(workspace_bytes >= p.total, "knn_search: workspace too small");
@@ -460,7 +526,7 @@ extern "C" int mimrl_knn_search(const float *keys, int n_keys, int width, const 
   float *q = reinterpret_cast<float *>(ws + p.off_q);
   if (int rc = mimrl_gather_rows(keys, n_keys, width, query_ids, n_queries, 1, width, q, stream)) return rc;
   if (int rc = knn_core(keys, n_keys, width, 0, q, n_queries, query_ids, n_queries, k, exact_form, nbr_orig, nbr_dist,
-                        p, ws, st))
+                        p, ws, st, fitted))
     return rc;
   if (nbr_comp) {
     const size_t n_out = (size_t)n_queries * k;

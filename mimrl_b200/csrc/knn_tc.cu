@@ -506,21 +506,25 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   return p;
 }
 
-int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcPlan &plan, unsigned char *ws, float *key_norms,
-                        cudaStream_t st) {
-  __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
-  knn_prep_keys_kernel<<<ceil_div(n_keys, 128), 256, 0, st>>>(keys, n_keys, width, key_norms,
-                                                             reinterpret_cast<float *>(ws + plan.off_tscale), k_hi, k_lo);
+KnnTcKeys knn_tc_keys_in_workspace(const KnnTcPlan &plan, unsigned char *ws) {
+  KnnTcKeys k;
+  k.hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), k.lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
+  k.tile_inv_scale = reinterpret_cast<float *>(ws + plan.off_tscale);
+  return k;
+}
+
+int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKeys &out, float *key_norms, cudaStream_t st) {
+  knn_prep_keys_kernel<<<ceil_div(n_keys, 128), 256, 0, st>>>(keys, n_keys, width, key_norms, out.tile_inv_scale,
+                                                             static_cast<__half *>(out.hi), static_cast<__half *>(out.lo));
   return check_launch("knn prepare keys");
 }
 
-int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int width, const float *queries,
+int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st) {
-  (void)keys;
   unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
   float *qn = reinterpret_cast<float *>(ws + plan.off_qn);
   __half *q_hi = reinterpret_cast<__half *>(ws + plan.off_q_hi), *q_lo = reinterpret_cast<__half *>(ws + plan.off_q_lo);
-  __half *k_hi = reinterpret_cast<__half *>(ws + plan.off_k_hi), *k_lo = reinterpret_cast<__half *>(ws + plan.off_k_lo);
+  __half *k_hi = static_cast<__half *>(pk.hi), *k_lo = static_cast<__half *>(pk.lo);
   cudaMemsetAsync(absmax, 0, 8, st);
   const size_t nq = (size_t)n_queries * width;
   int blocks = (int)((nq + 2047) / 2048);
@@ -541,7 +545,7 @@ int knn_filter_tc(const float *keys, const float *key_norms, int n_keys, int wid
   p.pub = reinterpret_cast<float *>(ws + plan.off_pub);
   cudaMemsetAsync(p.pub, 0x7f, (size_t)ceil_div(n_queries, 128) * 128 * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
   p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
-  p.tile_inv_scale = reinterpret_cast<const float *>(ws + plan.off_tscale);
+  p.tile_inv_scale = pk.tile_inv_scale;
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
   p.splits = plan.splits;
   p.q_tiles = ceil_div(n_queries, 128);

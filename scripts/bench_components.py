@@ -30,9 +30,23 @@ if "knn" in which:      # config 4: 1M x 128 keys, batch 8192, k = 2..16
         ms = timeit(lambda: knn_search(Z, ids, k), reps=3, warm=1)
         out(component="knn_search", N=N, width=128, queries=m, k=k, ms=ms, gflops=2 * 128 * m * N / ms / 1e6,
             key_gbs=4 * 128 * N / ms / 1e6)
+    from mimrl_b200.model import KnnPool
+    out(component="knn_fit", N=N, width=128, ms=timeit(lambda: KnnPool(Z), 3, 1))
+    pool = KnnPool(Z)             # fitted once (per epoch in the training loop), searched many times
+    for k in (2, 16):
+        m = 8192 // k
+        ids = torch.randperm(N, device=dev, generator=g)[:m]
+        ms = timeit(lambda: knn_search(pool, ids, k), reps=3, warm=1)
+        out(component="knn_search_fitted_pool", N=N, width=128, queries=m, k=k, ms=ms, gflops=2 * 128 * m * N / ms / 1e6,
+            key_gbs=4 * 128 * N / ms / 1e6)
     Zl = torch.randn(N, 1, device=dev, generator=g)
-    ids = torch.randperm(N, device=dev, generator=g)[:4096]
-    out(component="knn_search_labels", N=N, width=1, queries=4096, k=2, ms=timeit(lambda: knn_search(Zl, ids, 2), 3, 1))
+    Zi = torch.randint(-3, 4, (N, 1), device=dev, generator=g).float()          # label-like: seven distinct values
+    for k in (2, 16):
+        ids = torch.randperm(N, device=dev, generator=g)[:8192 // k]
+        out(component="knn_search_labels", N=N, width=1, queries=8192 // k, k=k, pool="normal",
+            ms=timeit(lambda: knn_search(Zl, ids, k), 3, 1))
+        out(component="knn_search_labels", N=N, width=1, queries=8192 // k, k=k, pool="7 distinct values",
+            ms=timeit(lambda: knn_search(Zi, ids, k), 3, 1))
 
 if "cubemlp" in which:  # config 5: [1024, 100, 3, 128] -> 50-3-128 -> 10-3-128
     enc = MLPEncoder("gelu", [100, 3, 128], [[50, 3, 128], [10, 3, 128]], [[50, 3, 128], [10, 3, 128]], [0.0] * 3, True,

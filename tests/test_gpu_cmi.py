@@ -186,6 +186,38 @@ def test_knn_width1_sorted_route_ties(kind, N, m, k):
     assert (nbr.cpu().numpy()[:, kk:] == -1).all()
 
 
+def test_knn_fitted_pool_is_bit_identical():
+    """KnnPool (mimrl_knn_fit + mimrl_knn_search_fitted): one fit, several searches with different query draws and k --
+    indices, compacted indices and float64 distances equal to the unfitted search bit for bit; the sampler accepts the
+    fitted pool in place of the tensor; narrow / small pools are wrapped without a fit."""
+    from mimrl_b200.model import KnnPool, knn_search, prod_knn_sample
+    N = 150000
+    Z = T(P.features(5, N, 128))
+    X = T(P.features(6, N, 128))
+    Y = T(P.features(7, N, 1))
+    pool = KnnPool(Z)
+    assert pool.fitted is not None
+    for seed, m, k in ((0, 300, 2), (1, 129, 16), (2, 1000, 4)):
+        ids = T(np.random.default_rng(seed).permutation(N)[:m])
+        a = knn_search(Z, ids, k, return_distance=True)
+        b = knn_search(pool, ids, k, return_distance=True)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+    np.random.seed(3)
+    ra = prod_knn_sample(X, Y, Z, 512, 4, 1.0)
+    np.random.seed(3)
+    rb = prod_knn_sample(X, Y, pool, 512, 4, 1.0)
+    for u, v in zip(ra, rb):
+        assert torch.equal(u, v)
+    assert KnnPool(Y).fitted is None and KnnPool(Z[:1000]).fitted is None
+    np.random.seed(4)
+    rc = prod_knn_sample(X, Z, Y, 512, 4, 1.0)
+    np.random.seed(4)
+    rd = prod_knn_sample(KnnPool(X), pool, KnnPool(Y), 512, 4, 1.0)
+    for u, v in zip(rc, rd):
+        assert torch.equal(u, v)
+
+
 def test_knn_shard_with_fewer_than_k_keys():
     """mimrl_knn_search_rows on a key shard that holds fewer than k keys (other shards fill in): legal, unfilled slots come
     back as index -1 (the global n_neighbors <= n_samples_fit check belongs to the caller)."""
