@@ -62,6 +62,7 @@ _SIGS = {
     "mimrl_gemm_split_blocked_acc": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "mimrl_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mimrl_knn_search": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "mimrl_legacy_permutation_head": (c_int, [_P, _P, c_int64, c_int64, _P]),
     "mimrl_knn_fit_bytes": (c_size_t, [c_int, c_int]),
     "mimrl_knn_fit": (c_int, [_P, c_int, c_int, _P, c_size_t, _P]),
     "mimrl_knn_search_fitted": (c_int, [_P, c_int, c_int, _P, c_size_t, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P,

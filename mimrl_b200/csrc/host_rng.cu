@@ -1,0 +1,105 @@
+// Host side of the k-NN sampler's query draw (Model.py:81: np.random.choice(range(N), size=m, replace=False)).
+// numpy's legacy RandomState.choice without replacement is permutation(N)[:m]: arange(N), then a Fisher-Yates pass
+// from i = N - 1 down to 1 with j = random_interval(i) (masked rejection on MT19937 32-bit outputs) -- N - 1 draws of
+// a variable number of outputs each, so neither the first m entries nor the generator state afterwards can be had
+// without walking the whole stream.  This file restates that published algorithm (numpy/random/mtrand.pyx
+// RandomState.shuffle/_shuffle_raw, src/distributions/distributions.c random_interval, src/mt19937/mt19937.c) on the
+// caller's copy of the generator state, so that the draw and the state afterwards are numpy's bit for bit, and runs it
+// faster than numpy does (12 ms at N = 2^20 on the B200 host): the j's depend on the stream only, not on the array, so
+// they are produced a block ahead and their cache lines prefetched before the swaps touch them; the array is int32.
+// No GPU work here; it lives in this library so that the reference-facing sampler needs nothing else.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMtN = 624, kMtM = 397;
+
+inline void mt_regenerate(uint32_t *mt) {
+  int kk = 0;
+  uint32_t y;
+  for (; kk < kMtN - kMtM; ++kk) {
+    y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+    mt[kk] = mt[kk + kMtM] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  }
+  for (; kk < kMtN - 1; ++kk) {
+    y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+    mt[kk] = mt[kk + (kMtM - kMtN)] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  }
+  y = (mt[kMtN - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+  mt[kMtN - 1] = mt[kMtM - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+}
+
+struct Mt {
+  uint32_t *key;
+  int pos;
+  uint32_t out[kMtN];          // the tempered words of the current block (tempering a whole block vectorises)
+  inline void temper() {
+    for (int k = 0; k < kMtN; ++k) {
+      uint32_t y = key[k];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      out[k] = y;
+    }
+  }
+  inline uint32_t next() {
+    if (pos == kMtN) mt_regenerate(key), temper(), pos = 0;
+    return out[pos++];
+  }
+};
+
+}  // namespace
+
+// key[624], *pos: numpy's np.random.get_state()[1:3]; updated in place.  out[m] = np.random.permutation(n)[:m].
+extern "C" int mimrl_legacy_permutation_head(uint32_t *key, int *pos, int64_t n, int64_t m, int64_t *out) {
+  MIMRL_REQUIRE(key && pos && out && n >= 1 && m >= 0 && m <= n && n <= 0x7fffffff && *pos >= 0 && *pos <= kMtN,
+                "legacy_permutation_head: bad arguments");
+  int32_t *arr = static_cast<int32_t *>(malloc((size_t)n * sizeof(int32_t)));
+  MIMRL_REQUIRE(arr, "legacy_permutation_head: out of memory");
+  for (int64_t i = 0; i < n; ++i) arr[i] = (int32_t)i;
+  Mt g;
+  g.key = key, g.pos = *pos;
+  g.temper();
+  // The swap targets depend on the stream only, not on the array: they are drawn one block ahead (branch-free masked
+  // rejection: a rejected value is overwritten by the next draw) and prefetched, then the previous block is swapped.
+  constexpr int kBlock = 64;
+  uint32_t js[2][kBlock];
+  int cnts[2] = {0, 0};
+  int64_t starts[2] = {0, 0};
+  int cur = 0;
+  int64_t i = n - 1;
+  auto draw_block = [&](int slot) {
+    const int want = i >= kBlock ? kBlock : (int)(i > 0 ? i : 0);
+    int cnt = 0;
+    while (cnt < want) {
+      const uint32_t mx = (uint32_t)(i - cnt);
+      const uint32_t v = g.next() & (0xffffffffu >> __builtin_clz(mx));
+      js[slot][cnt] = v;
+      cnt += v <= mx ? 1 : 0;
+    }
+    for (int b = 0; b < want; ++b) __builtin_prefetch(arr + js[slot][b], 1);
+    starts[slot] = i, cnts[slot] = want;
+    i -= want;
+  };
+  draw_block(cur);
+  while (cnts[cur] > 0) {
+    draw_block(cur ^ 1);
+    const int64_t i0 = starts[cur];
+    for (int b = 0; b < cnts[cur]; ++b) {
+      const uint32_t j = js[cur][b];
+      const int32_t t = arr[j];
+      arr[j] = arr[i0 - b];
+      arr[i0 - b] = t;
+    }
+    cur ^= 1;
+  }
+  for (int64_t t = 0; t < m; ++t) out[t] = arr[t];
+  free(arr);
+  *pos = g.pos;
+  return 0;
+}

@@ -25,7 +25,8 @@ class HostIdSource:
         self.recording = False
 
     def next(self, N: int, m: int, device) -> torch.Tensor:
-        ids = torch.from_numpy(np.random.permutation(N)[:m].astype(np.int64))
+        from .model import legacy_permutation_head
+        ids = torch.from_numpy(legacy_permutation_head(N, m))
         if not self.recording:
             return ids.to(device, non_blocking=True)
         pinned = torch.empty(m, dtype=torch.int64).pin_memory()
@@ -34,8 +35,9 @@ class HostIdSource:
         return pinned.to(device, non_blocking=True)          # a memcpy node of the graph
 
     def refill(self):
+        from .model import legacy_permutation_head
         for N, m, pinned in self.calls:
-            pinned.copy_(torch.from_numpy(np.random.permutation(N)[:m].astype(np.int64)))
+            pinned.copy_(torch.from_numpy(legacy_permutation_head(N, m)))
 
 
 class GraphedCallable:

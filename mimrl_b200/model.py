@@ -97,6 +97,23 @@ def _gather(src, idx, repeat, out_width):
 _ID_SOURCE = None          # set by graphs.GraphedCallable while it warms up / captures a step
 
 
+def legacy_permutation_head(N, m, _min_n=4096):
+    """``np.random.permutation(N)[:m]`` on numpy's GLOBAL legacy generator -- same values, same generator state afterwards
+    (what Model.py:81's ``np.random.choice(range(N), size=m, replace=False)`` draws and leaves behind) -- computed by
+    ``mimrl_legacy_permutation_head`` (csrc/host_rng.cu) on a copy of the state, which is then written back.  The
+    Fisher-Yates pass over all N elements is inherent to stream parity; this one runs ~3x faster than numpy's."""
+    import ctypes
+    st = np.random.get_state()
+    if st[0] != "MT19937" or N < _min_n:          # small pools: numpy's own call is cheaper than the state round trip
+        return np.random.permutation(N)[:m].astype(np.int64)
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int(int(st[2]))
+    out = np.empty(m, np.int64)
+    L.check(L.lib.mimrl_legacy_permutation_head(key.ctypes.data, ctypes.addressof(pos), N, m, out.ctypes.data))
+    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+    return out
+
+
 def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
     """Model.py:75-106.  Draws m = batch_size // k query rows with numpy's GLOBAL
     RNG (same draw and same RNG state afterwards as the reference's
@@ -114,8 +131,7 @@ def prod_knn_sample(X, Y, Z, batch_size, k_neighbor, radius):
     if _ID_SOURCE is not None:            # CUDA-graph capture (graphs.py): same draw, staged through a pinned buffer
         ids = _ID_SOURCE.next(N, m, Z.device)
     else:
-        ids_host = np.random.permutation(N)[:m]
-        ids = torch.from_numpy(ids_host.astype(np.int64)).to(Z.device, non_blocking=True)
+        ids = torch.from_numpy(legacy_permutation_head(N, m)).to(Z.device, non_blocking=True)
     nbr_orig, _ = knn_search(pool if isinstance(pool, KnnPool) else Z, ids, k_neighbor, radius)
     wmax = max(X.shape[1], Y.shape[1], Z.shape[1])
     batch_x = _gather(X, nbr_orig.reshape(-1), 1, wmax)
@@ -196,7 +212,7 @@ def prod_knn_sample_sharded(X_local, Y_local, Z_local, batch_size, k_neighbor, r
     if m > N:
         raise ValueError("Cannot take a larger sample than population when 'replace=False'")
     dev = Z_local.device
-    ids = torch.from_numpy(np.random.permutation(N)[:m].astype(np.int64)).to(dev)
+    ids = torch.from_numpy(legacy_permutation_head(N, m)).to(dev)
     if rb.sharded:
         torch.distributed.broadcast(ids, src=torch.distributed.get_global_rank(rb.group, 0) if rb.group is not None else 0,
                                     group=rb.group)

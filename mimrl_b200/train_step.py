@@ -33,9 +33,21 @@ class FeaturePool:
     A: Optional[torch.Tensor] = None
     V: Optional[torch.Tensor] = None
     _next: dict = field(default_factory=lambda: {k: [] for k in "CFTAV"})
+    _fit: dict = field(default_factory=dict)
 
     def __len__(self):
         return 0 if self.C is None else int(self.C.shape[0])
+
+    def keys(self, name):
+        """Pool ``name`` as a fitted k-NN key pool (model.KnnPool): fitted on first use, reused by every sampler call until
+        the pool tensor is replaced (``roll``, assignment) or modified in place through torch (version counter).  The
+        reference refits inside every prod_knn_sample call (Model.py:82-85)."""
+        from .model import KnnPool
+        t = getattr(self, name)
+        hit = self._fit.get(name)
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = self._fit[name] = (t, t._version, KnnPool(t))
+        return hit[2]
 
     def append(self, labels, F_F, T_F, A_F, V_F):
         for k, v in zip("CFTAV", (labels.reshape(-1, 1), F_F, T_F, A_F, V_F)):
@@ -47,6 +59,7 @@ class FeaturePool:
             for k in "CFTAV":
                 setattr(self, k, torch.cat(self._next[k], 0))
                 self._next[k] = []
+            self._fit = {}
 
 
 class TwoStageStep:
@@ -68,7 +81,8 @@ class TwoStageStep:
         if len(pool) == 0:                                   # Customization.py:97-98
             return torch.zeros((), device=pred.device), []
         mis, losses = self.heads.compute_vmi_loss_stage1(pred.reshape(-1, 1), labels.reshape(-1, 1), F_F, T_F, A_F, V_F,
-                                                         pool.C, pool.F, pool.T, pool.A, pool.V)
+                                                         pool.C, pool.F, pool.keys("T"), pool.keys("A"),
+                                                         pool.keys("V"))
         loss = sum(l * c for l, c in zip(losses, self.coef1))
         self.opt_vmi.zero_grad(set_to_none=True)
         loss.backward()
@@ -84,7 +98,8 @@ class TwoStageStep:
         mis = []
         if len(pool) > 0:                                    # Customization.py:105-106
             mis, losses = self.heads.compute_vmi_loss_stage2(pred.reshape(-1, 1), labels.reshape(-1, 1), F_F, T_F, A_F,
-                                                             V_F, pool.C, pool.F, pool.T, pool.A, pool.V)
+                                                             V_F, pool.C, pool.F, pool.keys("T"), pool.keys("A"),
+                                                             pool.keys("V"))
             loss = loss + sum(l * c for l, c in zip(losses, self.coef2))
         self.opt_main.zero_grad(set_to_none=True)
         loss.backward()

@@ -140,7 +140,7 @@ if "step" in which:     # config 1 / 5 shape: one stage-1 + one stage-2 step of 
     from types import SimpleNamespace
     from mimrl_b200.model import MIHeads
     from mimrl_b200.train_step import FeaturePool, TwoStageStep
-    for bs, N in ((128, 1284), (1024, 16326)):
+    for bs, N in ((128, 1284), (1024, 16326), (8192, 1 << 20)):          # last: BASELINE config 4 pool size
         opt = SimpleNamespace(critic_type="separate", baseline_type="constant", bound_type="infonce", k_neighbor=2,
                               radius=1.0, cmi_last_acticate="hardtanh", d_common=128)
         heads = MIHeads(opt).to(dev)
