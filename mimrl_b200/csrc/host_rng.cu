@@ -53,13 +53,28 @@ struct Mt {
   }
 };
 
+struct Scratch {
+  int32_t *p = nullptr;
+  size_t n = 0;
+  int32_t *get(size_t want) {
+    if (want > n) {
+      free(p);
+      p = static_cast<int32_t *>(malloc(want * sizeof(int32_t)));
+      n = p ? want : 0;
+    }
+    return p;
+  }
+  ~Scratch() { free(p); }
+};
+
 }  // namespace
 
 // key[624], *pos: numpy's np.random.get_state()[1:3]; updated in place.  out[m] = np.random.permutation(n)[:m].
 extern "C" int mimrl_legacy_permutation_head(uint32_t *key, int *pos, int64_t n, int64_t m, int64_t *out) {
   MIMRL_REQUIRE(key && pos && out && n >= 1 && m >= 0 && m <= n && n <= 0x7fffffff && *pos >= 0 && *pos <= kMtN,
                 "legacy_permutation_head: bad arguments");
-  int32_t *arr = static_cast<int32_t *>(malloc((size_t)n * sizeof(int32_t)));
+  static thread_local Scratch scratch;          // kept between calls: no page faults on a fresh 4 MB block per draw
+  int32_t *arr = scratch.get((size_t)n);
   MIMRL_REQUIRE(arr, "legacy_permutation_head: out of memory");
   for (int64_t i = 0; i < n; ++i) arr[i] = (int32_t)i;
   Mt g;
@@ -76,11 +91,32 @@ extern "C" int mimrl_legacy_permutation_head(uint32_t *key, int *pos, int64_t n,
   auto draw_block = [&](int slot) {
     const int want = i >= kBlock ? kBlock : (int)(i > 0 ? i : 0);
     int cnt = 0;
-    while (cnt < want) {
-      const uint32_t mx = (uint32_t)(i - cnt);
-      const uint32_t v = g.next() & (0xffffffffu >> __builtin_clz(mx));
-      js[slot][cnt] = v;
-      cnt += v <= mx ? 1 : 0;
+    if (want > 0 && __builtin_clz((uint32_t)i) == __builtin_clz((uint32_t)(i - want + 1))) {
+      // one mask for the whole block (i crosses a power of two ~20 times per draw): the only chain left between
+      // consecutive draws is the count itself
+      const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+      const uint32_t top = (uint32_t)i, lo = top - (uint32_t)want;
+      uint32_t *dst = js[slot];
+      while (cnt < want) {
+        if (g.pos == kMtN) mt_regenerate(g.key), g.temper(), g.pos = 0;
+        // v <= lo is accepted and v > top rejected whatever the count; only the `want` values in between need it
+        int k = g.pos;
+        for (; k < kMtN && cnt < want; ++k) {
+          const uint32_t v = g.out[k] & mask;
+          dst[cnt] = v;
+          uint32_t ok = v <= lo ? 1u : 0u;
+          if (__builtin_expect(v - lo - 1u < (uint32_t)want, 0)) ok = v <= top - (uint32_t)cnt ? 1u : 0u;
+          cnt += (int)ok;
+        }
+        g.pos = k;
+      }
+    } else {
+      while (cnt < want) {
+        const uint32_t mx = (uint32_t)(i - cnt);
+        const uint32_t v = g.next() & (0xffffffffu >> __builtin_clz(mx));
+        js[slot][cnt] = v;
+        cnt += v <= mx ? 1 : 0;
+      }
     }
     for (int b = 0; b < want; ++b) __builtin_prefetch(arr + js[slot][b], 1);
     starts[slot] = i, cnts[slot] = want;
@@ -99,7 +135,6 @@ extern "C" int mimrl_legacy_permutation_head(uint32_t *key, int *pos, int64_t n,
     cur ^= 1;
   }
   for (int64_t t = 0; t < m; ++t) out[t] = arr[t];
-  free(arr);
   *pos = g.pos;
   return 0;
 }
