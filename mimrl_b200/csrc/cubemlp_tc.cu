@@ -788,10 +788,13 @@ __device__ __forceinline__ void cube_prep_body(const CubePrepArgs &a, const int 
       size_t head = 0;
       if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
         const float4 *p4 = reinterpret_cast<const float4 *>(p);
-        for (size_t i = t0; i < n / 4; i += st) {
-          const float4 v = __ldg(p4 + i);
-          m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        auto take = [&](const float4 v) { m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w))); };
+        size_t i = t0;
+        for (; i + 3 * st < n / 4; i += 4 * st) {          // four independent 16-byte loads in flight per thread
+          const float4 v0 = __ldg(p4 + i), v1 = __ldg(p4 + i + st), v2 = __ldg(p4 + i + 2 * st), v3 = __ldg(p4 + i + 3 * st);
+          take(v0), take(v1), take(v2), take(v3);
         }
+        for (; i < n / 4; i += st) take(__ldg(p4 + i));
         head = (n / 4) * 4;
       }
       for (size_t i = head + t0; i < n; i += st) m = fmaxf(m, fabsf(p[i]));
