@@ -60,6 +60,12 @@ __global__ void __launch_bounds__(256) knn_prep_keys_kernel(const float *__restr
       }
     }
     v[j] = q;
+  }
+  // (a second loop: the shuffles below would otherwise sit between the loads and serialise them)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const size_t row = (size_t)blockIdx.x * 128 + w + 8 * j;
+    const float4 q = v[j];
     float nrm = fmaf(q.w, q.w, fmaf(q.z, q.z, fmaf(q.y, q.y, q.x * q.x)));
 #pragma unroll
     for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);

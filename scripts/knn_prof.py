@@ -11,3 +11,8 @@ ids = torch.randperm(N, device="cuda", generator=g)[:m]
 for _ in range(2):
     knn_search(Z, ids, k)
 torch.cuda.synchronize()
+if len(sys.argv) > 3:          # also one search of the width-1 label pool (sorted route, knn_1d.cu)
+    Zl = torch.randn(N, 1, device="cuda", generator=g)
+    for _ in range(2):
+        knn_search(Zl, ids, k)
+    torch.cuda.synchronize()
