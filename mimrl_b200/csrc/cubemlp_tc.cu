@@ -790,9 +790,12 @@ __device__ __forceinline__ void cube_prep_body(const CubePrepArgs &a, const int 
         const float4 *p4 = reinterpret_cast<const float4 *>(p);
         auto take = [&](const float4 v) { m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w))); };
         size_t i = t0;
-        for (; i + 3 * st < n / 4; i += 4 * st) {          // four independent 16-byte loads in flight per thread
-          const float4 v0 = __ldg(p4 + i), v1 = __ldg(p4 + i + st), v2 = __ldg(p4 + i + 2 * st), v3 = __ldg(p4 + i + 3 * st);
-          take(v0), take(v1), take(v2), take(v3);
+        for (; i + 7 * st < n / 4; i += 8 * st) {          // eight independent 16-byte loads in flight per thread
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(p4 + i + k * st);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) take(v[k]);
         }
         for (; i < n / 4; i += st) take(__ldg(p4 + i));
         head = (n / 4) * 4;
@@ -996,7 +999,7 @@ CubePrepArgs cube_fwd_prep_args(const CubeWs &w, const float *x, long long n_col
   for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
   pa.b1 = b1, pa.ln_w = ln_w, pa.A = a_in, pa.H = a_hid, pa.A2 = a_out, pa.backward = 0, pa.tail = w.tail;
   const size_t want = (pa.nx + 32767) / 32768;
-  pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
+  pa.n_abs = (int)(want > 145 ? 145 : (want < 1 ? 1 : want));          // one wave of 1024-thread blocks (one resident per SM)
   return pa;
 }
 }  // namespace
@@ -1023,6 +1026,8 @@ extern "C" int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n
     b.a[m] = cube_fwd_prep_args(w, m == 0 ? x : nullptr, n_cols[m], a_in[m], a_hid[m], a_out[m], w1[m], b1[m], w2[m], wres[m], ln_w[m],
                                 prev_ln_w[m], prev_ln_b[m], prev_n[m]);
     MIMRL_REQUIRE(m != 0 || b.a[0].prev_ln_w || x, "cubemlp_prep_many: mix 0 needs x or a LayerNorm bound");
+    // 1024-thread blocks at 56 registers: one resident block per SM -- keep the whole launch to one wave
+    if (m == 0 && b.a[0].n_abs > 148 - 3 * n) b.a[0].n_abs = 148 - 3 * n;
     b.first[m] = first;
     first += b.a[m].n_abs + 3;
   }
@@ -1134,7 +1139,7 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   pa.hdr_op[0] = (unsigned *)op_x, pa.hdr_op[1] = (unsigned *)op_h, pa.hdr_op[2] = (unsigned *)op_gz, pa.hdr_op[3] = (unsigned *)op_gpre;
   {
     const size_t want = ((ws_from_forward ? 0 : pa.nx) + pa.ngy + 32767) / 32768;
-    pa.n_abs = (int)(want > 148 * 2 ? 148 * 2 : (want < 1 ? 1 : want));
+    pa.n_abs = (int)(want > 145 ? 145 : (want < 1 ? 1 : want));          // one wave of 1024-thread blocks (one resident per SM)
   }
   cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
   if (check_launch("cubemlp prep")) return 1;
