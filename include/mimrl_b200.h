@@ -326,7 +326,8 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
  * carry prev_ln_w / prev_ln_b / prev_n (its input is the previous mix's LayerNorm output); x and n_cols[0] describe the
  * input of mix 0.  Afterwards mimrl_cubemlp_mix_fwd_tc is called with prepared = 1 on the same workspaces. */
 int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n_cols, const int *a_in, const int *a_hid,
-                            const int *a_out, const float *const *w1, const float *const *b1, const float *const *w2,
+                            const int *a_out, const int *inner, const int *act, const float *const *w1,
+                            const float *const *b1, const float *const *w2,
                             const float *const *wres, const float *const *ln_w, const float *const *prev_ln_w,
                             const float *const *prev_ln_b, const int *prev_n, void *const *workspace, void *stream);
 

@@ -79,7 +79,7 @@ _SIGS = {
     "mimrl_cubemlp_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mimrl_cubemlp_mix_fwd_tc": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P, _P,
                                          _P, c_size_t, _P, _P, c_int, c_int, _P]),
-    "mimrl_cubemlp_prep_many": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mimrl_cubemlp_prep_many": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mimrl_cubemlp_mix_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, c_int,
                                       c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mimrl_cubemlp_small_supported": (c_int, [c_int, c_int, c_int]),

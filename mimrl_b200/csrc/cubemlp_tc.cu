@@ -895,6 +895,7 @@ __device__ __forceinline__ void cube_prep_body(const CubePrepArgs &a, const int 
     const float m_gy = __uint_as_float(tl[1]), m_rstd = __uint_as_float(tl[2]);
     if (prev_bound > 0.f) m_x = prev_bound, tl[0] = __float_as_uint(prev_bound);
     float *scales = reinterpret_cast<float *>(a.tail + 4);
+    tl[14] = __float_as_uint(b1_max);             // (with tail[12]: what a per-fibre bound of |h| needs)
     const float m_h = m_x * row1_max + b1_max;
     scales[0] = pow2_scale(m_x), scales[1] = pow2_scale(m_h);
     if (a.backward) {
@@ -988,12 +989,20 @@ int cube_weight_maps(const CubeWs &w, int a_in, int a_hid, int a_out, bool has_r
 }  // namespace
 
 namespace {
+// The compile-time specialised sequence-mix forward (cubemlp_tc2.cu) holds a whole fibre per thread: with an input that is
+// not a LayerNorm output (the first mix of an encoder) it takes the operand scales per fibre instead of from a pass over x.
+bool cube_fibre_scale(const float *prev_ln_w, int prev_n, int a_in, int a_hid, int a_out, int inner, long long n_cols, int act,
+                      bool has_res) {
+  const bool bounded = prev_ln_w != nullptr && prev_n > 0 && prev_n <= 256;
+  return !bounded && !getenv("MIMRL_CUBE_FIBRE_SCALE_OFF") && cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, has_res ? 1 : 0);
+}
 CubePrepArgs cube_fwd_prep_args(const CubeWs &w, const float *x, long long n_cols, int a_in, int a_hid, int a_out, const float *w1,
                                 const float *b1, const float *w2, const float *wres, const float *ln_w, const float *prev_ln_w,
-                                const float *prev_ln_b, int prev_n) {
+                                const float *prev_ln_b, int prev_n, bool scale_in_kernel) {
   CubePrepArgs pa{};
   const bool bounded = prev_ln_w != nullptr && prev_n > 0 && prev_n <= 256;
-  pa.x = bounded ? nullptr : x, pa.nx = bounded ? 0 : (size_t)n_cols * a_in;
+  // scale_in_kernel (cube_fibre_scale): the forward kernel scales every fibre by its own max|x| -- no pass over x here
+  pa.x = bounded || scale_in_kernel ? nullptr : x, pa.nx = bounded || scale_in_kernel ? 0 : (size_t)n_cols * a_in;
   pa.prev_ln_w = bounded ? prev_ln_w : nullptr, pa.prev_ln_b = bounded ? prev_ln_b : nullptr, pa.prev_n = bounded ? prev_n : 0;
   pa.w[0] = w1, pa.w[1] = w2, pa.w[2] = wres;
   for (int m = 0; m < 3; ++m) pa.split[m] = w.s[m], pa.hdr[m] = w.s[m];
@@ -1010,7 +1019,8 @@ CubePrepArgs cube_fwd_prep_args(const CubeWs &w, const float *x, long long n_col
 // describe the input of mix 0 (ignored when mix 0 has prev_ln_w).  Afterwards call mimrl_cubemlp_mix_fwd_tc with
 // prepared = 1 on the same workspaces.
 extern "C" int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n_cols, const int *a_in, const int *a_hid,
-                                       const int *a_out, const float *const *w1, const float *const *b1,
+                                       const int *a_out, const int *inner, const int *act, const float *const *w1,
+                                       const float *const *b1,
                                        const float *const *w2, const float *const *wres, const float *const *ln_w,
                                        const float *const *prev_ln_w, const float *const *prev_ln_b, const int *prev_n,
                                        void *const *workspace, void *stream) {
@@ -1023,8 +1033,9 @@ extern "C" int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n
                   "cubemlp_prep_many: mix %d is outside the tensor-core kernels", m);
     MIMRL_REQUIRE(m == 0 || (prev_ln_w[m] && prev_n[m] > 0 && prev_n[m] <= 256), "cubemlp_prep_many: mix %d needs the LayerNorm bound of its input", m);
     const CubeWs w = cube_ws(workspace[m], a_in[m], a_hid[m], a_out[m]);
+    const bool fs = cube_fibre_scale(prev_ln_w[m], prev_n[m], a_in[m], a_hid[m], a_out[m], inner[m], n_cols[m], act[m], wres[m] != nullptr);
     b.a[m] = cube_fwd_prep_args(w, m == 0 ? x : nullptr, n_cols[m], a_in[m], a_hid[m], a_out[m], w1[m], b1[m], w2[m], wres[m], ln_w[m],
-                                prev_ln_w[m], prev_ln_b[m], prev_n[m]);
+                                prev_ln_w[m], prev_ln_b[m], prev_n[m], fs);
     MIMRL_REQUIRE(m != 0 || b.a[0].prev_ln_w || x, "cubemlp_prep_many: mix 0 needs x or a LayerNorm bound");
     // 1024-thread blocks at 56 registers: one resident block per SM -- keep the whole launch to one wave
     if (m == 0 && b.a[0].n_abs > 148 - 3 * n) b.a[0].n_abs = 148 - 3 * n;
@@ -1049,9 +1060,10 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   cudaStream_t st = (cudaStream_t)stream;
   const CubeWs w = cube_ws(workspace, a_in, a_hid, a_out);
   const long long n_cols = (long long)outer * inner;
+  const bool fs = cube_fibre_scale(prev_ln_w, prev_n, a_in, a_hid, a_out, inner, n_cols, act, wres != nullptr);
   if (!prepared) {
     cudaMemsetAsync(w.tail, 0, 16, st);
-    const CubePrepArgs pa = cube_fwd_prep_args(w, x, n_cols, a_in, a_hid, a_out, w1, b1, w2, wres, ln_w, prev_ln_w, prev_ln_b, prev_n);
+    const CubePrepArgs pa = cube_fwd_prep_args(w, x, n_cols, a_in, a_hid, a_out, w1, b1, w2, wres, ln_w, prev_ln_w, prev_ln_b, prev_n, fs);
     cube_prep_kernel<<<pa.n_abs + 3, kPrepThreads, 0, st>>>(pa);
     if (check_launch("cubemlp prep")) return 1;
   }
@@ -1063,6 +1075,7 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   p.sc_wr = reinterpret_cast<const unsigned *>(w.s[2]);
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
   p.n_cols = n_cols;
+  p.fibre_scale = fs ? 1 : 0;
   CUtensorMap maps[6];
   if (cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res)) {
     int r1, r2, rr, handled = 0;

@@ -15,6 +15,8 @@ struct CubeTcParams {
   unsigned *absmax;                                    // [0] max|x| [1] max|gy| [2] max rstd (the forward adds its rstd here)
   int outer, A, H, A2, inner, act, has_res;
   long long n_cols;
+  int fibre_scale;          // cube2 forward: operand scales per fibre from the fibre's own max|x| (no pass over x before
+                            // the kernel); the kernel publishes max|x| to absmax[0] for a backward that reuses the workspace
 };
 
 struct CubeBwdParams {
@@ -33,6 +35,14 @@ __device__ __forceinline__ float cube_act(int act, float z) {
   if (act == 0) return gelu_fwd(z);
   if (act == 1) return fmaxf(z, 0.f);
   return tanhf(z);
+}
+
+// the same scale from the exponent bits (per-fibre use inside a kernel): 2^(14 - e), amax = f * 2^e with f in [0.5, 1)
+__device__ __forceinline__ float pow2_scale_bits(float amax) {
+  const int E = (int)((__float_as_uint(amax) >> 23) & 0xffu);          // amax >= 0
+  int sh = 14 - (E - 126);
+  sh = sh > 60 ? 60 : (sh < -60 ? -60 : sh);
+  return __uint_as_float((uint32_t)(127 + sh) << 23);
 }
 
 __device__ __forceinline__ float pow2_scale(float amax) {      // amax * scale in [2^13, 2^14)

@@ -130,10 +130,13 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
   } else {
     const int r = threadIdx.x;
     const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const float sx = p.scales[0], sh = p.scales[1];
-    const float i_pre = 1.f / (sx * scale_from_absmax(p.sc_w1[0])), i_o = 1.f / (sh * scale_from_absmax(p.sc_w2[0]));
-    const float i_r = 1.f / (sx * scale_from_absmax(p.sc_wr[0]));
-    float rstd_max = 0.f;
+    float sx = p.scales[0], sh = p.scales[1];
+    const float sw1 = scale_from_absmax(p.sc_w1[0]), sw2 = scale_from_absmax(p.sc_w2[0]), swr = scale_from_absmax(p.sc_wr[0]);
+    float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr);
+    // fibre_scale: |h| <= max|x_fibre| * max_h sum_a |W1[h,a]| + max|b1| (the preparation kernel left both in the tail)
+    const bool fibre_scale = p.fibre_scale != 0;
+    const float row1_max = fibre_scale ? __uint_as_float(p.absmax[12]) : 0.f, b1_max = fibre_scale ? __uint_as_float(p.absmax[14]) : 0.f;
+    float rstd_max = 0.f, x_max = 0.f;
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -142,15 +145,70 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
       const float *xf = p.x + (size_t)o * A * INNER + i0;
       float *yf = p.y + (size_t)o * Q * INNER + i0;
       // ---- 1. fibre -> X operand (fp16 hi / lo)
+      if (!fibre_scale) {
 #pragma unroll
-      for (int u = 0; u < PA / 16; ++u) {
-        float v[16];
+        for (int u = 0; u < PA / 16; ++u) {
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = u * 16 + j < A ? __ldg(xf + (size_t)(u * 16 + j) * INNER) * sx : 0.f;
-        uint32_t hi[8], lo[8];
-        split16(v, hi, lo);
-        tmem_st8(tb + u * 8, hi);
-        tmem_st8(tb + PA / 2 + u * 8, lo);
+          for (int j = 0; j < 16; ++j) v[j] = u * 16 + j < A ? __ldg(xf + (size_t)(u * 16 + j) * INNER) * sx : 0.f;
+          uint32_t hi[8], lo[8];
+          split16(v, hi, lo);
+          tmem_st8(tb + u * 8, hi);
+          tmem_st8(tb + PA / 2 + u * 8, lo);
+        }
+      } else if constexpr (PH + PS >= PA) {
+        // the scale needs the fibre's max first: the raw values are parked in the (idle) pre | r columns of this
+        // thread's TMEM lane, sixteen at a time as they arrive, and read back once the scale is known
+        float m = 0.f;
+#pragma unroll
+        for (int u = 0; u < PA / 16; ++u) {
+          uint32_t raw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = u * 16 + j < A ? __ldg(xf + (size_t)(u * 16 + j) * INNER) : 0.f;
+            m = fmaxf(m, fabsf(v));
+            raw[j] = __float_as_uint(v);
+          }
+          tmem_st8(tb + B0 + u * 16, raw);
+          tmem_st8(tb + B0 + u * 16 + 8, raw + 8);
+        }
+        tmem_st_wait();
+        x_max = fmaxf(x_max, m);
+        sx = pow2_scale_bits(m), sh = pow2_scale_bits(fmaf(m, row1_max, b1_max));
+        i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr);
+#pragma unroll
+        for (int u = 0; u < PA / 16; ++u) {
+          uint32_t d[16];
+          tmem_ld16(tb + B0 + u * 16, d);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(d[j]) * sx;
+          uint32_t hi[8], lo[8];
+          split16(v, hi, lo);
+          tmem_st8(tb + u * 8, hi);
+          tmem_st8(tb + PA / 2 + u * 8, lo);
+        }
+      } else {
+        float xv[PA];
+#pragma unroll
+        for (int j = 0; j < PA; ++j) xv[j] = j < A ? __ldg(xf + (size_t)j * INNER) : 0.f;
+        float m = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) m = fmaxf(m, fabsf(xv[j]));
+        x_max = fmaxf(x_max, m);
+        sx = pow2_scale_bits(m), sh = pow2_scale_bits(fmaf(m, row1_max, b1_max));
+        i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr);
+#pragma unroll
+        for (int u = 0; u < PA / 16; ++u) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = xv[u * 16 + j] * sx;
+          uint32_t hi[8], lo[8];
+          split16(v, hi, lo);
+          tmem_st8(tb + u * 8, hi);
+          tmem_st8(tb + PA / 2 + u * 8, lo);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -223,8 +281,12 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
       reinterpret_cast<float2 *>(p.saved)[tile * 128 + r] = make_float2(mean, rstd);
       rstd_max = fmaxf(rstd_max, rstd);
     }
-    for (int o = 16; o; o >>= 1) rstd_max = fmaxf(rstd_max, __shfl_xor_sync(0xffffffffu, rstd_max, o));
+    for (int o = 16; o; o >>= 1) {
+      rstd_max = fmaxf(rstd_max, __shfl_xor_sync(0xffffffffu, rstd_max, o));
+      x_max = fmaxf(x_max, __shfl_xor_sync(0xffffffffu, x_max, o));
+    }
     if (lane == 0) atomicMax(p.absmax + 2, __float_as_uint(rstd_max));
+    if (lane == 0 && fibre_scale) atomicMax(p.absmax, __float_as_uint(x_max));
   }
   tc_fence_before();
   __syncthreads();

@@ -279,7 +279,7 @@ class MLPEncoder(nn.Module):
         if not (USE_TC and x.is_cuda and x.dim() == 4 and len(self.layers_stack) * 2 <= 8):
             return None
         bs, Ld, Kd, Dd = x.shape
-        plan = []          # (A, H, A2, n_cols, mlp, wres, ln, prev_ln)
+        plan = []          # (A, H, A2, n_cols, mlp, wres, ln, prev_ln, inner, act)
         prev = None
         for blk in self.layers_stack:
             if not blk._fusable(mask) or blk.ln_fist:
@@ -292,7 +292,8 @@ class MLPEncoder(nn.Module):
                     if n_cols < 1024 or not L.lib.mimrl_cubemlp_tc_supported(A, H, A2, 0, _ACT_IDS[blk.activate]):
                         return None
                     wres = getattr(blk, "res_projection_" + ax).weight if blk.res_project else None
-                    plan.append((A, H, A2, n_cols, mlp, wres, ln, prev if ax == "l" else blk.ln_k))
+                    plan.append((A, H, A2, n_cols, mlp, wres, ln, prev if ax == "l" else blk.ln_k,
+                                 Kd * Dd if ax == "l" else 1, _ACT_IDS[blk.activate]))
                 if ax == "l":
                     Ld = A2
                 elif ax == "k":
@@ -311,7 +312,8 @@ class MLPEncoder(nn.Module):
         x32 = L.f32(x)
         L.check(L.lib.mimrl_cubemlp_prep_many(
             n, L.ptr(x32), (ctypes.c_longlong * n)(*[p_[3] for p_ in plan]), arr_i([p_[0] for p_ in plan]),
-            arr_i([p_[1] for p_ in plan]), arr_i([p_[2] for p_ in plan]),
+            arr_i([p_[1] for p_ in plan]), arr_i([p_[2] for p_ in plan]), arr_i([p_[8] for p_ in plan]),
+            arr_i([p_[9] for p_ in plan]),
             arr_p([f(p_[4].fc1.weight) for p_ in plan]), arr_p([f(p_[4].fc1.bias) for p_ in plan]),
             arr_p([f(p_[4].fc2.weight) for p_ in plan]), arr_p([f(p_[5]) for p_ in plan]),
             arr_p([f(p_[6].weight) for p_ in plan]),
