@@ -1076,6 +1076,7 @@ extern "C" int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
   p.n_cols = n_cols;
   p.fibre_scale = fs ? 1 : 0;
+  if (!getenv("MIMRL_CUBE2_PREFETCH_OFF")) p.fibre_scale |= 2;          // bit 1: L2 prefetch of the next tile's rows
   CUtensorMap maps[6];
   if (cube2_supported(a_in, a_hid, a_out, inner, n_cols, act, p.has_res)) {
     int r1, r2, rr, handled = 0;
@@ -1165,6 +1166,7 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
   p.sc_wr = reinterpret_cast<const unsigned *>(w.s[2]);
   p.outer = outer, p.A = a_in, p.H = a_hid, p.A2 = a_out, p.inner = inner, p.act = act, p.has_res = wres ? 1 : 0;
   p.n_cols = n_cols;
+  p.fibre_scale = 0;          // (forward-only switches; the same prefetch in the backward kernel measured no gain)
   bp.gy = gy, bp.gx = gx, bp.g_b1 = g_b1, bp.g_b2 = g_b2, bp.g_lnw = gln_w, bp.g_lnb = gln_b;
   bp.scales = p.scales;
   const long long n_tiles = (n_cols + 127) / 128;

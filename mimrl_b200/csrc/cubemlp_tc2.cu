@@ -134,7 +134,7 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
     const float sw1 = scale_from_absmax(p.sc_w1[0]), sw2 = scale_from_absmax(p.sc_w2[0]), swr = scale_from_absmax(p.sc_wr[0]);
     float i_pre = 1.f / (sx * sw1), i_o = 1.f / (sh * sw2), i_r = 1.f / (sx * swr);
     // fibre_scale: |h| <= max|x_fibre| * max_h sum_a |W1[h,a]| + max|b1| (the preparation kernel left both in the tail)
-    const bool fibre_scale = p.fibre_scale != 0;
+    const bool fibre_scale = (p.fibre_scale & 1) != 0;
     const float row1_max = fibre_scale ? __uint_as_float(p.absmax[12]) : 0.f, b1_max = fibre_scale ? __uint_as_float(p.absmax[14]) : 0.f;
     float rstd_max = 0.f, x_max = 0.f;
     int it = 0;
@@ -214,6 +214,15 @@ cube2_fwd_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bX);
+      if (p.fibre_scale & 2) {          // next tile's fibre rows towards L2 while this tile computes
+        const long long nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const long long no = nt / C::TPO;
+          const float *nx = p.x + (size_t)no * A * INNER + (int)(nt - no * C::TPO) * 128 + r;
+#pragma unroll 4
+          for (int j = 0; j < A; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * INNER));
+        }
+      }
       // ---- 2. h = gelu(pre + b1) -> H operand over the dead X columns
       mbar_wait(bD1, ph);
       tc_fence_after();
