@@ -117,6 +117,10 @@ struct GemmParams {
   // MN-major operand exist (the second one is not loaded when the operand has <= 64 features), output transposed
   int n_mma, a_boxes, b_boxes, trans_out, ldc;
   int b_rows;     // blocked-K layout: box height of the B operand (its rows rounded up to 16)
+  // blocked-K layout: ring geometry chosen by the host from the box heights (narrow operands -> small stages -> a deep
+  // ring, so that enough bytes are in flight per SM); 0 stages = the fixed 3 x 64 KB ring
+  int n_stages, kbs;          // kbs: k-blocks per stage (one TMA box per plane carries kbs consecutive k-tiles)
+  uint32_t stage_bytes, a_plane, b_plane;          // plane = kbs x (box rows x 128 bytes)
 };
 
 // A_MN / B_MN: operand stored with the contraction index as the SLOW one (read MN-major)
@@ -131,8 +135,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - raw);
   const uint32_t bars = base + kGStages * kGStage;
-  const uint32_t bFull = bars, bEmpty = bars + 32;
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kGStages * kGStage + 128);
+  const uint32_t bFull = bars, bEmpty = bars + 128;          // up to 16 stages
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + kGStages * kGStage + 384);
+  const bool ring = BLK && p.n_stages > 0;
+  const int n_st = ring ? p.n_stages : kGStages;
+  const uint32_t st_bytes = ring ? p.stage_bytes : kGStage;
+  const uint32_t o_a1 = ring ? p.a_plane : kOp16, o_b0 = ring ? 2u * p.a_plane : 2u * kOp16,
+                 o_b1 = ring ? 2u * p.a_plane + p.b_plane : 3u * kOp16;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // Persistent over work items (m tile, n tile, k split): the ring keeps streaming across items and the two TMEM
@@ -140,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int n_kb = (p.K + 63) / 64;
   const int tiles_m = (p.M + 127) / 128, tiles_n = (p.N + 127) / 128;
   const long long n_items = (long long)tiles_m * tiles_n * p.splits;
-  const uint32_t bAccFull = bars + 64, bAccEmpty = bars + 80;
+  const uint32_t bAccFull = bars + 256, bAccEmpty = bars + 272;
   auto item_of = [&](long long it, int &m0, int &n0, int &split, int &kb0, int &T) {
     split = (int)(it / ((long long)tiles_m * tiles_n));
     const int rem = (int)(it - (long long)split * tiles_m * tiles_n);
@@ -151,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kGStages; ++i) {
+    for (int i = 0; i < n_st; ++i) {
       mbar_init(bFull + 8 * i, 1);
       mbar_init(bEmpty + 8 * i, 1);
     }
@@ -162,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(gen + kGStages * kGStage + 128), 256);
+    tmem_alloc(smem_u32(gen + kGStages * kGStage + 384), 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -179,13 +188,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
         int m0, n0, split, kb0, T;
         item_of(it, m0, n0, split, kb0, T);
-        for (int i = 0; i < T; ++i, ++n) {
-          const int stage = n % kGStages, k0 = (kb0 + i) * 64;
-          mbar_wait(bEmpty + 8 * stage, ((n / kGStages) & 1) ^ 1);
+        const int kstep = ring ? p.kbs : 1;
+        for (int i = 0; i < T; i += kstep, ++n) {
+          const int stage = n % n_st, k0 = (kb0 + i) * 64;
+          mbar_wait(bEmpty + 8 * stage, ((n / n_st) & 1) ^ 1);
           const uint32_t fb = bFull + 8 * stage;
           mbar_expect_tx(fb, (A_MN && B_MN) ? (uint32_t)(p.a_boxes + p.b_boxes) * 2u * 8192u
+                                 : ring ? 2u * p.a_plane + 2u * p.b_plane
                                  : BLK ? 2u * kOp16 + 2u * (uint32_t)p.b_rows * 128u : kGStage);
-          const uint32_t dst = base + stage * kGStage;
+          const uint32_t dst = base + stage * st_bytes;
           if (A_MN) {   // rows = contraction index, 64 per box; two boxes cover 128 M
             tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, m0, k0);
             tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, m0, k0);
@@ -194,8 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               tma_load_2d(dst + 1 * kOp16 + 8192, &map_a_lo, fb, m0 + 64, k0);
             }
           } else if (BLK) {
-            tma_load_3d(dst + 0 * kOp16, &map_a_hi, fb, 0, m0, kb0 + i);
-            tma_load_3d(dst + 1 * kOp16, &map_a_lo, fb, 0, m0, kb0 + i);
+            tma_load_3d(dst, &map_a_hi, fb, 0, m0, kb0 + i);
+            tma_load_3d(dst + o_a1, &map_a_lo, fb, 0, m0, kb0 + i);
           } else {
             tma_load_2d(dst + 0 * kOp16, &map_a_hi, fb, k0, m0);
             tma_load_2d(dst + 1 * kOp16, &map_a_lo, fb, k0, m0);
@@ -208,8 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               tma_load_2d(dst + 3 * kOp16 + 8192, &map_b_lo, fb, n0 + 64, k0);
             }
           } else if (BLK) {
-            tma_load_3d(dst + 2 * kOp16, &map_b_hi, fb, 0, n0, kb0 + i);
-            tma_load_3d(dst + 3 * kOp16, &map_b_lo, fb, 0, n0, kb0 + i);
+            tma_load_3d(dst + o_b0, &map_b_hi, fb, 0, n0, kb0 + i);
+            tma_load_3d(dst + o_b1, &map_b_lo, fb, 0, n0, kb0 + i);
           } else {
             tma_load_2d(dst + 2 * kOp16, &map_b_hi, fb, k0, n0);
             tma_load_2d(dst + 3 * kOp16, &map_b_lo, fb, k0, n0);
@@ -227,21 +238,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t acc = j & 1, tacc = tmem_base + acc * 128;
       mbar_wait(bAccEmpty + 8 * acc, ((j >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
       tc_fence_after();
-      for (int i = 0; i < T; ++i, ++n) {
-        const int stage = n % kGStages;
-        mbar_wait(bFull + 8 * stage, (n / kGStages) & 1);
+      const int kstep = ring ? p.kbs : 1;
+      const uint32_t a_sub = ring ? p.a_plane / (uint32_t)p.kbs : 0u, b_sub = ring ? p.b_plane / (uint32_t)p.kbs : 0u;
+      for (int i = 0; i < T; i += kstep, ++n) {
+        const int stage = n % n_st;
+        mbar_wait(bFull + 8 * stage, (n / n_st) & 1);
         tc_fence_after();
         if (leader) {
-          const uint32_t s0 = base + stage * kGStage;
+          const uint32_t s0 = base + stage * st_bytes;
+          const int subs = min(kstep, T - i);          // (a box past the end of this split is loaded but not used)
+          for (int sub = 0; sub < subs; ++sub) {
 #pragma unroll
-          for (int prod = 0; prod < 3; ++prod) {
-            const uint32_t a_base = s0 + (prod == 2 ? 1 : 0) * kOp16;          // A hi, hi, lo
-            const uint32_t b_base = s0 + (prod == 1 ? 3 : 2) * kOp16;          // B hi, lo, hi
+            for (int prod = 0; prod < 3; ++prod) {
+              const uint32_t a_base = s0 + (prod == 2 ? o_a1 : 0u) + sub * a_sub;               // A hi, hi, lo
+              const uint32_t b_base = s0 + (prod == 1 ? o_b1 : o_b0) + sub * b_sub;             // B hi, lo, hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = A_MN ? smem_desc_sw128_mn(a_base + k * 2048, 8192, 1024) : smem_desc_sw128(a_base + k * 32);
-              const uint64_t bd = B_MN ? smem_desc_sw128_mn(b_base + k * 2048, 8192, 1024) : smem_desc_sw128(b_base + k * 32);
-              umma_f16(tacc, ad, bd, idesc, (i | prod | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = A_MN ? smem_desc_sw128_mn(a_base + k * 2048, 8192, 1024) : smem_desc_sw128(a_base + k * 32);
+                const uint64_t bd = B_MN ? smem_desc_sw128_mn(b_base + k * 2048, 8192, 1024) : smem_desc_sw128(b_base + k * 32);
+                umma_f16(tacc, ad, bd, idesc, (i | sub | prod | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(bEmpty + 8 * stage);
@@ -504,7 +520,7 @@ extern "C" int mimrl_gemm_split(int mode, const void *a_split, const void *b_spl
   if (make_map(&al, pa + la.off_lo, g.a_cols, g.a_rows, la.ld, a_mn ? 64 : 128)) return 1;
   if (make_map(&bh, pb + lb.off_hi, g.b_cols, g.b_rows, lb.ld, b_mn ? 64 : 128)) return 1;
   if (make_map(&bl, pb + lb.off_lo, g.b_cols, g.b_rows, lb.ld, b_mn ? 64 : 128)) return 1;
-  GemmParams p;
+  GemmParams p{};
   p.M = M, p.N = N, p.K = K;
   p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
   p.splits = g.splits;
@@ -550,7 +566,7 @@ extern "C" int mimrl_gemm_split_blocked(const void *a_split, const void *b_split
   if (make_map_blocked(&ah, pa + la.off_hi, M, kt, 128) || make_map_blocked(&al, pa + la.off_lo, M, kt, 128) ||
       make_map_blocked(&bh, pb + lb.off_hi, N, kt, 128) || make_map_blocked(&bl, pb + lb.off_lo, N, kt, 128))
     return 1;
-  GemmParams p;
+  GemmParams p{};
   p.M = M, p.N = N, p.K = K;
   p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
   p.splits = g.splits;
@@ -590,15 +606,29 @@ extern "C" int mimrl_gemm_split_blocked_acc(const void *a_split, const void *b_s
   const SplitLayout lm = split_layout(Mm, K), ln = split_layout(Nn, K);
   CUtensorMap mh, ml, nh, nl;
   const uint64_t kt = (uint64_t)K / 64;
-  if (make_map_blocked(&mh, pm + lm.off_hi, Mm, kt, 128) || make_map_blocked(&ml, pm + lm.off_lo, Mm, kt, 128) ||
-      make_map_blocked(&nh, pn + ln.off_hi, Nn, kt, n_pad) || make_map_blocked(&nl, pn + ln.off_lo, Nn, kt, n_pad))
+  // box heights = the operands' own rows (rounded to the 8-row swizzle atom / to the MMA N): a stage is as small as the
+  // data it carries and the ring as deep as fits (<= 16 stages, 176 KB -- the MMA reads 128 rows from the A plane, so
+  // the last 16 KB of the ring stay unused; rows past the box are other planes' finite or not, they only reach
+  // accumulator rows >= M that are never written out)
+  static const bool deep = !getenv("MIMRL_GEMM_RING_OFF");
+  const int m_box = deep ? (Mm + 7) & ~7 : 128;
+  // several consecutive k-tiles per TMA box when the operands are narrow (a 10 x 10 gradient over 393216 fibres was
+  // bound by the number of 2 KB boxes the TMA unit issues, not by bytes): ~40 KB per stage
+  int kbs = 1;
+  if (deep) {
+    kbs = (int)(40960u / (2u * (uint32_t)(m_box + n_pad) * 128u));
+    kbs = kbs < 1 ? 1 : (kbs > 8 ? 8 : kbs);
+    if (getenv("MIMRL_GEMM_KBS")) kbs = atoi(getenv("MIMRL_GEMM_KBS"));
+  }
+  if (make_map_blocked(&mh, pm + lm.off_hi, Mm, kt, m_box, kbs) || make_map_blocked(&ml, pm + lm.off_lo, Mm, kt, m_box, kbs) ||
+      make_map_blocked(&nh, pn + ln.off_hi, Nn, kt, n_pad, kbs) || make_map_blocked(&nl, pn + ln.off_lo, Nn, kt, n_pad, kbs))
     return 1;
   // enough pieces of the contraction for every SM, at most 32 k-blocks per accumulator (tensor-core adds truncate)
   const int n_kb = K / 64;
   const int want = ceil_div(n_kb, 32);
   int splits = want <= 148 ? 148 : 148 * ceil_div(want, 148);
   if (splits > n_kb) splits = n_kb;
-  GemmParams p;
+  GemmParams p{};
   p.M = Mm, p.N = Nn, p.K = K;
   p.kblocks_per_split = ceil_div(n_kb, splits);
   p.splits = ceil_div(n_kb, p.kblocks_per_split);
@@ -607,6 +637,14 @@ extern "C" int mimrl_gemm_split_blocked_acc(const void *a_split, const void *b_s
   p.absmax_b = reinterpret_cast<const unsigned *>(pn);
   p.atomic_out = 1;
   p.n_mma = n_pad, p.a_boxes = 2, p.b_boxes = 2, p.trans_out = swap ? 1 : 0, p.ldc = N, p.b_rows = n_pad;
+  if (deep) {
+    p.kbs = kbs;
+    p.a_plane = (uint32_t)kbs * m_box * 128u, p.b_plane = (uint32_t)kbs * n_pad * 128u;
+    p.stage_bytes = 2u * p.a_plane + 2u * p.b_plane;          // multiples of 1024: the swizzle atoms stay aligned
+    const uint32_t room = kGStages * kGStage - (m_box == 128 ? 0u : kOp16);          // (a full-height A plane needs no slack)
+    p.n_stages = (int)(room / p.stage_bytes);
+    if (p.n_stages > 16) p.n_stages = 16;
+  }
   p.bias = nullptr;
   p.C = C;
   dim3 grid(1, 1, p.splits);
@@ -652,7 +690,7 @@ extern "C" int mimrl_gemm_f32x3(int mode, const float *A, const float *a_mask, c
   if (make_map(&al, a_lo, g.a_cols, g.a_rows, g.lda, a_mn ? 64 : 128)) return 1;
   if (make_map(&bh, b_hi, g.b_cols, g.b_rows, g.ldb, b_mn ? 64 : 128)) return 1;
   if (make_map(&bl, b_lo, g.b_cols, g.b_rows, g.ldb, b_mn ? 64 : 128)) return 1;
-  GemmParams p;
+  GemmParams p{};
   p.M = M, p.N = N, p.K = K;
   p.kblocks_per_split = ceil_div(ceil_div(K, 64), g.splits);
   p.splits = g.splits;

@@ -274,7 +274,8 @@ inline int make_map(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t ro
 // Blocked-K fp16 matrix [rows, K]: tiles of 64 consecutive k, each tile [rows][64] contiguous (tile t at
 // t * rows * 64 elements).  A [box_rows x 64] box of one tile is ONE contiguous run of box_rows * 128 bytes in
 // memory -- the layout for operands whose K runs over millions of entries (weight gradients over pairs / fibres).
-inline int make_map_blocked(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t k_tiles, uint32_t box_rows) {
+inline int make_map_blocked(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t k_tiles, uint32_t box_rows,
+                            uint32_t box_k_tiles = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -282,7 +283,7 @@ inline int make_map_blocked(CUtensorMap *m, const void *ptr, uint64_t rows, uint
   }
   cuuint64_t dims[3] = {64, rows, k_tiles};
   cuuint64_t strides[2] = {64 * sizeof(__half), rows * 64 * sizeof(__half)};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {64, box_rows, box_k_tiles};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
