@@ -442,6 +442,26 @@ def extra_configs(args, world, rank, dev, flush):
             nbr, _ = knn_search_sharded(Z, ids, k, rb)
             c4[f"k{k}"] = {"queries": m, "search_ms": ms, "key_gbs": N * width * 4 / ms * 1e-6,
                            "algorithmic_tflops": 2.0 * width * m * N / ms * 1e-9, "checksum": int(nbr.sum().item())}
+        if world == 1:          # the single-GPU sampler paths around the sharded search above
+            import time as _t
+            from mimrl_b200.model import KnnPool, knn_search, legacy_permutation_head
+            c4["fit_ms"] = timed(lambda: KnnPool(Z), warm=1, reps=3)
+            pool = KnnPool(Z)
+            for k in (2, 16):
+                ids = torch.from_numpy(np.random.RandomState(0).permutation(N)[:bs // k].astype(np.int64)).to(dev)
+                c4[f"k{k}"]["unsharded_search_ms"] = timed(lambda: knn_search(Z, ids, k), warm=1, reps=3)
+                c4[f"k{k}"]["fitted_pool_search_ms"] = timed(lambda: knn_search(pool, ids, k), warm=1, reps=3)
+            gen.manual_seed(7)
+            Zl = torch.randn(N, 1, device=dev, generator=gen)
+            ids = torch.from_numpy(np.random.RandomState(0).permutation(N)[:bs // 2].astype(np.int64)).to(dev)
+            c4["label_pool_width1_k2_search_ms"] = timed(lambda: knn_search(Zl, ids, 2), warm=1, reps=3)
+            st = np.random.get_state()
+            t0 = _t.perf_counter(); np.random.permutation(N)[:bs // 2]; t1 = _t.perf_counter()
+            legacy_permutation_head(N, bs // 2); t2 = _t.perf_counter()
+            np.random.set_state(st)
+            c4["host_id_draw_ms"] = {"numpy_permutation": (t1 - t0) * 1e3, "mimrl_legacy_permutation_head": (t2 - t1) * 1e3,
+                                     "what": "np.random.choice(range(N), m, replace=False) stream of Model.py:81, N = 2^20"}
+            del pool, Zl
         out["config4_knn_1Mx128"] = c4
         del Z
         torch.cuda.empty_cache()

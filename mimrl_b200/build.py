@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libmimrl_b200.so")
-SOURCES = ["bound_small.cu", "sep_ffma.cu", "sep_tc.cu", "gemm_tc.cu", "knn.cu", "knn_tc.cu", "knn_1d.cu", "vcmi.cu", "cubemlp.cu", "cubemlp_tc.cu", "cubemlp_tc2.cu", "cubemlp_tc3.cu", "concat_tc.cu", "mlp_tc.cu", "features.cu", "linear_small.cu", "host_rng.cu"]
+SOURCES = ["bound_small.cu", "sep_ffma.cu", "sep_tc.cu", "gemm_tc.cu", "knn.cu", "knn_tc.cu", "knn_1d.cu", "vcmi.cu", "cubemlp.cu", "cubemlp_tc.cu", "cubemlp_tc2.cu", "cubemlp_tc3.cu", "cubemlp_wgrad.cu", "concat_tc.cu", "mlp_tc.cu", "features.cu", "linear_small.cu", "host_rng.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

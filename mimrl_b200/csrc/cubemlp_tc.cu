@@ -1185,6 +1185,9 @@ extern "C" int mimrl_cubemlp_mix_bwd_tc(const float *x, const float *gy, int out
     bp.op[t][1] = reinterpret_cast<__half *>((unsigned char *)ops[t] + 256 + align256((size_t)feats[t] * bp.ld * 2));
   }
   auto wgrads = [&]() -> int {
+    int fused = 0;
+    if (int rc = cube_wgrad_fused(op_x, op_h, op_gz, op_gpre, a_in, a_hid, a_out, R, gw1, gw2, wres ? gwres : nullptr, st, &fused)) return rc;
+    if (fused) return 0;
     if (int rc = mimrl_gemm_split_blocked_acc(op_gpre, op_x, a_hid, a_in, (int)R, gw1, stream)) return rc;
     if (int rc = mimrl_gemm_split_blocked_acc(op_gz, op_h, a_out, a_hid, (int)R, gw2, stream)) return rc;
     if (wres)

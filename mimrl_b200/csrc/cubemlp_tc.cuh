@@ -215,6 +215,10 @@ __device__ __forceinline__ void c2_store_op(__half *hi_base, __half *lo_base, si
 
 }  // namespace
 
+// cubemlp_wgrad.cu: the three weight-gradient contractions of a mix in one kernel (every operand read once)
+int cube_wgrad_fused(const void *op_x, const void *op_h, const void *op_gz, const void *op_gpre, int A, int H, int Q, long long R,
+                     float *gw1, float *gw2, float *gwr, cudaStream_t st, int *handled);
+
 // cubemlp_tc2.cu: returns 0 and sets *handled = 1 when a compile-time specialisation exists for the shape
 int cube2_fwd(const CUtensorMap *maps, const CubeTcParams &p, cudaStream_t st, int *handled);
 int cube2_bwd(const CUtensorMap *maps, const CubeBwdParams &bp, cudaStream_t st, int *handled);
