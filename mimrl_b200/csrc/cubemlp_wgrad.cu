@@ -16,7 +16,7 @@ namespace mimrl {
 namespace {
 
 constexpr int kWgThreads = 192;
-constexpr uint32_t kWgRing = 192 * 1024;
+constexpr uint32_t kWgRing = 216 * 1024;
 constexpr uint32_t kWgSmem = kWgRing + 512 + 1024;
 constexpr int kChunk = 4;          // k-blocks per turn when two gradient tiles share a sweep
 
@@ -95,7 +95,9 @@ cube_wgrad_kernel(const __grid_constant__ CUtensorMap m_x_hi, const __grid_const
             const int stage = n % n_st, kb = kb0 + i;
             mbar_wait(bEmpty + 8 * stage, ((n / n_st) & 1) ^ 1);
             const uint32_t fb = bFull + 8 * stage;
-            mbar_expect_tx(fb, 2u * p.a_plane + 2u * p.b_plane);
+            // (two tiles: the gpre tile needs x only -- gpre^T h is not a gradient)
+            const bool with_h = p.n_mtiles == 1 || mt == 1;
+            mbar_expect_tx(fb, 2u * p.a_plane + (with_h ? 2u * p.b_plane : 2u * (uint32_t)p.cols_x * 128u));
             const uint32_t dst = base + stage * p.stage_bytes;
             if (p.n_mtiles == 1) {
               tma_load_3d(dst, &m_gp_hi, fb, 0, 0, kb);
@@ -108,15 +110,17 @@ cube_wgrad_kernel(const __grid_constant__ CUtensorMap m_x_hi, const __grid_const
             }
             const uint32_t db = dst + 2u * p.a_plane;
             tma_load_3d(db, &m_x_hi, fb, 0, 0, kb);
-            tma_load_3d(db + p.cols_x * 128u, &m_h_hi, fb, 0, 0, kb);
             tma_load_3d(db + p.b_plane, &m_x_lo, fb, 0, 0, kb);
-            tma_load_3d(db + p.b_plane + p.cols_x * 128u, &m_h_lo, fb, 0, 0, kb);
+            if (with_h) {
+              tma_load_3d(db + p.cols_x * 128u, &m_h_hi, fb, 0, 0, kb);
+              tma_load_3d(db + p.b_plane + p.cols_x * 128u, &m_h_lo, fb, 0, 0, kb);
+            }
           }
       }
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
-    const uint32_t idesc = instr_desc_f16(128, n_mma);
+    const uint32_t idesc_full = instr_desc_f16(128, n_mma), idesc_x = instr_desc_f16(128, p.cols_x);
     uint32_t n = 0, j = 0;
     for (int split = blockIdx.x; split < p.splits; split += gridDim.x) {
       int kb0, T;
@@ -132,6 +136,7 @@ cube_wgrad_kernel(const __grid_constant__ CUtensorMap m_x_hi, const __grid_const
       for (int c0 = 0; c0 < T; c0 += CH)
       for (int mt = 0; mt < p.n_mtiles; ++mt) {
         const uint32_t acc = p.n_mtiles == 2 ? (uint32_t)mt : (j & 1), tacc = tmem_base + acc * 256;
+        const uint32_t idesc = (p.n_mtiles == 2 && mt == 0) ? idesc_x : idesc_full;
         for (int i = c0; i < T && i < c0 + CH; ++i, ++n) {
           const int stage = n % n_st;
           mbar_wait(bFull + 8 * stage, (n / n_st) & 1);
@@ -237,9 +242,10 @@ int cube_wgrad_fused(const void *op_x, const void *op_h, const void *op_gz, cons
   p.a_plane = (uint32_t)(p.n_mtiles == 1 ? p.rows_gp + p.rows_gz : 128) * 128u;
   p.b_plane = (uint32_t)(p.cols_x + p.cols_h) * 128u;
   p.stage_bytes = 2u * p.a_plane + 2u * p.b_plane;
-  // the MMA reads 128 rows of the G plane: keep 16 KB of the ring unused behind a shorter one
-  const uint32_t room = kWgRing - (p.a_plane == 16384u ? 0u : 16384u);
-  p.n_stages = (int)(room / p.stage_bytes);
+  // (the MMA reads 128 rows = 16 KB from each G plane; behind a shorter plane that runs into the P planes of the same
+  // stage -- a_plane + 16 KB <= stage_bytes for every shape accepted here -- and only feeds accumulator rows nobody reads)
+  if (p.a_plane + 16384u > p.stage_bytes) return 0;
+  p.n_stages = (int)(kWgRing / p.stage_bytes);
   if (p.n_stages > 16) p.n_stages = 16;
   if (p.n_stages < 2) return 0;
   p.n_kb = (int)(R / 64);
