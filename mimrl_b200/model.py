@@ -149,9 +149,12 @@ def _sum_over_ranks(t, rb):
 def _rows_from_shards(local, ids, rb):
     """rows ``ids`` (global row numbers) of a matrix whose row blocks live on different ranks: every rank
     contributes the rows it owns, one all-reduce assembles them everywhere."""
-    out = torch.zeros(ids.numel(), local.shape[1], dtype=torch.float32, device=local.device)
+    local = L.f32(local)
+    if local.shape[0] == 0:
+        return _sum_over_ranks(torch.zeros(ids.numel(), local.shape[1], dtype=torch.float32, device=local.device), rb)
     mine = (ids >= rb.offset) & (ids < rb.offset + rb.n_own)
-    out[mine] = L.f32(local)[ids[mine] - rb.offset]
+    # (clamped gather times the ownership mask: no boolean indexing, i.e. no device-to-host sync)
+    out = local[(ids - rb.offset).clamp(0, local.shape[0] - 1)] * mine.unsqueeze(1).to(torch.float32)
     return _sum_over_ranks(out, rb)
 
 
@@ -179,6 +182,8 @@ def knn_search_sharded(Z_local, ids, k, rb, return_distance=False):
     world * k candidates per query are all-gathered and merged by (distance, index) -- the same total order the
     single-GPU search uses, so the result is bit-identical to it.  ``ids`` are global row numbers, the same on
     every rank.  Returns (nbr_orig, nbr_comp[, dist]) replicated on every rank."""
+    if not rb.sharded:          # one rank holds the whole pool: the plain search (bit-identical, tests/test_gpu_multi.py)
+        return knn_search(Z_local, ids, k, return_distance=return_distance)
     Z_local = L.f32(Z_local)
     dev = Z_local.device
     width = Z_local.shape[1]
