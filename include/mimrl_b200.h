@@ -313,7 +313,9 @@ int mimrl_cubemlp_small_bwd(const float *x, const float *gy, int outer, int a_in
  * lanes, W1 / W2 / Wres resident in shared memory, LayerNorm thread-local in the epilogue.  Writes the same
  * `saved` statistics, so mimrl_cubemlp_mix_bwd applies unchanged.  prev_ln_w / prev_ln_b [prev_n] (nullable): x is the
  * unmodified output of a LayerNorm with these parameters over prev_n features (the previous mix of the block); its
- * operand scale then comes from the bound max|ln_w| sqrt(prev_n - 1) + max|ln_b| instead of a pass over x. */
+ * operand scale then comes from the bound max|ln_w| sqrt(prev_n - 1) + max|ln_b| instead of a pass over x.  Without
+ * such a bound the compile-time specialised sequence-mix kernel (README shapes) scales every fibre by its own max|x|
+ * inside the kernel; other shapes take one pass over x.  prepared != 0: mimrl_cubemlp_prep_many has filled `workspace`. */
 int mimrl_cubemlp_tc_supported(int a_in, int a_hid, int a_out, int ln_first, int act);
 size_t mimrl_cubemlp_tc_workspace_bytes(int a_in, int a_hid, int a_out);
 int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, const float *w1, const float *b1,
@@ -324,7 +326,9 @@ int mimrl_cubemlp_mix_fwd_tc(const float *x, int outer, int a_in, int inner, con
 /* The preparation (weight split, operand scales) of n <= 8 mixes of an encoder forward in ONE launch.  Every array has n
  * entries, in execution order; workspace[m] must be ZERO-FILLED (mimrl_cubemlp_tc_workspace_bytes each).  Mix m > 0 must
  * carry prev_ln_w / prev_ln_b / prev_n (its input is the previous mix's LayerNorm output); x and n_cols[0] describe the
- * input of mix 0.  Afterwards mimrl_cubemlp_mix_fwd_tc is called with prepared = 1 on the same workspaces. */
+ * input of mix 0; inner[m] / act[m] are the `inner` and `act` arguments the forward call of mix m will get (they
+ * decide whether that mix takes its input scale inside the kernel).  Afterwards mimrl_cubemlp_mix_fwd_tc is called with
+ * prepared = 1 on the same workspaces. */
 int mimrl_cubemlp_prep_many(int n, const float *x, const long long *n_cols, const int *a_in, const int *a_hid,
                             const int *a_out, const int *inner, const int *act, const float *const *w1,
                             const float *const *b1, const float *const *w2,
