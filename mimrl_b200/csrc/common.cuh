@@ -115,7 +115,11 @@ KnnTcKeys knn_tc_keys_in_workspace(const KnnTcPlan &plan, unsigned char *ws);
 int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKeys &out, float *key_norms, cudaStream_t st);
 // after knn_tc_prepare_keys (and after excluded rows got +inf norms)
 int knn_filter_tc(const KnnTcKeys &keys, const float *key_norms, int n_keys, int width, const float *queries,
-                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st);
+                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st,
+                  bool q_ready = false);
+// queries = rows `ids` of the key pool: gather + squared norms + max|q| in one pass (then knn_filter_tc with q_ready)
+int knn_tc_gather_queries(const float *keys, int width, const int64_t *ids, int n_queries, const KnnTcPlan &plan,
+                          unsigned char *ws, float *q_out, cudaStream_t st);
 
 // width-1 pools on the kd_tree route (knn_1d.cu): sort + per-query two-sided walk
 bool knn1d_supported(int width, int exact_form);

@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(128)
 knn_rerank_kernel(const float *__restrict__ keys, int n_keys, int width, int64_t key_offset,
                   const float *__restrict__ queries, int n_queries, const Cand *__restrict__ cand, int n_lists,
                   int list_len, int k, int exact_form, int64_t *__restrict__ nbr_orig,
-                  double *__restrict__ nbr_dist) {
+                  double *__restrict__ nbr_dist, const int64_t *__restrict__ comp_ids, int n_comp_ids,
+                  int64_t *__restrict__ nbr_comp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_cand = n_lists * list_len;
   Cand *cs = reinterpret_cast<Cand *>(smem_raw);                   // [n_cand]
@@ -301,6 +302,22 @@ knn_rerank_kernel(const float *__restrict__ keys, int n_keys, int width, int64_t
       if (nbr_dist) nbr_dist[(size_t)q * k + rank] = d;
     }
   }
+  // 4. nbr_comp = index with the query rows removed (what sklearn returns in the reference): nbr_orig minus the number
+  // of removed ids below it, counted by the whole block for each of its k outputs
+  if (nbr_comp) {
+    __syncthreads();          // this block's nbr_orig entries are visible to all its threads
+    for (int o = 0; o < k; ++o) {
+      const int64_t v = nbr_orig[(size_t)q * k + o];
+      int below = 0;
+      for (int i = tid; i < n_comp_ids; i += blockDim.x) below += __ldg(comp_ids + i) < v ? 1 : 0;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
+      if (lane == 0) w_i[warp] = below;
+      __syncthreads();
+      if (tid == 0) nbr_comp[(size_t)q * k + o] = v - (w_i[0] + w_i[1] + w_i[2] + w_i[3]);
+      __syncthreads();
+    }
+  }
 }
 
 // nbr_comp = nbr_orig - #(excluded ids < nbr_orig); one warp per output, the ids split over its lanes
@@ -385,7 +402,8 @@ KnnTcKeys fitted_keys(const FitLayout &f, unsigned char *fitted) {
 
 int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const float *queries, int n_queries,
              const int64_t *excluded, int n_excluded, int k, int exact_form, int64_t *nbr_orig, double *nbr_dist,
-             const Plan &p, unsigned char *ws, cudaStream_t st, const unsigned char *fitted = nullptr) {
+             const Plan &p, unsigned char *ws, cudaStream_t st, const unsigned char *fitted = nullptr,
+             int64_t *nbr_comp = nullptr, bool *comp_done = nullptr, bool q_ready = false) {
   if (knn1d_supported(width, exact_form))          // label pools: sort once, walk per query
     return knn1d_search(keys, n_keys, key_offset, queries, n_queries, excluded, n_excluded, k, nbr_orig, nbr_dist,
                         ws + p.off_1d, st);
@@ -408,7 +426,7 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
     if (check_launch("knn mark_excluded")) return 1;
   }
   if (p.use_tc) {
-    if (knn_filter_tc(tck, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st)) return 1;
+    if (knn_filter_tc(tck, kn, n_keys, width, queries, n_queries, p.tc, ws + p.off_tc, cand, st, q_ready)) return 1;
   } else {
     dim3 grid(ceil_div(n_queries, kQT), p.splits);
     if (width <= 15) {
@@ -425,8 +443,10 @@ int knn_core(const float *keys, int n_keys, int width, int64_t key_offset, const
   const size_t rsmem = (size_t)p.n_lists * p.list_len * sizeof(Cand) + (size_t)((p.list_len + 1) & ~1) * 4 +
                        (size_t)p.list_len * 8;
   cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+  // (the compacted indices come out of the same kernel when the caller wants them: excluded = the removed query rows)
   knn_rerank_kernel<<<n_queries, 128, rsmem, st>>>(keys, n_keys, width, key_offset, queries, n_queries, cand, p.n_lists,
-                                                  p.list_len, k, exact_form, nbr_orig, nbr_dist);
+                                                  p.list_len, k, exact_form, nbr_orig, nbr_dist, excluded, n_excluded, nbr_comp);
+  if (comp_done) *comp_done = nbr_comp != nullptr;
   return check_launch("knn_rerank");
 }
 
@@ -524,11 +544,17 @@ static int knn_search_impl(const float *keys, int n_keys, int width, const unsig
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *ws = (unsigned char *)workspace;
   float *q = reinterpret_cast<float *>(ws + p.off_q);
-  if (int rc = mimrl_gather_rows(keys, n_keys, width, query_ids, n_queries, 1, width, q, stream)) return rc;
-  if (int rc = knn_core(keys, n_keys, width, 0, q, n_queries, query_ids, n_queries, k, exact_form, nbr_orig, nbr_dist,
-                        p, ws, st, fitted))
+  const bool tc_route = p.use_tc && !knn1d_supported(width, exact_form);
+  if (tc_route) {          // gather, query norms and max|q| in one pass
+    if (int rc = knn_tc_gather_queries(keys, width, query_ids, n_queries, p.tc, ws + p.off_tc, q, st)) return rc;
+  } else if (int rc = mimrl_gather_rows(keys, n_keys, width, query_ids, n_queries, 1, width, q, stream)) {
     return rc;
-  if (nbr_comp) {
+  }
+  bool comp_done = false;
+  if (int rc = knn_core(keys, n_keys, width, 0, q, n_queries, query_ids, n_queries, k, exact_form, nbr_orig, nbr_dist,
+                        p, ws, st, fitted, nbr_comp, &comp_done, tc_route))
+    return rc;
+  if (nbr_comp && !comp_done) {          // (the sorted width-1 route has no re-rank kernel)
     const size_t n_out = (size_t)n_queries * k;
     compact_index_kernel<<<(int)((n_out * 32 + 255) / 256), 256, 0, st>>>(nbr_orig, n_out, query_ids, n_queries, nbr_comp);
     return check_launch("knn compact_index");

@@ -125,6 +125,32 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
   if (lane == 0) out[w] = acc;
 }
 
+// Queries of the sampler are rows of the key pool: gather them, their squared norms and max|q| in one pass (one warp per
+// query; same summation order as knn_row_norms_kernel)
+__global__ void knn_gather_queries_kernel(const float *__restrict__ keys, int width, const int64_t *__restrict__ ids, int n,
+                                          float *__restrict__ q, float *__restrict__ qn, unsigned *__restrict__ absmax) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float *src = keys + (size_t)ids[w] * width;
+  float *dst = q + (size_t)w * width;
+  float acc = 0.f, mx = 0.f;
+  for (int e = lane; e < width; e += 32) {
+    const float v = __ldg(src + e);
+    dst[e] = v;
+    acc = fmaf(v, v, acc);
+    mx = fmaxf(mx, fabsf(v));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  if (lane == 0) {
+    qn[w] = acc;
+    if (mx > 0.f) atomicMax(absmax, __float_as_uint(mx));
+  }
+}
+
 struct KnnTcParams {
   int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group, refresh_mask;
   float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
@@ -525,22 +551,33 @@ int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKey
   return check_launch("knn prepare keys");
 }
 
+int knn_tc_gather_queries(const float *keys, int width, const int64_t *ids, int n_queries, const KnnTcPlan &plan,
+                          unsigned char *ws, float *q_out, cudaStream_t st) {
+  unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
+  cudaMemsetAsync(absmax, 0, 8, st);
+  knn_gather_queries_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(keys, width, ids, n_queries, q_out,
+                                                                          reinterpret_cast<float *>(ws + plan.off_qn), absmax);
+  return check_launch("knn gather queries");
+}
+
 int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int width, const float *queries,
-                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st) {
+                  int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st, bool q_ready) {
   unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
   float *qn = reinterpret_cast<float *>(ws + plan.off_qn);
   __half *q_hi = reinterpret_cast<__half *>(ws + plan.off_q_hi), *q_lo = reinterpret_cast<__half *>(ws + plan.off_q_lo);
   __half *k_hi = static_cast<__half *>(pk.hi), *k_lo = static_cast<__half *>(pk.lo);
-  cudaMemsetAsync(absmax, 0, 8, st);
-  const size_t nq = (size_t)n_queries * width;
-  int blocks = (int)((nq + 2047) / 2048);
-  blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
-  knn_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(queries, nq, nullptr, 0, absmax);
-  if (check_launch("knn absmax")) return 1;
+  if (!q_ready) {          // (knn_tc_gather_queries has filled max|q| and the norms otherwise)
+    cudaMemsetAsync(absmax, 0, 8, st);
+    const size_t nq = (size_t)n_queries * width;
+    int blocks = (int)((nq + 2047) / 2048);
+    blocks = blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
+    knn_absmax_kernel<<<dim3(blocks, 1), 256, 0, st>>>(queries, nq, nullptr, 0, absmax);
+    if (check_launch("knn absmax")) return 1;
+    knn_row_norms_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(queries, n_queries, width, qn);
+    if (check_launch("knn query norms")) return 1;
+  }
   knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
   if (check_launch("knn split q")) return 1;
-  knn_row_norms_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(queries, n_queries, width, qn);
-  if (check_launch("knn query norms")) return 1;
   CUtensorMap mh, ml;
   if (make_map(&mh, k_hi, 128, n_keys, 128, 128)) return 1;
   if (make_map(&ml, k_lo, 128, n_keys, 128, 128)) return 1;
