@@ -100,7 +100,7 @@ struct KnnCand {
 };
 struct KnnTcPlan {
   int splits, tiles_per_split, n_lists, list_len;
-  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, off_pub, off_tscale, bytes;
+  size_t off_absmax, off_qn, off_q_hi, off_q_lo, off_k_hi, off_k_lo, off_pub, off_tscale, off_qscale, bytes;
 };
 bool knn_tc_supported(int n_keys, int n_queries, int width, int list_len);
 KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len);
@@ -117,7 +117,8 @@ int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKey
 int knn_filter_tc(const KnnTcKeys &keys, const float *key_norms, int n_keys, int width, const float *queries,
                   int n_queries, const KnnTcPlan &plan, unsigned char *ws, KnnCand *cand, cudaStream_t st,
                   bool q_ready = false);
-// queries = rows `ids` of the key pool: gather + squared norms + max|q| in one pass (then knn_filter_tc with q_ready)
+// queries = rows `ids` of the key pool: gather + squared norms + per-tile scale + fp16 split in one launch (then
+// knn_filter_tc with q_ready)
 int knn_tc_gather_queries(const float *keys, int width, const int64_t *ids, int n_queries, const KnnTcPlan &plan,
                           unsigned char *ws, float *q_out, cudaStream_t st);
 

@@ -544,7 +544,8 @@ static int knn_search_impl(const float *keys, int n_keys, int width, const unsig
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *ws = (unsigned char *)workspace;
   float *q = reinterpret_cast<float *>(ws + p.off_q);
-  const bool tc_route = p.use_tc && !knn1d_supported(width, exact_form);
+  static const bool qprep_off = getenv("MIMRL_KNN_QPREP_OFF") != nullptr;
+  const bool tc_route = p.use_tc && !knn1d_supported(width, exact_form) && !qprep_off;
   if (tc_route) {          // gather, query norms and max|q| in one pass
     if (int rc = knn_tc_gather_queries(keys, width, query_ids, n_queries, p.tc, ws + p.off_tc, q, st)) return rc;
   } else if (int rc = mimrl_gather_rows(keys, n_keys, width, query_ids, n_queries, 1, width, q, stream)) {

@@ -125,36 +125,71 @@ __global__ void knn_row_norms_kernel(const float *__restrict__ x, int n, int wid
   if (lane == 0) out[w] = acc;
 }
 
-// Queries of the sampler are rows of the key pool: gather them, their squared norms and max|q| in one pass (one warp per
-// query; same summation order as knn_row_norms_kernel)
-__global__ void knn_gather_queries_kernel(const float *__restrict__ keys, int width, const int64_t *__restrict__ ids, int n,
-                                          float *__restrict__ q, float *__restrict__ qn, unsigned *__restrict__ absmax) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n) return;
-  const float *src = keys + (size_t)ids[w] * width;
-  float *dst = q + (size_t)w * width;
-  float acc = 0.f, mx = 0.f;
-  for (int e = lane; e < width; e += 32) {
-    const float v = __ldg(src + e);
-    dst[e] = v;
-    acc = fmaf(v, v, acc);
-    mx = fmaxf(mx, fabsf(v));
+// Queries of the sampler are rows of the key pool.  One CTA per 128-query tile (the tile a filter CTA parks in TMEM):
+// gather the rows, squared norms (same summation order as knn_row_norms_kernel), the tile's max|q| -> a power-of-two
+// scale of its own, fp16 hi / lo split (K zero-padded to 128).  One launch instead of gather + absmax + norms + split.
+__global__ void __launch_bounds__(256) knn_prep_queries_kernel(const float *__restrict__ keys, int width,
+                                                               const int64_t *__restrict__ ids, int n, float *__restrict__ q,
+                                                               float *__restrict__ qn, unsigned *__restrict__ tile_absmax,
+                                                               __half *__restrict__ hi, __half *__restrict__ lo) {
+  __shared__ float s_max[8];
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  // warp w owns rows w, w + 8, ... of the tile; a lane owns columns lane, lane + 32, lane + 64, lane + 96
+  float v[16][4];
+  float mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int row = blockIdx.x * 128 + w + 8 * j;
+    const float *src = row < n ? keys + (size_t)__ldg(ids + row) * width : nullptr;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[j][c] = (src && lane + 32 * c < width) ? __ldg(src + lane + 32 * c) : 0.f;
   }
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  for (int j = 0; j < 16; ++j) {
+    const int row = blockIdx.x * 128 + w + 8 * j;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (lane + 32 * c < width) acc = fmaf(v[j][c], v[j][c], acc);
+      mx = fmaxf(mx, fabsf(v[j][c]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < n) {
+      if (lane == 0) qn[row] = acc;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (lane + 32 * c < width) q[(size_t)row * width + lane + 32 * c] = v[j][c];
+    }
   }
-  if (lane == 0) {
-    qn[w] = acc;
-    if (mx > 0.f) atomicMax(absmax, __float_as_uint(mx));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_max[w] = mx;
+  __syncthreads();
+  mx = s_max[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, s_max[k]);
+  if (t == 0) tile_absmax[blockIdx.x] = __float_as_uint(mx);
+  const float sc = scale_from_absmax(__float_as_uint(mx));
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int row = blockIdx.x * 128 + w + 8 * j;
+    if (row >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float a = v[j][c] * sc;
+      const __half h = __float2half_rn(a);
+      hi[(size_t)row * 128 + lane + 32 * c] = h;
+      lo[(size_t)row * 128 + lane + 32 * c] = __float2half_rn(a - __half2float(h));
+    }
   }
 }
 
 struct KnnTcParams {
   int n_keys, n_queries, tiles_per_split, list_len, n_lists, jth, splits, q_tiles, q_group, refresh_mask;
   float *pub;                      // [n_queries][n_lists]: jth-smallest distance each (split, warpgroup) part has seen
-  const unsigned *absmax;          // [0] queries
+  const unsigned *absmax;          // max|q|: [0] for all queries (absmax_stride 0) or one per 128-query tile (stride 1)
+  int absmax_stride;
   const float *tile_inv_scale;     // 1 / (power-of-two scale) of every 128-key tile (knn_prep_keys_kernel)
   const __half *q_hi, *q_lo;
   const float *qn, *kn;
@@ -329,7 +364,7 @@ knn_filter_tc_kernel(const __grid_constant__ CUtensorMap map_k_hi, const __grid_
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const bool row_ok = row0 + r < p.n_queries;
-    const float m2q = -2.f / scale_from_absmax(p.absmax[0]);        // times 1 / (scale of the key tile), per tile
+    const float m2q = -2.f / scale_from_absmax(p.absmax[(row0 >> 7) * p.absmax_stride]);        // times 1 / (scale of the key tile), per tile
     const float qn = row_ok ? p.qn[row0 + r] : 0.f;
     KnnCand *lst = lists + (size_t)(wg * 128 + r) * kListMax;
     float *kn_s = knbuf + wg * 128;
@@ -534,6 +569,7 @@ KnnTcPlan knn_tc_plan(int n_keys, int n_queries, int width, int list_len) {
   p.off_k_lo = o, o += align256((size_t)n_keys * 128 * 2);
   p.off_pub = o, o += align256((size_t)q_tiles * 128 * p.n_lists * 4);
   p.off_tscale = o, o += align256((size_t)k_tiles * 4);
+  p.off_qscale = o, o += align256((size_t)q_tiles * 4);
   p.bytes = o;
   return p;
 }
@@ -553,11 +589,11 @@ int knn_tc_prepare_keys(const float *keys, int n_keys, int width, const KnnTcKey
 
 int knn_tc_gather_queries(const float *keys, int width, const int64_t *ids, int n_queries, const KnnTcPlan &plan,
                           unsigned char *ws, float *q_out, cudaStream_t st) {
-  unsigned *absmax = reinterpret_cast<unsigned *>(ws + plan.off_absmax);
-  cudaMemsetAsync(absmax, 0, 8, st);
-  knn_gather_queries_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(keys, width, ids, n_queries, q_out,
-                                                                          reinterpret_cast<float *>(ws + plan.off_qn), absmax);
-  return check_launch("knn gather queries");
+  knn_prep_queries_kernel<<<ceil_div(n_queries, 128), 256, 0, st>>>(
+      keys, width, ids, n_queries, q_out, reinterpret_cast<float *>(ws + plan.off_qn),
+      reinterpret_cast<unsigned *>(ws + plan.off_qscale), reinterpret_cast<__half *>(ws + plan.off_q_hi),
+      reinterpret_cast<__half *>(ws + plan.off_q_lo));
+  return check_launch("knn prepare queries");
 }
 
 int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int width, const float *queries,
@@ -566,7 +602,7 @@ int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int w
   float *qn = reinterpret_cast<float *>(ws + plan.off_qn);
   __half *q_hi = reinterpret_cast<__half *>(ws + plan.off_q_hi), *q_lo = reinterpret_cast<__half *>(ws + plan.off_q_lo);
   __half *k_hi = static_cast<__half *>(pk.hi), *k_lo = static_cast<__half *>(pk.lo);
-  if (!q_ready) {          // (knn_tc_gather_queries has filled max|q| and the norms otherwise)
+  if (!q_ready) {          // (knn_tc_gather_queries has produced norms, per-tile max|q| and the fp16 planes otherwise)
     cudaMemsetAsync(absmax, 0, 8, st);
     const size_t nq = (size_t)n_queries * width;
     int blocks = (int)((nq + 2047) / 2048);
@@ -575,9 +611,9 @@ int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int w
     if (check_launch("knn absmax")) return 1;
     knn_row_norms_kernel<<<ceil_div(n_queries * 32, 256), 256, 0, st>>>(queries, n_queries, width, qn);
     if (check_launch("knn query norms")) return 1;
+    knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
+    if (check_launch("knn split q")) return 1;
   }
-  knn_split_kernel<<<ceil_div(n_queries * 64, 256), 256, 0, st>>>(queries, n_queries, width, absmax, 0, q_hi, q_lo);
-  if (check_launch("knn split q")) return 1;
   CUtensorMap mh, ml;
   if (make_map(&mh, k_hi, 128, n_keys, 128, 128)) return 1;
   if (make_map(&ml, k_lo, 128, n_keys, 128, 128)) return 1;
@@ -587,7 +623,8 @@ int knn_filter_tc(const KnnTcKeys &pk, const float *key_norms, int n_keys, int w
   p.jth = ceil_div(plan.list_len, plan.n_lists);
   p.pub = reinterpret_cast<float *>(ws + plan.off_pub);
   cudaMemsetAsync(p.pub, 0x7f, (size_t)ceil_div(n_queries, 128) * 128 * plan.n_lists * 4, st);     // 3.39e38: "nothing seen yet"
-  p.absmax = absmax, p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
+  p.absmax = q_ready ? reinterpret_cast<const unsigned *>(ws + plan.off_qscale) : absmax, p.absmax_stride = q_ready ? 1 : 0;
+  p.q_hi = q_hi, p.q_lo = q_lo, p.qn = qn, p.kn = key_norms, p.cand = cand;
   p.tile_inv_scale = pk.tile_inv_scale;
   cudaFuncSetAttribute(knn_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnSmem);
   p.splits = plan.splits;
