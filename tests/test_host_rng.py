@@ -46,3 +46,30 @@ def test_other_bit_generators_fall_back_to_numpy():
     a = legacy_permutation_head(100, 10)              # small pools: numpy's own call
     np.random.seed(1)
     assert np.array_equal(a, np.random.permutation(100)[:10])
+
+
+def test_feature_pool_refits_keys_when_the_pool_changes(monkeypatch):
+    """train_step.FeaturePool.keys: one fit per pool tensor, refitted after roll(), after assignment of a new tensor and
+    after an in-place torch write (version counter) -- host logic, KnnPool replaced by a counter."""
+    import torch
+    import mimrl_b200.model as M
+    from mimrl_b200.train_step import FeaturePool
+    made = []
+
+    class FakePool:
+        def __init__(self, Z):
+            made.append(Z)
+    monkeypatch.setattr(M, "KnnPool", FakePool)
+    pool = FeaturePool()
+    pool.T = torch.zeros(8, 4)
+    a = pool.keys("T")
+    assert pool.keys("T") is a and len(made) == 1                 # cached
+    pool.T.add_(1.0)                                               # in-place write through torch
+    b = pool.keys("T")
+    assert b is not a and len(made) == 2
+    pool.T = torch.ones(8, 4)                                      # replaced
+    assert pool.keys("T") is not b and len(made) == 3
+    pool.append(torch.zeros(3), torch.zeros(3, 4), torch.zeros(3, 4), torch.zeros(3, 4), torch.zeros(3, 4))
+    pool.roll()                                                    # epoch boundary
+    c = pool.keys("T")
+    assert len(made) == 4 and made[-1] is pool.T and pool.keys("T") is c
