@@ -546,7 +546,7 @@ static int knn_search_impl(const float *keys, int n_keys, int width, const unsig
   float *q = reinterpret_cast<float *>(ws + p.off_q);
   static const bool qprep_off = getenv("MIMRL_KNN_QPREP_OFF") != nullptr;
   const bool tc_route = p.use_tc && !knn1d_supported(width, exact_form) && !qprep_off;
-  if (tc_route) {          // gather, query norms and max|q| in one pass
+  if (tc_route) {          // gather, norms, per-tile scale and fp16 split of the queries in one launch
     if (int rc = knn_tc_gather_queries(keys, width, query_ids, n_queries, p.tc, ws + p.off_tc, q, st)) return rc;
   } else if (int rc = mimrl_gather_rows(keys, n_keys, width, query_ids, n_queries, 1, width, q, stream)) {
     return rc;
