@@ -25,7 +25,7 @@ struct WgParams {
   int rows_gp, rows_gz;          // box heights of gpre / gz (multiples of 8; 128 each when n_mtiles == 2)
   int cols_x, cols_h;            // box heights of x / h (multiples of 16): MMA N = cols_x + cols_h <= 256
   int A, H, Q;                   // true feature counts of x, h (= gpre), gz
-  int n_kb, kb_per_split, splits, n_stages;
+  int n_kb, kb_per_split, splits, n_stages, chunk;
   uint32_t stage_bytes, a_plane, b_plane;
   const unsigned *hdr_x, *hdr_h, *hdr_gz, *hdr_gp;
   float *gw1, *gw2, *gwr;        // [H, A], [Q, H], [Q, A] (gwr NULL without res_projection)
@@ -88,7 +88,7 @@ cube_wgrad_kernel(const __grid_constant__ CUtensorMap m_x_hi, const __grid_const
       for (int split = blockIdx.x; split < p.splits; split += gridDim.x) {
         int kb0, T;
         range_of(split, kb0, T);
-        const int CH = p.n_mtiles == 2 ? kChunk : (T > 0 ? T : 1);
+        const int CH = p.n_mtiles == 2 ? p.chunk : (T > 0 ? T : 1);
         for (int c0 = 0; c0 < T; c0 += CH)
         for (int mt = 0; mt < p.n_mtiles; ++mt)
           for (int i = c0; i < T && i < c0 + CH; ++i, ++n) {
@@ -127,7 +127,7 @@ cube_wgrad_kernel(const __grid_constant__ CUtensorMap m_x_hi, const __grid_const
       range_of(split, kb0, T);
       // one gradient tile: accumulators alternate between splits; two tiles: accumulator = tile, and the sweep alternates
       // between the tiles every kChunk k-blocks so that the second tile finds the activation operand in L2
-      const int CH = p.n_mtiles == 2 ? kChunk : (T > 0 ? T : 1);
+      const int CH = p.n_mtiles == 2 ? p.chunk : (T > 0 ? T : 1);
       for (int mt = 0; mt < p.n_mtiles; ++mt) {
         const uint32_t acc = p.n_mtiles == 2 ? (uint32_t)mt : (j & 1);
         mbar_wait(bAccEmpty + 8 * acc, ((p.n_mtiles == 2 ? j : (j >> 1)) & 1) ^ 1);
@@ -248,6 +248,8 @@ int cube_wgrad_fused(const void *op_x, const void *op_h, const void *op_gz, cons
   p.n_stages = (int)(kWgRing / p.stage_bytes);
   if (p.n_stages > 16) p.n_stages = 16;
   if (p.n_stages < 2) return 0;
+  static const int chunk = getenv("MIMRL_WGRAD_CHUNK") ? atoi(getenv("MIMRL_WGRAD_CHUNK")) : kChunk;
+  p.chunk = chunk > 0 ? chunk : kChunk;
   p.n_kb = (int)(R / 64);
   const int want = (p.n_kb + 31) / 32;            // <= 32 k-blocks per accumulator (the tensor core adds with truncation)
   int splits = want <= 148 ? 148 : 148 * ((want + 147) / 148);
