@@ -84,7 +84,7 @@ def test_knn_size_functions_without_gpu(lib):
     """Host-only planning of the k-NN entry points: which pools have a fit (tensor-core route: width > 15 and at least
     2048 rows), and the width-1 workspace carries the sorted pool (four N-entry arrays + the radix-sort scratch)."""
     N = 1 << 20
-    assert lib.mimrl_knn_fit_bytes(N, 128) >= 2 * N * 128 * 2 + N * 4          # fp16 hi / lo planes + norms
-    assert lib.mimrl_knn_fit_bytes(5000, 40) > 0
-    assert lib.mimrl_knn_fit_bytes(N, 1) == 0 and lib.mimrl_knn_fit_bytes(1000, 128) == 0 and lib.mimrl_knn_fit_bytes(0, 128) == 0
-    assert lib.mimrl_knn_workspace_bytes(N, 4096, 1, 2) - lib.mimrl_knn_workspace_bytes(N, 4096, 2, 2) >= 4 * N * 4
+    assert lib.lib.mimrl_knn_fit_bytes(N, 128) >= 2 * N * 128 * 2 + N * 4          # fp16 hi / lo planes + norms
+    assert lib.lib.mimrl_knn_fit_bytes(5000, 40) > 0
+    assert lib.lib.mimrl_knn_fit_bytes(N, 1) == 0 and lib.lib.mimrl_knn_fit_bytes(1000, 128) == 0 and lib.lib.mimrl_knn_fit_bytes(0, 128) == 0
+    assert lib.lib.mimrl_knn_workspace_bytes(N, 4096, 1, 2) - lib.lib.mimrl_knn_workspace_bytes(N, 4096, 2, 2) >= 4 * N * 4
