@@ -87,4 +87,4 @@ def test_knn_size_functions_without_gpu(lib):
     assert lib.lib.mimrl_knn_fit_bytes(N, 128) >= 2 * N * 128 * 2 + N * 4          # fp16 hi / lo planes + norms
     assert lib.lib.mimrl_knn_fit_bytes(5000, 40) > 0
     assert lib.lib.mimrl_knn_fit_bytes(N, 1) == 0 and lib.lib.mimrl_knn_fit_bytes(1000, 128) == 0 and lib.lib.mimrl_knn_fit_bytes(0, 128) == 0
-    assert lib.lib.mimrl_knn_workspace_bytes(N, 4096, 1, 2) - lib.lib.mimrl_knn_workspace_bytes(N, 4096, 2, 2) >= 4 * N * 4
+    assert lib.lib.mimrl_knn_workspace_bytes(N, 4096, 1, 2) >= 4 * N * 4 + N * 4 > lib.lib.mimrl_knn_workspace_bytes(N, 4096, 2, 2)
