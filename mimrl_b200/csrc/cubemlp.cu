@@ -20,6 +20,7 @@
 // and leaves gz / h / g_pre (and u = LN(x) for ln_first) in scratch tensors laid
 // out like x, from which the weight gradients are three plain contractions.
 #include "common.cuh"
+#include "tc_common.cuh"          // packed fp32 helpers (ffma2 / fmul2 / fadd2)
 
 namespace mimrl {
 namespace {
@@ -761,6 +762,47 @@ __device__ __forceinline__ void k3_forward(const K3Params &sp, const float (&x)[
   rstd = rsqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) * (1.f / 3.f) + 1e-6f);
 }
 
+// gelu of two values (same Abramowitz-Stegun evaluation as gauss_cdf_pdf, packed)
+__device__ __forceinline__ float2 k3_gelu2(float2 z) {
+  const float2 ax = make_float2(fabsf(z.x) * 0.70710678118654752f, fabsf(z.y) * 0.70710678118654752f);
+  const float2 den = ffma2(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.f, 1.f));
+  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
+  const float2 arg = fmul2(fmul2(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(ex2(arg.x), ex2(arg.y));
+  float2 poly = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  poly = ffma2(t, poly, make_float2(1.421413741f, 1.421413741f));
+  poly = ffma2(t, poly, make_float2(-0.284496736f, -0.284496736f));
+  poly = ffma2(t, poly, make_float2(0.254829592f, 0.254829592f));
+  const float2 q = fmul2(fmul2(t, poly), fmul2(e, make_float2(0.5f, 0.5f)));
+  const float2 cdf = make_float2(z.x < 0.f ? q.x : 1.f - q.x, z.y < 0.f ? q.y : 1.f - q.y);
+  return fmul2(z, cdf);
+}
+
+// forward of TWO fibres at once (gelu): the arithmetic of k3_forward in packed fp32 -- the modality mix is bound by
+// instruction issue, and a float2 operation costs one slot for both fibres
+__device__ __forceinline__ void k3_forward_pair(const K3Params &sp, const float2 (&x)[3], float2 (&yo)[3], float2 &mean,
+                                                float2 &rstd) {
+  auto B = [](float v) { return make_float2(v, v); };
+  float2 h[3], z[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float2 pre = ffma2(B(sp.w1[3 * r + 2]), x[2], ffma2(B(sp.w1[3 * r + 1]), x[1], ffma2(B(sp.w1[3 * r]), x[0], B(sp.b1[r]))));
+    h[r] = k3_gelu2(pre);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float2 acc = ffma2(B(sp.w2[3 * r + 2]), h[2], ffma2(B(sp.w2[3 * r + 1]), h[1], ffma2(B(sp.w2[3 * r]), h[0], B(sp.b2[r]))));
+    z[r] = ffma2(B(sp.wr[3 * r + 2]), x[2], ffma2(B(sp.wr[3 * r + 1]), x[1], ffma2(B(sp.wr[3 * r]), x[0], acc)));
+  }
+  mean = fmul2(fadd2(fadd2(z[0], z[1]), z[2]), B(1.f / 3.f));
+  const float2 d0 = fsub2(z[0], mean), d1 = fsub2(z[1], mean), d2 = fsub2(z[2], mean);
+  const float2 var = ffma2(d0, d0, ffma2(d1, d1, fmul2(d2, d2)));
+  rstd = make_float2(rsqrtf(var.x * (1.f / 3.f) + 1e-6f), rsqrtf(var.y * (1.f / 3.f) + 1e-6f));
+  yo[0] = ffma2(fmul2(d0, rstd), B(sp.lw[0]), B(sp.lb[0]));
+  yo[1] = ffma2(fmul2(d1, rstd), B(sp.lw[1]), B(sp.lb[1]));
+  yo[2] = ffma2(fmul2(d2, rstd), B(sp.lw[2]), B(sp.lb[2]));
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(256)
 cubemlp_k3_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict__ saved) {
@@ -774,15 +816,26 @@ cubemlp_k3_fwd_kernel(const MixArgs m, float *__restrict__ y, float *__restrict_
     const int i4 = (int)(u - o * q4);
     const float4 *xp = reinterpret_cast<const float4 *>(m.x + (size_t)o * 3 * inner) + i4;
     const float4 a0 = __ldg(xp), a1 = __ldg(xp + q4), a2 = __ldg(xp + 2 * q4);
-    const float xs[4][3] = {{a0.x, a1.x, a2.x}, {a0.y, a1.y, a2.y}, {a0.z, a1.z, a2.z}, {a0.w, a1.w, a2.w}};
     float yo[3][4], st[8];
+    if (ACT == 0) {          // gelu: two fibres per packed instruction
+      const float2 xa[3] = {make_float2(a0.x, a0.y), make_float2(a1.x, a1.y), make_float2(a2.x, a2.y)};
+      const float2 xb[3] = {make_float2(a0.z, a0.w), make_float2(a1.z, a1.w), make_float2(a2.z, a2.w)};
+      float2 ya[3], yb[3], ma, ra, mb, rb;
+      k3_forward_pair(sp, xa, ya, ma, ra);
+      k3_forward_pair(sp, xb, yb, mb, rb);
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      float pre[3], h[3], z[3], mean, rstd;
-      k3_forward<ACT>(sp, xs[f], pre, h, z, mean, rstd);
+      for (int r = 0; r < 3; ++r) yo[r][0] = ya[r].x, yo[r][1] = ya[r].y, yo[r][2] = yb[r].x, yo[r][3] = yb[r].y;
+      st[0] = ma.x, st[1] = ra.x, st[2] = ma.y, st[3] = ra.y, st[4] = mb.x, st[5] = rb.x, st[6] = mb.y, st[7] = rb.y;
+    } else {
+      const float xs[4][3] = {{a0.x, a1.x, a2.x}, {a0.y, a1.y, a2.y}, {a0.z, a1.z, a2.z}, {a0.w, a1.w, a2.w}};
 #pragma unroll
-      for (int r = 0; r < 3; ++r) yo[r][f] = fmaf((z[r] - mean) * rstd, sp.lw[r], sp.lb[r]);
-      st[2 * f] = mean, st[2 * f + 1] = rstd;
+      for (int f = 0; f < 4; ++f) {
+        float pre[3], h[3], z[3], mean, rstd;
+        k3_forward<ACT>(sp, xs[f], pre, h, z, mean, rstd);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) yo[r][f] = fmaf((z[r] - mean) * rstd, sp.lw[r], sp.lb[r]);
+        st[2 * f] = mean, st[2 * f + 1] = rstd;
+      }
     }
     float4 *yp = reinterpret_cast<float4 *>(y + (size_t)o * 3 * inner) + i4;
 #pragma unroll
